@@ -1,0 +1,340 @@
+"""Host-side mirror of `vkjit_core::Ir` (libs/vkjit-core/src/internal.rs:126-542).
+
+Same method names, argument order and error behaviour as the reference's `Ir`, so
+the parity tests read like libs/vkjit-core/src/test.rs.  Every method is a thin
+call through the C ABI (include/vkjit_b200.h); all work happens in the native
+library.  Var ids are plain ints (`VarId`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from ._capi import CApi, Stats, product_api
+
+
+class VarType:
+    """vartype.rs:24-33 — codes as in include/vkjit_b200.h; struct types are interned per Ir."""
+    Void, Bool, U32, I32, F32 = 1, 2, 3, 4, 5
+    STRUCT_BASE = 16
+    _names = {1: "Void", 2: "Bool", 3: "U32", 4: "I32", 5: "F32"}
+    _np = {2: np.uint32, 3: np.uint32, 4: np.int32, 5: np.float32}
+
+    @classmethod
+    def name(cls, ty: int) -> str:
+        return cls._names.get(ty, f"Struct#{ty - 16}")
+
+    @classmethod
+    def numpy(cls, ty: int):
+        return cls._np[ty]
+
+
+class Bop:
+    Add, Sub, Mul, Div, Lt, Gt, Eq, Leq, Geq, Neq = range(10)
+    And, Or, Xor, Shl, Shr, Min, Max = range(16, 23)
+
+
+class Uop:
+    Neg, Abs, Not, Sqrt, Exp, Log, Sin, Cos = range(8)
+
+
+class Red:
+    Sum, Min, Max = range(3)
+
+
+def _u32arr(ids: Sequence[int]):
+    return (C.c_uint32 * len(ids))(*[int(i) for i in ids])
+
+
+class Ir:
+    def __init__(self, _api: Optional[CApi] = None):
+        self.api = _api or product_api()
+        h = C.c_void_p()
+        self.api.call("ir_create", C.byref(h))
+        self._h = h
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self.api.call("ir_destroy", self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------
+    def _new(self, name, *args) -> int:
+        out = C.c_uint32()
+        self.api.call(name, self._h, *args, C.byref(out))
+        return out.value
+
+    def struct_type(self, elems: Sequence[int]) -> int:
+        return self._new("type_struct", _u32arr(elems), len(elems))
+
+    def struct_type_elems(self, ty: int):
+        n = C.c_size_t()
+        self.api.call("type_struct_len", self._h, ty, C.byref(n))
+        out = []
+        for i in range(n.value):
+            e = C.c_uint32()
+            self.api.call("type_struct_elem", self._h, ty, i, C.byref(e))
+            out.append(e.value)
+        return out
+
+    # -- constructors (internal.rs:229-400) -------------------------------
+    def const_f32(self, v: float) -> int:
+        return self._new("const_f32", C.c_float(v))
+
+    def const_i32(self, v: int) -> int:
+        return self._new("const_i32", C.c_int32(v))
+
+    def const_u32(self, v: int) -> int:
+        return self._new("const_u32", C.c_uint32(v))
+
+    def const_bool(self, v: bool) -> int:
+        return self._new("const_bool", C.c_int32(1 if v else 0))
+
+    def _array(self, name, data, dtype) -> int:
+        a = np.ascontiguousarray(data, dtype=dtype)
+        return self._new(name, a.ctypes.data_as(C.c_void_p), a.size)
+
+    def array_f32(self, data) -> int:
+        return self._array("array_f32", data, np.float32)
+
+    def array_i32(self, data) -> int:
+        return self._array("array_i32", data, np.int32)
+
+    def array_u32(self, data) -> int:
+        return self._array("array_u32", data, np.uint32)
+
+    def array_bool(self, data) -> int:
+        return self._array("array_bool", np.asarray(data).astype(np.uint32), np.uint32)
+
+    def array_empty(self, ty: int, n: int) -> int:
+        return self._new("array_empty", ty, n)
+
+    def arange(self, ty: int, num: int) -> int:
+        return self._new("arange", ty, num)
+
+    def linspace(self, ty: int, start: int, stop: int, num: int) -> int:
+        return self._new("linspace", ty, start, stop, num)
+
+    def zeros(self, ty: int) -> int:
+        return self._new("zeros", ty)
+
+    def ones(self, ty: int) -> int:
+        return self._new("ones", ty)
+
+    def cast(self, src: int, ty: int) -> int:
+        return self._new("cast", src, ty)
+
+    def bop(self, kind: int, lhs: int, rhs: int) -> int:
+        return self._new("bop", kind, lhs, rhs)
+
+    def uop(self, kind: int, src: int) -> int:
+        return self._new("uop", kind, src)
+
+    def bitcast(self, src: int, ty: int) -> int:
+        return self._new("bitcast", src, ty)
+
+    def select(self, cond: int, lhs: int, rhs: int) -> int:
+        return self._new("select", cond, lhs, rhs)
+
+    def struct_init(self, elems: Sequence[int]) -> int:
+        return self._new("struct_init", _u32arr(elems), len(elems))
+
+    def getattr(self, src: int, idx: int) -> int:
+        return self._new("getattr", src, idx)
+
+    def setattr(self, dst: int, src: int, idx: int) -> int:
+        return self._new("setattr", dst, src, idx)
+
+    def gather(self, src: int, idx: int, active: Optional[int] = None) -> int:
+        return self._new("gather", src, idx, 0 if active is None else 1, 0 if active is None else active)
+
+    def scatter(self, src: int, dst: int, idx: int, active: Optional[int] = None) -> int:
+        return self._new("scatter", src, dst, idx, 0 if active is None else 1, 0 if active is None else active)
+
+    def scatter_add(self, src: int, dst: int, idx: int, active: Optional[int] = None) -> int:
+        return self._new("scatter_add", src, dst, idx, 0 if active is None else 1, 0 if active is None else active)
+
+    # extension unary helpers
+    def neg(self, a): return self.uop(Uop.Neg, a)
+    def abs(self, a): return self.uop(Uop.Abs, a)
+    def not_(self, a): return self.uop(Uop.Not, a)
+    def sqrt(self, a): return self.uop(Uop.Sqrt, a)
+    def exp(self, a): return self.uop(Uop.Exp, a)
+    def log(self, a): return self.uop(Uop.Log, a)
+    def sin(self, a): return self.uop(Uop.Sin, a)
+    def cos(self, a): return self.uop(Uop.Cos, a)
+
+    # -- introspection / lifetime ------------------------------------------
+    def ty(self, id: int) -> int:
+        return self._new("var_type", id)
+
+    def ref_count(self, id: int) -> int:
+        return self._new("var_ref_count", id)
+
+    def num_vars(self) -> int:
+        n = C.c_size_t()
+        self.api.call("var_count", self._h, C.byref(n))
+        return n.value
+
+    def num_arrays(self) -> int:
+        n = C.c_size_t()
+        self.api.call("array_count", self._h, C.byref(n))
+        return n.value
+
+    def is_buffer(self, id: int) -> bool:
+        o = C.c_int32()
+        self.api.call("is_buffer", self._h, id, C.byref(o))
+        return bool(o.value)
+
+    def size(self, id: int) -> int:
+        n = C.c_size_t()
+        self.api.call("var_size", self._h, id, C.byref(n))
+        return n.value
+
+    def device_ptr(self, id: int) -> int:
+        p = C.c_uint64()
+        self.api.call("var_device_ptr", self._h, id, C.byref(p))
+        return p.value
+
+    def inc_ref_count(self, id: int):
+        self.api.call("inc_ref", self._h, id)
+
+    def dec_ref_count(self, id: int):
+        self.api.call("dec_ref", self._h, id)
+
+    def _string(self, name, *args) -> str:
+        n = C.c_size_t()
+        self.api.call(name, self._h, *args, None, 0, C.byref(n))
+        buf = C.create_string_buffer(n.value + 1)
+        self.api.call(name, self._h, *args, buf, n.value + 1, C.byref(n))
+        return buf.value.decode("utf-8", "replace")
+
+    def repr(self) -> str:
+        """`format!("{:#?}", ir)`"""
+        return self._string("ir_repr")
+
+    def str(self, id: int) -> str:
+        """Ir::str for buffers (internal.rs:404-422), `{:?}` of the Var otherwise."""
+        return self._string("var_repr", id)
+
+    # -- execute -----------------------------------------------------------
+    def schedule(self, ids: Iterable[int]):
+        ids = list(ids)
+        self.api.call("schedule", self._h, _u32arr(ids), len(ids))
+
+    def eval(self, ids: Iterable[int]):
+        ids = list(ids)
+        self.api.call("eval", self._h, _u32arr(ids), len(ids))
+
+    def as_slice(self, id: int, ty: int) -> np.ndarray:
+        """Ir::as_slice::<T> (internal.rs:443-449): `ty` plays the role of T."""
+        n = self.size(id)
+        out = np.empty(n, dtype=VarType.numpy(ty))
+        self.api.call("read", self._h, id, ty, out.ctypes.data_as(C.c_void_p), out.nbytes)
+        return out
+
+    def read_into(self, id: int, ty: int, ptr: int, nbytes: int):
+        self.api.call("read", self._h, id, ty, C.c_void_p(ptr), nbytes)
+
+    def to_numpy(self, id: int) -> np.ndarray:
+        ty = self.ty(id)
+        a = self.as_slice(id, ty)
+        return a.astype(bool) if ty == VarType.Bool else a
+
+    # -- runtime primitives (extensions) -------------------------------------
+    def reduce(self, red: int, id: int) -> int:
+        return self._new("reduce", red, id)
+
+    def sum(self, id): return self.reduce(Red.Sum, id)
+    def min(self, id): return self.reduce(Red.Min, id)
+    def max(self, id): return self.reduce(Red.Max, id)
+
+    def prefix_sum(self, id: int, exclusive: bool = True) -> int:
+        return self._new("prefix_sum", id, 1 if exclusive else 0)
+
+    def compress(self, mask: int):
+        out, n = C.c_uint32(), C.c_size_t()
+        self.api.call("compress", self._h, mask, C.byref(out), C.byref(n))
+        return out.value, n.value
+
+    def compress_values(self, values: int, mask: int):
+        out, n = C.c_uint32(), C.c_size_t()
+        self.api.call("compress_values", self._h, values, mask, C.byref(out), C.byref(n))
+        return out.value, n.value
+
+    # -- multi-GPU (product only) ----------------------------------------------
+    def arange_sharded(self, ty: int, n: int) -> int:
+        return self._new("arange_sharded", ty, n)
+
+    def array_sharded(self, ty: int, data) -> int:
+        a = np.ascontiguousarray(data, dtype=VarType.numpy(ty))
+        return self._new("array_sharded", ty, a.ctypes.data_as(C.c_void_p), a.size)
+
+    def is_sharded(self, id: int) -> bool:
+        o = C.c_int32()
+        self.api.call("var_is_sharded", self._h, id, C.byref(o))
+        return bool(o.value)
+
+    def debug_codegen(self, ids: Sequence[int], compile: bool = False):
+        ids = list(ids)
+        n, cub = C.c_size_t(), C.c_size_t()
+        self.api.call("debug_codegen", self._h, _u32arr(ids), len(ids), 0, None, 0, C.byref(n), C.byref(cub))
+        buf = C.create_string_buffer(n.value + 1)
+        self.api.call("debug_codegen", self._h, _u32arr(ids), len(ids), 1 if compile else 0, buf, n.value + 1,
+                      C.byref(n), C.byref(cub))
+        return buf.value.decode(), cub.value
+
+
+# convenience: named binary ops exactly as the reference's bop! expansion (internal.rs:218-227)
+def _mk(kind):
+    def f(self, lhs: int, rhs: int) -> int:
+        return self.bop(kind, lhs, rhs)
+    return f
+
+
+for _n, _k in (("add", Bop.Add), ("sub", Bop.Sub), ("mul", Bop.Mul), ("div", Bop.Div), ("lt", Bop.Lt),
+               ("gt", Bop.Gt), ("eq", Bop.Eq), ("leq", Bop.Leq), ("geq", Bop.Geq), ("neq", Bop.Neq),
+               ("and_", Bop.And), ("or_", Bop.Or), ("xor", Bop.Xor), ("shl", Bop.Shl), ("shr", Bop.Shr),
+               ("minimum", Bop.Min), ("maximum", Bop.Max)):
+    setattr(Ir, _n, _mk(_k))
+
+
+# -- backend lifecycle (product) ---------------------------------------------
+def init(device: int = -1):
+    product_api().call("init", device)
+
+
+def shutdown():
+    product_api().call("shutdown")
+
+
+def sync():
+    product_api().call("sync")
+
+
+def stream_ptr() -> int:
+    p = C.c_void_p()
+    product_api().call("stream", C.byref(p))
+    return p.value or 0
+
+
+def stats() -> dict:
+    s = Stats()
+    product_api().call("stats", C.byref(s))
+    return s.as_dict()
+
+
+def stats_reset():
+    product_api().call("stats_reset")
+
+
+def cache_clear():
+    product_api().call("cache_clear")
