@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — the hot path measured on B200 (contract: one JSON line on rank 0).
+
+Workload (BASELINE.json configs[1]): horizontal sum + max over 2^28 f32, contiguously sharded
+over the N GPUs of one box, per-GPU partials combined by an all-reduce over NVLink.
+One step = sum(x) and max(x) over the whole 2^28-lane array = 2 GiB of algorithmic reads.
+
+  python bench.py [--gpus N --steps K --warmup W]       our CUDA path (through the C ABI)
+  python bench.py --impl reference ...                   the CPU restatement of the reference
+                                                         (oracle port) on the box's host cores
+
+Timing: CUDA events on the backend stream around each reduction (L2 flushed by a 256 MiB write
+between every timed interval, outside the events), max over ranks; clocks sampled with
+nvidia-smi during the timed region.  `e2e` goes through the same API with pinned HOST buffers:
+H2D of the step's input, both reductions, D2H of the two results, wall clock.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG2N = 28
+N_TOTAL = 1 << LOG2N
+SEED_R28 = 0xB2000001 + 2 * 16  # 0xB200_0001 + config*16 + array#
+METRIC = "fused elementwise/reduce HBM GB/s (sum+max over 2^28 f32, sharded)"
+UNIT = "GB/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 6:
+                    continue
+                try:
+                    sm.append(float(p[0])); mx.append(float(p[1]))
+                except ValueError:
+                    continue
+                for nme, v in zip(names, p[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic input: the stateless generator of SURVEY.md §8d, built as a vkjit trace
+# ------------------------------------------------------------------------------------------
+def hash_trace(ir, lane_u32, seed):
+    from vkjit_b200.ir import Bop
+    c = ir.const_u32
+    x = ir.bop(Bop.Xor, lane_u32, c(seed))
+    s = ir.add(ir.mul(x, c(747796405)), c(2891336453))
+    sh = ir.add(ir.bop(Bop.Shr, s, c(28)), c(4))
+    w = ir.mul(ir.bop(Bop.Xor, ir.bop(Bop.Shr, s, sh), s), c(277803737))
+    return ir.bop(Bop.Xor, ir.bop(Bop.Shr, w, c(22)), w)
+
+
+def uniform_trace(ir, lane_u32, seed):
+    from vkjit_b200.ir import Bop, VarType as T
+    h = hash_trace(ir, lane_u32, seed)
+    return ir.mul(ir.cast(ir.bop(Bop.Shr, h, ir.const_u32(8)), T.F32), ir.const_f32(2.0 ** -24))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------
+def cpu_reduce_arm(steps, warmup, log2n=LOG2N):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import oracle_api
+    from vkjit_b200.ir import Ir, Red, VarType as T
+    api = oracle_api()
+    cores = os.cpu_count() or 1
+    api.call("set_threads", cores)
+    n = 1 << log2n
+    ir = Ir(_api=api)
+    x = ir.array_empty(T.F32, n)
+    p = C.c_void_p()
+    api.call("var_host_ptr", ir._h, x, C.byref(p))
+    api.call("fill_hash", p, n, 0, SEED_R28, 1)
+    times, res = [], None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        s, m = ir.reduce(Red.Sum, x), ir.reduce(Red.Max, x)
+        dt = time.perf_counter() - t0
+        res = (float(ir.as_slice(s, T.F32)[0]), float(ir.as_slice(m, T.F32)[0]))
+        ir.dec_ref_count(s); ir.dec_ref_count(m)
+        if it >= warmup:
+            times.append(dt)
+    ir.close()
+    t = sum(times) / len(times)
+    return {"value": 2 * n * 4 / t / 1e9, "seconds_per_step": t, "cores": cores, "n": n, "sum": res[0], "max": res[1]}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reduce_arm(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "R28: sum+max over 2^28 f32 (BASELINE.json configs[1])", "n": N_TOTAL,
+                   "note": "CPU restatement of the reference semantics (oracle port), NOT the reference's Vulkan backend on Mesa "
+                           "lavapipe: no Rust/Vulkan toolchain exists in this image"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": "full workload: sum+max over 2^28 f32 per step, all host threads"},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as td
+
+    import vkjit_b200 as vk
+    from vkjit_b200.ir import Ir, Red, VarType as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    vk.init(local_rank)
+    api = vk.product_api()
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            host = (C.c_uint8 * 128)()
+            api.call("dist_unique_id", host)
+            idbuf.copy_(torch.tensor(list(host), dtype=torch.uint8))
+        td.broadcast(idbuf, 0)
+        raw = bytes(idbuf.cpu().tolist())
+        api.call("dist_init", rank, world, C.create_string_buffer(raw, 128))
+    stream = torch.cuda.ExternalStream(vk.stream_ptr(), device=dev)
+    ir = Ir()
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        vk.sync()
+        torch.cuda.synchronize()
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush_buf.fill_(1)
+
+    # ---- input: 2^28 f32 uniform[0,1), this rank's contiguous shard, generated on the device
+    lanes = ir.arange_sharded(T.U32, N_TOTAL)
+    x = uniform_trace(ir, lanes, SEED_R28)
+    ir.eval([x])
+    n_local = ir.size(x)
+    vk.sync()
+
+    def step(timed):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+        flush_l2()
+        if timed: ev[0].record(stream)
+        s = ir.reduce(Red.Sum, x)
+        if timed: ev[1].record(stream)
+        flush_l2()
+        if timed: ev[2].record(stream)
+        m = ir.reduce(Red.Max, x)
+        if timed: ev[3].record(stream)
+        return s, m, ev
+
+    for _ in range(max(3, args.warmup)):
+        s, m, _ = step(False)
+        ir.dec_ref_count(s); ir.dec_ref_count(m)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    vk.stats_reset()
+    evs, results = [], None
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        s, m, ev = step(True)
+        evs.append(ev)
+        if results is not None:
+            ir.dec_ref_count(results[0]); ir.dec_ref_count(results[1])
+        results = (s, m)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    st = vk.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_sum = [e[0].elapsed_time(e[1]) for e in evs]
+    ms_max = [e[2].elapsed_time(e[3]) for e in evs]
+    step_ms = torch.tensor([sum(ms_sum) / len(evs) + sum(ms_max) / len(evs)], device=dev, dtype=torch.float64)
+    if world > 1:
+        td.all_reduce(step_ms, op=td.ReduceOp.MAX)
+    ms_per_step = float(step_ms.item())
+    total_bytes = 2 * N_TOTAL * 4
+    value = total_bytes / (ms_per_step * 1e-3) / 1e9
+    gpu_sum = float(ir.as_slice(results[0], T.F32)[0])
+    gpu_max = float(ir.as_slice(results[1], T.F32)[0])
+    launches = st["trace_launches"] + st["prim_launches"]
+
+    # ---- roofline of the dominant kernel (reduce_kernel<float,SUM>): kernel-only, no collective
+    peak, peak_src = peaks()
+    if world == 1:
+        kern_ms = sum(ms_sum) / len(ms_sum)
+    else:
+        xl = uniform_trace(ir, ir.arange(T.U32, n_local), SEED_R28)
+        ir.eval([xl])
+        ks = []
+        for i in range(3 + args.steps):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); r = ir.reduce(Red.Sum, xl); b.record(stream)
+            vk.sync(); ir.dec_ref_count(r)
+            if i >= 3:
+                ks.append(a.elapsed_time(b))
+        kern_ms = sum(ks) / len(ks)
+        ir.dec_ref_count(xl)
+    achieved = n_local * 4 / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "reduce_kernel<float, SUM, 512>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "launch_ms": kern_ms,
+                "algorithmic_bytes_per_launch": n_local * 4}
+
+    # ---- e2e: same metric through the public API with pinned HOST buffers, copies inside the timed region
+    e2e_steps = max(2, min(args.steps, 5))
+    hp = C.c_void_p()
+    api.call("host_alloc", n_local * 4, C.byref(hp))
+    ir.read_into(x, T.F32, hp.value, n_local * 4)       # the step input now lives in pinned host memory
+    out2 = np.zeros(2, np.float32)
+    e2e_t = []
+    for i in range(1 + e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        xv = ir.array_shard_local(T.F32, ptr=hp.value, n=n_local)            # H2D of this step's input
+        s2, m2 = ir.reduce(Red.Sum, xv), ir.reduce(Red.Max, xv)
+        out2[0] = ir.as_slice(s2, T.F32)[0]; out2[1] = ir.as_slice(m2, T.F32)[0]  # D2H of the results
+        dt = time.perf_counter() - t0
+        for v in (s2, m2, xv):
+            ir.dec_ref_count(v)
+        if i >= 1:
+            e2e_t.append(dt)
+    api.call("host_free", hp)
+    e2e_s = torch.tensor([sum(e2e_t) / len(e2e_t)], device=dev, dtype=torch.float64)
+    if world > 1:
+        td.all_reduce(e2e_s, op=td.ReduceOp.MAX)
+    e2e = {"value": total_bytes / float(e2e_s.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": N_TOTAL * 4,
+           "d2h_bytes_per_step": 8 * world, "steps": e2e_steps, "seconds_per_step": float(e2e_s.item())}
+    assert abs(out2[0] - gpu_sum) <= 1e-5 * abs(gpu_sum) and out2[1] == gpu_max
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "R28: sum+max over 2^28 f32 (BASELINE.json configs[1])", "n": N_TOTAL, "n_per_gpu": n_local,
+                       "parallelism": f"contiguous 1-D shards x{world}, per-GPU partial + NCCL all-reduce" if world > 1 else "single GPU",
+                       "l2": "flushed (256 MiB write) before every timed reduction; inputs 1 GiB/N per GPU",
+                       "timing": "CUDA events on the backend stream per reduction, mean over steps, max over ranks"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "wall_s_timed_region": t_wall, "result": {"sum": gpu_sum, "max": gpu_max},
+            "hbm_frac_whole_job": value / (peak * world),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reduce_arm(2, 1)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
+                                    "sample": "full workload (sum+max over 2^28 f32), 2 timed passes, all host threads; CPU restatement "
+                                              "of the reference semantics, not Mesa lavapipe"}
+            tol = 1e-6 * LOG2N * abs(cb["sum"])
+            line["check"] = {"sum_abs_err": abs(gpu_sum - cb["sum"]), "sum_tol": tol, "max_equal": gpu_max == cb["max"],
+                             "ok": bool(abs(gpu_sum - cb["sum"]) <= tol and gpu_max == cb["max"])}
+        if world == 1 and not args.no_extras:
+            try:
+                import bench_extras
+                line["extras"] = bench_extras.run(ir, vk, stream, flush_l2, peak)
+            except Exception as ex:  # extras never take the headline down
+                line["extras"] = {"error": repr(ex)}
+        print(json.dumps(line), flush=True)
+    barrier()
+    ir.close()
+    if world > 1:
+        api.call("dist_shutdown")
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

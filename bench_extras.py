@@ -1,0 +1,148 @@
+"""Secondary measurements reported under "extras" in bench.py's JSON line (N=1 only).
+
+The other BASELINE.json configs, each against the roofline that bounds it:
+  E28  fused elementwise z = x*y + c over 2^28 f32      12 B/lane   HBM
+  E20  arange*y + c over 2^20 f32 with readback          latency (config 0 shape)
+  LAUNCH  cached-trace launch overhead, n = 1024          host us per eval
+  C28  prefix sum / compress over 2^28 u32               8 / ~10 B/lane  HBM
+  H26  gather + scatter-add, 2^26 indices -> 2^16 bins   atomic throughput
+  M26  ~200-op Monte-Carlo trace over 2^26 lanes         SM issue rate; compile ms
+"""
+import time
+
+import numpy as np
+import torch
+
+from bench import hash_trace, uniform_trace
+from vkjit_b200.ir import Bop, Red, VarType as T
+
+
+def _timed(stream, flush_l2, sync, fn, reps=5, warm=2):
+    ts, last = [], None
+    for i in range(warm + reps):
+        flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        last = fn()
+        b.record(stream)
+        sync()
+        if i >= warm:
+            ts.append(a.elapsed_time(b))
+    return sum(ts) / len(ts), min(ts), last
+
+
+def run(ir, vk, stream, flush_l2, peak):
+    out = {}
+    sync = vk.sync
+    c = ir.const_u32
+
+    # ---------------- E28: z = x*y + c
+    n = 1 << 28
+    lanes = ir.arange(T.U32, n)
+    x = uniform_trace(ir, lanes, 0xB2000001 + 1 * 16 + 0)
+    y = uniform_trace(ir, lanes, 0xB2000001 + 1 * 16 + 1)
+    ir.eval([x, y])
+    half = ir.const_f32(0.5)
+
+    def e28():
+        z = ir.add(ir.mul(x, y), half)
+        ir.eval([z])
+        ir.dec_ref_count(z)
+
+    ms, best, _ = _timed(stream, flush_l2, sync, e28)
+    gbs = 12 * n / (ms * 1e-3) / 1e9
+    out["E28_fused_elementwise"] = {"ms": ms, "best_ms": best, "GBps": gbs, "hbm_frac": gbs / peak, "bytes_per_lane": 12, "n": n}
+
+    # fused elementwise -> reduce pipeline: sum(x*y + c) (materialises z: 12 + 4 B/lane)
+    def e28r():
+        z = ir.add(ir.mul(x, y), half)
+        s = ir.reduce(Red.Sum, z)
+        ir.dec_ref_count(z); ir.dec_ref_count(s)
+
+    ms, best, _ = _timed(stream, flush_l2, sync, e28r, reps=3)
+    out["E28_then_sum"] = {"ms": ms, "GBps_algorithmic_8B": 8 * n / (ms * 1e-3) / 1e9}
+
+    # ---------------- C28: prefix sum and compress over 2^28 u32
+    vals = hash_trace(ir, lanes, 0xB2000001 + 4 * 16 + 0)
+    ir.eval([vals])
+
+    def scan():
+        r = ir.prefix_sum(vals, True)
+        ir.dec_ref_count(r)
+
+    ms, best, _ = _timed(stream, flush_l2, sync, scan)
+    gbs = 8 * n / (ms * 1e-3) / 1e9
+    out["C28_prefix_sum"] = {"ms": ms, "best_ms": best, "GBps": gbs, "hbm_frac": gbs / peak, "bytes_per_lane": 8}
+    ir.dec_ref_count(y)
+    mask = ir.neq(ir.bop(Bop.And, hash_trace(ir, lanes, 0xB2000001 + 4 * 16 + 1), c(1)), c(0))
+    ir.eval([mask])
+    cnt = [0]
+
+    def comp():
+        r, k = ir.compress_values(vals, mask)
+        cnt[0] = k
+        ir.dec_ref_count(r)
+
+    ms, best, _ = _timed(stream, flush_l2, sync, comp, reps=3)
+    bpl = 8 + 4 * cnt[0] / n
+    gbs = bpl * n / (ms * 1e-3) / 1e9
+    out["C28_compress"] = {"ms_incl_count_readback": ms, "GBps": gbs, "hbm_frac": gbs / peak, "bytes_per_lane": bpl, "selected": cnt[0]}
+    ir.dec_ref_count(mask); ir.dec_ref_count(vals); ir.dec_ref_count(x)
+
+    # ---------------- H26: gather + scatter-add histogram
+    m = 1 << 26
+    lanes26 = ir.arange(T.U32, m)
+    idx = ir.bop(Bop.And, hash_trace(ir, lanes26, 0xB2000001 + 3 * 16 + 0), c(0xFFFF))
+    table = hash_trace(ir, ir.arange(T.U32, 1 << 16), 0xB2000001 + 3 * 16 + 1)
+    ir.eval([idx])
+    ir.eval([table])
+    bins = ir.array_u32(np.zeros(1 << 16, np.uint32))
+
+    def hist():
+        w = ir.gather(table, idx)
+        s = ir.scatter_add(w, bins, idx)
+        ir.eval([s])
+        ir.dec_ref_count(s)
+
+    ms, best, _ = _timed(stream, flush_l2, sync, hist)
+    out["H26_gather_scatter_add"] = {"ms": ms, "best_ms": best, "Gelem_per_s": m / (ms * 1e-3) / 1e9,
+                                     "GBps_algorithmic_4B": 4 * m / (ms * 1e-3) / 1e9, "bins": 1 << 16, "bound": "atomics"}
+    ir.dec_ref_count(idx)
+
+    # ---------------- E20 with readback + cached launch overhead
+    n20 = 1 << 20
+    y20 = uniform_trace(ir, ir.arange(T.U32, n20), 7)
+    ir.eval([y20])
+    host = np.empty(n20, np.float32)
+    t = []
+    for i in range(12):
+        t0 = time.perf_counter()
+        z = ir.add(ir.mul(ir.arange(T.F32, n20), y20), half)
+        ir.eval([z])
+        ir.read_into(z, T.F32, host.ctypes.data, host.nbytes)
+        t.append(time.perf_counter() - t0)
+        ir.dec_ref_count(z)
+    out["E20_eval_plus_readback_us"] = {"median": 1e6 * sorted(t[2:])[len(t[2:]) // 2], "n": n20, "readback_bytes": 4 * n20}
+
+    a1k = ir.arange(T.F32, 1024)
+    sync()
+    reps = 3000
+    evals = []
+    vk.stats_reset()
+    t0 = time.perf_counter()
+    for i in range(reps):
+        z = ir.add(ir.mul(a1k, half), half)
+        ir.eval([z])
+        evals.append(vk.stats()["last_eval_ns"]) if i % 50 == 0 else None
+        ir.dec_ref_count(z)
+    host_us = (time.perf_counter() - t0) / reps * 1e6
+    sync()
+    st = vk.stats()
+    out["LAUNCH_cached_trace"] = {"python_loop_us_per_iter": host_us, "vkjit_eval_us_median": sorted(evals)[len(evals) // 2] / 1e3,
+                                  "cache_hits": st["cache_hits"], "cache_misses": st["cache_misses"], "n": 1024}
+    try:
+        import monte_carlo
+        out["M26_monte_carlo"] = monte_carlo.bench(vk, stream, flush_l2)
+    except ImportError:
+        pass
+    return out

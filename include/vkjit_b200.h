@@ -236,6 +236,8 @@ vkjit_status vkjit_shard_range(size_t n, int32_t rank, int32_t world, size_t* ou
 vkjit_status vkjit_arange_sharded(vkjit_ir* ir, vkjit_type ty, size_t n, vkjit_var* out);
 /* Upload this rank's slice of a replicated HOST array of n elements. */
 vkjit_status vkjit_array_sharded(vkjit_ir* ir, vkjit_type ty, const void* data, size_t n, vkjit_var* out);
+/* Upload this rank's slice directly: `data` holds the n_local elements this rank owns. */
+vkjit_status vkjit_array_shard_local(vkjit_ir* ir, vkjit_type ty, const void* data, size_t n_local, vkjit_var* out);
 vkjit_status vkjit_var_is_sharded(vkjit_ir* ir, vkjit_var id, int32_t* out);
 
 /* ------------------------------------------------------------------ */

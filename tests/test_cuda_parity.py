@@ -1,0 +1,278 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): bit-exact for integer / index / mask / scatter / compress work and,
+in practice, for f32 + - * / sqrt and casts (IEEE on both sides, no FMA contraction); f32 sums
+within 1e-6*log2(n) relative of the f64-accumulated oracle; transcendentals within 2 ulp of the
+f64 libm value rounded to f32 (CUDA's documented bound for expf; logf/sinf/cosf: 1 ulp).
+Everything outside the reference's own golden tests is "parity unpinned": the oracle is the spec.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from trace_gen import BOOL, F32, I32, U32, TraceBuilder, same_bits, special_f32, special_u32, ulp_diff
+from vkjit_b200.ir import Bop, Red, Uop
+
+pytestmark = pytest.mark.gpu
+
+
+def both(cir, oir):
+    return (cir, oir)
+
+
+def read(ir, v):
+    return ir.as_slice(v, ir.ty(v))
+
+
+# ---------------------------------------------------------------- fused elementwise traces
+@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1023, 4099])
+def test_random_trace_bit_exact(cir, oir, seed, n):
+    if n > 5 and seed >= 8:
+        pytest.skip("large sizes: 8 seeds are enough")
+    outs = []
+    for ir in (cir, oir):
+        tb = TraceBuilder(ir, seed * 7919 + n, n)
+        roots = tb.build()
+        ir.eval(roots)
+        outs.append([(ir.ty(r), read(ir, r)) for r in roots])
+    for (ty_c, a), (ty_o, b) in zip(*outs):
+        assert ty_c == ty_o
+        assert same_bits(a, b, ty_c == F32), (seed, n, ty_c, a[:8], b[:8])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_trace_transcendentals_ulp(cir, oir, seed):
+    n = 2048
+    outs = []
+    for ir in (cir, oir):
+        x = ir.array_f32(np.random.default_rng(seed).uniform(-20, 20, n).astype(np.float32))
+        p = ir.array_f32(np.random.default_rng(seed + 100).uniform(1e-6, 1e6, n).astype(np.float32))
+        r = [ir.exp(x), ir.log(p), ir.sin(x), ir.cos(x), ir.sqrt(p)]
+        ir.eval(r)
+        outs.append([read(ir, v) for v in r])
+    budget = {"exp": 2, "log": 1, "sin": 2, "cos": 2, "sqrt": 0}
+    for name, a, b in zip(budget, *outs):
+        d = int(ulp_diff(a, b).max())
+        assert d <= budget[name], (name, d)
+
+
+def test_large_elementwise_and_cache_hit(cuda_backend, cir, oir):
+    """x*y+c at 2^20 (config-1 shape); second eval of the same structure must be a cache hit."""
+    n = 1 << 20
+    rng = np.random.default_rng(1)
+    xs, ys = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+    res = []
+    for ir in (cir, oir):
+        x, y, c = ir.array_f32(xs), ir.array_f32(ys), ir.const_f32(0.5)
+        z = ir.add(ir.mul(x, y), c)
+        ir.eval([z])
+        res.append(read(ir, z))
+    assert same_bits(res[0], res[1], True)
+    # the reference semantics are two roundings (OpFMul then OpFAdd), not an FMA
+    assert same_bits(res[0], (xs * ys + np.float32(0.5)).astype(np.float32), True)
+    cuda_backend.stats_reset()
+    x, y, c = cir.array_f32(ys), cir.array_f32(xs), cir.const_f32(0.5)
+    z = cir.add(cir.mul(x, y), c)
+    cir.eval([z])
+    st = cuda_backend.stats()
+    assert st["cache_hits"] == 1 and st["cache_misses"] == 0, st
+
+
+def test_ragged_sizes_and_tail(cir, oir):
+    for n in (1, 2, 3, 5, 6, 7, 255, 257, 1025):
+        res = []
+        for ir in (cir, oir):
+            a = ir.array_u32(np.arange(n, dtype=np.uint32) * 3)
+            z = ir.add(ir.mul(a, ir.arange(U32, n)), ir.const_u32(7))
+            ir.eval([z])
+            res.append(read(ir, z))
+        assert same_bits(res[0], res[1], False), n
+
+
+# ---------------------------------------------------------------- gather / scatter / scatter_add
+@pytest.mark.parametrize("n,m", [(7, 3), (1000, 64), (65536, 1024), (100003, 65536)])
+def test_gather_masked_and_unmasked(cir, oir, n, m):
+    rng = np.random.default_rng(n)
+    table = special_u32(rng, m)
+    idx = rng.integers(0, m, n).astype(np.uint32)
+    res = []
+    for ir in (cir, oir):
+        t, i = ir.array_u32(table), ir.array_u32(idx)
+        g = ir.gather(t, i)
+        act = ir.lt(i, ir.const_u32(m // 2))
+        gm = ir.gather(t, i, act)
+        tf = ir.array_f32(table.view(np.float32))
+        gf = ir.gather(tf, i, act)
+        ir.eval([g, gm, gf])
+        res.append([read(ir, g), read(ir, gm), read(ir, gf)])
+    for a, b in zip(*res):
+        assert same_bits(a, b, False)
+    assert np.array_equal(res[0][0], table[idx])
+
+
+def test_scatter_permutation(cir, oir):
+    n = 5000
+    perm = np.random.default_rng(3).permutation(n).astype(np.uint32)
+    vals = special_f32(np.random.default_rng(4), n)
+    res = []
+    for ir in (cir, oir):
+        dst = ir.array_f32(np.zeros(n, np.float32))
+        s = ir.scatter(ir.array_f32(vals), dst, ir.array_u32(perm))
+        ir.eval([s])
+        res.append(read(ir, dst))
+    assert same_bits(res[0], res[1], True)
+
+
+@pytest.mark.parametrize("bins", [1, 16, 65536])
+def test_scatter_add_histogram_u32_bit_exact(cir, oir, bins):
+    n = 200003
+    rng = np.random.default_rng(bins)
+    idx = rng.integers(0, bins, n).astype(np.uint32)
+    table = special_u32(rng, bins)
+    res = []
+    for ir in (cir, oir):
+        t, i = ir.array_u32(table), ir.array_u32(idx)
+        b1 = ir.array_u32(np.zeros(bins, np.uint32))
+        b2 = ir.array_u32(np.zeros(bins, np.uint32))
+        w = ir.gather(t, i)
+        s1 = ir.scatter_add(w, b1, i)                       # weighted histogram (gather + scatter-add)
+        s2 = ir.scatter_add(ir.const_u32(1), b2, i, ir.lt(i, ir.const_u32(max(1, bins // 2))))  # masked count
+        ir.eval([s1, s2])
+        res.append([read(ir, b1), read(ir, b2)])
+    for a, b in zip(*res):
+        assert same_bits(a, b, False)
+    assert int(res[0][1].sum()) == int((idx < max(1, bins // 2)).sum())
+
+
+def test_scatter_add_f32_tolerance(cir, oir):
+    n, bins = 100000, 37
+    rng = np.random.default_rng(9)
+    idx = rng.integers(0, bins, n).astype(np.uint32)
+    vals = rng.random(n, dtype=np.float32)
+    res = []
+    for ir in (cir, oir):
+        b = ir.array_f32(np.zeros(bins, np.float32))
+        s = ir.scatter_add(ir.array_f32(vals), b, ir.array_u32(idx))
+        ir.eval([s])
+        res.append(read(ir, b))
+    tol = 1e-6 * math.log2(n)  # order-dependent f32 accumulation, same budget as f32 sums
+    assert np.all(np.abs(res[0] - res[1]) <= tol * np.abs(res[1]) + 1e-30)
+
+
+# ---------------------------------------------------------------- horizontal reductions
+SIZES = [1, 2, 3, 4, 5, 31, 32, 33, 511, 2048, 2049, 65537, (1 << 20) + 3]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_reduce_int_bit_exact(cir, oir, n):
+    data = special_u32(np.random.default_rng(n), n)
+    res = []
+    for ir in (cir, oir):
+        u = ir.array_u32(data)
+        s = ir.array_i32(data.view(np.int32))
+        outs = [ir.reduce(r, v) for v in (u, s) for r in (Red.Sum, Red.Min, Red.Max)]
+        res.append([read(ir, o) for o in outs])
+    for a, b in zip(*res):
+        assert a.shape == (1,) and same_bits(a, b, False), (n, a, b)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_reduce_f32(cir, oir, n):
+    rng = np.random.default_rng(n)
+    for data in (rng.random(n, dtype=np.float32), (rng.random(n, dtype=np.float32) * 2 - 1).astype(np.float32)):
+        res = []
+        for ir in (cir, oir):
+            x = ir.array_f32(data)
+            res.append([read(ir, ir.reduce(r, x)) for r in (Red.Sum, Red.Min, Red.Max)])
+        (cs, cmin, cmax), (os_, omin, omax) = res
+        assert same_bits(cmin, omin, True) and same_bits(cmax, omax, True)
+        # tolerance from BASELINE.json: 1e-6*log2(n) relative (to the sum of magnitudes for the
+        # cancelling [-1,1) data set, where the result itself can be arbitrarily close to 0)
+        scale = max(float(np.abs(data.astype(np.float64)).sum()), 1e-30)
+        tol = 1e-6 * max(1.0, math.log2(n)) * scale
+        assert abs(float(cs[0]) - float(os_[0])) <= tol, (n, cs, os_)
+
+
+def test_reduce_of_unevaluated_trace(cir, oir):
+    """reduce evaluates its operand first (fused elementwise -> reduce pipeline)."""
+    n = 100000
+    res = []
+    for ir in (cir, oir):
+        x = ir.mul(ir.arange(U32, n), ir.const_u32(2654435761))
+        res.append(read(ir, ir.reduce(Red.Sum, x)))
+        assert ir.is_buffer(x)
+    assert same_bits(res[0], res[1], False)
+
+
+# ---------------------------------------------------------------- prefix sum / compress
+SCAN_SIZES = [1, 2, 3, 4, 5, 1023, 4095, 4096, 4097, 8192, 12289, (1 << 20) + 1, 3 * (1 << 20) + 7]
+
+
+@pytest.mark.parametrize("n", SCAN_SIZES)
+def test_prefix_sum_bit_exact(cir, oir, n):
+    data = special_u32(np.random.default_rng(n), n)
+    res = []
+    for ir in (cir, oir):
+        u = ir.array_u32(data)
+        s = ir.array_i32(data.view(np.int32))
+        outs = [ir.prefix_sum(u, True), ir.prefix_sum(u, False), ir.prefix_sum(s, True)]
+        res.append([read(ir, o) for o in outs])
+    for a, b in zip(*res):
+        assert same_bits(a, b, False), n
+    ref = np.cumsum(data.astype(np.uint64)).astype(np.uint32)
+    assert np.array_equal(res[0][1], ref)
+
+
+@pytest.mark.parametrize("n", SCAN_SIZES)
+@pytest.mark.parametrize("density", [0.0, 0.01, 0.5, 1.0])
+def test_compress_bit_exact(cir, oir, n, density):
+    rng = np.random.default_rng(n + int(density * 100))
+    mask = (rng.random(n) < density)
+    vals = special_u32(rng, n)
+    res = []
+    for ir in (cir, oir):
+        m = ir.array_bool(mask)
+        idx, c1 = ir.compress(m)
+        out, c2 = ir.compress_values(ir.array_u32(vals), m)
+        res.append((c1, c2, read(ir, idx), read(ir, out)))
+    assert res[0][0] == res[1][0] == res[0][1] == res[1][1] == int(mask.sum())
+    assert same_bits(res[0][2], res[1][2], False) and same_bits(res[0][3], res[1][3], False)
+    assert np.array_equal(res[0][2], np.nonzero(mask)[0].astype(np.uint32))
+    assert np.array_equal(res[0][3], vals[mask])
+
+
+def test_compress_of_traced_mask(cir, oir):
+    n = 50000
+    res = []
+    for ir in (cir, oir):
+        i = ir.arange(U32, n)
+        h = ir.mul(i, ir.const_u32(747796405))
+        m = ir.neq(ir.bop(Bop.And, h, ir.const_u32(4)), ir.const_u32(0))
+        idx, c = ir.compress(m)
+        res.append((c, read(ir, idx)))
+    assert res[0][0] == res[1][0] and same_bits(res[0][1], res[1][1], False)
+
+
+# ---------------------------------------------------------------- errors (reference panics -> status)
+def test_errors_match_oracle(cir, oir):
+    from vkjit_b200 import VkjitError, VkjitSizeError, VkjitTypeError
+    for ir in (cir, oir):
+        a, b = ir.array_f32([1, 2, 3]), ir.array_f32([1, 2])
+        with pytest.raises(VkjitSizeError):
+            ir.eval([ir.add(a, b)])                      # internal.rs:699-702
+        with pytest.raises(VkjitSizeError):
+            ir.eval([ir.add(ir.const_f32(1), ir.const_f32(2))])  # internal.rs:1202 num.unwrap()
+        with pytest.raises(VkjitTypeError):
+            ir.select(ir.lt(a, a), a, ir.array_u32([1, 2, 3]))   # internal.rs:232
+        z = ir.add(a, a)
+        ir.eval([z])
+        with pytest.raises(VkjitTypeError):
+            ir.as_slice(z, U32)                                  # internal.rs:447
+        with pytest.raises(VkjitError):
+            ir.eval([ir.gather(ir.add(a, a), ir.arange(U32, 3))])  # internal.rs:1054
+        with pytest.raises(VkjitError):
+            ir.eval([ir.scatter(a, ir.const_f32(0), ir.arange(U32, 3))])  # internal.rs:1059-1062
+        # the Ir stays usable after an error
+        ir.eval([ir.add(a, a)])

@@ -1,0 +1,191 @@
+"""CPU-side tests of the product library (no GPU): the C ABI loads and exports every declared
+symbol, trace construction / typing / ref-counting match the oracle, generated CUDA C compiles
+for sm_100a under NVRTC, and every compute entry point fails loudly without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import vkjit_b200
+from trace_gen import BOOL, F32, I32, U32, TraceBuilder
+from vkjit_b200 import Ir, VkjitError, VkjitNoDeviceError, VkjitTypeError
+from vkjit_b200._capi import PRODUCT_LIB
+from vkjit_b200.ir import Bop, Uop
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_capi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "vkjit_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(vkjit_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 60
+    lib = ctypes.CDLL(PRODUCT_LIB)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.vkjit_abi_version.restype = ctypes.c_uint32
+    assert lib.vkjit_abi_version() == 1
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(VkjitNoDeviceError):
+        vkjit_b200.init()
+    ir = Ir()
+    x = ir.add(ir.arange(F32, 4), ir.const_f32(1.0))
+    with pytest.raises(VkjitNoDeviceError):
+        ir.eval([x])
+    with pytest.raises(VkjitNoDeviceError):
+        ir.array_f32([1, 2, 3])
+    with pytest.raises(VkjitNoDeviceError):
+        ir.reduce(0, x)
+    with pytest.raises(VkjitNoDeviceError):
+        vkjit_b200.sync()
+
+
+def test_promotion_and_types_match_oracle(oir):
+    """bop!: operate in max(lhs, rhs) under Bool < U32 < I32 < F32 (internal.rs:146-166, vartype.rs:24-33)."""
+    pir = Ir()
+    for ir in (pir, oir):
+        u, i, f = ir.const_u32(1), ir.const_i32(-1), ir.const_f32(2.0)
+        assert ir.ty(ir.add(u, i)) == I32
+        assert ir.ty(ir.add(u, f)) == F32
+        assert ir.ty(ir.mul(i, f)) == F32
+        assert ir.ty(ir.lt(u, f)) == BOOL
+        assert ir.cast(u, U32) == u                      # identity-eliding cast (internal.rs:283-290)
+        st = ir.struct_type([F32, U32])
+        z = ir.zeros(st)
+        assert ir.ty(ir.getattr(z, 0)) == F32 and ir.ty(ir.getattr(z, 1)) == U32
+        assert ir.struct_type_elems(st) == [F32, U32]
+        with pytest.raises(VkjitTypeError):
+            ir.select(ir.lt(u, u), u, f)                 # internal.rs:232
+        with pytest.raises(VkjitError):
+            ir.add(ir.lt(u, u), ir.lt(u, u))             # Bool operands: unimplemented!()
+        with pytest.raises(VkjitError):
+            ir.getattr(u, 0)
+        with pytest.raises(VkjitError):
+            ir.add(u, 10 ** 6)                           # invalid VarId
+
+
+def test_ref_counts_reference_semantics(oir):
+    """internal.rs:186-209 / :450-469 on a DAG without implicit casts: product == oracle."""
+    pir = Ir()
+    for ir in (pir, oir):
+        a, b = ir.arange(F32, 8), ir.const_f32(3.0)
+        c = ir.add(a, b)
+        d = ir.mul(c, a)
+        assert [ir.ref_count(v) for v in (a, b, c, d)] == [3, 2, 2, 1]
+        ir.inc_ref_count(d)
+        assert ir.ref_count(d) == 2
+        ir.dec_ref_count(d)
+        ir.dec_ref_count(d)                              # d dies -> releases c and a
+        assert ir.ref_count(d) == 0 and ir.ref_count(c) == 1 and ir.ref_count(a) == 2
+        with pytest.raises(VkjitError):
+            ir.dec_ref_count(d)                          # underflow is an error, not a wrap
+        s = ir.scatter(b, a, a)                          # side effect target is referenced too (internal.rs:203-205)
+        assert ir.ref_count(a) == 4 and ir.ref_count(b) == 3 and ir.ref_count(s) == 1
+
+
+def test_documented_ref_count_deviations(oir):
+    """The reference never releases implicit casts / linspace temporaries (leak); the product does."""
+    pir = Ir()
+    u, f = pir.const_u32(1), pir.const_f32(1.0)
+    z = pir.add(u, f)
+    n_before = pir.num_vars()
+    pir.dec_ref_count(z)                                  # frees z, its implicit cast, and nothing else
+    assert pir.ref_count(u) == 1 and pir.ref_count(f) == 1
+    x = pir.linspace(F32, f, pir.const_f32(4.0), 4)
+    pir.dec_ref_count(x)                                  # every temporary of linspace dies with it
+    assert pir.ref_count(f) == 1
+    assert pir.num_vars() <= n_before + 8                 # slots are recycled
+    # oracle keeps the reference's behaviour: the cast stays alive and pins `u`
+    u, f = oir.const_u32(1), oir.const_f32(1.0)
+    z = oir.add(u, f)
+    oir.dec_ref_count(z)
+    assert oir.ref_count(u) == 2
+
+
+def test_repr_matches_oracle(oir):
+    pir = Ir()
+    out = []
+    for ir in (pir, oir):
+        a = ir.arange(U32, 10)
+        c = ir.const_f32(2.5)
+        b = ir.mul(ir.cast(a, F32), c)
+        k = ir.const_i32(-3)
+        s = ir.zeros(ir.struct_type([F32, BOOL]))
+        g = ir.getattr(s, 1)
+        out.append((ir.repr(), ir.str(b), ir.str(k)))
+    assert out[0][0] == out[1][0]
+    assert out[0][1] == out[1][1] and out[0][2] == out[1][2]
+    assert "Const(Int32(-3))" in out[0][2] and "Arange(\n            10,\n        )" in out[0][0]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_generated_cuda_compiles_for_sm100a(seed):
+    """Random traces over arange/const leaves (no device memory needed) must produce CUDA C that
+    NVRTC accepts for sm_100a; the cubin is produced offline."""
+    ir = Ir()
+    tb = TraceBuilder(ir, seed, 1000, n_ops=40, transcendental=True, arrays=False)
+    roots = tb.build(4)
+    src, cubin = ir.debug_codegen(roots, compile=True)
+    assert "vkjit_trace" in src and cubin > 1000
+    assert "uint4" in src                                  # 128-bit vectorised main loop
+    assert "fma" not in src.lower()                        # never contract mul+add (OpFMul/OpFAdd are separate)
+
+
+def test_struct_select_gather_scatter_codegen():
+    ir = Ir()
+    i = ir.arange(U32, 64)
+    f = ir.cast(i, F32)
+    st = ir.struct_init([f, i])
+    st2 = ir.setattr(st, ir.add(f, ir.const_f32(1.0)), 0)
+    sel = ir.select(ir.lt(i, ir.const_u32(3)), st, st2)
+    r0, r1 = ir.getattr(sel, 0), ir.getattr(sel, 1)
+    src, cubin = ir.debug_codegen([r0, r1], compile=True)
+    assert cubin > 0 and src.count("vk_lane(") == 6       # definition + 4 vector lanes + scalar tail
+    with pytest.raises(VkjitError):
+        ir.debug_codegen([sel])                            # struct roots: stride() unimplemented!()
+
+
+def test_trace_hash_is_address_and_size_free():
+    """Two structurally identical traces of different n give the same kernel source (key)."""
+    srcs = []
+    for n in (100, 5000):
+        ir = Ir()
+        x = ir.add(ir.mul(ir.arange(F32, n), ir.const_f32(2.0)), ir.const_f32(0.5))
+        srcs.append(ir.debug_codegen([x])[0])
+    assert srcs[0] == srcs[1]
+    ir = Ir()
+    y = ir.add(ir.mul(ir.arange(F32, 100), ir.const_f32(2.0)), ir.const_f32(0.75))
+    assert ir.debug_codegen([y])[0] != srcs[0]             # constants are part of the key
+
+
+def test_size_rule_errors():
+    from vkjit_b200 import VkjitSizeError
+    ir = Ir()
+    with pytest.raises(VkjitSizeError):
+        ir.debug_codegen([ir.add(ir.arange(U32, 3), ir.arange(U32, 4))])   # internal.rs:699-702
+    with pytest.raises(VkjitSizeError):
+        ir.debug_codegen([ir.add(ir.const_u32(1), ir.const_u32(2))])       # internal.rs:1202
+
+
+def test_shard_range_properties(oracle_api):
+    import ctypes as C
+    from vkjit_b200._capi import product_api
+    for api in (product_api(), oracle_api):
+        for n in (0, 1, 3, 4, 5, 1000, 1 << 20, (1 << 28) + 5):
+            for world in (1, 2, 4, 8):
+                prev = 0
+                for r in range(world):
+                    lo, hi = C.c_size_t(), C.c_size_t()
+                    api.call("shard_range", n, r, world, C.byref(lo), C.byref(hi))
+                    assert lo.value == prev and hi.value >= lo.value
+                    if r < world - 1:
+                        assert (hi.value - lo.value) % 4 == 0      # 16-byte aligned shards
+                    prev = hi.value
+                assert prev == n

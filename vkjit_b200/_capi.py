@@ -117,6 +117,7 @@ _PRODUCT_SIGS = {
     "dist_info": [_pi32, _pi32],
     "arange_sharded": [_p, _u32, _sz, _pu32],
     "array_sharded": [_p, _u32, _p, _sz, _pu32],
+    "array_shard_local": [_p, _u32, _p, _sz, _pu32],
     "var_is_sharded": [_p, _u32, _pi32],
     "stats": [C.POINTER(Stats)],
     "stats_reset": [],

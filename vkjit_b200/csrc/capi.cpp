@@ -1,0 +1,379 @@
+// capi.cpp — extern "C" surface declared in include/vkjit_b200.h.
+// Every entry point turns the reference's panics into a status + thread-local message.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "dist.h"
+#include "ir.h"
+#include "prims.h"
+#include "program.h"
+#include "runtime.h"
+
+using namespace vkjit;
+
+struct vkjit_ir {
+  Ir ir;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <class F>
+vkjit_status guard(F&& f) {
+  try {
+    f();
+    return VKJIT_OK;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return VKJIT_ERR_INVALID;
+  }
+}
+
+template <class F>
+vkjit_status with_ir(vkjit_ir* h, F&& f) {
+  if (!h) { g_last_error = "null vkjit_ir"; return VKJIT_ERR_INVALID; }
+  return guard([&] {
+    std::lock_guard<std::mutex> lock(h->ir.mu);
+    f(h->ir);
+  });
+}
+
+vkjit_status copy_out(const std::string& s, char* buf, size_t cap, size_t* out_len) {
+  if (out_len) *out_len = s.size();
+  if (buf && cap) {
+    const size_t m = std::min(cap - 1, s.size());
+    memcpy(buf, s.data(), m);
+    buf[m] = 0;
+  }
+  return VKJIT_OK;
+}
+
+// Ir::array_* (internal.rs:313-348): fresh device array + H2D copy
+VarId upload(Ir& ir, TypeId ty, const void* data, size_t n, bool sharded) {
+  Backend& be = Backend::get();
+  Array* a = be.new_array(n * 4);
+  try {
+    if (n) be.h2d(a->ptr, data, n * 4);
+  } catch (...) { release_array(a); throw; }
+  return ir.binding(ty, a, sharded);
+}
+
+void ensure_buffer(Ir& ir, VarId id) {
+  if (!ir.is_buffer(id)) eval(ir, &id, 1);
+}
+
+// Buffer::str (internal.rs:404-422) through a D2H copy
+std::string buffer_str(Ir& ir, VarId id) {
+  const Var& v = ir.var(id);
+  const size_t n = v.array->bytes / 4;
+  std::vector<uint32_t> w(n);
+  Backend::get().d2h(w.data(), v.array->ptr, n * 4);
+  std::string o = "[";
+  auto sep = [&](size_t i) { if (i) o += ", "; };
+  for (size_t i = 0; i < n; ++i) {
+    if (v.ty == VKJIT_TY_BOOL) {  // printed as raw u8 (internal.rs:417-419): 4 bytes per element
+      const uint8_t* b = (const uint8_t*)&w[i];
+      for (int k = 0; k < 4; ++k) { sep(i * 4 + k); o += std::to_string(b[k]); }
+      continue;
+    }
+    sep(i);
+    if (v.ty == VKJIT_TY_U32) o += std::to_string(w[i]);
+    else if (v.ty == VKJIT_TY_I32) o += std::to_string((int32_t)w[i]);
+    else if (v.ty == VKJIT_TY_F32) o += format_f32(bits_f32(w[i]));
+    else return "Undefined Type!";
+  }
+  return o + "]";
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- lifecycle ------------------------------------------------------------------------------
+vkjit_status vkjit_init(int32_t device) { return guard([&] { Backend::init(device); }); }
+vkjit_status vkjit_shutdown(void) { return guard([&] { dist::shutdown(); Backend::shutdown(); }); }
+int32_t vkjit_is_initialized(void) { return Backend::initialized() ? 1 : 0; }
+const char* vkjit_last_error(void) { return g_last_error.c_str(); }
+uint32_t vkjit_abi_version(void) { return VKJIT_B200_ABI_VERSION; }
+vkjit_status vkjit_stream(void** out) { return guard([&] { *out = Backend::get().stream; }); }
+vkjit_status vkjit_sync(void) { return guard([&] { Backend::get().sync(); }); }
+vkjit_status vkjit_host_alloc(size_t bytes, void** out) {
+  return guard([&] {
+    Backend::get();
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 16);
+    if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+  });
+}
+vkjit_status vkjit_host_free(void* p) {
+  return guard([&] { if (p) cudaFreeHost(p); });
+}
+
+vkjit_status vkjit_ir_create(vkjit_ir** out) { return guard([&] { *out = new vkjit_ir(); }); }
+vkjit_status vkjit_ir_destroy(vkjit_ir* h) { return guard([&] { delete h; }); }
+
+// ---- types ------------------------------------------------------------------------------------
+vkjit_status vkjit_type_struct(vkjit_ir* h, const vkjit_type* e, size_t n, vkjit_type* out) {
+  return with_ir(h, [&](Ir& ir) { *out = ir.struct_type(e, n); });
+}
+vkjit_status vkjit_type_struct_len(vkjit_ir* h, vkjit_type t, size_t* out) {
+  return with_ir(h, [&](Ir& ir) { *out = ir.struct_elems(t).size(); });
+}
+vkjit_status vkjit_type_struct_elem(vkjit_ir* h, vkjit_type t, size_t i, vkjit_type* out) {
+  return with_ir(h, [&](Ir& ir) {
+    const auto& e = ir.struct_elems(t);
+    if (i >= e.size()) fail(VKJIT_ERR_INVALID, "struct member index out of range");
+    *out = e[i];
+  });
+}
+
+// ---- constructors -------------------------------------------------------------------------------
+vkjit_status vkjit_const_f32(vkjit_ir* h, float v, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.constant(VKJIT_TY_F32, f32_bits(v)); }); }
+vkjit_status vkjit_const_i32(vkjit_ir* h, int32_t v, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.constant(VKJIT_TY_I32, (uint32_t)v); }); }
+vkjit_status vkjit_const_u32(vkjit_ir* h, uint32_t v, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.constant(VKJIT_TY_U32, v); }); }
+vkjit_status vkjit_const_bool(vkjit_ir* h, int32_t v, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.constant(VKJIT_TY_BOOL, v ? 1u : 0u); }); }
+vkjit_status vkjit_array_f32(vkjit_ir* h, const float* d, size_t n, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = upload(ir, VKJIT_TY_F32, d, n, false); }); }
+vkjit_status vkjit_array_i32(vkjit_ir* h, const int32_t* d, size_t n, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = upload(ir, VKJIT_TY_I32, d, n, false); }); }
+vkjit_status vkjit_array_u32(vkjit_ir* h, const uint32_t* d, size_t n, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = upload(ir, VKJIT_TY_U32, d, n, false); }); }
+vkjit_status vkjit_array_bool(vkjit_ir* h, const uint32_t* d, size_t n, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = upload(ir, VKJIT_TY_BOOL, d, n, false); }); }
+vkjit_status vkjit_array_empty(vkjit_ir* h, vkjit_type ty, size_t n, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) {
+    if (!ty_is_scalar(ty)) fail(VKJIT_ERR_TYPE, "array of a non-scalar type");
+    *out = ir.binding(ty, Backend::get().new_array(n * 4), false);
+  });
+}
+vkjit_status vkjit_arange(vkjit_ir* h, vkjit_type ty, size_t n, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.arange(ty, n, 0, false); }); }
+vkjit_status vkjit_linspace(vkjit_ir* h, vkjit_type ty, vkjit_var a, vkjit_var b, size_t n, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) { *out = ir.linspace(ty, a, b, n); });
+}
+vkjit_status vkjit_zeros(vkjit_ir* h, vkjit_type ty, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.zeros(ty); }); }
+vkjit_status vkjit_ones(vkjit_ir* h, vkjit_type ty, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.ones(ty); }); }
+vkjit_status vkjit_cast(vkjit_ir* h, vkjit_var s, vkjit_type ty, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.cast(s, ty); }); }
+vkjit_status vkjit_bop(vkjit_ir* h, int32_t k, vkjit_var l, vkjit_var r, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.bop(k, l, r); }); }
+vkjit_status vkjit_uop(vkjit_ir* h, int32_t k, vkjit_var s, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.uop(k, s); }); }
+vkjit_status vkjit_bitcast(vkjit_ir* h, vkjit_var s, vkjit_type ty, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.bitcast(s, ty); }); }
+vkjit_status vkjit_select(vkjit_ir* h, vkjit_var c, vkjit_var l, vkjit_var r, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.select(c, l, r); }); }
+vkjit_status vkjit_struct_init(vkjit_ir* h, const vkjit_var* e, size_t n, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.struct_init(e, n); }); }
+vkjit_status vkjit_getattr(vkjit_ir* h, vkjit_var s, size_t i, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.getattr(s, i); }); }
+vkjit_status vkjit_setattr(vkjit_ir* h, vkjit_var d, vkjit_var s, size_t i, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.setattr(d, s, i); }); }
+vkjit_status vkjit_gather(vkjit_ir* h, vkjit_var s, vkjit_var i, int32_t ha, vkjit_var a, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) { *out = ir.gather(s, i, ha != 0, a); });
+}
+vkjit_status vkjit_scatter(vkjit_ir* h, vkjit_var s, vkjit_var d, vkjit_var i, int32_t ha, vkjit_var a, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) { *out = ir.scatter(OP_SCATTER, s, d, i, ha != 0, a); });
+}
+vkjit_status vkjit_scatter_add(vkjit_ir* h, vkjit_var s, vkjit_var d, vkjit_var i, int32_t ha, vkjit_var a, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) { *out = ir.scatter(OP_SCATTER_ADD, s, d, i, ha != 0, a); });
+}
+
+// ---- introspection / lifetime ---------------------------------------------------------------------
+vkjit_status vkjit_var_type(vkjit_ir* h, vkjit_var id, vkjit_type* out) { return with_ir(h, [&](Ir& ir) { *out = ir.var(id).ty; }); }
+vkjit_status vkjit_var_ref_count(vkjit_ir* h, vkjit_var id, uint32_t* out) {
+  return with_ir(h, [&](Ir& ir) {
+    if (id >= ir.vars.size()) fail(VKJIT_ERR_INVALID, "invalid VarId");
+    *out = ir.vars[id].ref_count;  // readable for dead vars too (test.rs:205)
+  });
+}
+vkjit_status vkjit_var_count(vkjit_ir* h, size_t* out) { return with_ir(h, [&](Ir& ir) { *out = ir.vars.size(); }); }
+vkjit_status vkjit_array_count(vkjit_ir* h, size_t* out) { return with_ir(h, [&](Ir& ir) { *out = ir.n_arrays; }); }
+vkjit_status vkjit_is_buffer(vkjit_ir* h, vkjit_var id, int32_t* out) { return with_ir(h, [&](Ir& ir) { ir.var(id); *out = ir.is_buffer(id); }); }
+vkjit_status vkjit_var_size(vkjit_ir* h, vkjit_var id, size_t* out) {
+  return with_ir(h, [&](Ir& ir) {
+    if (!ir.is_buffer(id)) fail(VKJIT_ERR_INVALID, "var is not a buffer");
+    *out = ir.var(id).array->bytes / 4;
+  });
+}
+vkjit_status vkjit_var_device_ptr(vkjit_ir* h, vkjit_var id, uint64_t* out) {
+  return with_ir(h, [&](Ir& ir) {
+    if (!ir.is_buffer(id)) fail(VKJIT_ERR_INVALID, "var is not a buffer");
+    *out = (uint64_t)(uintptr_t)ir.var(id).array->ptr;
+  });
+}
+vkjit_status vkjit_inc_ref(vkjit_ir* h, vkjit_var id) { return with_ir(h, [&](Ir& ir) { ir.inc_ref(id); }); }
+vkjit_status vkjit_dec_ref(vkjit_ir* h, vkjit_var id) { return with_ir(h, [&](Ir& ir) { ir.dec_ref(id); }); }
+vkjit_status vkjit_ir_repr(vkjit_ir* h, char* buf, size_t cap, size_t* out_len) {
+  return with_ir(h, [&](Ir& ir) { copy_out(ir.repr(), buf, cap, out_len); });
+}
+vkjit_status vkjit_var_repr(vkjit_ir* h, vkjit_var id, char* buf, size_t cap, size_t* out_len) {
+  return with_ir(h, [&](Ir& ir) { copy_out(ir.is_buffer(id) ? buffer_str(ir, id) : ir.var_debug(id), buf, cap, out_len); });
+}
+
+// ---- execute -----------------------------------------------------------------------------------------
+vkjit_status vkjit_schedule(vkjit_ir* h, const vkjit_var* ids, size_t n) { return with_ir(h, [&](Ir& ir) { ir.do_schedule(ids, n); }); }
+vkjit_status vkjit_eval(vkjit_ir* h, const vkjit_var* ids, size_t n) { return with_ir(h, [&](Ir& ir) { eval(ir, ids, n); }); }
+// Ir::as_slice<T> (internal.rs:443-449)
+vkjit_status vkjit_read(vkjit_ir* h, vkjit_var id, vkjit_type ty, void* dst, size_t bytes) {
+  return with_ir(h, [&](Ir& ir) {
+    if (!ir.is_buffer(id)) fail(VKJIT_ERR_INVALID, "as_slice on a var that is not a buffer (internal.rs:446)");
+    const Var& v = ir.var(id);
+    if (v.ty != ty) fail(VKJIT_ERR_TYPE, "as_slice type mismatch (internal.rs:447)");
+    Backend::get().d2h(dst, v.array->ptr, std::min(bytes, v.array->bytes));
+  });
+}
+
+// ---- runtime primitives ----------------------------------------------------------------------------------
+vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) {
+    const TypeId ty = ir.var(id).ty;
+    if (!ty_is_num(ty)) fail(VKJIT_ERR_TYPE, "reduce needs U32/I32/F32");
+    if (red < VKJIT_RED_SUM || red > VKJIT_RED_MAX) fail(VKJIT_ERR_INVALID, "unknown reduction");
+    Backend& be = Backend::get();
+    ensure_buffer(ir, id);
+    const Var& v = ir.var(id);
+    const size_t n = v.array->bytes / 4;
+    if (n == 0) fail(VKJIT_ERR_SIZE, "reduce of an empty array");
+    const bool sharded = v.sharded;
+    Array* o = be.new_array(4);
+    try {
+      prims::reduce(red, ty, v.array->ptr, n, o->ptr, be.scratch, be.sm_count, be.stream);
+      Backend::counters().prim_launches += 1;
+      if (sharded && dist::active()) dist::allreduce(o->ptr, ty, red, 1);  // per-GPU partial -> replicated result
+    } catch (...) { release_array(o); throw; }
+    *out = ir.binding(ty, o, false);
+  });
+}
+
+vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) {
+    const TypeId ty = ir.var(id).ty;
+    if (ty != VKJIT_TY_U32 && ty != VKJIT_TY_I32) fail(VKJIT_ERR_TYPE, "prefix_sum needs U32/I32");
+    Backend& be = Backend::get();
+    ensure_buffer(ir, id);
+    const Var& v = ir.var(id);
+    if (v.sharded && dist::active() && dist::world() > 1) fail(VKJIT_ERR_UNSUPPORTED, "prefix_sum of a sharded array (single-GPU primitive, SURVEY.md §8e)");
+    const size_t n = v.array->bytes / 4;
+    be.ensure_scan_scratch(n);
+    Array* o = be.new_array(n * 4);
+    try {
+      prims::prefix_sum((const uint32_t*)v.array->ptr, (uint32_t*)o->ptr, n, exclusive != 0, be.scratch, be.stream);
+      Backend::counters().prim_launches += 1;
+    } catch (...) { release_array(o); throw; }
+    *out = ir.binding(ty, o, false);
+  });
+}
+
+static void do_compress(Ir& ir, bool with_values, VarId values, VarId mask, vkjit_var* out, size_t* count) {
+  if (ir.var(mask).ty != VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "compress mask must be Bool");
+  TypeId oty = VKJIT_TY_U32;
+  if (with_values) {
+    oty = ir.var(values).ty;
+    if (!ty_is_scalar(oty)) fail(VKJIT_ERR_TYPE, "compress values must be scalar");
+  }
+  Backend& be = Backend::get();
+  if (with_values) ensure_buffer(ir, values);
+  ensure_buffer(ir, mask);
+  const Var& m = ir.var(mask);
+  if (m.sharded && dist::active() && dist::world() > 1) fail(VKJIT_ERR_UNSUPPORTED, "compress of a sharded array (single-GPU primitive, SURVEY.md §8e)");
+  const size_t n = m.array->bytes / 4;
+  const uint32_t* vals = nullptr;
+  if (with_values) {
+    const Var& vv = ir.var(values);
+    if (vv.array->bytes / 4 != n) fail(VKJIT_ERR_SIZE, "compress: values and mask sizes differ");
+    vals = (const uint32_t*)vv.array->ptr;
+  }
+  be.ensure_scan_scratch(n);
+  Array* o = be.new_array(n * 4);  // worst case; logical size is trimmed to the count below
+  void* cnt = be.alloc(4);
+  uint32_t c = 0;
+  try {
+    if (n) {
+      prims::compress((const uint32_t*)m.array->ptr, vals, (uint32_t*)o->ptr, (uint32_t*)cnt, n, be.scratch, be.stream);
+      Backend::counters().prim_launches += 1;
+      be.d2h(&c, cnt, 4);  // the size of the result is data dependent: one 4-byte readback
+    }
+  } catch (...) { be.free_async(cnt, 4); release_array(o); throw; }
+  be.free_async(cnt, 4);
+  o->bytes = (size_t)c * 4;
+  *count = c;
+  *out = ir.binding(oty, o, false);
+}
+
+vkjit_status vkjit_compress(vkjit_ir* h, vkjit_var mask, vkjit_var* out, size_t* count) {
+  return with_ir(h, [&](Ir& ir) { do_compress(ir, false, 0, mask, out, count); });
+}
+vkjit_status vkjit_compress_values(vkjit_ir* h, vkjit_var values, vkjit_var mask, vkjit_var* out, size_t* count) {
+  return with_ir(h, [&](Ir& ir) { do_compress(ir, true, values, mask, out, count); });
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------------
+vkjit_status vkjit_dist_unique_id(void* out) { return guard([&] { dist::unique_id(out); }); }
+vkjit_status vkjit_dist_init(int32_t rank, int32_t world, const void* id) { return guard([&] { dist::init(rank, world, id); }); }
+vkjit_status vkjit_dist_shutdown(void) { return guard([&] { dist::shutdown(); }); }
+vkjit_status vkjit_dist_info(int32_t* rank, int32_t* world) {
+  return guard([&] { *rank = dist::rank(); *world = dist::world(); });
+}
+vkjit_status vkjit_shard_range(size_t n, int32_t rank, int32_t world, size_t* lo, size_t* hi) {
+  return guard([&] { dist::shard_range(n, rank, world, *lo, *hi); });
+}
+vkjit_status vkjit_arange_sharded(vkjit_ir* h, vkjit_type ty, size_t n, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) {
+    size_t lo, hi;
+    dist::shard_range(n, dist::rank(), dist::world(), lo, hi);
+    *out = ir.arange(ty, hi - lo, lo, true);
+  });
+}
+vkjit_status vkjit_array_sharded(vkjit_ir* h, vkjit_type ty, const void* data, size_t n, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) {
+    if (!ty_is_scalar(ty)) fail(VKJIT_ERR_TYPE, "array of a non-scalar type");
+    size_t lo, hi;
+    dist::shard_range(n, dist::rank(), dist::world(), lo, hi);
+    *out = upload(ir, ty, (const char*)data + lo * 4, hi - lo, true);
+  });
+}
+vkjit_status vkjit_array_shard_local(vkjit_ir* h, vkjit_type ty, const void* data, size_t n_local, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) {
+    if (!ty_is_scalar(ty)) fail(VKJIT_ERR_TYPE, "array of a non-scalar type");
+    *out = upload(ir, ty, data, n_local, true);
+  });
+}
+vkjit_status vkjit_var_is_sharded(vkjit_ir* h, vkjit_var id, int32_t* out) { return with_ir(h, [&](Ir& ir) { *out = ir.var(id).sharded; }); }
+
+// ---- counters ----------------------------------------------------------------------------------------------------
+vkjit_status vkjit_stats(vkjit_stats_t* out) {
+  return guard([&] {
+    Counters& c = Backend::counters();
+    out->cache_hits = c.cache_hits; out->cache_misses = c.cache_misses;
+    out->trace_launches = c.trace_launches; out->prim_launches = c.prim_launches;
+    out->last_compile_ns = c.last_compile_ns; out->last_eval_ns = c.last_eval_ns;
+    out->bytes_h2d = c.bytes_h2d; out->bytes_d2h = c.bytes_d2h;
+    out->pool_bytes_live = c.pool_bytes_live; out->collectives = c.collectives;
+  });
+}
+vkjit_status vkjit_stats_reset(void) {
+  return guard([&] {
+    Counters& c = Backend::counters();
+    c.cache_hits = 0; c.cache_misses = 0; c.trace_launches = 0; c.prim_launches = 0;
+    c.last_compile_ns = 0; c.last_eval_ns = 0; c.bytes_h2d = 0; c.bytes_d2h = 0; c.collectives = 0;
+  });
+}
+vkjit_status vkjit_cache_clear(void) { return guard([&] { Backend::get().clear_cache(); }); }
+
+vkjit_status vkjit_debug_codegen(vkjit_ir* h, const vkjit_var* ids, size_t n, int32_t compile, char* buf, size_t cap,
+                                 size_t* out_len, size_t* out_cubin) {
+  return with_ir(h, [&](Ir& ir) {
+    std::vector<VarId> sched(ir.schedule);
+    for (size_t i = 0; i < n; ++i) {
+      ir.var(ids[i]);
+      if (std::find(sched.begin(), sched.end(), ids[i]) == sched.end()) sched.push_back(ids[i]);
+    }
+    Program p;
+    build_program(ir, sched, true, p);
+    const std::string src = generate_cuda(ir, p);
+    if (out_cubin) *out_cubin = 0;
+    if (compile) {
+      std::vector<char> cubin;
+      std::string log;
+      if (!nvrtc_compile(src, cubin, log)) fail(VKJIT_ERR_COMPILE, "NVRTC rejected the generated kernel:\n" + log + "\n--- source ---\n" + src);
+      if (out_cubin) *out_cubin = cubin.size();
+    }
+    copy_out(src, buf, cap, out_len);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// dist.cpp — see dist.h.  NCCL is bound with dlopen so that single-GPU use (and loading the
+// library on a machine without NCCL) needs nothing; inside a torch process the already loaded
+// libnccl.so.2 is reused.
+#include "dist.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <string>
+
+#include "runtime.h"
+
+namespace vkjit {
+namespace dist {
+namespace {
+
+struct Nccl {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  void load() {
+    if (handle) return;
+    handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!handle) fail(VKJIT_ERR_DIST, std::string("cannot load libnccl.so.2: ") + dlerror());
+    GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString)
+      fail(VKJIT_ERR_DIST, "libnccl.so.2 lacks required entry points");
+  }
+};
+
+Nccl g_nccl;
+ncclComm_t g_comm = nullptr;
+int g_rank = 0, g_world = 1;
+bool g_active = false;
+
+void ckn(ncclResult_t r, const char* what) {
+  if (r != ncclSuccess) fail(VKJIT_ERR_DIST, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error"));
+}
+
+}  // namespace
+
+bool active() { return g_active; }
+int rank() { return g_rank; }
+int world() { return g_world; }
+
+void unique_id(void* out128) {
+  g_nccl.load();
+  ncclUniqueId id;
+  ckn(g_nccl.GetUniqueId(&id), "ncclGetUniqueId");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out128, &id, 128);
+}
+
+void init(int rank, int world, const void* id128) {
+  if (world < 1 || rank < 0 || rank >= world) fail(VKJIT_ERR_INVALID, "bad rank/world");
+  if (g_active) fail(VKJIT_ERR_DIST, "vkjit_dist_init called twice");
+  Backend::get();  // needs the device bound first
+  g_rank = rank; g_world = world;
+  if (world > 1) {
+    g_nccl.load();
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ckn(g_nccl.CommInitRank(&g_comm, world, id, rank), "ncclCommInitRank");
+  }
+  g_active = true;
+}
+
+void shutdown() {
+  if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+  g_active = false; g_rank = 0; g_world = 1;
+}
+
+void allreduce(void* buf, uint32_t ty, int red, size_t count) {
+  if (!g_active || g_world == 1) return;
+  ncclDataType_t dt = ty == VKJIT_TY_F32 ? ncclFloat32 : ty == VKJIT_TY_I32 ? ncclInt32 : ncclUint32;
+  ncclRedOp_t op = red == VKJIT_RED_SUM ? ncclSum : red == VKJIT_RED_MIN ? ncclMin : ncclMax;
+  ckn(g_nccl.AllReduce(buf, buf, count, dt, op, g_comm, (cudaStream_t)Backend::get().stream), "ncclAllReduce");
+  Backend::counters().collectives += 1;
+}
+
+void shard_range(size_t n, int rank, int world, size_t& lo, size_t& hi) {
+  if (world < 1 || rank < 0 || rank >= world) fail(VKJIT_ERR_INVALID, "bad rank/world");
+  const size_t q = (n / 4) / (size_t)world * 4;
+  lo = q * (size_t)rank;
+  hi = rank == world - 1 ? n : q * (size_t)(rank + 1);
+}
+
+}  // namespace dist
+}  // namespace vkjit

@@ -1,0 +1,384 @@
+// prims.cu — hand-written CUDA primitives for sm_100a: horizontal reductions and
+// decoupled look-back prefix-sum / stream compaction.  All of them are HBM-bound integer /
+// byte movers: the design rules that matter are coalesced 128-bit accesses, enough loads in
+// flight per SM to cover HBM latency, and grids sized in multiples of the SM count
+// (148 on B200).  No tensor cores on purpose.
+//
+// There is no reference implementation of these operations; the CPU oracle
+// (oracle/oracle.cpp) is the specification they are tested against.
+#include "prims.h"
+
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace vkjit {
+namespace prims {
+
+// ---------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------
+// Streaming 128-bit load: read-only path, do not allocate in L1 (every byte is used once).
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+template <typename T> __device__ __forceinline__ T from_bits(uint32_t w);
+template <> __device__ __forceinline__ uint32_t from_bits<uint32_t>(uint32_t w) { return w; }
+template <> __device__ __forceinline__ int32_t from_bits<int32_t>(uint32_t w) { return (int32_t)w; }
+template <> __device__ __forceinline__ float from_bits<float>(uint32_t w) { return __uint_as_float(w); }
+__device__ __forceinline__ uint32_t to_bits(uint32_t v) { return v; }
+__device__ __forceinline__ uint32_t to_bits(int32_t v) { return (uint32_t)v; }
+__device__ __forceinline__ uint32_t to_bits(float v) { return __float_as_uint(v); }
+
+template <typename T, int RED> struct RedOp;
+template <typename T> struct RedOp<T, VKJIT_RED_SUM> {
+  __device__ static T identity() { return T(0); }
+  __device__ static T apply(T a, T b) { return a + b; }  // u32/i32 wrap mod 2^32; f32 any association
+};
+template <> struct RedOp<int32_t, VKJIT_RED_SUM> {
+  __device__ static int32_t identity() { return 0; }
+  __device__ static int32_t apply(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+};
+template <> struct RedOp<uint32_t, VKJIT_RED_MIN> {
+  __device__ static uint32_t identity() { return 0xFFFFFFFFu; }
+  __device__ static uint32_t apply(uint32_t a, uint32_t b) { return min(a, b); }
+};
+template <> struct RedOp<uint32_t, VKJIT_RED_MAX> {
+  __device__ static uint32_t identity() { return 0u; }
+  __device__ static uint32_t apply(uint32_t a, uint32_t b) { return max(a, b); }
+};
+template <> struct RedOp<int32_t, VKJIT_RED_MIN> {
+  __device__ static int32_t identity() { return 0x7FFFFFFF; }
+  __device__ static int32_t apply(int32_t a, int32_t b) { return min(a, b); }
+};
+template <> struct RedOp<int32_t, VKJIT_RED_MAX> {
+  __device__ static int32_t identity() { return (int32_t)0x80000000; }
+  __device__ static int32_t apply(int32_t a, int32_t b) { return max(a, b); }
+};
+// fminf/fmaxf: NaN-ignoring, -0 < +0 (PTX min/max.f32) — matches the oracle's fmin_spec/fmax_spec.
+// Identity = NaN so that it is ignored by every real operand.
+template <> struct RedOp<float, VKJIT_RED_MIN> {
+  __device__ static float identity() { return __uint_as_float(0x7FC00000u); }
+  __device__ static float apply(float a, float b) { return fminf(a, b); }
+};
+template <> struct RedOp<float, VKJIT_RED_MAX> {
+  __device__ static float identity() { return __uint_as_float(0x7FC00000u); }
+  __device__ static float apply(float a, float b) { return fmaxf(a, b); }
+};
+
+template <typename T, int RED>
+__device__ __forceinline__ T warp_reduce(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = RedOp<T, RED>::apply(v, from_bits<T>(__shfl_xor_sync(0xFFFFFFFFu, to_bits(v), o)));
+  return v;
+}
+
+// Block-wide reduction: warp shuffle, then a shared-memory tree over the warp results.
+template <typename T, int RED, int THREADS>
+__device__ __forceinline__ T block_reduce(T v, T* smem /* THREADS/32 */) {
+  constexpr int WARPS = THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_reduce<T, RED>(v);
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    T w = lane < WARPS ? smem[lane] : RedOp<T, RED>::identity();
+    w = warp_reduce<T, RED>(w);
+    if (lane == 0) smem[0] = w;
+  }
+  __syncthreads();
+  T r = smem[0];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// horizontal reduction
+// ---------------------------------------------------------------------------------------
+// Algorithmic traffic: 4 B/lane read, 4 B written in total.
+template <typename T, int RED, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ partials, unsigned int* __restrict__ ticket,
+              uint32_t* __restrict__ out) {
+  using O = RedOp<T, RED>;
+  __shared__ T smem[THREADS / 32];
+  __shared__ bool is_last;
+
+  const size_t tid = (size_t)blockIdx.x * THREADS + threadIdx.x;
+  const size_t nthreads = (size_t)gridDim.x * THREADS;
+  const size_t n4 = n >> 2;
+  const uint4* in4 = reinterpret_cast<const uint4*>(in);
+
+  T a0 = O::identity(), a1 = O::identity(), a2 = O::identity(), a3 = O::identity();
+  size_t v = tid;
+  // 4 independent 128-bit loads in flight per thread (64 B/thread, 128 KB/SM at full occupancy)
+  for (; v + 3 * nthreads < n4; v += 4 * nthreads) {
+    const uint4 x0 = ld_stream(in4 + v);
+    const uint4 x1 = ld_stream(in4 + v + nthreads);
+    const uint4 x2 = ld_stream(in4 + v + 2 * nthreads);
+    const uint4 x3 = ld_stream(in4 + v + 3 * nthreads);
+    a0 = O::apply(a0, from_bits<T>(x0.x)); a1 = O::apply(a1, from_bits<T>(x0.y));
+    a2 = O::apply(a2, from_bits<T>(x0.z)); a3 = O::apply(a3, from_bits<T>(x0.w));
+    a0 = O::apply(a0, from_bits<T>(x1.x)); a1 = O::apply(a1, from_bits<T>(x1.y));
+    a2 = O::apply(a2, from_bits<T>(x1.z)); a3 = O::apply(a3, from_bits<T>(x1.w));
+    a0 = O::apply(a0, from_bits<T>(x2.x)); a1 = O::apply(a1, from_bits<T>(x2.y));
+    a2 = O::apply(a2, from_bits<T>(x2.z)); a3 = O::apply(a3, from_bits<T>(x2.w));
+    a0 = O::apply(a0, from_bits<T>(x3.x)); a1 = O::apply(a1, from_bits<T>(x3.y));
+    a2 = O::apply(a2, from_bits<T>(x3.z)); a3 = O::apply(a3, from_bits<T>(x3.w));
+  }
+  for (; v < n4; v += nthreads) {
+    const uint4 x0 = ld_stream(in4 + v);
+    a0 = O::apply(a0, from_bits<T>(x0.x)); a1 = O::apply(a1, from_bits<T>(x0.y));
+    a2 = O::apply(a2, from_bits<T>(x0.z)); a3 = O::apply(a3, from_bits<T>(x0.w));
+  }
+  for (size_t i = (n4 << 2) + tid; i < n; i += nthreads) a0 = O::apply(a0, from_bits<T>(in[i]));
+
+  T acc = O::apply(O::apply(a0, a1), O::apply(a2, a3));
+  acc = block_reduce<T, RED, THREADS>(acc, smem);
+
+  // publish the CTA partial; the last CTA to arrive folds all partials in a fixed order
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = to_bits(acc);
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    T f = O::identity();
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) f = O::apply(f, from_bits<T>(__ldcg(partials + i)));
+    f = block_reduce<T, RED, THREADS>(f, smem);
+    if (threadIdx.x == 0) {
+      out[0] = to_bits(f);
+      *ticket = 0u;  // self-reset for the next launch on this stream
+    }
+  }
+}
+
+template <typename T, int RED>
+static void launch_reduce(const void* in, size_t n, void* out, const Scratch& sc, int sm_count, cudaStream_t s) {
+  const size_t n4 = n >> 2;
+  size_t ctas = (std::max<size_t>(n4, 1) + kReduceThreads - 1) / kReduceThreads;
+  const size_t cap = (size_t)sm_count * (2048 / kReduceThreads);  // one full wave: 4 CTAs of 512 threads per SM
+  if (ctas > cap) ctas = cap;
+  if (ctas > (size_t)kReduceMaxCtas) ctas = kReduceMaxCtas;
+  reduce_kernel<T, RED, kReduceThreads><<<(unsigned)ctas, kReduceThreads, 0, s>>>(
+      (const uint32_t*)in, n, (uint32_t*)sc.partials, sc.ticket, (uint32_t*)out);
+}
+
+void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+#define VK_DISPATCH(T)                                                                          \
+  switch (red) {                                                                                \
+    case VKJIT_RED_SUM: launch_reduce<T, VKJIT_RED_SUM>(in, n, out, sc, sm_count, s); break;    \
+    case VKJIT_RED_MIN: launch_reduce<T, VKJIT_RED_MIN>(in, n, out, sc, sm_count, s); break;    \
+    case VKJIT_RED_MAX: launch_reduce<T, VKJIT_RED_MAX>(in, n, out, sc, sm_count, s); break;    \
+    default: fail(VKJIT_ERR_INVALID, "unknown reduction");                                      \
+  }
+  switch (ty) {
+    case VKJIT_TY_U32: VK_DISPATCH(uint32_t) break;
+    case VKJIT_TY_I32: VK_DISPATCH(int32_t) break;
+    case VKJIT_TY_F32: VK_DISPATCH(float) break;
+    default: fail(VKJIT_ERR_TYPE, "reduce needs U32/I32/F32");
+  }
+#undef VK_DISPATCH
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(e));
+}
+
+// ---------------------------------------------------------------------------------------
+// decoupled look-back scan (Merrill & Garland) — prefix sum and stream compaction
+// ---------------------------------------------------------------------------------------
+// Tile = 256 threads x 4 vectors x 4 lanes = 4096 lanes.  Vector q = j*256 + t of a tile is held
+// by thread t in register slot j, so every load/store instruction of a warp covers 512
+// contiguous bytes.  Tile status words pack {flag:32 | value:32} into one 64-bit word so flag
+// and value travel in a single (volatile, L2-coherent) access and no fence is needed between
+// them.  Tiles are handed out by an atomic counter, so a tile only ever waits on tiles that
+// are already running (forward progress does not depend on CTA dispatch order).
+enum : uint32_t { ST_INVALID = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2 };
+enum ScanMode { MODE_EXCLUSIVE = 0, MODE_INCLUSIVE = 1, MODE_COMPRESS_INDEX = 2, MODE_COMPRESS_VALUE = 3 };
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
+
+// Executed by warp 0 of the CTA owning `tile`.  Returns the exclusive prefix of the tile.
+__device__ __forceinline__ uint32_t look_back(volatile uint64_t* status, uint32_t tile, uint32_t aggregate) {
+  const int lane = threadIdx.x & 31;
+  if (tile == 0) {
+    if (lane == 0) status[0] = ((uint64_t)ST_INCLUSIVE << 32) | aggregate;
+    return 0u;
+  }
+  if (lane == 0) status[tile] = ((uint64_t)ST_AGGREGATE << 32) | aggregate;
+  uint32_t exclusive = 0;
+  int top = (int)tile - 1;  // nearest predecessor examined by lane 0
+  for (;;) {
+    const int idx = top - lane;
+    uint64_t s = (uint64_t)ST_INCLUSIVE << 32;  // virtual tile before tile 0: inclusive prefix 0
+    if (idx >= 0) {
+      do { s = status[idx]; } while ((uint32_t)(s >> 32) == ST_INVALID);
+    }
+    const unsigned incl = __ballot_sync(0xFFFFFFFFu, (uint32_t)(s >> 32) == ST_INCLUSIVE);
+    if (incl) {
+      const int first = __ffs(incl) - 1;  // nearest tile that already knows its inclusive prefix
+      exclusive += warp_sum(lane <= first ? (uint32_t)s : 0u);
+      break;
+    }
+    exclusive += warp_sum((uint32_t)s);
+    top -= 32;
+  }
+  if (lane == 0) status[tile] = ((uint64_t)ST_INCLUSIVE << 32) | (exclusive + aggregate);
+  return exclusive;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kScanThreads)
+scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: mask words
+            const uint32_t* __restrict__ values,  // MODE_COMPRESS_VALUE only
+            uint32_t* __restrict__ out, uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles,
+            uint64_t* __restrict__ state) {
+  constexpr int T = kScanThreads;
+  constexpr int VPT = 4;  // vectors per thread
+  constexpr bool COMPRESS = MODE >= MODE_COMPRESS_INDEX;
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_warp_tot[VPT * (T / 32)];  // 32 entries: exactly one warp-scan wide
+  __shared__ uint32_t s_tile_excl;
+
+  if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd((unsigned long long*)state, 1ull);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  if (tile >= num_tiles) return;
+  volatile uint64_t* status = state + 1;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t tile_base = (size_t)tile * kScanTile;
+  const bool full = tile_base + kScanTile <= n;
+
+  uint4 x[VPT];  // scan: addends; compress: 0/1 flags
+  uint4 val[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+    if (full || e + 3 < n) {
+      x[j] = ld_stream(reinterpret_cast<const uint4*>(in + e));
+      if (MODE == MODE_COMPRESS_VALUE) val[j] = ld_stream(reinterpret_cast<const uint4*>(values + e));
+    } else {
+      x[j].x = e + 0 < n ? in[e + 0] : 0u; x[j].y = e + 1 < n ? in[e + 1] : 0u;
+      x[j].z = e + 2 < n ? in[e + 2] : 0u; x[j].w = 0u;
+      if (MODE == MODE_COMPRESS_VALUE) {
+        val[j].x = e + 0 < n ? values[e + 0] : 0u; val[j].y = e + 1 < n ? values[e + 1] : 0u;
+        val[j].z = e + 2 < n ? values[e + 2] : 0u; val[j].w = 0u;
+      }
+    }
+    if (COMPRESS) { x[j].x = x[j].x != 0u; x[j].y = x[j].y != 0u; x[j].z = x[j].z != 0u; x[j].w = x[j].w != 0u; }
+  }
+
+  // 1) per-vector sums, 2) inclusive warp scan per register slot, 3) one warp scans the 32
+  // (slot, warp) totals in tile order, 4) look-back gives the tile's global offset.
+  uint32_t vsum[VPT], wincl[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    vsum[j] = x[j].x + x[j].y + x[j].z + x[j].w;
+    uint32_t s = vsum[j];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+      if (lane >= o) s += t;
+    }
+    wincl[j] = s;
+    if (lane == 31) s_warp_tot[j * (T / 32) + warp] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t tot = s_warp_tot[lane];
+    uint32_t s = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+      if (lane >= o) s += t;
+    }
+    s_warp_tot[lane] = s - tot;  // exclusive offset of (slot, warp) inside the tile
+    const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
+    const uint32_t excl = look_back(status, tile, aggregate);
+    if (lane == 0) {
+      s_tile_excl = excl;
+      if (COMPRESS && tile == num_tiles - 1) *count_out = excl + aggregate;
+    }
+  }
+  __syncthreads();
+  const uint32_t tile_excl = s_tile_excl;
+
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+    uint32_t p = tile_excl + s_warp_tot[j * (T / 32) + warp] + (wincl[j] - vsum[j]);  // exclusive prefix of lane e
+    if (!COMPRESS) {
+      uint4 r;
+      if (MODE == MODE_EXCLUSIVE) { r.x = p; r.y = p + x[j].x; r.z = r.y + x[j].y; r.w = r.z + x[j].z; }
+      else { r.x = p + x[j].x; r.y = r.x + x[j].y; r.z = r.y + x[j].z; r.w = r.z + x[j].w; }
+      if (full || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
+      else {
+        if (e + 0 < n) out[e + 0] = r.x;
+        if (e + 1 < n) out[e + 1] = r.y;
+        if (e + 2 < n) out[e + 2] = r.z;
+      }
+    } else {
+      // selected lanes are written at their rank; flags of out-of-range lanes are 0
+      if (x[j].x) { out[p] = MODE == MODE_COMPRESS_VALUE ? val[j].x : (uint32_t)(e + 0); ++p; }
+      if (x[j].y) { out[p] = MODE == MODE_COMPRESS_VALUE ? val[j].y : (uint32_t)(e + 1); ++p; }
+      if (x[j].z) { out[p] = MODE == MODE_COMPRESS_VALUE ? val[j].z : (uint32_t)(e + 2); ++p; }
+      if (x[j].w) { out[p] = MODE == MODE_COMPRESS_VALUE ? val[j].w : (uint32_t)(e + 3); ++p; }
+    }
+  }
+}
+
+size_t scan_state_words(size_t n) { return 1 + (n + kScanTile - 1) / kScanTile; }
+
+static uint32_t prepare_scan(size_t n, const Scratch& sc, cudaStream_t s) {
+  const size_t tiles = (n + kScanTile - 1) / kScanTile;
+  if (1 + tiles > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
+  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, (1 + tiles) * sizeof(uint64_t), s);
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
+  return (uint32_t)tiles;
+}
+
+void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, void* stream) {
+  if (n == 0) return;
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t tiles = prepare_scan(n, sc, s);
+  if (exclusive) scan_kernel<MODE_EXCLUSIVE><<<tiles, kScanThreads, 0, s>>>(in, nullptr, out, nullptr, n, tiles, sc.tile_state);
+  else scan_kernel<MODE_INCLUSIVE><<<tiles, kScanThreads, 0, s>>>(in, nullptr, out, nullptr, n, tiles, sc.tile_state);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
+}
+
+void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
+              const Scratch& sc, void* stream) {
+  if (n == 0) return;
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t tiles = prepare_scan(n, sc, s);
+  if (values) scan_kernel<MODE_COMPRESS_VALUE><<<tiles, kScanThreads, 0, s>>>(mask, values, out, count_out, n, tiles, sc.tile_state);
+  else scan_kernel<MODE_COMPRESS_INDEX><<<tiles, kScanThreads, 0, s>>>(mask, nullptr, out, count_out, n, tiles, sc.tile_state);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("compress launch: ") + cudaGetErrorString(e));
+}
+
+__global__ void fill_kernel(uint32_t* out, uint32_t value, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = value;
+}
+void fill_u32(uint32_t* out, uint32_t value, size_t n, void* stream) {
+  if (n == 0) return;
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+  fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, value, n);
+}
+
+}  // namespace prims
+}  // namespace vkjit

@@ -1,0 +1,44 @@
+// prims.h — hand-written sm_100a runtime primitives (no reference counterpart; the reference
+// has no reductions, scans or compaction — SURVEY.md §2a, Appendix A.3).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace vkjit {
+namespace prims {
+
+// Scratch the primitives need between launches; owned by the backend, zero-initialised once.
+struct Scratch {
+  void* partials = nullptr;       // reduce: one 4-byte partial per CTA
+  unsigned int* ticket = nullptr; // reduce: last-CTA election (self-resetting)
+  uint64_t* tile_state = nullptr; // scan: [0] = dynamic tile counter, [1..] = look-back status words
+  size_t tile_state_words = 0;
+};
+
+constexpr int kReduceThreads = 512;
+constexpr int kReduceMaxCtas = 2048;
+constexpr int kScanThreads = 256;
+constexpr int kScanTile = 4096;  // lanes per look-back tile (256 threads x 4 x uint4)
+
+// number of 8-byte words `tile_state` must hold for n lanes
+size_t scan_state_words(size_t n);
+
+// out[0] = reduce(in[0..n)).  ty: VKJIT_TY_{U32,I32,F32}; red: VKJIT_RED_*.  One launch:
+// vectorised grid-stride partials -> warp shuffle -> shared-memory tree -> last CTA folds the
+// per-CTA partials in a fixed order (deterministic for a given n and grid).
+// `mailbox` (optional): the last CTA additionally stores the result there (peer-mapped slot).
+void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream);
+
+// Single-pass decoupled look-back prefix sum (mod 2^32) over u32 words.
+void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, void* stream);
+
+// Stream compaction: lanes whose mask word is non-zero, stable order.  values == nullptr writes the
+// lane index.  *count_out (device) receives the number of selected lanes.
+void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
+              const Scratch& sc, void* stream);
+
+// out[i] = value for i in [0, n)
+void fill_u32(uint32_t* out, uint32_t value, size_t n, void* stream);
+
+}  // namespace prims
+}  // namespace vkjit

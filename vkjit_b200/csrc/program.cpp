@@ -1,0 +1,486 @@
+// program.cpp — trace walk, canonical key + hash, CUDA C generation.
+// Reference counterparts: Kernel::record_kernel_size (internal.rs:710-729), record_ops
+// (:874-1117), compile (:1148-1305).  See program.h.
+#include "program.h"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace vkjit {
+
+void Program::clear() {
+  key.clear(); order.clear(); params.clear(); roots.clear();
+  n = 0; have_n = false; base = 0; have_base = false; sharded = false; vectorized = true;
+  hash = Hash128();
+}
+
+namespace {
+
+struct Frame { VarId id; uint32_t next; };
+
+// internal.rs:697-706
+inline void set_num(Program& p, uint64_t n) {
+  if (p.have_n) {
+    if (p.n != n)
+      fail(VKJIT_ERR_SIZE, "All variables in the kernel have to have the same number of elements! (" +
+                               std::to_string(p.n) + " vs " + std::to_string(n) + ", internal.rs:699-702)");
+  } else { p.have_n = true; p.n = n; }
+}
+
+// Child k of a node in the order record_ops recurses (internal.rs:874-1117); returns false
+// when there is no k-th child.  `ptr_only` marks operands that are addressed, not evaluated.
+inline bool child_of(const Var& v, uint32_t k, VarId& out, uint8_t& ptr_use) {
+  ptr_use = 0;
+  const VarId* d = v.deps();
+  switch (v.op) {
+    case OP_GATHER:
+      if (k == 0) { out = d[0]; ptr_use = USE_GATHER; return true; }
+      if (k < v.ndeps) { out = d[k]; return true; }
+      return false;
+    case OP_SCATTER: case OP_SCATTER_ADD:
+      if (k == 0) { out = d[0]; return true; }
+      if (k == 1) { out = v.side_effect; ptr_use = USE_SCATTER; return true; }
+      if (k - 1 < v.ndeps) { out = d[k - 1]; return true; }
+      return false;
+    default:
+      if (k < v.ndeps) { out = d[k]; return true; }
+      return false;
+  }
+}
+
+inline void mix(Hash128& h, uint64_t w) {
+  h.lo = (h.lo ^ w) * 0x9E3779B97F4A7C15ull; h.lo ^= h.lo >> 32;
+  h.hi = (h.hi + w) * 0xC2B2AE3D27D4EB4Full; h.hi ^= h.hi >> 29;
+}
+
+void type_signature(const Ir& ir, TypeId t, std::vector<uint32_t>& key) {
+  if (!ty_is_struct(t)) { key.push_back(t); return; }
+  const auto& e = ir.struct_elems(t);
+  key.push_back(0x80000000u | (uint32_t)e.size());
+  for (TypeId x : e) type_signature(ir, x, key);
+}
+
+int g_unroll = -1;
+int unroll_factor() {
+  if (g_unroll < 0) {
+    const char* s = getenv("VKJIT_UNROLL");
+    g_unroll = s ? std::max(1, atoi(s)) : 2;
+  }
+  return g_unroll;
+}
+
+}  // namespace
+
+void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p) {
+  p.clear();
+  p.vectorized = vectorized;
+  const uint32_t stamp = ir.next_stamp();
+  static thread_local std::vector<Frame> stack;
+  stack.clear();
+
+  auto touch_binding = [&](VarId id, uint8_t use) {
+    Var& v = ir.vars[id];
+    Param& pr = p.params[v.aux];
+    if ((use & USE_STREAM) && !(pr.use & USE_STREAM)) {  // internal.rs:717-721
+      set_num(p, v.array->bytes / 4);
+      if (v.sharded) p.sharded = true;
+    }
+    pr.use |= use;
+  };
+
+  for (VarId root : schedule) {
+    {
+      const Var& rv = ir.var(root);
+      if (!ty_is_scalar(rv.ty))  // Struct: stride() is unimplemented!() (vartype.rs:45-53)
+        fail(VKJIT_ERR_UNSUPPORTED, "only scalar-typed vars can be scheduled (vartype.rs:45-53)");
+    }
+    if (ir.vars[root].stamp == stamp) {
+      if (ir.vars[root].op == OP_BINDING) touch_binding(root, USE_STREAM);
+      p.roots.push_back(ir.vars[root].local);
+      continue;
+    }
+    stack.push_back({root, 0});
+    while (!stack.empty()) {
+      Frame& f = stack.back();
+      Var& v = ir.vars[f.id];
+      VarId c; uint8_t ptr_use;
+      if (child_of(v, f.next, c, ptr_use)) {
+        ++f.next;
+        Var& cv = ir.var(c);
+        if (ptr_use) {
+          if (ptr_use == USE_GATHER && (cv.op != OP_BINDING || !cv.array))
+            fail(VKJIT_ERR_INVALID, "Can only gather from buffer! (internal.rs:1054)");
+          if (ptr_use == USE_SCATTER && (cv.op != OP_BINDING || !cv.array))
+            fail(VKJIT_ERR_INVALID, "Cannot scatter into non buffer variables! (internal.rs:1061)");
+          if (cv.stamp != stamp) {
+            cv.stamp = stamp; cv.local = (uint32_t)p.order.size();
+            p.order.push_back(c);
+            cv.aux = (uint32_t)p.params.size();
+            p.params.push_back({c, 0, cv.local});
+          }
+          touch_binding(c, ptr_use);
+        } else if (cv.stamp != stamp) {
+          stack.push_back({c, 0});  // invalidates f
+        } else if (cv.op == OP_BINDING) {
+          touch_binding(c, USE_STREAM);
+        }
+        continue;
+      }
+      // all children done: number this node (post-order)
+      const VarId id = f.id;
+      stack.pop_back();
+      if (v.stamp == stamp) continue;  // reached twice through different parents while pending
+      v.stamp = stamp; v.local = (uint32_t)p.order.size();
+      p.order.push_back(id);
+      switch (v.op) {
+        case OP_BINDING:
+          if (!v.array) fail(VKJIT_ERR_INVALID, "Binding without an array");
+          v.aux = (uint32_t)p.params.size();
+          p.params.push_back({id, 0, v.local});
+          touch_binding(id, USE_STREAM);
+          break;
+        case OP_ARANGE:  // internal.rs:722-725
+          set_num(p, v.num);
+          if (v.sharded) {
+            p.sharded = true;
+            if (p.have_base && p.base != v.base) fail(VKJIT_ERR_SIZE, "sharded aranges with different bases in one kernel");
+            p.have_base = true; p.base = v.base;
+          }
+          break;
+        case OP_GATHER: case OP_SCATTER: case OP_SCATTER_ADD: {
+          const TypeId it = ir.vars[v.deps()[1]].ty;
+          if (it != VKJIT_TY_U32 && it != VKJIT_TY_I32) fail(VKJIT_ERR_TYPE, "gather/scatter index must be U32 or I32");
+          if (v.ndeps >= 3 && ir.vars[v.deps()[2]].ty != VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "gather/scatter mask must be Bool");
+          if (!ty_is_scalar(v.ty)) fail(VKJIT_ERR_UNSUPPORTED, "gather/scatter of a struct");
+          if (v.op != OP_GATHER && ir.vars[v.side_effect].ty != v.ty) fail(VKJIT_ERR_TYPE, "scatter: source and target types differ");
+          if (v.op == OP_SCATTER_ADD && v.ty == VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "scatter_add on Bool");
+          break;
+        }
+        case OP_SELECT:
+          if (ir.vars[v.deps()[0]].ty != VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "select condition must be Bool");
+          break;
+        default: break;
+      }
+    }
+    p.roots.push_back(ir.vars[root].local);
+  }
+
+  if (!p.have_n) fail(VKJIT_ERR_SIZE, "schedule has no Binding/Arange: kernel size unknown (internal.rs:1202 num.unwrap())");
+  if (p.n == 0) fail(VKJIT_ERR_SIZE, "zero-sized kernel");
+  if (p.n > 0xFFFFFFFFull) fail(VKJIT_ERR_SIZE, "kernel size exceeds the 32-bit invocation index");
+  if (p.params.size() + p.roots.size() > 480) fail(VKJIT_ERR_UNSUPPORTED, "too many arrays in one kernel (4 KB parameter limit)");
+
+  // canonical key: structure only — no VarIds, no addresses, no n
+  std::vector<uint32_t>& key = p.key;
+  key.push_back(0x564B4A31u);  // "VKJ1"
+  key.push_back((vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8));
+  for (uint32_t li = 0; li < p.order.size(); ++li) {
+    const Var& v = ir.vars[p.order[li]];
+    const uint32_t tycode = ty_is_struct(v.ty) ? 0xFu : v.ty;
+    key.push_back((uint32_t)v.op | ((uint32_t)v.kind << 8) | (tycode << 24) | ((uint32_t)(v.has_se ? 1u : 0u) << 28));
+    key.push_back(v.ndeps);
+    if (tycode == 0xFu) type_signature(ir, v.ty, key);
+    switch (v.op) {
+      case OP_CONST: case OP_GETATTR: case OP_SETATTR: key.push_back(v.aux); break;
+      case OP_ARANGE: key.push_back(v.sharded); break;
+      case OP_BINDING: key.push_back(v.aux | ((uint32_t)p.params[v.aux].use << 16)); break;
+      default: break;
+    }
+    const VarId* d = v.deps();
+    for (uint32_t k = 0; k < v.ndeps; ++k) key.push_back(ir.vars[d[k]].local);
+    if (v.has_se) key.push_back(ir.vars[v.side_effect].local);
+  }
+  key.push_back(0xFFFFFFFFu);
+  for (uint32_t r : p.roots) key.push_back(r);
+  Hash128 h{0x243F6A8885A308D3ull, 0x13198A2E03707344ull};
+  for (uint32_t w : key) mix(h, w);
+  mix(h, key.size());
+  p.hash = h;
+}
+
+// ---------------------------------------------------------------------------------------
+// CUDA C generation
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct Val {
+  std::string name;        // scalar expression name
+  TypeId ty = VKJIT_TY_VOID;
+  std::vector<Val> elems;  // struct members (scalar replacement: structs never reach memory)
+};
+
+const char* ctype(TypeId t) {
+  switch (t) {
+    case VKJIT_TY_BOOL: return "bool";
+    case VKJIT_TY_U32: return "u32";
+    case VKJIT_TY_I32: return "i32";
+    case VKJIT_TY_F32: return "f32";
+    default: return "void";
+  }
+}
+
+std::string hex32(uint32_t w) { char b[16]; snprintf(b, sizeof b, "0x%08xu", w); return b; }
+
+// 4-byte word -> typed value and back (Bool arrays hold 0/1 words, vartype.rs:45-64)
+std::string from_word(TypeId t, const std::string& w) {
+  switch (t) {
+    case VKJIT_TY_BOOL: return "(" + w + " != 0u)";
+    case VKJIT_TY_I32: return "(i32)" + w;
+    case VKJIT_TY_F32: return "__uint_as_float(" + w + ")";
+    default: return w;
+  }
+}
+std::string to_word(TypeId t, const std::string& v) {
+  switch (t) {
+    case VKJIT_TY_BOOL: return "(" + v + " ? 1u : 0u)";
+    case VKJIT_TY_I32: return "(u32)" + v;
+    case VKJIT_TY_F32: return "__float_as_uint(" + v + ")";
+    default: return v;
+  }
+}
+
+struct Gen {
+  const Ir& ir;
+  const Program& p;
+  std::string body;
+  std::vector<Val> vals;
+
+  Gen(const Ir& i, const Program& pr) : ir(i), p(pr) { vals.resize(pr.order.size()); }
+
+  void line(const std::string& s) { body += "  " + s + "\n"; }
+  void def(uint32_t li, TypeId ty, const std::string& expr) {
+    vals[li].name = "v" + std::to_string(li);
+    vals[li].ty = ty;
+    line(std::string("const ") + ctype(ty) + " v" + std::to_string(li) + " = " + expr + ";");
+  }
+  const Val& dep(const Var& v, uint32_t k) const { return vals[ir.vars[v.deps()[k]].local]; }
+
+  // componentwise select for struct values (reference: OpSelect-by-branch, internal.rs:1096-1112)
+  Val select_val(const std::string& c, const Val& a, const Val& b, const std::string& name, int& counter) {
+    Val r; r.ty = a.ty;
+    if (a.elems.empty() && ty_is_scalar(a.ty)) {
+      r.name = name + (counter ? "_" + std::to_string(counter) : "");
+      ++counter;
+      line(std::string("const ") + ctype(a.ty) + " " + r.name + " = " + c + " ? " + a.name + " : " + b.name + ";");
+    } else {
+      for (size_t i = 0; i < a.elems.size(); ++i) r.elems.push_back(select_val(c, a.elems[i], b.elems[i], name, counter));
+    }
+    return r;
+  }
+
+  std::string bop_expr(const Var& v, const std::string& a, const std::string& b) {
+    const TypeId ot = ir.vars[v.deps()[0]].ty;  // operand type after promotion (internal.rs:887, :914)
+    const bool f = ot == VKJIT_TY_F32, s = ot == VKJIT_TY_I32, bl = ot == VKJIT_TY_BOOL;
+    auto wrap = [&](const char* op) {  // modular 2^32 arithmetic; signed overflow is UB in C
+      return s ? "(i32)((u32)" + a + " " + op + " (u32)" + b + ")" : a + " " + op + " " + b;
+    };
+    switch (v.kind) {
+      // f32: round-to-nearest intrinsics are never contracted into FMA, whatever the flags
+      case VKJIT_BOP_ADD: return f ? "__fadd_rn(" + a + ", " + b + ")" : wrap("+");
+      case VKJIT_BOP_SUB: return f ? "__fsub_rn(" + a + ", " + b + ")" : wrap("-");
+      case VKJIT_BOP_MUL: return f ? "__fmul_rn(" + a + ", " + b + ")" : wrap("*");
+      case VKJIT_BOP_DIV: return f ? "__fdiv_rn(" + a + ", " + b + ")" : a + " / " + b;  // OpFDiv / OpSDiv / OpUDiv
+      case VKJIT_BOP_LT: return a + " < " + b;     // FOrdLessThan / SLessThan / ULessThan by operand type
+      case VKJIT_BOP_GT: return a + " > " + b;
+      case VKJIT_BOP_LEQ: return a + " <= " + b;
+      case VKJIT_BOP_GEQ: return a + " >= " + b;
+      case VKJIT_BOP_EQ: return a + " == " + b;    // FOrdEqual: false on NaN, as C ==
+      case VKJIT_BOP_NEQ: return f ? "(" + a + " < " + b + ") || (" + a + " > " + b + ")"  // FOrdNotEqual (C != is unordered)
+                                   : a + " != " + b;
+      case VKJIT_BOP_AND: return bl ? a + " && " + b : a + " & " + b;
+      case VKJIT_BOP_OR: return bl ? a + " || " + b : a + " | " + b;
+      case VKJIT_BOP_XOR: return bl ? a + " != " + b : a + " ^ " + b;
+      case VKJIT_BOP_SHL: return s ? "(i32)((u32)" + a + " << ((u32)" + b + " & 31u))" : a + " << (" + b + " & 31u)";
+      case VKJIT_BOP_SHR: return s ? a + " >> ((u32)" + b + " & 31u)" : a + " >> (" + b + " & 31u)";
+      case VKJIT_BOP_MIN: return f ? "fminf(" + a + ", " + b + ")" : "min(" + a + ", " + b + ")";
+      case VKJIT_BOP_MAX: return f ? "fmaxf(" + a + ", " + b + ")" : "max(" + a + ", " + b + ")";
+      default: fail(VKJIT_ERR_INVALID, "unknown bop");
+    }
+  }
+
+  std::string uop_expr(const Var& v, const std::string& a) {
+    const TypeId t = v.ty;
+    switch (v.kind) {
+      case VKJIT_UOP_NEG:
+        if (t == VKJIT_TY_F32) return "__uint_as_float(__float_as_uint(" + a + ") ^ 0x80000000u)";
+        return t == VKJIT_TY_I32 ? "(i32)(0u - (u32)" + a + ")" : "0u - " + a;
+      case VKJIT_UOP_ABS:
+        if (t == VKJIT_TY_F32) return "__uint_as_float(__float_as_uint(" + a + ") & 0x7fffffffu)";
+        return t == VKJIT_TY_I32 ? "(" + a + " < 0) ? (i32)(0u - (u32)" + a + ") : " + a : a;
+      case VKJIT_UOP_NOT: return t == VKJIT_TY_BOOL ? "!" + a : "~" + a;
+      case VKJIT_UOP_SQRT: return "__fsqrt_rn(" + a + ")";
+      case VKJIT_UOP_EXP: return "expf(" + a + ")";
+      case VKJIT_UOP_LOG: return "logf(" + a + ")";
+      case VKJIT_UOP_SIN: return "sinf(" + a + ")";
+      case VKJIT_UOP_COS: return "cosf(" + a + ")";
+      default: fail(VKJIT_ERR_INVALID, "unknown uop");
+    }
+  }
+
+  std::string cast_expr(TypeId s, TypeId t, const std::string& a) {  // internal.rs:957-992
+    if (s == t) return a;
+    if (s == VKJIT_TY_U32 && t == VKJIT_TY_I32) return "(i32)" + a;            // bit reinterpret
+    if (s == VKJIT_TY_I32 && t == VKJIT_TY_U32) return "(u32)" + a;
+    if (s == VKJIT_TY_U32 && t == VKJIT_TY_F32) return "__uint2float_rn(" + a + ")";  // ConvertUToF
+    if (s == VKJIT_TY_I32 && t == VKJIT_TY_F32) return "__int2float_rn(" + a + ")";   // ConvertSToF
+    if (s == VKJIT_TY_F32 && t == VKJIT_TY_U32) return "__float2uint_rz(" + a + ")";  // intended ConvertFToU
+    if (s == VKJIT_TY_F32 && t == VKJIT_TY_I32) return "__float2int_rz(" + a + ")";   // intended ConvertFToS
+    if (s == VKJIT_TY_BOOL && t == VKJIT_TY_U32) return a + " ? 1u : 0u";
+    if (s == VKJIT_TY_BOOL && t == VKJIT_TY_I32) return a + " ? 1 : 0";
+    if (s == VKJIT_TY_BOOL && t == VKJIT_TY_F32) return a + " ? 1.0f : 0.0f";
+    if (t == VKJIT_TY_BOOL && s == VKJIT_TY_F32) return a + " != 0.0f";
+    if (t == VKJIT_TY_BOOL) return a + " != 0";
+    fail(VKJIT_ERR_UNSUPPORTED, "cast");
+  }
+
+  void emit_node(uint32_t li) {
+    const Var& v = ir.vars[p.order[li]];
+    const std::string me = "v" + std::to_string(li);
+    switch (v.op) {
+      case OP_CONST: {
+        std::string lit;
+        switch (v.ty) {
+          case VKJIT_TY_BOOL: lit = v.aux ? "true" : "false"; break;
+          case VKJIT_TY_U32: lit = std::to_string(v.aux) + "u"; break;
+          case VKJIT_TY_I32: lit = "(i32)" + hex32(v.aux); break;
+          default: lit = "__uint_as_float(" + hex32(v.aux) + ")"; break;
+        }
+        def(li, v.ty, lit);
+        break;
+      }
+      case OP_ARANGE: {  // internal.rs:1078-1094
+        const char* idx = v.sharded ? "gi" : "li";
+        if (v.ty == VKJIT_TY_U32) def(li, v.ty, idx);
+        else if (v.ty == VKJIT_TY_I32) def(li, v.ty, std::string("(i32)") + idx);
+        else def(li, v.ty, std::string("__uint2float_rn(") + idx + ")");
+        break;
+      }
+      case OP_BINDING: {
+        const Param& pr = p.params[v.aux];
+        if (pr.use & USE_STREAM) def(li, v.ty, from_word(v.ty, "in" + std::to_string(v.aux)));
+        else { vals[li].name = "/*ptr*/"; vals[li].ty = v.ty; }
+        break;
+      }
+      case OP_BOP: def(li, v.ty, bop_expr(v, dep(v, 0).name, dep(v, 1).name)); break;
+      case OP_UOP: def(li, v.ty, uop_expr(v, dep(v, 0).name)); break;
+      case OP_CAST: def(li, v.ty, cast_expr(dep(v, 0).ty, v.ty, dep(v, 0).name)); break;
+      case OP_BITCAST: def(li, v.ty, from_word(v.ty, to_word(dep(v, 0).ty, dep(v, 0).name))); break;
+      case OP_GETATTR: vals[li] = dep(v, 0).elems.at(v.aux); break;
+      case OP_SETATTR: {  // deps = [src, dst]
+        Val r = dep(v, 1);
+        r.elems.at(v.aux) = dep(v, 0);
+        vals[li] = r;
+        break;
+      }
+      case OP_STRUCTINIT: {
+        Val r; r.ty = v.ty;
+        for (uint32_t k = 0; k < v.ndeps; ++k) r.elems.push_back(dep(v, k));
+        vals[li] = r;
+        break;
+      }
+      case OP_SELECT: {
+        int counter = 0;
+        vals[li] = select_val(dep(v, 0).name, dep(v, 1), dep(v, 2), me, counter);
+        break;
+      }
+      case OP_GATHER: {  // out = active ? src[idx] : 0 (the reference lowering is broken)
+        const uint32_t ps = ir.vars[v.deps()[0]].aux;
+        const std::string ld = "g" + std::to_string(ps) + "[(u32)" + dep(v, 1).name + "]";
+        const std::string w = v.ndeps >= 3 ? "(" + dep(v, 2).name + " ? " + ld + " : 0u)" : ld;
+        def(li, v.ty, from_word(v.ty, w));
+        break;
+      }
+      case OP_SCATTER: case OP_SCATTER_ADD: {  // internal.rs:1056-1077
+        const uint32_t pd = ir.vars[v.side_effect].aux;
+        const Val& src = dep(v, 0);
+        const std::string at = "g" + std::to_string(pd) + " + (u32)" + dep(v, 1).name;
+        std::string stmt;
+        if (v.op == OP_SCATTER) stmt = "*(" + at + ") = " + to_word(v.ty, src.name) + ";";
+        else if (v.ty == VKJIT_TY_F32) stmt = "atomicAdd(reinterpret_cast<f32*>(" + at + "), " + src.name + ");";
+        else stmt = "atomicAdd(" + at + ", " + to_word(v.ty, src.name) + ");";  // mod 2^32 for U32 and I32 alike
+        if (v.ndeps >= 3) stmt = "if (" + dep(v, 2).name + ") { " + stmt + " }";
+        line(stmt);
+        vals[li] = src;  // value of the scatter var = src (internal.rs:1076)
+        break;
+      }
+      default: fail(VKJIT_ERR_INVALID, "cannot lower a freed var");
+    }
+  }
+};
+
+}  // namespace
+
+std::string generate_cuda(const Ir& ir, const Program& p) {
+  Gen g(ir, p);
+  for (uint32_t li = 0; li < p.order.size(); ++li) g.emit_node(li);
+  for (size_t r = 0; r < p.roots.size(); ++r) {
+    const Val& v = g.vals[p.roots[r]];
+    g.line("out" + std::to_string(r) + " = " + to_word(v.ty, v.name) + ";");
+  }
+
+  std::vector<uint32_t> streams, ptrs;
+  for (uint32_t k = 0; k < p.params.size(); ++k) {
+    if (p.params[k].use & USE_STREAM) streams.push_back(k);
+    if (p.params[k].use & (USE_GATHER | USE_SCATTER)) ptrs.push_back(k);
+  }
+  const size_t nroots = p.roots.size();
+
+  std::string s;
+  s += "// vkjit-b200 fused trace kernel; key " + std::to_string(p.hash.lo) + ":" + std::to_string(p.hash.hi) + "\n";
+  s += "typedef unsigned int u32;\ntypedef int i32;\ntypedef float f32;\n\n";
+
+  // per-lane body
+  s += "__device__ __forceinline__ void vk_lane(const u32 gi, const u32 li";
+  for (uint32_t k : streams) s += ", const u32 in" + std::to_string(k);
+  for (size_t r = 0; r < nroots; ++r) s += ", u32& out" + std::to_string(r);
+  for (uint32_t k : ptrs) {
+    const bool w = p.params[k].use & USE_SCATTER;
+    s += std::string(", ") + (w ? "u32* " : "const u32* __restrict__ ") + "g" + std::to_string(k);
+  }
+  s += ") {\n" + g.body + "}\n\n";
+
+  auto call = [&](const std::string& gi, const std::string& li, const char* comp, bool vec) {
+    std::string c = "vk_lane(" + gi + ", " + li;
+    for (uint32_t k : streams) c += ", a" + std::to_string(k) + (vec ? std::string(".") + comp : "");
+    for (size_t r = 0; r < nroots; ++r) c += ", r" + std::to_string(r) + (vec ? std::string(".") + comp : "");
+    for (uint32_t k : ptrs) c += ", p" + std::to_string(k);
+    return c + ");";
+  };
+
+  s += "extern \"C\" __global__ void __launch_bounds__(256) vkjit_trace(const u32 n, const u32 base";
+  for (uint32_t k = 0; k < p.params.size(); ++k) {
+    const bool w = p.params[k].use & USE_SCATTER;
+    s += std::string(",\n    ") + (w ? "u32* " : "const u32* __restrict__ ") + "p" + std::to_string(k);
+  }
+  for (size_t r = 0; r < nroots; ++r) s += ",\n    u32* __restrict__ o" + std::to_string(r);
+  s += ") {\n";
+  s += "  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;\n";
+  s += "  const u32 nthreads = gridDim.x * blockDim.x;\n";
+  if (p.vectorized) {
+    // 128-bit vectorised, coalesced main loop: 4 consecutive lanes per thread and iteration
+    s += "  const u32 nvec = n >> 2;\n";
+    s += "#pragma unroll " + std::to_string(unroll_factor()) + "\n";
+    s += "  for (u32 v = tid; v < nvec; v += nthreads) {\n";
+    for (uint32_t k : streams)
+      s += "    const uint4 a" + std::to_string(k) + " = reinterpret_cast<const uint4*>(p" + std::to_string(k) + ")[v];\n";
+    for (size_t r = 0; r < nroots; ++r) s += "    uint4 r" + std::to_string(r) + ";\n";
+    s += "    const u32 l0 = v << 2;\n";
+    const char* comps[4] = {"x", "y", "z", "w"};
+    for (int j = 0; j < 4; ++j)
+      s += "    " + call("base + l0 + " + std::to_string(j) + "u", "l0 + " + std::to_string(j) + "u", comps[j], true) + "\n";
+    for (size_t r = 0; r < nroots; ++r)
+      s += "    reinterpret_cast<uint4*>(o" + std::to_string(r) + ")[v] = r" + std::to_string(r) + ";\n";
+    s += "  }\n";
+    s += "  for (unsigned long long i = (unsigned long long)(nvec << 2) + tid; i < n; i += nthreads) {\n";
+  } else {
+    s += "  for (unsigned long long i = tid; i < n; i += nthreads) {\n";
+  }
+  for (uint32_t k : streams) s += "    const u32 a" + std::to_string(k) + " = p" + std::to_string(k) + "[i];\n";
+  for (size_t r = 0; r < nroots; ++r) s += "    u32 r" + std::to_string(r) + ";\n";
+  s += "    " + call("base + (u32)i", "(u32)i", "", false) + "\n";
+  for (size_t r = 0; r < nroots; ++r) s += "    o" + std::to_string(r) + "[i] = r" + std::to_string(r) + ";\n";
+  s += "  }\n}\n";
+  return s;
+}
+
+}  // namespace vkjit

@@ -1,0 +1,334 @@
+// runtime.cpp — CUDA backend (see runtime.h).
+#include "runtime.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+namespace vkjit {
+
+uint64_t now_ns() {
+  return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+namespace {
+
+// libcuda is bound at run time so that the library loads (and traces can be built, hashed and
+// compiled) on a machine without a driver; cudart is linked statically.
+struct Driver {
+  void* handle = nullptr;
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  bool load(std::string& why) {
+    if (handle) return true;
+    handle = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!handle) { why = std::string("cannot load libcuda.so.1: ") + dlerror(); return false; }
+    auto sym = [&](const char* n) { return dlsym(handle, n); };
+    ModuleLoadData = (decltype(ModuleLoadData))sym("cuModuleLoadData");
+    ModuleUnload = (decltype(ModuleUnload))sym("cuModuleUnload");
+    ModuleGetFunction = (decltype(ModuleGetFunction))sym("cuModuleGetFunction");
+    LaunchKernel = (decltype(LaunchKernel))sym("cuLaunchKernel");
+    GetErrorString = (decltype(GetErrorString))sym("cuGetErrorString");
+    if (!ModuleLoadData || !ModuleUnload || !ModuleGetFunction || !LaunchKernel || !GetErrorString) {
+      why = "libcuda.so.1 lacks required entry points";
+      return false;
+    }
+    return true;
+  }
+};
+
+Driver g_drv;
+Backend* g_backend = nullptr;
+std::mutex g_init_mu;
+Counters g_counters;
+
+void ck(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+void cku(CUresult r, const char* what) {
+  if (r != CUDA_SUCCESS) {
+    const char* s = nullptr;
+    if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+    fail(VKJIT_ERR_CUDA, std::string(what) + ": " + (s ? s : "unknown driver error"));
+  }
+}
+
+}  // namespace
+
+Counters& Backend::counters() { return g_counters; }
+bool Backend::initialized() { return g_backend != nullptr; }
+
+Backend& Backend::get() {
+  if (!g_backend)
+    fail(VKJIT_ERR_NO_DEVICE, "vkjit_b200 backend is not initialised (call vkjit_init on a machine with a B200); there is no CPU fallback");
+  return *g_backend;
+}
+
+void Backend::init(int device) {
+  std::lock_guard<std::mutex> g(g_init_mu);
+  if (g_backend) return;
+  if (device < 0) {
+    const char* lr = getenv("LOCAL_RANK");
+    device = lr ? atoi(lr) : 0;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    fail(VKJIT_ERR_NO_DEVICE, std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
+                                  "); vkjit_b200 has no CPU fallback");
+  if (device >= count) fail(VKJIT_ERR_NO_DEVICE, "device index " + std::to_string(device) + " out of range");
+  std::string why;
+  if (!g_drv.load(why)) fail(VKJIT_ERR_NO_DEVICE, why);
+  ck(cudaSetDevice(device), "cudaSetDevice");
+  ck(cudaFree(nullptr), "context creation");
+  int major = 0, minor = 0, sms = 0;
+  ck(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device), "attr");
+  ck(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device), "attr");
+  ck(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "attr");
+  if (major != 10)
+    fail(VKJIT_ERR_NO_DEVICE, "device compute capability " + std::to_string(major) + "." + std::to_string(minor) +
+                                  " is not sm_100: this backend only generates sm_100a (B200) code");
+  auto* b = new Backend();
+  b->device = device;
+  b->sm_count = sms;
+  cudaStream_t s;
+  ck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+  b->stream = s;
+  cudaMemPool_t pool;
+  ck(cudaDeviceGetDefaultMemPool(&pool, device), "cudaDeviceGetDefaultMemPool");
+  uint64_t keep = ~0ull;  // never trim: freed blocks stay in the pool for the next eval
+  ck(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep), "cudaMemPoolSetAttribute");
+  b->pool_ = pool;
+  void* p = nullptr;
+  ck(cudaMalloc(&p, (size_t)prims::kReduceMaxCtas * 4), "scratch");
+  b->scratch.partials = p;
+  ck(cudaMalloc(&p, 256), "scratch");
+  ck(cudaMemset(p, 0, 256), "scratch");
+  b->scratch.ticket = (unsigned int*)p;
+  g_backend = b;
+}
+
+void Backend::shutdown() {
+  std::lock_guard<std::mutex> g(g_init_mu);
+  if (!g_backend) return;
+  Backend* b = g_backend;
+  cudaStreamSynchronize((cudaStream_t)b->stream);
+  b->clear_cache();
+  cudaFree(b->scratch.partials);
+  cudaFree(b->scratch.ticket);
+  if (b->scratch.tile_state) cudaFree(b->scratch.tile_state);
+  cudaStreamDestroy((cudaStream_t)b->stream);
+  g_backend = nullptr;
+  delete b;
+}
+
+void* Backend::alloc(size_t bytes) {
+  void* p = nullptr;
+  const size_t sz = bytes ? bytes : 16;
+  ck(cudaMallocAsync(&p, sz, (cudaStream_t)stream), "cudaMallocAsync");
+  g_counters.pool_bytes_live += sz;
+  return p;
+}
+
+void Backend::free_async(void* p, size_t bytes) {
+  if (!p) return;
+  cudaFreeAsync(p, (cudaStream_t)stream);
+  g_counters.pool_bytes_live -= bytes ? bytes : 16;
+}
+
+Array* Backend::new_array(size_t bytes) {
+  Array* a = new Array();
+  a->ptr = alloc(bytes);
+  a->bytes = bytes;
+  a->capacity = bytes;
+  return a;
+}
+
+void release_array(Array* a) {
+  if (!a) return;
+  if (g_backend) g_backend->free_async(a->ptr, a->capacity);
+  delete a;
+}
+
+void Backend::h2d(void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+  ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), "H2D copy");
+  // the caller may reuse `src` as soon as we return (Backend::create_array_from_slice copies
+  // synchronously into mapped memory, vulkan/mod.rs:56-73)
+  ck(cudaStreamSynchronize((cudaStream_t)stream), "H2D sync");
+  g_counters.bytes_h2d += bytes;
+}
+
+void Backend::d2h(void* dst, const void* src, size_t bytes) {
+  if (bytes) ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H copy");
+  ck(cudaStreamSynchronize((cudaStream_t)stream), "D2H sync");
+  g_counters.bytes_d2h += bytes;
+}
+
+void Backend::d2d(void* dst, const void* src, size_t bytes) {
+  if (bytes) ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "D2D copy");
+}
+
+void Backend::sync() { ck(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
+
+void Backend::ensure_scan_scratch(size_t n) {
+  const size_t need = prims::scan_state_words(n);
+  if (need <= scratch.tile_state_words) return;
+  if (scratch.tile_state) {
+    ck(cudaStreamSynchronize((cudaStream_t)stream), "sync");
+    cudaFree(scratch.tile_state);
+  }
+  size_t words = std::max<size_t>(need, 1 << 16);
+  void* p = nullptr;
+  ck(cudaMalloc(&p, words * 8), "scan scratch");
+  scratch.tile_state = (uint64_t*)p;
+  scratch.tile_state_words = words;
+}
+
+// ---- NVRTC -----------------------------------------------------------------------------
+bool nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string& log) {
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, src.c_str(), "vkjit_trace.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+    log = "nvrtcCreateProgram failed";
+    return false;
+  }
+  // --fmad=false: the reference's OpFMul/OpFAdd are separate roundings (no contraction); f32
+  // + - * / are additionally emitted as __f*_rn intrinsics, which never contract.  IEEE
+  // division/sqrt and no flush-to-zero are the NVRTC defaults and are stated explicitly.
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--prec-div=true", "--prec-sqrt=true",
+                        "--ftz=false",               "-lineinfo",    "--std=c++17",     "-default-device"};
+  nvrtcResult r = nvrtcCompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+  size_t ls = 0;
+  nvrtcGetProgramLogSize(prog, &ls);
+  if (ls > 1) { log.resize(ls); nvrtcGetProgramLog(prog, &log[0]); }
+  if (r != NVRTC_SUCCESS) {
+    if (log.empty()) log = nvrtcGetErrorString(r);
+    nvrtcDestroyProgram(&prog);
+    return false;
+  }
+  size_t cs = 0;
+  if (nvrtcGetCUBINSize(prog, &cs) != NVRTC_SUCCESS || cs == 0) {
+    log += "\nnvrtcGetCUBINSize failed";
+    nvrtcDestroyProgram(&prog);
+    return false;
+  }
+  cubin.resize(cs);
+  nvrtcGetCUBIN(prog, cubin.data());
+  nvrtcDestroyProgram(&prog);
+  return true;
+}
+
+// ---- kernel cache ------------------------------------------------------------------------
+CachedKernel* Backend::lookup(const Program& p) {
+  std::lock_guard<std::mutex> g(cache_mu_);
+  auto it = cache_.find(p.hash);
+  if (it == cache_.end()) return nullptr;
+  CachedKernel* k = it->second;
+  if (k->key.size() != p.key.size() || memcmp(k->key.data(), p.key.data(), p.key.size() * 4) != 0) return nullptr;  // 128-bit collision
+  g_counters.cache_hits += 1;
+  return k;
+}
+
+CachedKernel* Backend::compile(const Ir& ir, const Program& p) {
+  const uint64_t t0 = now_ns();
+  const std::string src = generate_cuda(ir, p);
+  if (getenv("VKJIT_DUMP")) fprintf(stderr, "%s\n", src.c_str());
+  std::vector<char> cubin;
+  std::string log;
+  if (!nvrtc_compile(src, cubin, log)) fail(VKJIT_ERR_COMPILE, "NVRTC rejected the generated kernel:\n" + log + "\n--- source ---\n" + src);
+  CUmodule mod;
+  cku(g_drv.ModuleLoadData(&mod, cubin.data()), "cuModuleLoadData");
+  CUfunction fn;
+  cku(g_drv.ModuleGetFunction(&fn, mod, "vkjit_trace"), "cuModuleGetFunction");
+  auto* k = new CachedKernel();
+  k->module = mod; k->function = fn; k->key = p.key;
+  k->nparams = (uint32_t)p.params.size(); k->nroots = (uint32_t)p.roots.size(); k->vectorized = p.vectorized;
+  {
+    std::lock_guard<std::mutex> g(cache_mu_);
+    auto it = cache_.find(p.hash);
+    if (it != cache_.end()) {  // hash collision with a different key: replace
+      g_drv.ModuleUnload((CUmodule)it->second->module);
+      delete it->second;
+      cache_.erase(it);
+    }
+    cache_[p.hash] = k;
+  }
+  g_counters.cache_misses += 1;
+  g_counters.last_compile_ns = now_ns() - t0;
+  return k;
+}
+
+void Backend::clear_cache() {
+  std::lock_guard<std::mutex> g(cache_mu_);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  for (auto& kv : cache_) {
+    if (g_drv.ModuleUnload) g_drv.ModuleUnload((CUmodule)kv.second->module);
+    delete kv.second;
+  }
+  cache_.clear();
+}
+
+void Backend::launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args) {
+  cku(g_drv.LaunchKernel((CUfunction)k->function, grid, 1, 1, block, 1, 1, 0, (CUstream)stream, args, nullptr), "cuLaunchKernel");
+  g_counters.trace_launches += 1;
+}
+
+// ---- Ir::eval (internal.rs:482-525) ---------------------------------------------------------
+void eval(Ir& ir, const VarId* ids, size_t n) {
+  const uint64_t t0 = now_ns();
+  Backend& be = Backend::get();
+  ir.do_schedule(ids, n);
+  if (ir.schedule.empty()) return;
+  static thread_local Program prog;
+  static thread_local std::vector<Array*> outs;
+  static thread_local std::vector<void*> argv;
+  static thread_local std::vector<uint64_t> ptrs;
+  outs.clear();
+  try {
+    build_program(ir, ir.schedule, true, prog);
+    bool aligned = true;
+    for (const Param& pr : prog.params)
+      if ((pr.use & USE_STREAM) && ((uintptr_t)ir.vars[pr.var].array->ptr & 15u)) aligned = false;
+    if (!aligned) build_program(ir, ir.schedule, false, prog);  // scalar ld/st variant for foreign pointers
+
+    CachedKernel* k = be.lookup(prog);
+    if (!k) k = be.compile(ir, prog);
+
+    // one fresh n*stride output per scheduled var (internal.rs:1192-1205), from the stream-ordered pool
+    for (size_t r = 0; r < prog.roots.size(); ++r) outs.push_back(be.new_array((size_t)prog.n * 4));
+
+    uint32_t n32 = (uint32_t)prog.n, base32 = (uint32_t)prog.base;
+    ptrs.clear(); argv.clear();
+    for (const Param& pr : prog.params) ptrs.push_back((uint64_t)(uintptr_t)ir.vars[pr.var].array->ptr);
+    for (Array* a : outs) ptrs.push_back((uint64_t)(uintptr_t)a->ptr);
+    argv.push_back(&n32); argv.push_back(&base32);
+    for (uint64_t& p : ptrs) argv.push_back(&p);
+
+    // grid-stride launch: enough CTAs of 256 threads to fill every SM (8 x 256 = 2048 threads/SM)
+    const uint64_t items = prog.vectorized ? std::max<uint64_t>(prog.n >> 2, 1) : prog.n;
+    uint64_t grid = (items + 255) / 256;
+    const uint64_t cap = (uint64_t)be.sm_count * 8;
+    if (grid > cap) grid = cap;
+    be.launch(k, (uint32_t)grid, 256, argv.data());
+
+    ir.commit_roots(ir.schedule, outs);
+    outs.clear();
+  } catch (...) {
+    for (Array* a : outs) release_array(a);
+    outs.clear();
+    ir.clear_schedule();
+    throw;
+  }
+  ir.clear_schedule();
+  g_counters.last_eval_ns = now_ns() - t0;
+}
+
+}  // namespace vkjit

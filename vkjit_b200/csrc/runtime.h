@@ -1,0 +1,81 @@
+// runtime.h — the CUDA backend: device, stream, stream-ordered memory pool, NVRTC, kernel
+// cache and launches.  Replaces the reference's Backend/Array traits and VulkanBackend
+// (libs/vkjit-core/src/backend/mod.rs:8-25, backend/vulkan/mod.rs:41-208, device.rs:74-240,
+// buffer.rs:24-92).  Where the reference rebuilds shader module, pipeline layout, pipeline
+// cache, pipeline, command pool and fence on every eval and then waits twice
+// (vulkan/mod.rs:88-208), this backend compiles a trace once (NVRTC -> sm_100a cubin), keys it
+// by the structural trace hash, and a repeated trace costs one cuLaunchKernel on an
+// asynchronous stream.
+#pragma once
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ir.h"
+#include "prims.h"
+#include "program.h"
+
+namespace vkjit {
+
+struct HashOf {
+  size_t operator()(const Hash128& h) const { return (size_t)(h.lo ^ (h.hi * 0x9E3779B97F4A7C15ull)); }
+};
+
+struct CachedKernel {
+  void* module = nullptr;    // CUmodule
+  void* function = nullptr;  // CUfunction
+  std::vector<uint32_t> key; // verified on every hit
+  uint32_t nparams = 0, nroots = 0;
+  bool vectorized = true;
+};
+
+struct Counters {
+  std::atomic<uint64_t> cache_hits{0}, cache_misses{0}, trace_launches{0}, prim_launches{0};
+  std::atomic<uint64_t> last_compile_ns{0}, last_eval_ns{0}, bytes_h2d{0}, bytes_d2h{0}, pool_bytes_live{0}, collectives{0};
+};
+
+// NVRTC front door; usable without a device (the cubin is produced offline for sm_100a).
+// Returns false and fills `log` on a compile error.
+bool nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string& log);
+
+class Backend {
+ public:
+  static void init(int device);     // throws VKJIT_ERR_NO_DEVICE when no usable GPU
+  static void shutdown();
+  static bool initialized();
+  static Backend& get();            // throws VKJIT_ERR_NO_DEVICE before init
+  static Counters& counters();
+
+  int device = 0;
+  int sm_count = 148;
+  void* stream = nullptr;           // cudaStream_t
+  prims::Scratch scratch;
+
+  // Backend::create_array (backend/mod.rs:22): stream-ordered allocation from the pool
+  Array* new_array(size_t bytes);
+  void* alloc(size_t bytes);
+  void free_async(void* p, size_t bytes);
+  void h2d(void* dst, const void* src, size_t bytes);
+  void d2h(void* dst, const void* src, size_t bytes);  // synchronises
+  void d2d(void* dst, const void* src, size_t bytes);
+  void sync();
+  void ensure_scan_scratch(size_t n);
+
+  // kernel cache keyed by trace hash
+  CachedKernel* lookup(const Program& p);
+  CachedKernel* compile(const Ir& ir, const Program& p);
+  void launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args);
+  void clear_cache();
+
+ private:
+  std::mutex cache_mu_;
+  std::unordered_map<Hash128, CachedKernel*, HashOf> cache_;
+  void* pool_ = nullptr;            // cudaMemPool_t
+};
+
+// Evaluate the Ir's schedule (+ ids): the body of Ir::eval (internal.rs:482-525).
+void eval(Ir& ir, const VarId* ids, size_t n);
+
+}  // namespace vkjit

@@ -278,6 +278,13 @@ class Ir:
         a = np.ascontiguousarray(data, dtype=VarType.numpy(ty))
         return self._new("array_sharded", ty, a.ctypes.data_as(C.c_void_p), a.size)
 
+    def array_shard_local(self, ty: int, data=None, ptr: int = 0, n: int = 0) -> int:
+        """This rank's slice given directly (numpy array, or raw host pointer + element count)."""
+        if data is not None:
+            a = np.ascontiguousarray(data, dtype=VarType.numpy(ty))
+            return self._new("array_shard_local", ty, a.ctypes.data_as(C.c_void_p), a.size)
+        return self._new("array_shard_local", ty, C.c_void_p(ptr), n)
+
     def is_sharded(self, id: int) -> bool:
         o = C.c_int32()
         self.api.call("var_is_sharded", self._h, id, C.byref(o))

@@ -1,0 +1,288 @@
+"""Drop-in mirror of the vkjit-python module (reference libs/vkjit-python/src/{lib,types,functions}.rs).
+
+Reference surface (lib.rs:18-26): class `Var`, functions `eval`, `var`, `ir`, `linspace`.  Same
+names, same argument coercion order (types.rs:50-81), same lazy `__str__` (types.rs:148-154),
+on top of one global `Ir` (lib.rs:14-16) — here the B200 backend's `Ir` through the C ABI.
+
+Additions the reference lacks (needed by the Monte-Carlo config, which is
+driven from Python): `arange`, comparisons, `select`, `gather`/`scatter`/`scatter_add`, bit ops,
+unary math, reductions, `prefix_sum`, `compress`, `numpy()`/`tolist()` for every dtype and
+`__truediv__` (the reference only defines the Python-2 `__div__`, types.rs:136-139).
+The known reference defect that `eval()` calls an unexported `.id()` (functions.rs:15 vs
+types.rs:99-102) is fixed: `Var.id()` exists.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+from . import ir as _ir
+from .ir import Bop, Red, Uop, VarType
+
+_lock = threading.RLock()
+_IR = None
+
+
+def _global_ir() -> _ir.Ir:
+    """`lazy_static! { pub static ref IR: Mutex<Ir> }` (lib.rs:14-16)"""
+    global _IR
+    with _lock:
+        if _IR is None:
+            _IR = _ir.Ir()
+        return _IR
+
+
+def _is_int(x):
+    return isinstance(x, (int, np.integer)) and not isinstance(x, (bool, np.bool_))
+
+
+def _coerce(value) -> "Var":
+    """TryFrom<&PyAny> for Var (types.rs:47-82): Var, u32, i32, f32, bool, [u32], [i32], [f32]."""
+    g = _global_ir()
+    if isinstance(value, Var):
+        return value._clone()
+    if isinstance(value, (bool, np.bool_)):
+        # pyo3 extracts a Python bool as u32 first (bool is an int): True -> UInt32(1)
+        return Var._own(g.const_u32(int(value)))
+    if _is_int(value):
+        v = int(value)
+        if 0 <= v <= 0xFFFFFFFF:
+            return Var._own(g.const_u32(v))
+        if -2 ** 31 <= v < 0:
+            return Var._own(g.const_i32(v))
+        raise TypeError("Not a valid argument!")
+    if isinstance(value, (float, np.floating)):
+        return Var._own(g.const_f32(float(value)))
+    if isinstance(value, np.ndarray):
+        if value.dtype == np.uint32:
+            return Var._own(g.array_u32(value))
+        if value.dtype == np.int32:
+            return Var._own(g.array_i32(value))
+        if value.dtype == np.float32:
+            return Var._own(g.array_f32(value))
+        if value.dtype == np.bool_:
+            return Var._own(g.array_bool(value))
+        value = value.tolist()
+    if isinstance(value, (list, tuple)):
+        items = list(value)
+        if all(_is_int(x) or isinstance(x, (bool, np.bool_)) for x in items):
+            if all(0 <= int(x) <= 0xFFFFFFFF for x in items):
+                return Var._own(g.array_u32(np.asarray(items, dtype=np.uint32)))
+            if all(-2 ** 31 <= int(x) < 2 ** 31 for x in items):
+                return Var._own(g.array_i32(np.asarray(items, dtype=np.int32)))
+            raise TypeError("Not a valid argument!")
+        if all(isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, bool) for x in items):
+            return Var._own(g.array_f32(np.asarray(items, dtype=np.float32)))
+    raise TypeError("Not a valid argument!")
+
+
+class Var:
+    """`#[pyclass] pub struct Var(VarId)` (types.rs:84-85).  Owns exactly one reference count:
+    cloning bumps it (types.rs:87-92), dropping releases it (types.rs:94-98)."""
+
+    __slots__ = ("_id",)
+
+    def __init__(self, arg):  # #[new] __new__(args) (types.rs:117-120)
+        self._id = _coerce(arg)._steal()
+
+    @classmethod
+    def _own(cls, var_id: int) -> "Var":
+        v = object.__new__(cls)
+        v._id = var_id
+        return v
+
+    def _steal(self) -> int:
+        i, self._id = self._id, None
+        return i
+
+    def _clone(self) -> "Var":
+        _global_ir().inc_ref_count(self._id)
+        return Var._own(self._id)
+
+    def __del__(self):
+        if getattr(self, "_id", None) is not None and _IR is not None:
+            try:
+                _IR.dec_ref_count(self._id)
+            except Exception:
+                pass
+            self._id = None
+
+    # -- reference methods ------------------------------------------------------
+    def id(self) -> int:
+        return self._id
+
+    def ty(self) -> int:
+        return _global_ir().ty(self._id)
+
+    def tolist(self):
+        """types.rs:121-123 reads f32 only; here every dtype is readable (evaluates if needed)."""
+        return self.numpy().tolist()
+
+    def _bop(self, kind, rhs, swap=False) -> "Var":
+        r = _coerce(rhs)
+        a, b = (r._id, self._id) if swap else (self._id, r._id)
+        return Var._own(_global_ir().bop(kind, a, b))
+
+    def __add__(self, rhs): return self._bop(Bop.Add, rhs)        # types.rs:124-127
+    def __sub__(self, rhs): return self._bop(Bop.Sub, rhs)        # types.rs:128-131
+    def __mul__(self, rhs): return self._bop(Bop.Mul, rhs)        # types.rs:132-135
+    def __div__(self, rhs): return self._bop(Bop.Div, rhs)        # types.rs:136-139
+    __truediv__ = __div__
+    def __radd__(self, lhs): return self._bop(Bop.Add, lhs, True)
+    def __rsub__(self, lhs): return self._bop(Bop.Sub, lhs, True)
+    def __rmul__(self, lhs): return self._bop(Bop.Mul, lhs, True)
+    def __rtruediv__(self, lhs): return self._bop(Bop.Div, lhs, True)
+
+    def __repr__(self):  # types.rs:140-147
+        g = _global_ir()
+        if g.is_buffer(self._id):
+            return f"array(dtype = {VarType.name(g.ty(self._id))}, {g.str(self._id)})"
+        return g.str(self._id)
+
+    def __str__(self):  # types.rs:148-154: evaluates on demand
+        g = _global_ir()
+        if not g.is_buffer(self._id):
+            g.eval([self._id])
+        return g.str(self._id)
+
+    # -- additions (N2) ------------------------------------------------------------
+    def lt(self, r): return self._bop(Bop.Lt, r)
+    def gt(self, r): return self._bop(Bop.Gt, r)
+    def eq(self, r): return self._bop(Bop.Eq, r)
+    def leq(self, r): return self._bop(Bop.Leq, r)
+    def geq(self, r): return self._bop(Bop.Geq, r)
+    def neq(self, r): return self._bop(Bop.Neq, r)
+    __lt__, __gt__, __le__, __ge__ = lt, gt, leq, geq
+    def __and__(self, r): return self._bop(Bop.And, r)
+    def __or__(self, r): return self._bop(Bop.Or, r)
+    def __xor__(self, r): return self._bop(Bop.Xor, r)
+    def __lshift__(self, r): return self._bop(Bop.Shl, r)
+    def __rshift__(self, r): return self._bop(Bop.Shr, r)
+    def __rand__(self, l): return self._bop(Bop.And, l, True)
+    def __ror__(self, l): return self._bop(Bop.Or, l, True)
+    def __rxor__(self, l): return self._bop(Bop.Xor, l, True)
+    def __neg__(self): return Var._own(_global_ir().uop(Uop.Neg, self._id))
+    def __invert__(self): return Var._own(_global_ir().uop(Uop.Not, self._id))
+    def __abs__(self): return Var._own(_global_ir().uop(Uop.Abs, self._id))
+
+    def cast(self, ty: int) -> "Var":
+        g = _global_ir()
+        out = g.cast(self._id, ty)
+        if out == self._id:  # Ir::cast returns the same id without a new reference
+            g.inc_ref_count(out)
+        return Var._own(out)
+
+    def bitcast(self, ty: int) -> "Var":
+        g = _global_ir()
+        out = g.bitcast(self._id, ty)
+        if out == self._id:
+            g.inc_ref_count(out)
+        return Var._own(out)
+
+    def then_else(self, then, other) -> "Var":  # vkjit-rust types.rs:160-168
+        return select(self, then, other)
+
+    def get(self, idx) -> "Var":  # vkjit-rust types.rs:190-192
+        return gather(self, idx)
+
+    def scatter(self, to: "Var", idx, condition=None):  # vkjit-rust types.rs:169-189
+        i = _coerce(idx)
+        c = None if condition is None else _coerce(condition)
+        g = _global_ir()
+        new = g.scatter(self._id, to._id, i._id, None if c is None else c._id)
+        g.dec_ref_count(self._id)
+        self._id = new
+
+    def scatter_add(self, to: "Var", idx, condition=None):
+        i = _coerce(idx)
+        c = None if condition is None else _coerce(condition)
+        g = _global_ir()
+        new = g.scatter_add(self._id, to._id, i._id, None if c is None else c._id)
+        g.dec_ref_count(self._id)
+        self._id = new
+
+    def numpy(self) -> np.ndarray:
+        g = _global_ir()
+        if not g.is_buffer(self._id):
+            g.eval([self._id])
+        return g.to_numpy(self._id)
+
+    def sum(self): return Var._own(_global_ir().reduce(Red.Sum, self._id))
+    def min(self): return Var._own(_global_ir().reduce(Red.Min, self._id))
+    def max(self): return Var._own(_global_ir().reduce(Red.Max, self._id))
+    def prefix_sum(self, exclusive=True): return Var._own(_global_ir().prefix_sum(self._id, exclusive))
+
+    def compress(self):
+        """Indices of the set lanes of a Bool var (stable), and their count."""
+        out, n = _global_ir().compress(self._id)
+        return Var._own(out), n
+
+
+# -- module functions (functions.rs:9-52) ---------------------------------------------------
+def eval(schedule):  # noqa: A001 - the reference's name
+    """`eval(schedule: &PyList)` (functions.rs:9-23)"""
+    _global_ir().eval([v.id() for v in schedule])
+
+
+def var(*args) -> Var:
+    """`var(*args)` (functions.rs:25-34): one argument is coerced as is, several form a sequence."""
+    return _coerce(args[0]) if len(args) == 1 else _coerce(list(args))
+
+
+def ir() -> str:
+    """`format!("{:#?}", IR)` (functions.rs:36-39)"""
+    return _global_ir().repr()
+
+
+def linspace(start, stop, num: int) -> Var:
+    """functions.rs:41-52 — asserts start.ty() == stop.ty(); endpoint excluded."""
+    a, b = _coerce(start), _coerce(stop)
+    assert a.ty() == b.ty()
+    return Var._own(_global_ir().linspace(a.ty(), a._id, b._id, num))
+
+
+# -- additions -------------------------------------------------------------------------------
+def arange(ty: int, num: int) -> Var:  # vkjit-rust functions.rs:9-11
+    return Var._own(_global_ir().arange(ty, num))
+
+
+def zeros(ty: int) -> Var:  # vkjit-rust functions.rs:5-7
+    return Var._own(_global_ir().zeros(ty))
+
+
+def select(condition, x, y) -> Var:  # vkjit-rust functions.rs:24-31
+    c, a, b = _coerce(condition), _coerce(x), _coerce(y)
+    return Var._own(_global_ir().select(c._id, a._id, b._id))
+
+
+def gather(src: Var, idx, condition=None) -> Var:  # vkjit-rust functions.rs:32-52
+    i = _coerce(idx)
+    c = None if condition is None else _coerce(condition)
+    return Var._own(_global_ir().gather(src._id, i._id, None if c is None else c._id))
+
+
+def _u(kind):
+    def f(x):
+        return Var._own(_global_ir().uop(kind, _coerce(x)._id))
+    return f
+
+
+sqrt, exp, log, sin, cos = _u(Uop.Sqrt), _u(Uop.Exp), _u(Uop.Log), _u(Uop.Sin), _u(Uop.Cos)
+
+
+def minimum(a, b) -> Var:
+    return _coerce(a)._bop(Bop.Min, b)
+
+
+def maximum(a, b) -> Var:
+    return _coerce(a)._bop(Bop.Max, b)
+
+
+def compress(values: Var, mask: Var):
+    out, n = _global_ir().compress_values(values._id, mask._id)
+    return Var._own(out), n
+
+
+def sync():
+    _ir.sync()
