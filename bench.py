@@ -48,53 +48,45 @@ def peaks():
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML (what nvidia-smi reads) every ~1 ms in a
+    background thread DURING the timed region (the region is only tens of ms long, too short for
+    `nvidia-smi -lms`)."""
 
     def __init__(self, device):
-        self.device, self.proc, self.path = device, None, None
+        self.device, self.samples, self.reasons, self.max_mhz = device, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.device)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+                time.sleep(0.001)
+        except Exception as ex:  # pragma: no cover
+            self.error = repr(ex)
 
     def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                p = [x.strip() for x in line.split(",")]
-                if len(p) < 6:
-                    continue
-                try:
-                    sm.append(float(p[0])); mx.append(float(p[1]))
-                except ValueError:
-                    continue
-                for nme, v in zip(names, p[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = max(mx)
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(sm)
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=5)
+        out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples), "how": "NVML, 1 ms period, during the timed region"}
+        if getattr(self, "error", None):
+            out["error"] = self.error
         return out
 
 
@@ -351,7 +343,7 @@ def ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true")

@@ -1,0 +1,72 @@
+"""One rank of the multi-GPU parity test (launched by torchrun, one process per GPU, NCCL)."""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import vkjit_b200 as vk  # noqa: E402
+from oracle_lib import OracleIr  # noqa: E402
+from vkjit_b200 import dist  # noqa: E402
+from vkjit_b200.ir import Bop, Ir, Red, VarType as T  # noqa: E402
+
+
+def trace_u32(ir, lanes):
+    h = ir.mul(ir.bop(Bop.Xor, lanes, ir.const_u32(0x9E3779B9)), ir.const_u32(747796405))
+    return ir.bop(Bop.Shr, h, ir.const_u32(7))
+
+
+def trace_f32(ir, lanes):
+    return ir.mul(ir.cast(ir.bop(Bop.Shr, trace_u32(ir, lanes), ir.const_u32(1)), T.F32), ir.const_f32(2.0 ** -24))
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    vk.init(local)
+    rank, world = dist.init_from_torch(torch.device("cuda", local))
+    for n in (5, 1000, (1 << 22) + 3):
+        ir = Ir()
+        lanes = ir.arange_sharded(T.U32, n)
+        lo, hi = dist.shard_range(n, rank, world)
+        xu, xf = trace_u32(ir, lanes), trace_f32(ir, lanes)
+        assert ir.is_sharded(xu)
+        got = {}
+        # every rank takes part in the collective, also when its shard of a tiny array is empty
+        for name, v, ty in (("u", xu, T.U32), ("f", xf, T.F32)):
+            for r in (Red.Sum, Red.Min, Red.Max):
+                got[(name, r)] = ir.as_slice(ir.reduce(r, v), ty)[0]
+        o = OracleIr()
+        ol = o.arange(T.U32, n)
+        ou, of = trace_u32(o, ol), trace_f32(o, ol)
+        o.eval([ou, of])
+        if hi > lo:
+            # elementwise: this rank's lanes equal the global lanes [lo, hi) bit for bit, no collective
+            assert ir.as_slice(xu, T.U32).tobytes() == o.as_slice(ou, T.U32)[lo:hi].tobytes()
+            assert ir.as_slice(xf, T.F32).tobytes() == o.as_slice(of, T.F32)[lo:hi].tobytes()
+        if True:
+            for r in (Red.Sum, Red.Min, Red.Max):
+                e = o.as_slice(o.reduce(r, ou), T.U32)[0]
+                assert got[("u", r)] == e, (n, r, got[("u", r)], e)       # bit-exact, replicated on every rank
+            es = float(o.as_slice(o.reduce(Red.Sum, of), T.F32)[0])
+            assert abs(float(got[("f", Red.Sum)]) - es) <= 1e-6 * max(1.0, math.log2(n)) * abs(es)
+            for r in (Red.Min, Red.Max):
+                assert got[("f", r)] == o.as_slice(o.reduce(r, of), T.F32)[0]
+        ir.close(); o.close()
+    st = vk.stats()
+    assert st["collectives"] > 0 or world == 1
+    td.barrier()
+    dist.shutdown()
+    td.destroy_process_group()
+    print(f"rank {rank}/{world} ok collectives={st['collectives']}")
+
+
+if __name__ == "__main__":
+    main()

@@ -207,7 +207,8 @@ def test_reduce_of_unevaluated_trace(cir, oir):
 
 
 # ---------------------------------------------------------------- prefix sum / compress
-SCAN_SIZES = [1, 2, 3, 4, 5, 1023, 4095, 4096, 4097, 8192, 12289, (1 << 20) + 1, 3 * (1 << 20) + 7]
+SCAN_SIZES = [1, 2, 3, 4, 5, 1023, 4095, 4096, 4097, 16383, 16384, 16385, 16387, 32768, 5 * 16384 + 3, (1 << 20) + 1,
+              3 * (1 << 20) + 7]
 
 
 @pytest.mark.parametrize("n", SCAN_SIZES)

@@ -218,22 +218,43 @@ vkjit_status vkjit_read(vkjit_ir* h, vkjit_var id, vkjit_type ty, void* dst, siz
 }
 
 // ---- runtime primitives ----------------------------------------------------------------------------------
+// identity element of a reduction, as a 4-byte pattern NCCL's min/max/sum treat as neutral
+static uint32_t reduce_identity(int red, TypeId ty) {
+  if (red == VKJIT_RED_SUM) return 0u;
+  if (ty == VKJIT_TY_F32) return red == VKJIT_RED_MIN ? 0x7F800000u : 0xFF800000u;  // +inf / -inf
+  if (ty == VKJIT_TY_I32) return red == VKJIT_RED_MIN ? 0x7FFFFFFFu : 0x80000000u;
+  return red == VKJIT_RED_MIN ? 0xFFFFFFFFu : 0u;
+}
+
 vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out) {
   return with_ir(h, [&](Ir& ir) {
     const TypeId ty = ir.var(id).ty;
     if (!ty_is_num(ty)) fail(VKJIT_ERR_TYPE, "reduce needs U32/I32/F32");
     if (red < VKJIT_RED_SUM || red > VKJIT_RED_MAX) fail(VKJIT_ERR_INVALID, "unknown reduction");
     Backend& be = Backend::get();
-    ensure_buffer(ir, id);
-    const Var& v = ir.var(id);
-    const size_t n = v.array->bytes / 4;
-    if (n == 0) fail(VKJIT_ERR_SIZE, "reduce of an empty array");
-    const bool sharded = v.sharded;
+    const bool sharded = ir.var(id).sharded;
+    const bool combine = sharded && dist::active() && dist::world() > 1;
+    // a rank whose shard of a tiny array is empty still has to take part in the collective
+    bool empty;
+    if (ir.is_buffer(id)) empty = ir.var(id).array->bytes == 0;
+    else {
+      Program p;
+      std::vector<VarId> roots{id};
+      build_program(ir, roots, true, p);
+      empty = p.n == 0;
+    }
+    if (empty && !combine) fail(VKJIT_ERR_SIZE, "reduce of an empty array");
     Array* o = be.new_array(4);
     try {
-      prims::reduce(red, ty, v.array->ptr, n, o->ptr, be.scratch, be.sm_count, be.stream);
+      if (empty) {
+        prims::fill_u32((uint32_t*)o->ptr, reduce_identity(red, ty), 1, be.stream);
+      } else {
+        ensure_buffer(ir, id);
+        const Var& v = ir.var(id);
+        prims::reduce(red, ty, v.array->ptr, v.array->bytes / 4, o->ptr, be.scratch, be.sm_count, be.stream);
+      }
       Backend::counters().prim_launches += 1;
-      if (sharded && dist::active()) dist::allreduce(o->ptr, ty, red, 1);  // per-GPU partial -> replicated result
+      if (combine) dist::allreduce(o->ptr, ty, red, 1);  // per-GPU partial -> replicated result
     } catch (...) { release_array(o); throw; }
     *out = ir.binding(ty, o, false);
   });

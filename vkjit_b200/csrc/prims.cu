@@ -199,12 +199,15 @@ void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scr
 // ---------------------------------------------------------------------------------------
 // decoupled look-back scan (Merrill & Garland) — prefix sum and stream compaction
 // ---------------------------------------------------------------------------------------
-// Tile = 256 threads x 4 vectors x 4 lanes = 4096 lanes.  Vector q = j*256 + t of a tile is held
-// by thread t in register slot j, so every load/store instruction of a warp covers 512
-// contiguous bytes.  Tile status words pack {flag:32 | value:32} into one 64-bit word so flag
-// and value travel in a single (volatile, L2-coherent) access and no fence is needed between
-// them.  Tiles are handed out by an atomic counter, so a tile only ever waits on tiles that
-// are already running (forward progress does not depend on CTA dispatch order).
+// Tile = 512 threads x 8 vectors x 4 lanes = 16384 lanes (64 KiB in, 64 KiB out).  Vector
+// q = j*512 + t of a tile is held by thread t in register slot j, so every load/store
+// instruction of a warp covers 512 contiguous bytes.  Tile status words pack
+// {flag:32 | value:32} into one 64-bit word so flag and value travel in a single (volatile,
+// L2-coherent) access and no fence is needed between them.
+// Why the tile is this large: the look-back frontier advances by at most 32 tiles (one warp-wide
+// window) per L2 round trip (~0.2 us), i.e. ~150 tiles/us; with 4096-lane tiles that caps the
+// kernel near 4 TB/s of traffic (measured: 2.9 TB/s), with 16384-lane tiles the cap is ~4x the
+// HBM rate and the kernel is bandwidth-bound again.
 enum : uint32_t { ST_INVALID = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2 };
 enum ScanMode { MODE_EXCLUSIVE = 0, MODE_INCLUSIVE = 1, MODE_COMPRESS_INDEX = 2, MODE_COMPRESS_VALUE = 3 };
 
@@ -240,22 +243,24 @@ __device__ __forceinline__ uint32_t look_back(volatile uint64_t* status, uint32_
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 2)
 scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: mask words
             const uint32_t* __restrict__ values,  // MODE_COMPRESS_VALUE only
             uint32_t* __restrict__ out, uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles,
             uint64_t* __restrict__ state) {
   constexpr int T = kScanThreads;
-  constexpr int VPT = 4;  // vectors per thread
+  constexpr int VPT = kScanTile / (T * 4);  // 128-bit vectors per thread
+  constexpr int WARPS = T / 32;
+  constexpr int NTOT = VPT * WARPS;         // (slot, warp) totals per tile
+  constexpr int PER_LANE = NTOT / 32;
   constexpr bool COMPRESS = MODE >= MODE_COMPRESS_INDEX;
-  __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_warp_tot[VPT * (T / 32)];  // 32 entries: exactly one warp-scan wide
+  static_assert(NTOT % 32 == 0, "tile totals must fill whole warp rows");
+  __shared__ uint32_t s_tot[NTOT];
   __shared__ uint32_t s_tile_excl;
 
-  if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd((unsigned long long*)state, 1ull);
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  if (tile >= num_tiles) return;
+  // Tile index = blockIdx.x: loads are issued immediately.  Forward progress of the look-back
+  // relies on CTAs of a 1-D grid being dispatched in blockIdx order (as CUB's DeviceScan does).
+  const uint32_t tile = blockIdx.x;
   volatile uint64_t* status = state + 1;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -263,30 +268,29 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   const bool full = tile_base + kScanTile <= n;
 
   uint4 x[VPT];  // scan: addends; compress: 0/1 flags
-  uint4 val[VPT];
 #pragma unroll
   for (int j = 0; j < VPT; ++j) {
     const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
     if (full || e + 3 < n) {
       x[j] = ld_stream(reinterpret_cast<const uint4*>(in + e));
-      if (MODE == MODE_COMPRESS_VALUE) val[j] = ld_stream(reinterpret_cast<const uint4*>(values + e));
     } else {
       x[j].x = e + 0 < n ? in[e + 0] : 0u; x[j].y = e + 1 < n ? in[e + 1] : 0u;
       x[j].z = e + 2 < n ? in[e + 2] : 0u; x[j].w = 0u;
-      if (MODE == MODE_COMPRESS_VALUE) {
-        val[j].x = e + 0 < n ? values[e + 0] : 0u; val[j].y = e + 1 < n ? values[e + 1] : 0u;
-        val[j].z = e + 2 < n ? values[e + 2] : 0u; val[j].w = 0u;
-      }
     }
-    if (COMPRESS) { x[j].x = x[j].x != 0u; x[j].y = x[j].y != 0u; x[j].z = x[j].z != 0u; x[j].w = x[j].w != 0u; }
+  }
+  uint32_t flags[VPT];  // compress: 4 selection bits per vector (frees the uint4 registers)
+  if (COMPRESS) {
+#pragma unroll
+    for (int j = 0; j < VPT; ++j)
+      flags[j] = (x[j].x != 0u ? 1u : 0u) | (x[j].y != 0u ? 2u : 0u) | (x[j].z != 0u ? 4u : 0u) | (x[j].w != 0u ? 8u : 0u);
   }
 
-  // 1) per-vector sums, 2) inclusive warp scan per register slot, 3) one warp scans the 32
+  // 1) per-vector sums, 2) inclusive warp scan per register slot, 3) one warp scans the
   // (slot, warp) totals in tile order, 4) look-back gives the tile's global offset.
   uint32_t vsum[VPT], wincl[VPT];
 #pragma unroll
   for (int j = 0; j < VPT; ++j) {
-    vsum[j] = x[j].x + x[j].y + x[j].z + x[j].w;
+    vsum[j] = COMPRESS ? (uint32_t)__popc(flags[j]) : x[j].x + x[j].y + x[j].z + x[j].w;
     uint32_t s = vsum[j];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -294,18 +298,22 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
       if (lane >= o) s += t;
     }
     wincl[j] = s;
-    if (lane == 31) s_warp_tot[j * (T / 32) + warp] = s;
+    if (lane == 31) s_tot[j * WARPS + warp] = s;
   }
   __syncthreads();
   if (warp == 0) {
-    const uint32_t tot = s_warp_tot[lane];
-    uint32_t s = tot;
+    uint32_t t[PER_LANE], run = 0;
+#pragma unroll
+    for (int k = 0; k < PER_LANE; ++k) { t[k] = s_tot[lane * PER_LANE + k]; run += t[k]; }
+    uint32_t s = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
-      if (lane >= o) s += t;
+      const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, s, o);
+      if (lane >= o) s += u;
     }
-    s_warp_tot[lane] = s - tot;  // exclusive offset of (slot, warp) inside the tile
+    uint32_t off = s - run;  // exclusive offset of this lane's first entry
+#pragma unroll
+    for (int k = 0; k < PER_LANE; ++k) { s_tot[lane * PER_LANE + k] = off; off += t[k]; }
     const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
     const uint32_t excl = look_back(status, tile, aggregate);
     if (lane == 0) {
@@ -319,7 +327,7 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
 #pragma unroll
   for (int j = 0; j < VPT; ++j) {
     const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
-    uint32_t p = tile_excl + s_warp_tot[j * (T / 32) + warp] + (wincl[j] - vsum[j]);  // exclusive prefix of lane e
+    uint32_t p = tile_excl + s_tot[j * WARPS + warp] + (wincl[j] - vsum[j]);  // exclusive prefix of lane e
     if (!COMPRESS) {
       uint4 r;
       if (MODE == MODE_EXCLUSIVE) { r.x = p; r.y = p + x[j].x; r.z = r.y + x[j].y; r.w = r.z + x[j].z; }
@@ -330,12 +338,21 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
         if (e + 1 < n) out[e + 1] = r.y;
         if (e + 2 < n) out[e + 2] = r.z;
       }
-    } else {
-      // selected lanes are written at their rank; flags of out-of-range lanes are 0
-      if (x[j].x) { out[p] = MODE == MODE_COMPRESS_VALUE ? val[j].x : (uint32_t)(e + 0); ++p; }
-      if (x[j].y) { out[p] = MODE == MODE_COMPRESS_VALUE ? val[j].y : (uint32_t)(e + 1); ++p; }
-      if (x[j].z) { out[p] = MODE == MODE_COMPRESS_VALUE ? val[j].z : (uint32_t)(e + 2); ++p; }
-      if (x[j].w) { out[p] = MODE == MODE_COMPRESS_VALUE ? val[j].w : (uint32_t)(e + 3); ++p; }
+    } else if (flags[j]) {
+      // selected lanes are written at their rank; flags of out-of-range lanes are 0.  Values are
+      // loaded only now (once from HBM, only for vectors with a selected lane).
+      uint4 v;
+      if (MODE == MODE_COMPRESS_VALUE) {
+        if (full || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
+        else {
+          v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
+          v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
+        }
+      } else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
+      if (flags[j] & 1u) out[p++] = v.x;
+      if (flags[j] & 2u) out[p++] = v.y;
+      if (flags[j] & 4u) out[p++] = v.z;
+      if (flags[j] & 8u) out[p++] = v.w;
     }
   }
 }

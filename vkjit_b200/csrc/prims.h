@@ -11,14 +11,14 @@ namespace prims {
 struct Scratch {
   void* partials = nullptr;       // reduce: one 4-byte partial per CTA
   unsigned int* ticket = nullptr; // reduce: last-CTA election (self-resetting)
-  uint64_t* tile_state = nullptr; // scan: [0] = dynamic tile counter, [1..] = look-back status words
+  uint64_t* tile_state = nullptr; // scan: [0] = reserved, [1..] = look-back status words
   size_t tile_state_words = 0;
 };
 
 constexpr int kReduceThreads = 512;
 constexpr int kReduceMaxCtas = 2048;
-constexpr int kScanThreads = 256;
-constexpr int kScanTile = 4096;  // lanes per look-back tile (256 threads x 4 x uint4)
+constexpr int kScanThreads = 512;
+constexpr int kScanTile = 16384;  // lanes per look-back tile (512 threads x 8 x uint4 = 64 KiB)
 
 // number of 8-byte words `tile_state` must hold for n lanes
 size_t scan_state_words(size_t n);

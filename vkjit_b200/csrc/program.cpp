@@ -166,7 +166,6 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   }
 
   if (!p.have_n) fail(VKJIT_ERR_SIZE, "schedule has no Binding/Arange: kernel size unknown (internal.rs:1202 num.unwrap())");
-  if (p.n == 0) fail(VKJIT_ERR_SIZE, "zero-sized kernel");
   if (p.n > 0xFFFFFFFFull) fail(VKJIT_ERR_SIZE, "kernel size exceeds the 32-bit invocation index");
   if (p.params.size() + p.roots.size() > 480) fail(VKJIT_ERR_UNSUPPORTED, "too many arrays in one kernel (4 KB parameter limit)");
 

@@ -294,6 +294,7 @@ void eval(Ir& ir, const VarId* ids, size_t n) {
   outs.clear();
   try {
     build_program(ir, ir.schedule, true, prog);
+    if (prog.n == 0) fail(VKJIT_ERR_SIZE, "zero-sized kernel");
     bool aligned = true;
     for (const Param& pr : prog.params)
       if ((pr.use & USE_STREAM) && ((uintptr_t)ir.vars[pr.var].array->ptr & 15u)) aligned = false;

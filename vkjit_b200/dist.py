@@ -1,0 +1,55 @@
+"""Multi-GPU plumbing for the sharded paths (one process per GPU).
+
+`torch.distributed` is only the rendezvous: rank 0 asks the native library for an NCCL unique id,
+the id travels through one broadcast, and every rank hands it to `vkjit_dist_init`.  From then on
+sharded reductions combine their per-GPU partials inside the native library (NCCL all-reduce on
+the backend stream).  Elementwise traces shard with no collective at all.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from ._capi import product_api
+
+UNIQUE_ID_BYTES = 128
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of a global 1-D range: multiples of 4 lanes (16-byte aligned
+    128-bit accesses), the last rank takes the ragged tail.  Same rule as the native library."""
+    lo, hi = C.c_size_t(), C.c_size_t()
+    product_api().call("shard_range", n, rank, world, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def exchange_unique_id(make_id, rank: int, device=None) -> bytes:
+    """Broadcast a 128-byte id from rank 0 over the default torch.distributed group.
+    Works with any backend (gloo on CPU in the tests, nccl on the GPUs)."""
+    import torch
+    import torch.distributed as td
+    buf = torch.zeros(UNIQUE_ID_BYTES, dtype=torch.uint8, device=device or "cpu")
+    if rank == 0:
+        raw = make_id()
+        assert len(raw) == UNIQUE_ID_BYTES
+        buf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+    td.broadcast(buf, 0)
+    return bytes(buf.cpu().tolist())
+
+
+def native_unique_id() -> bytes:
+    host = (C.c_uint8 * UNIQUE_ID_BYTES)()
+    product_api().call("dist_unique_id", host)
+    return bytes(host)
+
+
+def init_from_torch(device=None):
+    """Call after torch.distributed.init_process_group and vkjit_b200.init(local_rank)."""
+    import torch.distributed as td
+    rank, world = td.get_rank(), td.get_world_size()
+    raw = exchange_unique_id(native_unique_id, rank, device) if world > 1 else bytes(UNIQUE_ID_BYTES)
+    product_api().call("dist_init", rank, world, C.create_string_buffer(raw, UNIQUE_ID_BYTES))
+    return rank, world
+
+
+def shutdown():
+    product_api().call("dist_shutdown")
