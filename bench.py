@@ -9,8 +9,8 @@ One step = sum(x) and max(x) over the whole 2^28-lane array = 2 GiB of algorithm
   python bench.py --impl reference ...                   the CPU restatement of the reference
                                                          (oracle port) on the box's host cores
 
-Timing: CUDA events on the backend stream around each reduction (L2 flushed by a 256 MiB write
-between every timed interval, outside the events), max over ranks; clocks sampled with
+Timing: CUDA events on the backend stream around each reduction (L2 evicted by a 256 MiB streaming
+read between every timed interval, outside the events), max over ranks; clocks sampled with
 nvidia-smi during the timed region.  `e2e` goes through the same API with pinned HOST buffers:
 H2D of the step's input, both reductions, D2H of the two results, wall clock.
 """
@@ -199,11 +199,14 @@ def ours(args):
         vk.sync()
         torch.cuda.synchronize()
 
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_buf = torch.zeros(64 << 20, dtype=torch.int32, device=dev)  # 256 MiB = 2x the 126 MB L2
 
     def flush_l2():
+        # Evict the inputs by streaming a 256 MiB READ through L2.  A write-flush would leave ~126 MB
+        # of dirty lines whose write-back lands inside the next timed kernel (measured: +10 % on a
+        # 1 GiB reduction, ncu shows the kernel itself at 154 us vs 173 us timed after a write-flush).
         with torch.cuda.stream(stream):
-            flush_buf.fill_(1)
+            flush_buf.sum()
 
     # ---- input: 2^28 f32 uniform[0,1), this rank's contiguous shard, generated on the device
     lanes = ir.arange_sharded(T.U32, N_TOTAL)
@@ -312,7 +315,7 @@ def ours(args):
             "data": "synthetic",
             "config": {"workload": "R28: sum+max over 2^28 f32 (BASELINE.json configs[1])", "n": N_TOTAL, "n_per_gpu": n_local,
                        "parallelism": f"contiguous 1-D shards x{world}, per-GPU partial + NCCL all-reduce" if world > 1 else "single GPU",
-                       "l2": "flushed (256 MiB write) before every timed reduction; inputs 1 GiB/N per GPU",
+                       "l2": "evicted before every timed reduction by streaming a 256 MiB read through L2 (clean lines: no write-back inside the timed kernel); inputs are 1 GiB/N per GPU, larger than the 126 MB L2",
                        "timing": "CUDA events on the backend stream per reduction, mean over steps, max over ranks"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "wall_s_timed_region": t_wall, "result": {"sum": gpu_sum, "max": gpu_max},

@@ -272,7 +272,7 @@ vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkji
     be.ensure_scan_scratch(n);
     Array* o = be.new_array(n * 4);
     try {
-      prims::prefix_sum((const uint32_t*)v.array->ptr, (uint32_t*)o->ptr, n, exclusive != 0, be.scratch, be.stream);
+      prims::prefix_sum((const uint32_t*)v.array->ptr, (uint32_t*)o->ptr, n, exclusive != 0, be.scratch, be.sm_count, be.stream);
       Backend::counters().prim_launches += 1;
     } catch (...) { release_array(o); throw; }
     *out = ir.binding(ty, o, false);
@@ -304,7 +304,7 @@ static void do_compress(Ir& ir, bool with_values, VarId values, VarId mask, vkji
   uint32_t c = 0;
   try {
     if (n) {
-      prims::compress((const uint32_t*)m.array->ptr, vals, (uint32_t*)o->ptr, (uint32_t*)cnt, n, be.scratch, be.stream);
+      prims::compress((const uint32_t*)m.array->ptr, vals, (uint32_t*)o->ptr, (uint32_t*)cnt, n, be.scratch, be.sm_count, be.stream);
       Backend::counters().prim_launches += 1;
       be.d2h(&c, cnt, 4);  // the size of the result is data dependent: one 4-byte readback
     }

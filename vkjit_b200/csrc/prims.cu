@@ -106,7 +106,7 @@ __device__ __forceinline__ T block_reduce(T v, T* smem /* THREADS/32 */) {
 // ---------------------------------------------------------------------------------------
 // Algorithmic traffic: 4 B/lane read, 4 B written in total.
 template <typename T, int RED, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS)
 reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ partials, unsigned int* __restrict__ ticket,
               uint32_t* __restrict__ out) {
   using O = RedOp<T, RED>;
@@ -199,15 +199,15 @@ void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scr
 // ---------------------------------------------------------------------------------------
 // decoupled look-back scan (Merrill & Garland) — prefix sum and stream compaction
 // ---------------------------------------------------------------------------------------
-// Tile = 512 threads x 8 vectors x 4 lanes = 16384 lanes (64 KiB in, 64 KiB out).  Vector
-// q = j*512 + t of a tile is held by thread t in register slot j, so every load/store
-// instruction of a warp covers 512 contiguous bytes.  Tile status words pack
+// Tile = 1024 threads x 4 vectors x 4 lanes = 16384 lanes (64 KiB in, 64 KiB out).  Vector
+// q = j*1024 + t of a tile is held by thread t in register slot j, so every shared-memory read
+// and every global store of a warp covers 512 contiguous bytes.  Tile status words pack
 // {flag:32 | value:32} into one 64-bit word so flag and value travel in a single (volatile,
 // L2-coherent) access and no fence is needed between them.
 // Why the tile is this large: the look-back frontier advances by at most 32 tiles (one warp-wide
 // window) per L2 round trip (~0.2 us), i.e. ~150 tiles/us; with 4096-lane tiles that caps the
 // kernel near 4 TB/s of traffic (measured: 2.9 TB/s), with 16384-lane tiles the cap is ~4x the
-// HBM rate and the kernel is bandwidth-bound again.
+// HBM rate.
 enum : uint32_t { ST_INVALID = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2 };
 enum ScanMode { MODE_EXCLUSIVE = 0, MODE_INCLUSIVE = 1, MODE_COMPRESS_INDEX = 2, MODE_COMPRESS_VALUE = 3 };
 
@@ -242,8 +242,39 @@ __device__ __forceinline__ uint32_t look_back(volatile uint64_t* status, uint32_
   return exclusive;
 }
 
+// ---- TMA bulk-copy / mbarrier helpers (sm_90+; SASS: UBLKCP + SYNCS) -----------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy performed by the TMA unit; completion is signalled on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_addr(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
+// Persistent kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The input
+// tiles arrive through a kScanStages-deep shared-memory ring filled by TMA bulk copies, so up to
+// (stages-1) x 64 KiB of loads per SM stay in flight while the CTA is scanning, waiting at a
+// barrier or looking back — the three serial phases no longer starve the memory system
+// (the first version, 2 non-persistent CTAs/SM with register loads, spent 60 % of its stall
+// samples at barriers and reached 45 % DRAM utilisation).
 template <int MODE>
-__global__ void __launch_bounds__(kScanThreads, 2)
+__global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: mask words
             const uint32_t* __restrict__ values,  // MODE_COMPRESS_VALUE only
             uint32_t* __restrict__ out, uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles,
@@ -253,107 +284,147 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   constexpr int WARPS = T / 32;
   constexpr int NTOT = VPT * WARPS;         // (slot, warp) totals per tile
   constexpr int PER_LANE = NTOT / 32;
+  constexpr int S = kScanStages;
+  constexpr uint32_t TILE_BYTES = kScanTile * 4;
   constexpr bool COMPRESS = MODE >= MODE_COMPRESS_INDEX;
   static_assert(NTOT % 32 == 0, "tile totals must fill whole warp rows");
-  __shared__ uint32_t s_tot[NTOT];
-  __shared__ uint32_t s_tile_excl;
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  uint32_t* ring = reinterpret_cast<uint32_t*>(ring_raw);  // S stages x kScanTile words
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ uint32_t s_tot[2][NTOT];
+  __shared__ uint32_t s_tile_excl[2];
 
-  // Tile index = blockIdx.x: loads are issued immediately.  Forward progress of the look-back
-  // relies on CTAs of a 1-D grid being dispatched in blockIdx order (as CUB's DeviceScan does).
-  const uint32_t tile = blockIdx.x;
   volatile uint64_t* status = state + 1;
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t tile_base = (size_t)tile * kScanTile;
-  const bool full = tile_base + kScanTile <= n;
+  const uint32_t first = blockIdx.x, stride = gridDim.x;
+  const uint32_t my_tiles = first < num_tiles ? (num_tiles - first + stride - 1) / stride : 0;
+  const bool ragged = (n % kScanTile) != 0;  // the globally last tile is partial: plain guarded loads
 
-  uint4 x[VPT];  // scan: addends; compress: 0/1 flags
+  if (threadIdx.x == 0) {
 #pragma unroll
-  for (int j = 0; j < VPT; ++j) {
-    const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
-    if (full || e + 3 < n) {
-      x[j] = ld_stream(reinterpret_cast<const uint4*>(in + e));
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t k = 0; k < (uint32_t)S && k < my_tiles; ++k) {
+      const uint32_t t = first + k * stride;
+      if (ragged && t == num_tiles - 1) continue;
+      mbar_expect_tx(&full[k], TILE_BYTES);
+      tma_load_1d(ring + (size_t)k * kScanTile, in + (size_t)t * kScanTile, TILE_BYTES, &full[k]);
+    }
+  }
+
+  for (uint32_t k = 0; k < my_tiles; ++k) {
+    const uint32_t tile = first + k * stride;
+    const int stage = k % S;
+    const int buf = k & 1;
+    const size_t tile_base = (size_t)tile * kScanTile;
+    const bool staged = !(ragged && tile == num_tiles - 1);
+
+    uint4 x[VPT];  // scan: addends; compress: mask words
+    if (staged) {
+      mbar_wait(&full[stage], (k / S) & 1);
+      const uint4* src = reinterpret_cast<const uint4*>(ring + (size_t)stage * kScanTile);
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) x[j] = src[j * T + threadIdx.x];  // conflict-free 128-bit shared loads
     } else {
-      x[j].x = e + 0 < n ? in[e + 0] : 0u; x[j].y = e + 1 < n ? in[e + 1] : 0u;
-      x[j].z = e + 2 < n ? in[e + 2] : 0u; x[j].w = 0u;
-    }
-  }
-  uint32_t flags[VPT];  // compress: 4 selection bits per vector (frees the uint4 registers)
-  if (COMPRESS) {
 #pragma unroll
-    for (int j = 0; j < VPT; ++j)
-      flags[j] = (x[j].x != 0u ? 1u : 0u) | (x[j].y != 0u ? 2u : 0u) | (x[j].z != 0u ? 4u : 0u) | (x[j].w != 0u ? 8u : 0u);
-  }
-
-  // 1) per-vector sums, 2) inclusive warp scan per register slot, 3) one warp scans the
-  // (slot, warp) totals in tile order, 4) look-back gives the tile's global offset.
-  uint32_t vsum[VPT], wincl[VPT];
-#pragma unroll
-  for (int j = 0; j < VPT; ++j) {
-    vsum[j] = COMPRESS ? (uint32_t)__popc(flags[j]) : x[j].x + x[j].y + x[j].z + x[j].w;
-    uint32_t s = vsum[j];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
-      if (lane >= o) s += t;
-    }
-    wincl[j] = s;
-    if (lane == 31) s_tot[j * WARPS + warp] = s;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t t[PER_LANE], run = 0;
-#pragma unroll
-    for (int k = 0; k < PER_LANE; ++k) { t[k] = s_tot[lane * PER_LANE + k]; run += t[k]; }
-    uint32_t s = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, s, o);
-      if (lane >= o) s += u;
-    }
-    uint32_t off = s - run;  // exclusive offset of this lane's first entry
-#pragma unroll
-    for (int k = 0; k < PER_LANE; ++k) { s_tot[lane * PER_LANE + k] = off; off += t[k]; }
-    const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
-    const uint32_t excl = look_back(status, tile, aggregate);
-    if (lane == 0) {
-      s_tile_excl = excl;
-      if (COMPRESS && tile == num_tiles - 1) *count_out = excl + aggregate;
-    }
-  }
-  __syncthreads();
-  const uint32_t tile_excl = s_tile_excl;
-
-#pragma unroll
-  for (int j = 0; j < VPT; ++j) {
-    const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
-    uint32_t p = tile_excl + s_tot[j * WARPS + warp] + (wincl[j] - vsum[j]);  // exclusive prefix of lane e
-    if (!COMPRESS) {
-      uint4 r;
-      if (MODE == MODE_EXCLUSIVE) { r.x = p; r.y = p + x[j].x; r.z = r.y + x[j].y; r.w = r.z + x[j].z; }
-      else { r.x = p + x[j].x; r.y = r.x + x[j].y; r.z = r.y + x[j].z; r.w = r.z + x[j].w; }
-      if (full || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
-      else {
-        if (e + 0 < n) out[e + 0] = r.x;
-        if (e + 1 < n) out[e + 1] = r.y;
-        if (e + 2 < n) out[e + 2] = r.z;
-      }
-    } else if (flags[j]) {
-      // selected lanes are written at their rank; flags of out-of-range lanes are 0.  Values are
-      // loaded only now (once from HBM, only for vectors with a selected lane).
-      uint4 v;
-      if (MODE == MODE_COMPRESS_VALUE) {
-        if (full || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
+      for (int j = 0; j < VPT; ++j) {
+        const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+        if (e + 3 < n) x[j] = ld_stream(reinterpret_cast<const uint4*>(in + e));
         else {
-          v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
-          v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
+          x[j].x = e + 0 < n ? in[e + 0] : 0u; x[j].y = e + 1 < n ? in[e + 1] : 0u;
+          x[j].z = e + 2 < n ? in[e + 2] : 0u; x[j].w = 0u;
         }
-      } else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
-      if (flags[j] & 1u) out[p++] = v.x;
-      if (flags[j] & 2u) out[p++] = v.y;
-      if (flags[j] & 4u) out[p++] = v.z;
-      if (flags[j] & 8u) out[p++] = v.w;
+      }
     }
+    uint32_t flags[VPT];  // compress: 4 selection bits per vector
+    if (COMPRESS) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j)
+        flags[j] = (x[j].x != 0u ? 1u : 0u) | (x[j].y != 0u ? 2u : 0u) | (x[j].z != 0u ? 4u : 0u) | (x[j].w != 0u ? 8u : 0u);
+    }
+
+    // 1) per-vector sums, 2) inclusive warp scan per register slot, 3) one warp scans the
+    // (slot, warp) totals in tile order, 4) look-back gives the tile's global offset.
+    uint32_t vsum[VPT], wincl[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      vsum[j] = COMPRESS ? (uint32_t)__popc(flags[j]) : x[j].x + x[j].y + x[j].z + x[j].w;
+      uint32_t s = vsum[j];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+        if (lane >= o) s += t;
+      }
+      wincl[j] = s;
+      if (lane == 31) s_tot[buf][j * WARPS + warp] = s;
+    }
+    __syncthreads();  // every thread has consumed its part of ring[stage]: the stage can be refilled
+    if (threadIdx.x == 0 && k + S < my_tiles) {
+      const uint32_t t2 = first + (k + S) * stride;
+      if (!(ragged && t2 == num_tiles - 1)) {
+        mbar_expect_tx(&full[stage], TILE_BYTES);
+        tma_load_1d(ring + (size_t)stage * kScanTile, in + (size_t)t2 * kScanTile, TILE_BYTES, &full[stage]);
+      }
+    }
+    if (warp == 0) {
+      uint32_t t[PER_LANE], run = 0;
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) { t[i] = s_tot[buf][lane * PER_LANE + i]; run += t[i]; }
+      uint32_t s = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, s, o);
+        if (lane >= o) s += u;
+      }
+      uint32_t off = s - run;  // exclusive offset of this lane's first entry
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) { s_tot[buf][lane * PER_LANE + i] = off; off += t[i]; }
+      const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
+      const uint32_t excl = look_back(status, tile, aggregate);
+      if (lane == 0) {
+        s_tile_excl[buf] = excl;
+        if (COMPRESS && tile == num_tiles - 1) *count_out = excl + aggregate;
+      }
+    }
+    __syncthreads();
+    const uint32_t tile_excl = s_tile_excl[buf];
+
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+      uint32_t p = tile_excl + s_tot[buf][j * WARPS + warp] + (wincl[j] - vsum[j]);  // exclusive prefix of lane e
+      if (!COMPRESS) {
+        uint4 r;
+        if (MODE == MODE_EXCLUSIVE) { r.x = p; r.y = p + x[j].x; r.z = r.y + x[j].y; r.w = r.z + x[j].z; }
+        else { r.x = p + x[j].x; r.y = r.x + x[j].y; r.z = r.y + x[j].z; r.w = r.z + x[j].w; }
+        if (staged || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
+        else {
+          if (e + 0 < n) out[e + 0] = r.x;
+          if (e + 1 < n) out[e + 1] = r.y;
+          if (e + 2 < n) out[e + 2] = r.z;
+        }
+      } else if (flags[j]) {
+        // selected lanes are written at their rank; flags of out-of-range lanes are 0.  Values are
+        // loaded only now (once from HBM, only for vectors with a selected lane).
+        uint4 v;
+        if (MODE == MODE_COMPRESS_VALUE) {
+          if (staged || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
+          else {
+            v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
+            v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
+          }
+        } else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
+        if (flags[j] & 1u) out[p++] = v.x;
+        if (flags[j] & 2u) out[p++] = v.y;
+        if (flags[j] & 4u) out[p++] = v.z;
+        if (flags[j] & 8u) out[p++] = v.w;
+      }
+    }
+    // s_tot/s_tile_excl are double-buffered: iteration k+2 rewrites buffer `buf` only after every
+    // thread passed the first barrier of iteration k+1, i.e. after it finished reading it here.
   }
 }
 
@@ -367,25 +438,40 @@ static uint32_t prepare_scan(size_t n, const Scratch& sc, cudaStream_t s) {
   return (uint32_t)tiles;
 }
 
-void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, void* stream) {
-  if (n == 0) return;
-  cudaStream_t s = (cudaStream_t)stream;
-  const uint32_t tiles = prepare_scan(n, sc, s);
-  if (exclusive) scan_kernel<MODE_EXCLUSIVE><<<tiles, kScanThreads, 0, s>>>(in, nullptr, out, nullptr, n, tiles, sc.tile_state);
-  else scan_kernel<MODE_INCLUSIVE><<<tiles, kScanThreads, 0, s>>>(in, nullptr, out, nullptr, n, tiles, sc.tile_state);
+constexpr size_t kScanSmem = (size_t)kScanStages * kScanTile * 4;
+
+template <int MODE>
+static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n, uint32_t tiles,
+                        const Scratch& sc, int sm_count, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem);
+    if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan smem attribute: ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  // one persistent CTA per SM: all CTAs are co-resident, so a tile only ever waits on tiles of
+  // CTAs that are running (forward progress of the look-back does not depend on dispatch order)
+  const unsigned grid = (unsigned)std::min<uint32_t>(tiles, (uint32_t)sm_count);
+  scan_kernel<MODE><<<grid, kScanThreads, kScanSmem, s>>>(in, values, out, count_out, n, tiles, sc.tile_state);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
 }
 
-void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
-              const Scratch& sc, void* stream) {
+void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream) {
   if (n == 0) return;
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t tiles = prepare_scan(n, sc, s);
-  if (values) scan_kernel<MODE_COMPRESS_VALUE><<<tiles, kScanThreads, 0, s>>>(mask, values, out, count_out, n, tiles, sc.tile_state);
-  else scan_kernel<MODE_COMPRESS_INDEX><<<tiles, kScanThreads, 0, s>>>(mask, nullptr, out, count_out, n, tiles, sc.tile_state);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("compress launch: ") + cudaGetErrorString(e));
+  if (exclusive) launch_scan<MODE_EXCLUSIVE>(in, nullptr, out, nullptr, n, tiles, sc, sm_count, s);
+  else launch_scan<MODE_INCLUSIVE>(in, nullptr, out, nullptr, n, tiles, sc, sm_count, s);
+}
+
+void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
+              const Scratch& sc, int sm_count, void* stream) {
+  if (n == 0) return;
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t tiles = prepare_scan(n, sc, s);
+  if (values) launch_scan<MODE_COMPRESS_VALUE>(mask, values, out, count_out, n, tiles, sc, sm_count, s);
+  else launch_scan<MODE_COMPRESS_INDEX>(mask, nullptr, out, count_out, n, tiles, sc, sm_count, s);
 }
 
 __global__ void fill_kernel(uint32_t* out, uint32_t value, size_t n) {

@@ -17,8 +17,9 @@ struct Scratch {
 
 constexpr int kReduceThreads = 512;
 constexpr int kReduceMaxCtas = 2048;
-constexpr int kScanThreads = 512;
-constexpr int kScanTile = 16384;  // lanes per look-back tile (512 threads x 8 x uint4 = 64 KiB)
+constexpr int kScanThreads = 1024;
+constexpr int kScanTile = 16384;  // lanes per look-back tile (1024 threads x 4 x uint4 = 64 KiB)
+constexpr int kScanStages = 3;    // TMA-fed shared-memory ring: 3 x 64 KiB per CTA, one CTA per SM
 
 // number of 8-byte words `tile_state` must hold for n lanes
 size_t scan_state_words(size_t n);
@@ -30,12 +31,12 @@ size_t scan_state_words(size_t n);
 void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream);
 
 // Single-pass decoupled look-back prefix sum (mod 2^32) over u32 words.
-void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, void* stream);
+void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream);
 
 // Stream compaction: lanes whose mask word is non-zero, stable order.  values == nullptr writes the
 // lane index.  *count_out (device) receives the number of selected lanes.
 void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
-              const Scratch& sc, void* stream);
+              const Scratch& sc, int sm_count, void* stream);
 
 // out[i] = value for i in [0, n)
 void fill_u32(uint32_t* out, uint32_t value, size_t n, void* stream);
