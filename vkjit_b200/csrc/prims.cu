@@ -214,6 +214,12 @@ enum ScanMode { MODE_EXCLUSIVE = 0, MODE_INCLUSIVE = 1, MODE_COMPRESS_INDEX = 2,
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 
 // Executed by warp 0 of the CTA owning `tile`.  Returns the exclusive prefix of the tile.
+// One round inspects kLookWide x 32 = 160 predecessors with all status loads in flight together:
+// the persistent grid runs its 148 CTAs in generations, so a single round (one L2 round trip)
+// spans the whole current generation plus the tail of the previous one, whose inclusive prefixes
+// are already published.  (A classic 32-wide window needs up to 5 dependent round trips here and
+// put every generation on a ~5 us critical path.)
+constexpr int kLookWide = 5;
 __device__ __forceinline__ uint32_t look_back(volatile uint64_t* status, uint32_t tile, uint32_t aggregate) {
   const int lane = threadIdx.x & 31;
   if (tile == 0) {
@@ -224,19 +230,29 @@ __device__ __forceinline__ uint32_t look_back(volatile uint64_t* status, uint32_
   uint32_t exclusive = 0;
   int top = (int)tile - 1;  // nearest predecessor examined by lane 0
   for (;;) {
-    const int idx = top - lane;
-    uint64_t s = (uint64_t)ST_INCLUSIVE << 32;  // virtual tile before tile 0: inclusive prefix 0
-    if (idx >= 0) {
-      do { s = status[idx]; } while ((uint32_t)(s >> 32) == ST_INVALID);
+    uint64_t s[kLookWide];
+#pragma unroll
+    for (int i = 0; i < kLookWide; ++i) {
+      const int idx = top - 32 * i - lane;
+      s[i] = idx >= 0 ? status[idx] : ((uint64_t)ST_INCLUSIVE << 32);  // virtual tile before tile 0: prefix 0
     }
-    const unsigned incl = __ballot_sync(0xFFFFFFFFu, (uint32_t)(s >> 32) == ST_INCLUSIVE);
-    if (incl) {
-      const int first = __ffs(incl) - 1;  // nearest tile that already knows its inclusive prefix
-      exclusive += warp_sum(lane <= first ? (uint32_t)s : 0u);
-      break;
+    bool done = false;
+#pragma unroll
+    for (int i = 0; i < kLookWide; ++i) {
+      if (done) continue;
+      const int idx = top - 32 * i - lane;
+      while ((uint32_t)(s[i] >> 32) == ST_INVALID) s[i] = status[idx];  // predecessor not published yet
+      const unsigned incl = __ballot_sync(0xFFFFFFFFu, (uint32_t)(s[i] >> 32) == ST_INCLUSIVE);
+      if (incl) {
+        const int first = __ffs(incl) - 1;  // nearest tile that already knows its inclusive prefix
+        exclusive += warp_sum(lane <= first ? (uint32_t)s[i] : 0u);
+        done = true;
+      } else {
+        exclusive += warp_sum((uint32_t)s[i]);
+      }
     }
-    exclusive += warp_sum((uint32_t)s);
-    top -= 32;
+    if (done) break;
+    top -= 32 * kLookWide;
   }
   if (lane == 0) status[tile] = ((uint64_t)ST_INCLUSIVE << 32) | (exclusive + aggregate);
   return exclusive;
