@@ -213,20 +213,34 @@ enum ScanMode { MODE_EXCLUSIVE = 0, MODE_INCLUSIVE = 1, MODE_COMPRESS_INDEX = 2,
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 
+// Status words are read and written with gpu-scope relaxed accesses (L2 is the coherence point;
+// `volatile` would compile to system-scope STRONG.SYS) and every tile owns a full 128-byte line:
+// a window of predecessors then maps to many L2 slices instead of hammering the one or two
+// slices that hold a packed status array (the packed layout made every poll round take ~0.7 us
+// and the nearest window was polled 6.6 times per tile — ncu source page, profiles/).
+constexpr int kStatusStride = 16;  // 64-bit words per tile status slot (128 bytes)
+__device__ __forceinline__ uint64_t status_load(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void status_store(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Executed by warp 0 of the CTA owning `tile`.  Returns the exclusive prefix of the tile.
 // One round inspects kLookWide x 32 = 160 predecessors with all status loads in flight together:
 // the persistent grid runs its 148 CTAs in generations, so a single round (one L2 round trip)
 // spans the whole current generation plus the tail of the previous one, whose inclusive prefixes
-// are already published.  (A classic 32-wide window needs up to 5 dependent round trips here and
-// put every generation on a ~5 us critical path.)
+// are already published.
 constexpr int kLookWide = 5;
-__device__ __forceinline__ uint32_t look_back(volatile uint64_t* status, uint32_t tile, uint32_t aggregate) {
+__device__ __forceinline__ uint32_t look_back(uint64_t* status, uint32_t tile, uint32_t aggregate) {
   const int lane = threadIdx.x & 31;
   if (tile == 0) {
-    if (lane == 0) status[0] = ((uint64_t)ST_INCLUSIVE << 32) | aggregate;
+    if (lane == 0) status_store(status, ((uint64_t)ST_INCLUSIVE << 32) | aggregate);
     return 0u;
   }
-  if (lane == 0) status[tile] = ((uint64_t)ST_AGGREGATE << 32) | aggregate;
+  if (lane == 0) status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_AGGREGATE << 32) | aggregate);
   uint32_t exclusive = 0;
   int top = (int)tile - 1;  // nearest predecessor examined by lane 0
   for (;;) {
@@ -234,14 +248,17 @@ __device__ __forceinline__ uint32_t look_back(volatile uint64_t* status, uint32_
 #pragma unroll
     for (int i = 0; i < kLookWide; ++i) {
       const int idx = top - 32 * i - lane;
-      s[i] = idx >= 0 ? status[idx] : ((uint64_t)ST_INCLUSIVE << 32);  // virtual tile before tile 0: prefix 0
+      s[i] = idx >= 0 ? status_load(status + (size_t)idx * kStatusStride) : ((uint64_t)ST_INCLUSIVE << 32);  // before tile 0: prefix 0
     }
     bool done = false;
 #pragma unroll
     for (int i = 0; i < kLookWide; ++i) {
       if (done) continue;
       const int idx = top - 32 * i - lane;
-      while ((uint32_t)(s[i] >> 32) == ST_INVALID) s[i] = status[idx];  // predecessor not published yet
+      while ((uint32_t)(s[i] >> 32) == ST_INVALID) {  // predecessor not published yet
+        __nanosleep(40);
+        s[i] = status_load(status + (size_t)idx * kStatusStride);
+      }
       const unsigned incl = __ballot_sync(0xFFFFFFFFu, (uint32_t)(s[i] >> 32) == ST_INCLUSIVE);
       if (incl) {
         const int first = __ffs(incl) - 1;  // nearest tile that already knows its inclusive prefix
@@ -254,7 +271,7 @@ __device__ __forceinline__ uint32_t look_back(volatile uint64_t* status, uint32_
     if (done) break;
     top -= 32 * kLookWide;
   }
-  if (lane == 0) status[tile] = ((uint64_t)ST_INCLUSIVE << 32) | (exclusive + aggregate);
+  if (lane == 0) status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_INCLUSIVE << 32) | (exclusive + aggregate));
   return exclusive;
 }
 
@@ -310,7 +327,7 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   __shared__ uint32_t s_tot[2][NTOT];
   __shared__ uint32_t s_tile_excl[2];
 
-  volatile uint64_t* status = state + 1;
+  uint64_t* status = state + kStatusStride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t first = blockIdx.x, stride = gridDim.x;
   const uint32_t my_tiles = first < num_tiles ? (num_tiles - first + stride - 1) / stride : 0;
@@ -444,12 +461,12 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   }
 }
 
-size_t scan_state_words(size_t n) { return 1 + (n + kScanTile - 1) / kScanTile; }
+size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (1 + (n + kScanTile - 1) / kScanTile); }
 
 static uint32_t prepare_scan(size_t n, const Scratch& sc, cudaStream_t s) {
   const size_t tiles = (n + kScanTile - 1) / kScanTile;
-  if (1 + tiles > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
-  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, (1 + tiles) * sizeof(uint64_t), s);
+  if (scan_state_words(n) > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
+  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, scan_state_words(n) * sizeof(uint64_t), s);
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
   return (uint32_t)tiles;
 }

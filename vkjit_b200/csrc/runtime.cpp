@@ -186,7 +186,7 @@ void Backend::ensure_scan_scratch(size_t n) {
     ck(cudaStreamSynchronize((cudaStream_t)stream), "sync");
     cudaFree(scratch.tile_state);
   }
-  size_t words = std::max<size_t>(need, 1 << 16);
+  size_t words = std::max<size_t>(need, 1 << 19);
   void* p = nullptr;
   ck(cudaMalloc(&p, words * 8), "scan scratch");
   scratch.tile_state = (uint64_t*)p;
