@@ -182,14 +182,10 @@ def ours(args):
     vk.init(local_rank)
     api = vk.product_api()
     if world > 1:
-        idbuf = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            host = (C.c_uint8 * 128)()
-            api.call("dist_unique_id", host)
-            idbuf.copy_(torch.tensor(list(host), dtype=torch.uint8))
-        td.broadcast(idbuf, 0)
-        raw = bytes(idbuf.cpu().tolist())
-        api.call("dist_init", rank, world, C.create_string_buffer(raw, 128))
+        from vkjit_b200 import dist
+        dist.init_from_torch(dev, p2p=True)   # NCCL unique id + cudaIpc mailbox handles through torch.distributed
+        if args.collective == "nccl":
+            dist.set_p2p(False)
     stream = torch.cuda.ExternalStream(vk.stream_ptr(), device=dev)
     ir = Ir()
 
@@ -314,7 +310,7 @@ def ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "R28: sum+max over 2^28 f32 (BASELINE.json configs[1])", "n": N_TOTAL, "n_per_gpu": n_local,
-                       "parallelism": f"contiguous 1-D shards x{world}, per-GPU partial + NCCL all-reduce" if world > 1 else "single GPU",
+                       "parallelism": (f"contiguous 1-D shards x{world}, per-GPU partial + " + ("all-reduce fused into the reduce kernel's last CTA over NVLink peer memory (P2P mailbox)" if args.collective == "p2p" else "NCCL all-reduce")) if world > 1 else "single GPU",
                        "l2": "evicted before every timed reduction by streaming a 256 MiB read through L2 (clean lines: no write-back inside the timed kernel); inputs are 1 GiB/N per GPU, larger than the 126 MB L2",
                        "timing": "CUDA events on the backend stream per reduction, mean over steps, max over ranks"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -349,6 +345,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory all-reduce (default) or NCCL")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

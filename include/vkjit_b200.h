@@ -226,6 +226,15 @@ vkjit_status vkjit_compress_values(vkjit_ir* ir, vkjit_var values, vkjit_var mas
 /* 128-byte NCCL unique id, created on rank 0 and shipped by the host. */
 vkjit_status vkjit_dist_unique_id(void* out_id128);
 vkjit_status vkjit_dist_init(int32_t rank, int32_t world, const void* id128);
+/* Fused reduce + all-reduce over NVLink peer memory (optional; NCCL is used until it is set up).
+ * vkjit_dist_mailbox_handle: allocate this rank's mailbox, return its 64-byte cudaIpc handle.
+ * vkjit_dist_mailbox_open: map all ranks' mailboxes (world x 64 bytes, rank order).  Afterwards the
+ * last CTA of every sharded reduction publishes the per-GPU partial into every peer's mailbox and
+ * combines in rank order (deterministic); $VKJIT_DIST=nccl keeps the NCCL path. */
+vkjit_status vkjit_dist_mailbox_handle(void* out_handle64);
+vkjit_status vkjit_dist_mailbox_open(const void* handles, int32_t world);
+/* Switch between the fused mailbox path (1) and NCCL (0); every rank must make the same call. */
+vkjit_status vkjit_dist_set_p2p(int32_t on);
 vkjit_status vkjit_dist_shutdown(void);
 vkjit_status vkjit_dist_info(int32_t* out_rank, int32_t* out_world);
 /* Shard [lo, hi) of a global 1-D range of n lanes owned by `rank` of `world`

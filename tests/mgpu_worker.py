@@ -32,7 +32,8 @@ def main():
     td.init_process_group("nccl", device_id=torch.device("cuda", local))
     vk.init(local)
     rank, world = dist.init_from_torch(torch.device("cuda", local))
-    for n in (5, 1000, (1 << 22) + 3):
+    for p2p, n in [(m, k) for m in (True, False) for k in (5, 1000, (1 << 22) + 3)]:
+        dist.set_p2p(p2p)  # fused reduce + all-reduce over NVLink peer memory, then the NCCL path
         ir = Ir()
         lanes = ir.arange_sharded(T.U32, n)
         lo, hi = dist.shard_range(n, rank, world)

@@ -113,6 +113,9 @@ _PRODUCT_SIGS = {
     "var_device_ptr": [_p, _u32, _pu64],
     "dist_unique_id": [_p],
     "dist_init": [_i32, _i32, _p],
+    "dist_mailbox_handle": [_p],
+    "dist_mailbox_open": [_p, _i32],
+    "dist_set_p2p": [_i32],
     "dist_shutdown": [],
     "dist_info": [_pi32, _pi32],
     "arange_sharded": [_p, _u32, _sz, _pu32],

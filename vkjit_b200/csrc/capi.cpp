@@ -246,15 +246,20 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
     if (empty && !combine) fail(VKJIT_ERR_SIZE, "reduce of an empty array");
     Array* o = be.new_array(4);
     try {
+      const bool fused = combine && dist::p2p_enabled();
+      prims::Mailbox mb;
+      if (fused) mb = dist::next_mailbox();
       if (empty) {
         prims::fill_u32((uint32_t*)o->ptr, reduce_identity(red, ty), 1, be.stream);
+        if (fused) prims::p2p_allreduce(red, ty, o->ptr, mb, be.stream);
       } else {
         ensure_buffer(ir, id);
         const Var& v = ir.var(id);
-        prims::reduce(red, ty, v.array->ptr, v.array->bytes / 4, o->ptr, be.scratch, be.sm_count, be.stream);
+        // fused: the last CTA of the reduction exchanges the per-GPU partial over NVLink peer memory
+        prims::reduce(red, ty, v.array->ptr, v.array->bytes / 4, o->ptr, be.scratch, be.sm_count, be.stream, fused ? &mb : nullptr);
       }
       Backend::counters().prim_launches += 1;
-      if (combine) dist::allreduce(o->ptr, ty, red, 1);  // per-GPU partial -> replicated result
+      if (combine && !fused) dist::allreduce(o->ptr, ty, red, 1);  // NCCL: per-GPU partial -> replicated result
     } catch (...) { release_array(o); throw; }
     *out = ir.binding(ty, o, false);
   });
@@ -325,6 +330,9 @@ vkjit_status vkjit_compress_values(vkjit_ir* h, vkjit_var values, vkjit_var mask
 // ---- multi-GPU ------------------------------------------------------------------------------------------------
 vkjit_status vkjit_dist_unique_id(void* out) { return guard([&] { dist::unique_id(out); }); }
 vkjit_status vkjit_dist_init(int32_t rank, int32_t world, const void* id) { return guard([&] { dist::init(rank, world, id); }); }
+vkjit_status vkjit_dist_mailbox_handle(void* out64) { return guard([&] { dist::mailbox_handle(out64); }); }
+vkjit_status vkjit_dist_mailbox_open(const void* handles, int32_t world) { return guard([&] { dist::mailbox_open(handles, world); }); }
+vkjit_status vkjit_dist_set_p2p(int32_t on) { return guard([&] { dist::set_p2p(on != 0); }); }
 vkjit_status vkjit_dist_shutdown(void) { return guard([&] { dist::shutdown(); }); }
 vkjit_status vkjit_dist_info(int32_t* rank, int32_t* world) {
   return guard([&] { *rank = dist::rank(); *world = dist::world(); });

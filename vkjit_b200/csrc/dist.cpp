@@ -4,7 +4,10 @@
 #include "dist.h"
 
 #include <dlfcn.h>
+#include <cuda_runtime.h>
 #include <nccl.h>
+
+#include <cstdlib>
 
 #include <string>
 
@@ -40,6 +43,12 @@ ncclComm_t g_comm = nullptr;
 int g_rank = 0, g_world = 1;
 bool g_active = false;
 
+// peer mailboxes
+uint64_t* g_mail_local = nullptr;
+uint64_t* g_mail_peer[prims::kMailRanks] = {};
+bool g_p2p = false;
+uint32_t g_seq = 0;
+
 void ckn(ncclResult_t r, const char* what) {
   if (r != ncclSuccess) fail(VKJIT_ERR_DIST, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error"));
 }
@@ -72,7 +81,67 @@ void init(int rank, int world, const void* id128) {
   g_active = true;
 }
 
+void mailbox_handle(void* out64) {
+  Backend::get();
+  if (!g_mail_local) {
+    void* p = nullptr;
+    const size_t bytes = (size_t)prims::kMailSlots * prims::kMailRanks * 8;
+    if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess) fail(VKJIT_ERR_CUDA, "mailbox allocation failed");
+    g_mail_local = (uint64_t*)p;
+  }
+  cudaIpcMemHandle_t hnd;
+  cudaError_t e = cudaIpcGetMemHandle(&hnd, g_mail_local);
+  if (e != cudaSuccess) fail(VKJIT_ERR_DIST, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  memcpy(out64, &hnd, 64);
+}
+
+void mailbox_open(const void* handles, int world) {
+  if (!g_active || world != g_world) fail(VKJIT_ERR_DIST, "mailbox_open: call vkjit_dist_init first with the same world size");
+  if (world > prims::kMailRanks) fail(VKJIT_ERR_DIST, "mailbox supports at most 8 ranks");
+  if (!g_mail_local) fail(VKJIT_ERR_DIST, "mailbox_open before mailbox_handle");
+  for (int r = 0; r < world; ++r) {
+    if (r == g_rank) { g_mail_peer[r] = g_mail_local; continue; }
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, (const char*)handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) fail(VKJIT_ERR_DIST, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+    g_mail_peer[r] = (uint64_t*)p;
+  }
+  const char* force = getenv("VKJIT_DIST");
+  g_p2p = !(force && std::string(force) == "nccl");
+  g_seq = 0;
+}
+
+bool p2p_enabled() { return g_active && g_world > 1 && g_p2p; }
+
+void set_p2p(bool on) {
+  if (on && !g_mail_peer[g_rank]) fail(VKJIT_ERR_DIST, "mailboxes are not open");
+  if (Backend::initialized()) Backend::get().sync();
+  g_p2p = on;
+}
+
+prims::Mailbox next_mailbox() {
+  prims::Mailbox mb;
+  for (int r = 0; r < prims::kMailRanks; ++r) mb.peer[r] = g_mail_peer[r];
+  mb.rank = g_rank; mb.world = g_world;
+  mb.seq = ++g_seq;
+  if (g_seq == 0xFFFFFFFFu) g_seq = 0;
+  Backend::counters().collectives += 1;
+  return mb;
+}
+
 void shutdown() {
+  if (g_p2p || g_mail_local) {
+    if (Backend::initialized()) Backend::get().sync();
+    for (int r = 0; r < prims::kMailRanks; ++r) {
+      if (g_mail_peer[r] && g_mail_peer[r] != g_mail_local) cudaIpcCloseMemHandle(g_mail_peer[r]);
+      g_mail_peer[r] = nullptr;
+    }
+    if (g_mail_local) { cudaFree(g_mail_local); g_mail_local = nullptr; }
+    g_p2p = false; g_seq = 0;
+  }
   if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
   g_active = false; g_rank = 0; g_world = 1;
 }

@@ -5,6 +5,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include "prims.h"
+
 namespace vkjit {
 namespace dist {
 
@@ -16,6 +18,15 @@ void init(int rank, int world, const void* id128);
 void shutdown();
 // in-place all-reduce of `count` 4-byte elements on the backend stream; result replicated
 void allreduce(void* buf, uint32_t ty, int red, size_t count);
+// Fused path: peer-mapped mailboxes (cudaIpc).  mailbox_handle allocates the local mailbox and
+// returns its 64-byte IPC handle; mailbox_open maps every rank's mailbox (world x 64 bytes, in rank
+// order).  Once open, reductions combine inside the reduce kernel over NVLink instead of NCCL.
+void mailbox_handle(void* out64);
+void mailbox_open(const void* handles, int world);
+bool p2p_enabled();
+void set_p2p(bool on);  // switch between the fused mailbox path and NCCL (all ranks must agree)
+prims::Mailbox next_mailbox();  // bumps the collective sequence number
+
 // contiguous shards in units of 4 lanes (16-byte aligned); the last rank takes the ragged tail
 void shard_range(size_t n, int rank, int world, size_t& lo, size_t& hi);
 

@@ -102,13 +102,54 @@ __device__ __forceinline__ T block_reduce(T v, T* smem /* THREADS/32 */) {
 }
 
 // ---------------------------------------------------------------------------------------
+// one-shot all-reduce over NVLink peer memory (called by ONE thread of ONE CTA per GPU)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void sys_store(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t sys_load(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <typename T, int RED>
+__device__ __forceinline__ T mailbox_allreduce(T mine, const Mailbox& mb) {
+  const size_t slot = (size_t)(mb.seq % kMailSlots) * kMailRanks;
+  const uint64_t word = ((uint64_t)mb.seq << 32) | to_bits(mine);
+  for (int p = 0; p < mb.world; ++p) sys_store(mb.peer[p] + slot + mb.rank, word);  // P2P stores over NVLink
+  const uint64_t* local = mb.peer[mb.rank] + slot;
+  T acc = RedOp<T, RED>::identity();
+  const unsigned long long t0 = global_ns();
+  for (int r = 0; r < mb.world; ++r) {  // fixed rank order: same bits on every GPU
+    uint64_t w = sys_load(local + r);
+    while ((uint32_t)(w >> 32) != mb.seq) {
+      if (global_ns() - t0 > 5000000000ull) __trap();  // a peer never arrived: fail loudly instead of hanging the GPU
+      w = sys_load(local + r);
+    }
+    acc = RedOp<T, RED>::apply(acc, from_bits<T>((uint32_t)w));
+  }
+  return acc;
+}
+
+template <typename T, int RED>
+__global__ void p2p_allreduce_kernel(uint32_t* out, Mailbox mb) {
+  if (threadIdx.x == 0) out[0] = to_bits(mailbox_allreduce<T, RED>(from_bits<T>(out[0]), mb));
+}
+
+// ---------------------------------------------------------------------------------------
 // horizontal reduction
 // ---------------------------------------------------------------------------------------
 // Algorithmic traffic: 4 B/lane read, 4 B written in total.
 template <typename T, int RED, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
 reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ partials, unsigned int* __restrict__ ticket,
-              uint32_t* __restrict__ out) {
+              uint32_t* __restrict__ out, const Mailbox mb) {
   using O = RedOp<T, RED>;
   __shared__ T smem[THREADS / 32];
   __shared__ bool is_last;
@@ -159,30 +200,36 @@ reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ 
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) f = O::apply(f, from_bits<T>(__ldcg(partials + i)));
     f = block_reduce<T, RED, THREADS>(f, smem);
     if (threadIdx.x == 0) {
-      out[0] = to_bits(f);
       *ticket = 0u;  // self-reset for the next launch on this stream
+      // fused collective: the per-GPU partial goes straight to every peer's mailbox (no second
+      // kernel, no NCCL launch); world == 1 compiles to the plain store
+      if (mb.world > 1) f = mailbox_allreduce<T, RED>(f, mb);
+      out[0] = to_bits(f);
     }
   }
 }
 
 template <typename T, int RED>
-static void launch_reduce(const void* in, size_t n, void* out, const Scratch& sc, int sm_count, cudaStream_t s) {
+static void launch_reduce(const void* in, size_t n, void* out, const Scratch& sc, int sm_count, cudaStream_t s, const Mailbox& mb) {
   const size_t n4 = n >> 2;
   size_t ctas = (std::max<size_t>(n4, 1) + kReduceThreads - 1) / kReduceThreads;
   const size_t cap = (size_t)sm_count * (2048 / kReduceThreads);  // one full wave: 4 CTAs of 512 threads per SM
   if (ctas > cap) ctas = cap;
   if (ctas > (size_t)kReduceMaxCtas) ctas = kReduceMaxCtas;
   reduce_kernel<T, RED, kReduceThreads><<<(unsigned)ctas, kReduceThreads, 0, s>>>(
-      (const uint32_t*)in, n, (uint32_t*)sc.partials, sc.ticket, (uint32_t*)out);
+      (const uint32_t*)in, n, (uint32_t*)sc.partials, sc.ticket, (uint32_t*)out, mb);
 }
 
-void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream) {
+void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream,
+            const Mailbox* mailbox) {
   cudaStream_t s = (cudaStream_t)stream;
+  Mailbox mb;
+  if (mailbox) mb = *mailbox;
 #define VK_DISPATCH(T)                                                                          \
   switch (red) {                                                                                \
-    case VKJIT_RED_SUM: launch_reduce<T, VKJIT_RED_SUM>(in, n, out, sc, sm_count, s); break;    \
-    case VKJIT_RED_MIN: launch_reduce<T, VKJIT_RED_MIN>(in, n, out, sc, sm_count, s); break;    \
-    case VKJIT_RED_MAX: launch_reduce<T, VKJIT_RED_MAX>(in, n, out, sc, sm_count, s); break;    \
+    case VKJIT_RED_SUM: launch_reduce<T, VKJIT_RED_SUM>(in, n, out, sc, sm_count, s, mb); break;    \
+    case VKJIT_RED_MIN: launch_reduce<T, VKJIT_RED_MIN>(in, n, out, sc, sm_count, s, mb); break;    \
+    case VKJIT_RED_MAX: launch_reduce<T, VKJIT_RED_MAX>(in, n, out, sc, sm_count, s, mb); break;    \
     default: fail(VKJIT_ERR_INVALID, "unknown reduction");                                      \
   }
   switch (ty) {
@@ -194,6 +241,26 @@ void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scr
 #undef VK_DISPATCH
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(e));
+}
+
+void p2p_allreduce(int red, uint32_t ty, void* out, const Mailbox& mb, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+#define VK_P2P(T)                                                                                             \
+  switch (red) {                                                                                              \
+    case VKJIT_RED_SUM: p2p_allreduce_kernel<T, VKJIT_RED_SUM><<<1, 32, 0, s>>>((uint32_t*)out, mb); break;   \
+    case VKJIT_RED_MIN: p2p_allreduce_kernel<T, VKJIT_RED_MIN><<<1, 32, 0, s>>>((uint32_t*)out, mb); break;   \
+    case VKJIT_RED_MAX: p2p_allreduce_kernel<T, VKJIT_RED_MAX><<<1, 32, 0, s>>>((uint32_t*)out, mb); break;   \
+    default: fail(VKJIT_ERR_INVALID, "unknown reduction");                                                    \
+  }
+  switch (ty) {
+    case VKJIT_TY_U32: VK_P2P(uint32_t) break;
+    case VKJIT_TY_I32: VK_P2P(int32_t) break;
+    case VKJIT_TY_F32: VK_P2P(float) break;
+    default: fail(VKJIT_ERR_TYPE, "reduce needs U32/I32/F32");
+  }
+#undef VK_P2P
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("p2p all-reduce launch: ") + cudaGetErrorString(e));
 }
 
 // ---------------------------------------------------------------------------------------

@@ -15,6 +15,20 @@ struct Scratch {
   size_t tile_state_words = 0;
 };
 
+// Peer-memory mailbox for the fused reduce + all-reduce (one process per GPU, NVLink P2P).
+// Every GPU owns kMailSlots x kMailRanks 64-bit words {seq:32 | value:32}; rank r publishes its
+// partial of collective number `seq` into word [seq % kMailSlots][r] of EVERY GPU's mailbox with
+// one system-scope store per peer, then combines the `world` words of its own mailbox in rank
+// order (deterministic, identical on every rank).  Value and sequence number travel in one
+// 64-bit store, so no fence is needed.
+constexpr int kMailSlots = 64;
+constexpr int kMailRanks = 8;
+struct Mailbox {
+  uint64_t* peer[kMailRanks];  // mailbox base of every rank (peer[rank] is the local one)
+  int rank = 0, world = 1;
+  uint32_t seq = 0;            // >= 1; identical on all ranks for the same collective
+};
+
 constexpr int kReduceThreads = 512;
 constexpr int kReduceMaxCtas = 2048;
 constexpr int kScanThreads = 1024;
@@ -28,7 +42,10 @@ size_t scan_state_words(size_t n);
 // vectorised grid-stride partials -> warp shuffle -> shared-memory tree -> last CTA folds the
 // per-CTA partials in a fixed order (deterministic for a given n and grid).
 // `mailbox` (optional): the last CTA additionally stores the result there (peer-mapped slot).
-void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream);
+void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream,
+            const Mailbox* mailbox = nullptr);
+// Stand-alone exchange: out[0] = combine over ranks of out[0] (used when a rank's shard is empty).
+void p2p_allreduce(int red, uint32_t ty, void* out, const Mailbox& mailbox, void* stream);
 
 // Single-pass decoupled look-back prefix sum (mod 2^32) over u32 words.
 void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream);

@@ -42,14 +42,36 @@ def native_unique_id() -> bytes:
     return bytes(host)
 
 
-def init_from_torch(device=None):
+def init_from_torch(device=None, p2p: bool = True):
     """Call after torch.distributed.init_process_group and vkjit_b200.init(local_rank)."""
     import torch.distributed as td
     rank, world = td.get_rank(), td.get_world_size()
     raw = exchange_unique_id(native_unique_id, rank, device) if world > 1 else bytes(UNIQUE_ID_BYTES)
     product_api().call("dist_init", rank, world, C.create_string_buffer(raw, UNIQUE_ID_BYTES))
+    if world > 1 and p2p:
+        open_mailboxes(rank, world, device)
     return rank, world
+
+
+def open_mailboxes(rank: int, world: int, device=None):
+    """Exchange the cudaIpc handles of the per-GPU mailboxes (64 bytes each) and map them, which
+    switches sharded reductions to the fused reduce + all-reduce kernel over NVLink peer memory."""
+    import torch
+    import torch.distributed as td
+    api = product_api()
+    mine = (C.c_uint8 * 64)()
+    api.call("dist_mailbox_handle", mine)
+    t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=device or "cpu")
+    allh = [torch.zeros(64, dtype=torch.uint8, device=device or "cpu") for _ in range(world)]
+    td.all_gather(allh, t)
+    raw = b"".join(bytes(h.cpu().tolist()) for h in allh)
+    api.call("dist_mailbox_open", C.create_string_buffer(raw, 64 * world), world)
 
 
 def shutdown():
     product_api().call("dist_shutdown")
+
+
+def set_p2p(on: bool):
+    """Fused mailbox all-reduce (True) or NCCL (False); every rank must make the same call."""
+    product_api().call("dist_set_p2p", 1 if on else 0)
