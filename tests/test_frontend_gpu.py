@@ -1,0 +1,99 @@
+"""The vkjit Python front-end mirror (`vkjit_b200.vkjit`: Var, eval, var, ir, linspace) on the CUDA path,
+and the Monte-Carlo mega-trace (BASELINE configs[4]) against the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+@pytest.fixture()
+def vkjit(cuda_backend):
+    from vkjit_b200 import vkjit as m
+    return m
+
+
+def test_reference_python_surface(vkjit):
+    """libs/vkjit-python/src/lib.rs:18-26 — Var, eval, var, ir, linspace; lazy __str__ (types.rs:148-154)."""
+    x = vkjit.linspace(2.0, 4.0, 4)
+    assert "Bop" in repr(x)                      # not evaluated yet: Debug of the node (types.rs:140-147)
+    assert str(x) == "[2.0, 2.5, 3.0, 3.5]"      # __str__ evaluates on demand
+    assert repr(x) == "array(dtype = F32, [2.0, 2.5, 3.0, 3.5])"
+    assert x.tolist() == [2.0, 2.5, 3.0, 3.5]
+    a = vkjit.Var([1.0, 2.0, 3.0])
+    b = vkjit.var(1.0, 1.0, 1.0)                 # several args form one sequence (functions.rs:25-34)
+    c = a + b
+    d = (a - 1.0) * b / 2.0
+    vkjit.eval([c, d])                           # eval([...]) works (the reference calls an unexported .id())
+    assert c.tolist() == [2.0, 3.0, 4.0] and d.tolist() == [0.0, 0.5, 1.0]
+    assert "Var {" in vkjit.ir()
+    with pytest.raises(TypeError):
+        vkjit.Var("nope")                        # "Not a valid argument!" (types.rs:81)
+    with pytest.raises(AssertionError):
+        vkjit.linspace(1, 2.0, 3)                # functions.rs:46 assert_eq!(start.ty(), stop.ty())
+
+
+def test_coercion_order(vkjit):
+    """types.rs:50-81: Var, u32, i32, f32, bool, [u32], [i32], [f32]"""
+    from vkjit_b200 import VarType as T
+    assert vkjit.var(3).ty() == T.U32 and vkjit.var(-3).ty() == T.I32 and vkjit.var(2.0).ty() == T.F32
+    assert vkjit.var(True).ty() == T.U32         # a Python bool extracts as u32 first
+    assert vkjit.var([1, 2]).ty() == T.U32 and vkjit.var([1, -2]).ty() == T.I32 and vkjit.var([1.0, 2]).ty() == T.F32
+    z = vkjit.var([1, 2]) + (-1)                 # autocast U32 + I32 -> I32 (test.rs:176-187)
+    assert z.ty() == T.I32 and z.tolist() == [0, 1]
+
+
+def test_var_lifetime_releases_device_memory(vkjit, cuda_backend):
+    """Clone/Drop own one reference each (types.rs:87-98): dropping the last handle frees the array."""
+    import gc
+    gc.collect()
+    base = cuda_backend.stats()["pool_bytes_live"]
+    x = vkjit.Var(np.ones(1 << 20, np.float32))
+    y = x * 2.0
+    vkjit.eval([y])
+    assert cuda_backend.stats()["pool_bytes_live"] >= base + 2 * (4 << 20)
+    del x, y
+    gc.collect()
+    assert cuda_backend.stats()["pool_bytes_live"] == base
+
+
+def test_frontend_extensions(vkjit):
+    from vkjit_b200 import VarType as T
+    i = vkjit.arange(T.U32, 1000)
+    m = (i & 1).eq(0)
+    idx, cnt = m.compress()
+    assert cnt == 500 and idx.tolist()[:3] == [0, 2, 4]
+    assert i.sum().tolist() == [499500] and i.max().tolist() == [999]
+    assert i.prefix_sum().tolist()[:4] == [0, 0, 1, 3]
+    bins = vkjit.Var(np.zeros(10, np.uint32))
+    one = vkjit.var(1)
+    one.scatter_add(bins, i / 100)
+    vkjit.eval([one])
+    assert bins.tolist() == [100] * 10
+    t = vkjit.select(i < 3, i.cast(T.F32), -1.0)
+    assert t.tolist()[:5] == [0.0, 1.0, 2.0, -1.0, -1.0]
+
+
+def test_monte_carlo_mega_trace_matches_oracle(vkjit, oir, cuda_backend):
+    """~215-op trace, PCG + Box-Muller + exp + masked select.  Integer RNG state is bit-exact; the f32
+    result accumulates 2-ulp transcendental differences -> relative tolerance 2e-5 (parity unpinned)."""
+    import monte_carlo
+    from ir_adapter import IrModule
+    n, rounds = 1 << 14, 5
+    y = monte_carlo.build(vkjit, n, rounds)
+    got = y.numpy()
+    om = IrModule(oir)
+    yo = monte_carlo.build(om, n, rounds)
+    oir.eval([yo.id])
+    exp = oir.as_slice(yo.id, 5)
+    assert got.shape == exp.shape and np.isfinite(got).all()
+    assert np.allclose(got, exp, rtol=2e-5, atol=1e-5), float(np.abs(got - exp).max())
+    # cached: building the same program again must not recompile
+    cuda_backend.stats_reset()
+    y2 = monte_carlo.build(vkjit, n, rounds)
+    vkjit.eval([y2])
+    st = cuda_backend.stats()
+    assert st["cache_hits"] == 1 and st["cache_misses"] == 0

@@ -60,6 +60,8 @@ void type_signature(const Ir& ir, TypeId t, std::vector<uint32_t>& key) {
   for (TypeId x : e) type_signature(ir, x, key);
 }
 
+constexpr size_t kMaxVectorNodes = 96;
+
 int g_unroll = -1;
 int unroll_factor() {
   if (g_unroll < 0) {
@@ -164,6 +166,12 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
     }
     p.roots.push_back(ir.vars[root].local);
   }
+
+  // ALU-heavy traces (config 5: ~200 ops/lane) are bound by SM issue rate, not by HBM: 128-bit
+  // accesses buy nothing there, while inlining the body 4x (+ unrolling) multiplies NVRTC time
+  // and I-cache footprint (measured: 3.1 s / 789 KB cubin vs 0.4 s).  They get the one-copy variant.
+  if (p.order.size() > kMaxVectorNodes) p.vectorized = false;
+  vectorized = p.vectorized;
 
   if (!p.have_n) fail(VKJIT_ERR_SIZE, "schedule has no Binding/Arange: kernel size unknown (internal.rs:1202 num.unwrap())");
   if (p.n > 0xFFFFFFFFull) fail(VKJIT_ERR_SIZE, "kernel size exceeds the 32-bit invocation index");
