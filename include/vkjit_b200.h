@@ -207,7 +207,9 @@ vkjit_status vkjit_read(vkjit_ir* ir, vkjit_var id, vkjit_type ty, void* dst, si
 /* ------------------------------------------------------------------ */
 /* Runtime primitives (extensions; hand-written CUDA).   */
 /* ------------------------------------------------------------------ */
-/* reduce_{sum,min,max}: evaluates `id` if needed, returns a 1-element Binding
+/* reduce_{sum,min,max}: returns a 1-element Binding of the same type.  A buffer operand runs the
+ * hand-written reduction; an UNEVALUATED operand is reduced by one generated kernel that fuses the
+ * trace with the reduction (the operand is not materialised and stays unevaluated).  Returns a 1-element Binding
  * of the same type.  With vkjit_dist_init active and a sharded operand the
  * per-GPU partial is combined across ranks (result replicated). */
 vkjit_status vkjit_reduce(vkjit_ir* ir, int32_t red, vkjit_var id, vkjit_var* out);
@@ -274,6 +276,9 @@ vkjit_status vkjit_cache_clear(void);
  * verdict; out_cubin_bytes receives the cubin size (0 if not compiled). */
 vkjit_status vkjit_debug_codegen(vkjit_ir* ir, const vkjit_var* ids, size_t n, int32_t compile,
                                  char* buf, size_t cap, size_t* out_len, size_t* out_cubin_bytes);
+/* Same for the fused trace -> reduce kernel of vkjit_reduce(red, id). */
+vkjit_status vkjit_debug_codegen_reduce(vkjit_ir* ir, vkjit_var id, int32_t red, int32_t compile,
+                                        char* buf, size_t cap, size_t* out_len, size_t* out_cubin_bytes);
 
 #ifdef __cplusplus
 }

@@ -687,29 +687,37 @@ static void record_kernel_size(Ir& ir, const std::vector<VarId>& schedule, bool&
   }
 }
 
+// Compile + execute of internal.rs:487-490: evaluates `sched` lane by lane, returns one output per entry.
+static std::vector<std::shared_ptr<Words>> run_schedule(Ir& ir, const std::vector<VarId>& sched) {
+  Plan P; P.ir = &ir;
+  bool have = false; size_t n = 0;
+  record_kernel_size(ir, sched, have, n);
+  if (!have) throw Error(E_SIZE, "schedule has no Binding/Arange: kernel size unknown (internal.rs:1202 num.unwrap())");
+  if (n == 0) throw Error(E_SIZE, "zero-sized kernel");
+  if (n > 0xFFFFFFFFull) throw Error(E_SIZE, "kernel size exceeds the 32-bit invocation index");
+  P.n = n;
+  for (VarId id : sched) {
+    const VarType& t = ir.var(id).ty;
+    stride_of(t);  // Struct roots: unimplemented!()
+    if (!t.scalar()) throw Error(E_UNSUPPORTED, "cannot schedule a Void var");
+  }
+  for (VarId id : sched) P.visit(id);
+  // internal.rs:1192-1205: one fresh output per scheduled var (duplicates included)
+  for (VarId id : sched) P.outputs.emplace_back(id, std::make_shared<Words>(n));
+  parallel_for(n, 1 << 16, [&](size_t lo, size_t hi, int) {
+    Lanes L; L.buf.resize((size_t)std::max(1, P.nslots) * BLK);
+    for (size_t b = lo; b < hi; b += BLK) run_block(P, L, b, std::min(hi, b + BLK));
+  });
+  std::vector<std::shared_ptr<Words>> outs;
+  for (auto& o : P.outputs) outs.push_back(o.second);
+  return outs;
+}
+
 // internal.rs:482-525
 void Ir::eval(const VarId* ids, size_t nids) {
   do_schedule(ids, nids);
   try {
-    Plan P; P.ir = this;
-    bool have = false; size_t n = 0;
-    record_kernel_size(*this, schedule, have, n);
-    if (!have) throw Error(E_SIZE, "schedule has no Binding/Arange: kernel size unknown (internal.rs:1202 num.unwrap())");
-    if (n == 0) throw Error(E_SIZE, "zero-sized kernel");
-    if (n > 0xFFFFFFFFull) throw Error(E_SIZE, "kernel size exceeds the 32-bit invocation index");
-    P.n = n;
-    for (VarId id : schedule) {
-      const VarType& t = var(id).ty;
-      stride_of(t);  // Struct roots: unimplemented!()
-      if (!t.scalar()) throw Error(E_UNSUPPORTED, "cannot schedule a Void var");
-    }
-    for (VarId id : schedule) P.visit(id);
-    // internal.rs:1192-1205: one fresh output per scheduled var (duplicates included)
-    for (VarId id : schedule) P.outputs.emplace_back(id, std::make_shared<Words>(n));
-    parallel_for(n, 1 << 16, [&](size_t lo, size_t hi, int) {
-      Lanes L; L.buf.resize((size_t)std::max(1, P.nslots) * BLK);
-      for (size_t b = lo; b < hi; b += BLK) run_block(P, L, b, std::min(hi, b + BLK));
-    });
+    std::vector<std::shared_ptr<Words>> outs = run_schedule(*this, schedule);
     // internal.rs:492-503
     std::vector<VarId> sched = schedule;
     for (VarId id : sched) {
@@ -722,7 +730,7 @@ void Ir::eval(const VarId* ids, size_t nids) {
       Var& v = var(sched[i]);
       Var nv; nv.op = OP_BINDING; nv.ty = v.ty; nv.ref_count = v.ref_count;
       v = nv;
-      arrays[sched[i]] = P.outputs[i].second;
+      arrays[sched[i]] = outs[i];
     }
   } catch (...) {
     // the reference panics here; leave the Ir usable: undo the schedule
@@ -741,8 +749,10 @@ static VarId reduce(Ir& ir, int red, VarId id) {
   const VarType ty = ir.var(id).ty;
   if (ty.k != K_U32 && ty.k != K_I32 && ty.k != K_F32) throw Error(E_TYPE, "reduce needs U32/I32/F32");
   if (red < 0 || red > 2) throw Error(E_INVALID, "unknown reduction");
-  ensure_buffer(ir, id);
-  const Words& w = *ir.arrays.at(id);
+  // SPEC: reducing an unevaluated var evaluates it on the fly and does NOT turn it into a buffer
+  // (the device fuses the trace with the reduction instead of materialising the operand)
+  std::shared_ptr<Words> held = ir.is_buffer(id) ? ir.arrays.at(id) : run_schedule(ir, std::vector<VarId>{id})[0];
+  const Words& w = *held;
   const size_t n = w.size();
   if (n == 0) throw Error(E_SIZE, "reduce of an empty array");
   int T = std::max(1, g_threads);

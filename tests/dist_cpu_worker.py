@@ -47,6 +47,7 @@ def main():
     api.call("arange_shard", ir._h, T.U32, n, rank, world, C.byref(out))
     x = trace(ir, out.value)
     part = {r: int(ir.as_slice(ir.reduce(r, x), T.U32)[0]) for r in (Red.Sum, Red.Min, Red.Max)}
+    ir.eval([x])
     assert ir.size(x) == hi - lo
     ts = torch.tensor([part[Red.Sum]], dtype=torch.int64); td.all_reduce(ts, op=td.ReduceOp.SUM)
     tmin = torch.tensor([part[Red.Min]], dtype=torch.int64); td.all_reduce(tmin, op=td.ReduceOp.MIN)
@@ -57,6 +58,7 @@ def main():
     assert int(ts.item()) % (1 << 32) == exp[Red.Sum], (int(ts.item()), exp)
     assert int(tmin.item()) == exp[Red.Min] and int(tmax.item()) == exp[Red.Max]
     # the shard holds exactly the global lanes [lo, hi)
+    full.eval([xf])
     assert np.array_equal(ir.as_slice(x, T.U32), full.as_slice(xf, T.U32)[lo:hi])
     td.barrier()
     td.destroy_process_group()

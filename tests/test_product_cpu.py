@@ -152,6 +152,15 @@ def test_struct_select_gather_scatter_codegen():
         ir.debug_codegen([sel])                            # struct roots: stride() unimplemented!()
 
 
+@pytest.mark.parametrize("red", [0, 1, 2])
+def test_fused_reduce_kernel_compiles_for_sm100a(red):
+    ir = Ir()
+    i = ir.arange(U32, 4096)
+    for v in (ir.mul(i, ir.const_u32(3)), ir.bitcast(i, I32), ir.mul(ir.cast(i, F32), ir.const_f32(0.5))):
+        src, cubin = ir.debug_codegen_reduce(v, red, compile=True)
+        assert cubin > 1000 and "vk_finish" in src and "o0[" not in src.split("vk_finish(VK_APPLY")[0].split("extern")[1]
+
+
 def test_trace_hash_is_address_and_size_free():
     """Two structurally identical traces of different n give the same kernel source (key)."""
     srcs = []

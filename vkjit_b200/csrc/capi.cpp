@@ -244,22 +244,28 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
       empty = p.n == 0;
     }
     if (empty && !combine) fail(VKJIT_ERR_SIZE, "reduce of an empty array");
-    Array* o = be.new_array(4);
+    const bool p2p = combine && dist::p2p_enabled();
+    prims::Mailbox mb;
+    if (p2p) mb = dist::next_mailbox();
+    Array* o = nullptr;
     try {
-      const bool fused = combine && dist::p2p_enabled();
-      prims::Mailbox mb;
-      if (fused) mb = dist::next_mailbox();
       if (empty) {
+        o = be.new_array(4);
         prims::fill_u32((uint32_t*)o->ptr, reduce_identity(red, ty), 1, be.stream);
-        if (fused) prims::p2p_allreduce(red, ty, o->ptr, mb, be.stream);
+        if (p2p) prims::p2p_allreduce(red, ty, o->ptr, mb, be.stream);
+      } else if (!ir.is_buffer(id)) {
+        // unevaluated operand: ONE generated kernel evaluates the trace and reduces it; the operand
+        // is not materialised and stays unevaluated
+        o = eval_reduce(ir, id, red);
+        if (p2p) prims::p2p_allreduce(red, ty, o->ptr, mb, be.stream);
       } else {
-        ensure_buffer(ir, id);
+        o = be.new_array(4);
         const Var& v = ir.var(id);
-        // fused: the last CTA of the reduction exchanges the per-GPU partial over NVLink peer memory
-        prims::reduce(red, ty, v.array->ptr, v.array->bytes / 4, o->ptr, be.scratch, be.sm_count, be.stream, fused ? &mb : nullptr);
+        // p2p: the last CTA of the reduction exchanges the per-GPU partial over NVLink peer memory
+        prims::reduce(red, ty, v.array->ptr, v.array->bytes / 4, o->ptr, be.scratch, be.sm_count, be.stream, p2p ? &mb : nullptr);
       }
       Backend::counters().prim_launches += 1;
-      if (combine && !fused) dist::allreduce(o->ptr, ty, red, 1);  // NCCL: per-GPU partial -> replicated result
+      if (combine && !p2p) dist::allreduce(o->ptr, ty, red, 1);  // NCCL: per-GPU partial -> replicated result
     } catch (...) { release_array(o); throw; }
     *out = ir.binding(ty, o, false);
   });
@@ -393,6 +399,26 @@ vkjit_status vkjit_debug_codegen(vkjit_ir* h, const vkjit_var* ids, size_t n, in
     }
     Program p;
     build_program(ir, sched, true, p);
+    const std::string src = generate_cuda(ir, p);
+    if (out_cubin) *out_cubin = 0;
+    if (compile) {
+      std::vector<char> cubin;
+      std::string log;
+      if (!nvrtc_compile(src, cubin, log)) fail(VKJIT_ERR_COMPILE, "NVRTC rejected the generated kernel:\n" + log + "\n--- source ---\n" + src);
+      if (out_cubin) *out_cubin = cubin.size();
+    }
+    copy_out(src, buf, cap, out_len);
+  });
+}
+
+vkjit_status vkjit_debug_codegen_reduce(vkjit_ir* h, vkjit_var id, int32_t red, int32_t compile, char* buf, size_t cap,
+                                        size_t* out_len, size_t* out_cubin) {
+  return with_ir(h, [&](Ir& ir) {
+    if (!ty_is_num(ir.var(id).ty)) fail(VKJIT_ERR_TYPE, "reduce needs U32/I32/F32");
+    if (red < VKJIT_RED_SUM || red > VKJIT_RED_MAX) fail(VKJIT_ERR_INVALID, "unknown reduction");
+    Program p;
+    std::vector<VarId> roots{id};
+    build_program(ir, roots, true, p, red);
     const std::string src = generate_cuda(ir, p);
     if (out_cubin) *out_cubin = 0;
     if (compile) {

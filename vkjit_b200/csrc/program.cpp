@@ -10,7 +10,7 @@ namespace vkjit {
 
 void Program::clear() {
   key.clear(); order.clear(); params.clear(); roots.clear();
-  n = 0; have_n = false; base = 0; have_base = false; sharded = false; vectorized = true;
+  n = 0; have_n = false; base = 0; have_base = false; sharded = false; vectorized = true; reduce = -1;
   hash = Hash128();
 }
 
@@ -73,9 +73,10 @@ int unroll_factor() {
 
 }  // namespace
 
-void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p) {
+void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce) {
   p.clear();
   p.vectorized = vectorized;
+  p.reduce = reduce;
   const uint32_t stamp = ir.next_stamp();
   static thread_local std::vector<Frame> stack;
   stack.clear();
@@ -180,7 +181,7 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   // canonical key: structure only — no VarIds, no addresses, no n
   std::vector<uint32_t>& key = p.key;
   key.push_back(0x564B4A31u);  // "VKJ1"
-  key.push_back((vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8));
+  key.push_back((vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16));
   for (uint32_t li = 0; li < p.order.size(); ++li) {
     const Var& v = ir.vars[p.order[li]];
     const uint32_t tycode = ty_is_struct(v.ty) ? 0xFu : v.ty;
@@ -417,7 +418,80 @@ struct Gen {
 
 }  // namespace
 
+namespace {
+
+// Reduction epilogue for fused trace -> reduce kernels (hand-written; prepended to the generated
+// source).  Same structure as prims.cu: warp shuffle -> shared-memory tree -> one partial per CTA ->
+// the last CTA to take a ticket folds the partials in a fixed order and resets the ticket.
+const char* kReduceEpilogue = R"CUDA(
+__device__ __forceinline__ acc_t vk_warp_reduce(acc_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = VK_APPLY(v, VK_FROM_WORD(__shfl_xor_sync(0xFFFFFFFFu, VK_TO_WORD(v), o)));
+  return v;
+}
+__device__ __forceinline__ acc_t vk_block_reduce(acc_t v, acc_t* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = vk_warp_reduce(v);
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    acc_t w = lane < (int)(blockDim.x >> 5) ? smem[lane] : VK_IDENTITY;
+    w = vk_warp_reduce(w);
+    if (lane == 0) smem[0] = w;
+  }
+  __syncthreads();
+  acc_t r = smem[0];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ void vk_finish(acc_t acc, u32* partials, unsigned int* ticket, u32* out) {
+  __shared__ acc_t smem[32];
+  __shared__ bool is_last;
+  acc = vk_block_reduce(acc, smem);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = VK_TO_WORD(acc);
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    acc_t f = VK_IDENTITY;
+    for (u32 i = threadIdx.x; i < gridDim.x; i += blockDim.x) f = VK_APPLY(f, VK_FROM_WORD(__ldcg(partials + i)));
+    f = vk_block_reduce(f, smem);
+    if (threadIdx.x == 0) { out[0] = VK_TO_WORD(f); *ticket = 0u; }
+  }
+}
+)CUDA";
+
+std::string reduce_defines(int red, TypeId ty) {
+  std::string d = std::string("typedef ") + ctype(ty) + " acc_t;\n";
+  d += "#define VK_FROM_WORD(w) (" + from_word(ty, "(w)") + ")\n";
+  d += "#define VK_TO_WORD(v) (" + to_word(ty, "(v)") + ")\n";
+  const bool f = ty == VKJIT_TY_F32, s = ty == VKJIT_TY_I32;
+  std::string apply, ident;
+  switch (red) {
+    case VKJIT_RED_SUM:
+      apply = f ? "__fadd_rn((a), (b))" : s ? "(i32)((u32)(a) + (u32)(b))" : "((a) + (b))";
+      ident = f ? "0.0f" : s ? "0" : "0u";
+      break;
+    case VKJIT_RED_MIN:
+      apply = f ? "fminf((a), (b))" : "min((a), (b))";
+      ident = f ? "__uint_as_float(0x7fc00000u)" : s ? "(i32)0x7fffffffu" : "0xffffffffu";
+      break;
+    default:
+      apply = f ? "fmaxf((a), (b))" : "max((a), (b))";
+      ident = f ? "__uint_as_float(0x7fc00000u)" : s ? "(i32)0x80000000u" : "0u";
+      break;
+  }
+  d += "#define VK_APPLY(a, b) (" + apply + ")\n#define VK_IDENTITY (" + ident + ")\n";
+  return d;
+}
+
+}  // namespace
+
 std::string generate_cuda(const Ir& ir, const Program& p) {
+  const bool reduce = p.reduce >= 0;
   Gen g(ir, p);
   for (uint32_t li = 0; li < p.order.size(); ++li) g.emit_node(li);
   for (size_t r = 0; r < p.roots.size(); ++r) {
@@ -435,6 +509,10 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   std::string s;
   s += "// vkjit-b200 fused trace kernel; key " + std::to_string(p.hash.lo) + ":" + std::to_string(p.hash.hi) + "\n";
   s += "typedef unsigned int u32;\ntypedef int i32;\ntypedef float f32;\n\n";
+  if (reduce) {
+    if (nroots != 1) fail(VKJIT_ERR_INVALID, "a fused reduction has exactly one root");
+    s += reduce_defines(p.reduce, g.vals[p.roots[0]].ty) + kReduceEpilogue + "\n";
+  }
 
   // per-lane body
   s += "__device__ __forceinline__ void vk_lane(const u32 gi, const u32 li";
@@ -459,8 +537,10 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
     const bool w = p.params[k].use & USE_SCATTER;
     s += std::string(",\n    ") + (w ? "u32* " : "const u32* __restrict__ ") + "p" + std::to_string(k);
   }
-  for (size_t r = 0; r < nroots; ++r) s += ",\n    u32* __restrict__ o" + std::to_string(r);
+  if (reduce) s += ",\n    u32* __restrict__ partials, unsigned int* __restrict__ ticket, u32* __restrict__ o0";
+  else for (size_t r = 0; r < nroots; ++r) s += ",\n    u32* __restrict__ o" + std::to_string(r);
   s += ") {\n";
+  if (reduce) s += "  acc_t c0 = VK_IDENTITY, c1 = VK_IDENTITY, c2 = VK_IDENTITY, c3 = VK_IDENTITY;\n";
   s += "  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;\n";
   s += "  const u32 nthreads = gridDim.x * blockDim.x;\n";
   if (p.vectorized) {
@@ -475,8 +555,12 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
     const char* comps[4] = {"x", "y", "z", "w"};
     for (int j = 0; j < 4; ++j)
       s += "    " + call("base + l0 + " + std::to_string(j) + "u", "l0 + " + std::to_string(j) + "u", comps[j], true) + "\n";
-    for (size_t r = 0; r < nroots; ++r)
-      s += "    reinterpret_cast<uint4*>(o" + std::to_string(r) + ")[v] = r" + std::to_string(r) + ";\n";
+    if (reduce)
+      s += "    c0 = VK_APPLY(c0, VK_FROM_WORD(r0.x)); c1 = VK_APPLY(c1, VK_FROM_WORD(r0.y));\n"
+           "    c2 = VK_APPLY(c2, VK_FROM_WORD(r0.z)); c3 = VK_APPLY(c3, VK_FROM_WORD(r0.w));\n";
+    else
+      for (size_t r = 0; r < nroots; ++r)
+        s += "    reinterpret_cast<uint4*>(o" + std::to_string(r) + ")[v] = r" + std::to_string(r) + ";\n";
     s += "  }\n";
     s += "  for (unsigned long long i = (unsigned long long)(nvec << 2) + tid; i < n; i += nthreads) {\n";
   } else {
@@ -485,8 +569,11 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   for (uint32_t k : streams) s += "    const u32 a" + std::to_string(k) + " = p" + std::to_string(k) + "[i];\n";
   for (size_t r = 0; r < nroots; ++r) s += "    u32 r" + std::to_string(r) + ";\n";
   s += "    " + call("base + (u32)i", "(u32)i", "", false) + "\n";
-  for (size_t r = 0; r < nroots; ++r) s += "    o" + std::to_string(r) + "[i] = r" + std::to_string(r) + ";\n";
-  s += "  }\n}\n";
+  if (reduce) s += "    c0 = VK_APPLY(c0, VK_FROM_WORD(r0));\n";
+  else for (size_t r = 0; r < nroots; ++r) s += "    o" + std::to_string(r) + "[i] = r" + std::to_string(r) + ";\n";
+  s += "  }\n";
+  if (reduce) s += "  vk_finish(VK_APPLY(VK_APPLY(c0, c1), VK_APPLY(c2, c3)), partials, ticket, o0);\n";
+  s += "}\n";
   return s;
 }
 

@@ -39,6 +39,7 @@ struct Program {
   bool have_base = false;
   bool sharded = false;
   bool vectorized = true;       // 128-bit ld/st variant
+  int reduce = -1;              // >= 0: fused trace -> reduce kernel (VKJIT_RED_*), the single root is not stored
   Hash128 hash;
 
   void clear();
@@ -47,7 +48,7 @@ struct Program {
 // Walks the schedule, fills `p` (key, order, params, n) and hashes it.  Throws Error on the
 // reference's panics: size mismatch (internal.rs:699-702), size-less schedule (:1202),
 // gather from a non-buffer (:1054), scatter into a non-buffer (:1059-1062), struct roots.
-void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p);
+void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce = -1);
 
 // CUDA C source of the kernel for `p` (entry point "vkjit_trace").
 std::string generate_cuda(const Ir& ir, const Program& p);

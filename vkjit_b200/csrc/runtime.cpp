@@ -332,4 +332,41 @@ void eval(Ir& ir, const VarId* ids, size_t n) {
   g_counters.last_eval_ns = now_ns() - t0;
 }
 
+
+// Fused trace -> reduce: evaluates the unevaluated var `id` lane by lane and reduces it in the same
+// kernel (8 B/lane for sum(x*y+c) instead of 16 B/lane when z is materialised first).  `id` stays
+// unevaluated; the result is a fresh 1-element array holding this GPU's value.
+Array* eval_reduce(Ir& ir, VarId id, int red) {
+  Backend& be = Backend::get();
+  static thread_local Program prog;
+  static thread_local std::vector<void*> argv;
+  static thread_local std::vector<uint64_t> ptrs;
+  std::vector<VarId> roots{id};
+  build_program(ir, roots, true, prog, red);
+  if (prog.n == 0) fail(VKJIT_ERR_SIZE, "reduce of an empty array");
+  bool aligned = true;
+  for (const Param& pr : prog.params)
+    if ((pr.use & USE_STREAM) && ((uintptr_t)ir.vars[pr.var].array->ptr & 15u)) aligned = false;
+  if (!aligned) build_program(ir, roots, false, prog, red);
+  CachedKernel* k = be.lookup(prog);
+  if (!k) k = be.compile(ir, prog);
+  Array* out = be.new_array(4);
+  uint32_t n32 = (uint32_t)prog.n, base32 = (uint32_t)prog.base;
+  ptrs.clear(); argv.clear();
+  for (const Param& pr : prog.params) ptrs.push_back((uint64_t)(uintptr_t)ir.vars[pr.var].array->ptr);
+  ptrs.push_back((uint64_t)(uintptr_t)be.scratch.partials);
+  ptrs.push_back((uint64_t)(uintptr_t)be.scratch.ticket);
+  ptrs.push_back((uint64_t)(uintptr_t)out->ptr);
+  argv.push_back(&n32); argv.push_back(&base32);
+  for (uint64_t& p : ptrs) argv.push_back(&p);
+  const uint64_t items = prog.vectorized ? std::max<uint64_t>(prog.n >> 2, 1) : prog.n;
+  uint64_t grid = (items + 255) / 256;
+  const uint64_t cap = std::min<uint64_t>((uint64_t)be.sm_count * 8, prims::kReduceMaxCtas);
+  if (grid > cap) grid = cap;
+  try {
+    be.launch(k, (uint32_t)grid, 256, argv.data());
+  } catch (...) { release_array(out); throw; }
+  return out;
+}
+
 }  // namespace vkjit

@@ -78,4 +78,7 @@ class Backend {
 // Evaluate the Ir's schedule (+ ids): the body of Ir::eval (internal.rs:482-525).
 void eval(Ir& ir, const VarId* ids, size_t n);
 
+// Fused trace -> reduce kernel for an unevaluated var (see runtime.cpp).
+Array* eval_reduce(Ir& ir, VarId id, int red);
+
 }  // namespace vkjit

@@ -300,6 +300,17 @@ class Ir:
         return buf.value.decode(), cub.value
 
 
+def _debug_codegen_reduce(self, id: int, red: int, compile: bool = False):
+    n, cub = C.c_size_t(), C.c_size_t()
+    self.api.call("debug_codegen_reduce", self._h, id, red, 0, None, 0, C.byref(n), C.byref(cub))
+    buf = C.create_string_buffer(n.value + 1)
+    self.api.call("debug_codegen_reduce", self._h, id, red, 1 if compile else 0, buf, n.value + 1, C.byref(n), C.byref(cub))
+    return buf.value.decode(), cub.value
+
+
+Ir.debug_codegen_reduce = _debug_codegen_reduce
+
+
 # convenience: named binary ops exactly as the reference's bop! expansion (internal.rs:218-227)
 def _mk(kind):
     def f(self, lhs: int, rhs: int) -> int:
