@@ -46,6 +46,7 @@ bool g_active = false;
 // peer mailboxes
 uint64_t* g_mail_local = nullptr;
 uint64_t* g_mail_peer[prims::kMailRanks] = {};
+uint64_t** g_mail_table = nullptr;  // device copy of g_mail_peer
 bool g_p2p = false;
 uint32_t g_seq = 0;
 
@@ -109,6 +110,13 @@ void mailbox_open(const void* handles, int world) {
     if (e != cudaSuccess) fail(VKJIT_ERR_DIST, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
     g_mail_peer[r] = (uint64_t*)p;
   }
+  if (!g_mail_table) {
+    void* t = nullptr;
+    if (cudaMalloc(&t, sizeof(g_mail_peer)) != cudaSuccess) fail(VKJIT_ERR_CUDA, "mailbox table allocation failed");
+    g_mail_table = (uint64_t**)t;
+  }
+  if (cudaMemcpy(g_mail_table, g_mail_peer, sizeof(g_mail_peer), cudaMemcpyHostToDevice) != cudaSuccess)
+    fail(VKJIT_ERR_CUDA, "mailbox table upload failed");
   const char* force = getenv("VKJIT_DIST");
   g_p2p = !(force && std::string(force) == "nccl");
   g_seq = 0;
@@ -124,7 +132,7 @@ void set_p2p(bool on) {
 
 prims::Mailbox next_mailbox() {
   prims::Mailbox mb;
-  for (int r = 0; r < prims::kMailRanks; ++r) mb.peer[r] = g_mail_peer[r];
+  mb.peers = g_mail_table; mb.local = g_mail_local;
   mb.rank = g_rank; mb.world = g_world;
   mb.seq = ++g_seq;
   if (g_seq == 0xFFFFFFFFu) g_seq = 0;
@@ -140,6 +148,7 @@ void shutdown() {
       g_mail_peer[r] = nullptr;
     }
     if (g_mail_local) { cudaFree(g_mail_local); g_mail_local = nullptr; }
+    if (g_mail_table) { cudaFree(g_mail_table); g_mail_table = nullptr; }
     g_p2p = false; g_seq = 0;
   }
   if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }

@@ -122,8 +122,8 @@ template <typename T, int RED>
 __device__ __forceinline__ T mailbox_allreduce(T mine, const Mailbox& mb) {
   const size_t slot = (size_t)(mb.seq % kMailSlots) * kMailRanks;
   const uint64_t word = ((uint64_t)mb.seq << 32) | to_bits(mine);
-  for (int p = 0; p < mb.world; ++p) sys_store(mb.peer[p] + slot + mb.rank, word);  // P2P stores over NVLink
-  const uint64_t* local = mb.peer[mb.rank] + slot;
+  for (int p = 0; p < mb.world; ++p) sys_store(mb.peers[p] + slot + mb.rank, word);  // P2P stores over NVLink
+  const uint64_t* local = mb.local + slot;
   T acc = RedOp<T, RED>::identity();
   const unsigned long long t0 = global_ns();
   for (int r = 0; r < mb.world; ++r) {  // fixed rank order: same bits on every GPU

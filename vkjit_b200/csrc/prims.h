@@ -24,7 +24,9 @@ struct Scratch {
 constexpr int kMailSlots = 64;
 constexpr int kMailRanks = 8;
 struct Mailbox {
-  uint64_t* peer[kMailRanks];  // mailbox base of every rank (peer[rank] is the local one)
+  uint64_t* const* peers = nullptr;  // DEVICE table: mailbox base of every rank (kept out of the kernel
+                                     // parameter so no thread needs a local copy to index it)
+  uint64_t* local = nullptr;         // this rank's mailbox
   int rank = 0, world = 1;
   uint32_t seq = 0;            // >= 1; identical on all ranks for the same collective
 };
