@@ -273,8 +273,16 @@ def ours(args):
         kern_ms = sum(ks) / len(ks)
         ir.dec_ref_count(xl)
     achieved = n_local * 4 / (kern_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:  # DRAM traffic of this kernel at this size from the committed ncu capture (never measured under the bench)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        ent = tr.get(f"reduce_kernel<float, SUM, 512> @ 2^{int(math.log2(n_local))} lanes") if n_local & (n_local - 1) == 0 else None
+        if ent:
+            traffic, traffic_src = ent["dram_read_bytes"] + ent["dram_write_bytes"], "profiles/r01_traffic.json (ncu --set full, round 1)"
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "reduce_kernel<float, SUM, 512>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "launch_ms": kern_ms,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": kern_ms,
                 "algorithmic_bytes_per_launch": n_local * 4}
 
     # ---- e2e: same metric through the public API with pinned HOST buffers, copies inside the timed region
@@ -303,6 +311,50 @@ def ours(args):
            "d2h_bytes_per_step": 8 * world, "steps": e2e_steps, "seconds_per_step": float(e2e_s.item())}
     assert abs(out2[0] - gpu_sum) <= 1e-5 * abs(gpu_sum) and out2[1] == gpu_max
 
+    # ---- N>1 extras (every rank takes part): weak scaling of the same reduction (2^28 lanes PER GPU) and
+    # the sharded fused elementwise trace E28 (2^28 lanes in total, no collective at all)
+    mgpu_extras = None
+    if world > 1 and not args.no_extras:
+        mgpu_extras = {}
+        big = uniform_trace(ir, ir.arange_sharded(T.U32, N_TOTAL * world), SEED_R28)
+        ir.eval([big])
+        ts = []
+        for i in range(3 + 10):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            r1 = ir.reduce(Red.Sum, big); r2 = ir.reduce(Red.Max, big)
+            b.record(stream)
+            vk.sync()
+            ir.dec_ref_count(r1); ir.dec_ref_count(r2)
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        t = torch.tensor([sum(ts) / len(ts)], device=dev, dtype=torch.float64)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        mgpu_extras["weak_R28_per_gpu"] = {"ms_per_step": float(t.item()), "GBps": 2 * N_TOTAL * world * 4 / (float(t.item()) * 1e-3) / 1e9,
+                                           "lanes_per_gpu": N_TOTAL, "note": "sum+max, 2^28 lanes per GPU (weak scaling), fused P2P all-reduce" if args.collective == "p2p" else "NCCL"}
+        ir.dec_ref_count(big)
+        xs = uniform_trace(ir, lanes, 0xB2000011)
+        ys = uniform_trace(ir, lanes, 0xB2000012)
+        ir.eval([xs, ys])
+        half = ir.const_f32(0.5)
+        ts = []
+        for i in range(3 + 10):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            z = ir.add(ir.mul(xs, ys), half); ir.eval([z])
+            b.record(stream)
+            vk.sync()
+            ir.dec_ref_count(z)
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        t = torch.tensor([sum(ts) / len(ts)], device=dev, dtype=torch.float64)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        mgpu_extras["E28_sharded_elementwise"] = {"ms": float(t.item()), "GBps": 12 * N_TOTAL / (float(t.item()) * 1e-3) / 1e9,
+                                                   "note": "z = x*y + c over 2^28 lanes in total, contiguous shards, no collective"}
+        ir.dec_ref_count(xs); ir.dec_ref_count(ys)
+
     line = None
     if rank == 0:
         line = {
@@ -325,6 +377,8 @@ def ours(args):
             tol = 1e-6 * LOG2N * abs(cb["sum"])
             line["check"] = {"sum_abs_err": abs(gpu_sum - cb["sum"]), "sum_tol": tol, "max_equal": gpu_max == cb["max"],
                              "ok": bool(abs(gpu_sum - cb["sum"]) <= tol and gpu_max == cb["max"])}
+        if world > 1:
+            line["extras"] = mgpu_extras
         if world == 1 and not args.no_extras:
             try:
                 import bench_extras

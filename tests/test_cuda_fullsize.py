@@ -68,8 +68,10 @@ def test_C28_prefix_sum_and_compress_full_size(cir, oir_mt):
     a, b = cir.as_slice(sd, T.U32), oir_mt.as_slice(so, T.U32)
     assert np.array_equal(a, b)
     total = int(cir.as_slice(cir.reduce(Red.Sum, vd), T.U32)[0])
-    last_in = int(cir.as_slice(cir.gather(vd, cir.add(cir.arange(T.U32, 1), cir.const_u32(N28 - 1))), T.U32)[0]) if False else None
-    assert a[0] == 0
+    # checksum property: exclusive[last] + in[last] == sum (mod 2^32)
+    last = cir.add(cir.arange(T.U32, 1), cir.const_u32(N28 - 1))
+    last_in = int(cir.as_slice_eval(cir.gather(vd, last), T.U32)[0])
+    assert a[0] == 0 and (int(a[-1]) + last_in) % (1 << 32) == total
     del a, b
     cir.dec_ref_count(sd); oir_mt.dec_ref_count(so)
     md, mo = device_array(cir, N28, 0xB2000042, MASK), oracle_array(oir_mt, N28, 0xB2000042, MASK)
@@ -83,10 +85,9 @@ def test_C28_prefix_sum_and_compress_full_size(cir, oir_mt):
     assert n2 == nd == n3 and np.array_equal(cir.as_slice(id_, T.U32), oir_mt.as_slice(io, T.U32))
     # round trip: gathering the values at the compressed indices reproduces compress_values
     back = cir.gather(vd, id_)
-    assert total == total and cir.size(id_) == nd
     cir.eval([back])
-    (cd2, _), = [cir.compress_values(vd, md)]
-    assert np.array_equal(cir.as_slice(back, T.U32), cir.as_slice(cd2, T.U32))
+    cd2, _ = cir.compress_values(vd, md)
+    assert cir.size(id_) == nd and np.array_equal(cir.as_slice(back, T.U32), cir.as_slice(cd2, T.U32))
 
 
 def test_H26_gather_scatter_add_full_size(cir, oir_mt):

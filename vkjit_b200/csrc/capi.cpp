@@ -411,6 +411,18 @@ vkjit_status vkjit_debug_codegen(vkjit_ir* h, const vkjit_var* ids, size_t n, in
   });
 }
 
+vkjit_status vkjit_debug_walk_ns(vkjit_ir* h, const vkjit_var* ids, size_t n, uint32_t reps, uint64_t* out_ns, uint32_t* out_nodes) {
+  return with_ir(h, [&](Ir& ir) {
+    std::vector<VarId> sched(ids, ids + n);
+    Program p;
+    build_program(ir, sched, true, p);
+    const uint64_t t0 = now_ns();
+    for (uint32_t i = 0; i < reps; ++i) build_program(ir, sched, true, p);
+    *out_ns = reps ? (now_ns() - t0) / reps : 0;
+    *out_nodes = (uint32_t)p.order.size();
+  });
+}
+
 vkjit_status vkjit_debug_codegen_reduce(vkjit_ir* h, vkjit_var id, int32_t red, int32_t compile, char* buf, size_t cap,
                                         size_t* out_len, size_t* out_cubin) {
   return with_ir(h, [&](Ir& ir) {

@@ -9,7 +9,7 @@
 namespace vkjit {
 
 void Program::clear() {
-  key.clear(); order.clear(); params.clear(); roots.clear();
+  key_len = 0; order.clear(); params.clear(); roots.clear();
   n = 0; have_n = false; base = 0; have_base = false; sharded = false; vectorized = true; reduce = -1;
   hash = Hash128();
 }
@@ -48,11 +48,6 @@ inline bool child_of(const Var& v, uint32_t k, VarId& out, uint8_t& ptr_use) {
   }
 }
 
-inline void mix(Hash128& h, uint64_t w) {
-  h.lo = (h.lo ^ w) * 0x9E3779B97F4A7C15ull; h.lo ^= h.lo >> 32;
-  h.hi = (h.hi + w) * 0xC2B2AE3D27D4EB4Full; h.hi ^= h.hi >> 29;
-}
-
 void type_signature(const Ir& ir, TypeId t, std::vector<uint32_t>& key) {
   if (!ty_is_struct(t)) { key.push_back(t); return; }
   const auto& e = ir.struct_elems(t);
@@ -80,9 +75,57 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   const uint32_t stamp = ir.next_stamp();
   static thread_local std::vector<Frame> stack;
   stack.clear();
+  Var* const vars = ir.vars.data();
+  const size_t nvars = ir.vars.size();
 
-  auto touch_binding = [&](VarId id, uint8_t use) {
-    Var& v = ir.vars[id];
+  // canonical key: structure only — no VarIds, no addresses, no n.  Words are emitted
+  // while nodes are numbered (single pass; this walk is the cache-hit critical path).
+  std::vector<uint32_t>& key = p.key;
+  if (key.size() < 2) key.resize(2);
+  key[0] = 0x564B4A31u;  // "VKJ1"; key[1] = variant word, patched below
+  static thread_local std::vector<uint32_t> sig;
+  static thread_local std::vector<uint32_t> binding_pos;  // key index of each param's word (use bits patched at the end)
+  binding_pos.clear();
+
+  // raw write cursor into the key buffer: push_back through the Program reference reloads and stores
+  // the vector's end pointer on every word (measured 36 -> 20 ns per node)
+  size_t kn = 2;
+  if (key.size() < 4096) key.resize(4096);  // the buffer keeps its size between walks; p.key_len is the logical length
+  uint32_t* kw = key.data();
+  auto number_node = [&](VarId id, Var& v) {
+    v.stamp = stamp; v.local = (uint32_t)p.order.size();
+    p.order.push_back(id);
+    const uint32_t tycode = ty_is_struct(v.ty) ? 0xFu : v.ty;
+    if (tycode == 0xFu) {  // struct-typed node: variable-length type signature
+      sig.clear();
+      type_signature(ir, v.ty, sig);
+      if (kn + 16 + v.ndeps + sig.size() > key.size()) { key.resize(std::max(key.size() * 2, kn + 64 + v.ndeps + sig.size())); kw = key.data(); }
+      kw[kn++] = (uint32_t)v.op | ((uint32_t)v.kind << 8) | (tycode << 24) | ((uint32_t)(v.has_se ? 1u : 0u) << 28);
+      kw[kn++] = v.ndeps;
+      for (uint32_t w : sig) kw[kn++] = w;
+      goto tail;
+    }
+    if (kn + 16 + v.ndeps > key.size()) { key.resize(std::max(key.size() * 2, kn + 64 + v.ndeps)); kw = key.data(); }
+    kw[kn++] = (uint32_t)v.op | ((uint32_t)v.kind << 8) | (tycode << 24) | ((uint32_t)(v.has_se ? 1u : 0u) << 28);
+    kw[kn++] = v.ndeps;
+  tail:
+    switch (v.op) {
+      case OP_CONST: case OP_GETATTR: case OP_SETATTR: kw[kn++] = v.aux; break;
+      case OP_ARANGE: kw[kn++] = v.sharded; break;
+      case OP_BINDING:
+        v.aux = (uint32_t)p.params.size();
+        p.params.push_back({id, 0, v.local});
+        binding_pos.push_back((uint32_t)kn);
+        kw[kn++] = v.aux;
+        break;
+      default: break;
+    }
+    const VarId* d = v.deps();
+    for (uint32_t k = 0; k < v.ndeps; ++k) kw[kn++] = vars[d[k]].local;
+    if (v.has_se) kw[kn++] = vars[v.side_effect].local;
+  };
+
+  auto touch_binding = [&](Var& v, uint8_t use) {
     Param& pr = p.params[v.aux];
     if ((use & USE_STREAM) && !(pr.use & USE_STREAM)) {  // internal.rs:717-721
       set_num(p, v.array->bytes / 4);
@@ -97,52 +140,70 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
       if (!ty_is_scalar(rv.ty))  // Struct: stride() is unimplemented!() (vartype.rs:45-53)
         fail(VKJIT_ERR_UNSUPPORTED, "only scalar-typed vars can be scheduled (vartype.rs:45-53)");
     }
-    if (ir.vars[root].stamp == stamp) {
-      if (ir.vars[root].op == OP_BINDING) touch_binding(root, USE_STREAM);
-      p.roots.push_back(ir.vars[root].local);
+    if (vars[root].stamp == stamp) {
+      if (vars[root].op == OP_BINDING) touch_binding(vars[root], USE_STREAM);
+      p.roots.push_back(vars[root].local);
       continue;
     }
     stack.push_back({root, 0});
     while (!stack.empty()) {
+    next_frame:
       Frame& f = stack.back();
-      Var& v = ir.vars[f.id];
-      VarId c; uint8_t ptr_use;
-      if (child_of(v, f.next, c, ptr_use)) {
-        ++f.next;
-        Var& cv = ir.var(c);
+      Var& v = vars[f.id];
+      const bool indexed = v.op == OP_GATHER || v.op == OP_SCATTER || v.op == OP_SCATTER_ADD;
+      for (;;) {
+        VarId c; uint8_t ptr_use = 0;
+        if (!indexed) {  // fast path: children are the deps in order
+          if (f.next >= v.ndeps) break;
+          c = v.deps()[f.next++];
+        } else {
+          if (!child_of(v, f.next, c, ptr_use)) break;
+          ++f.next;
+        }
+        if (c >= nvars || vars[c].op == OP_FREE) fail(VKJIT_ERR_INVALID, "invalid VarId " + std::to_string(c));
+        Var& cv = vars[c];
         if (ptr_use) {
           if (ptr_use == USE_GATHER && (cv.op != OP_BINDING || !cv.array))
             fail(VKJIT_ERR_INVALID, "Can only gather from buffer! (internal.rs:1054)");
           if (ptr_use == USE_SCATTER && (cv.op != OP_BINDING || !cv.array))
             fail(VKJIT_ERR_INVALID, "Cannot scatter into non buffer variables! (internal.rs:1061)");
-          if (cv.stamp != stamp) {
-            cv.stamp = stamp; cv.local = (uint32_t)p.order.size();
-            p.order.push_back(c);
-            cv.aux = (uint32_t)p.params.size();
-            p.params.push_back({c, 0, cv.local});
+          if (cv.stamp != stamp) number_node(c, cv);
+          touch_binding(cv, ptr_use);
+        } else if (cv.stamp == stamp) {
+          if (cv.op == OP_BINDING) touch_binding(cv, USE_STREAM);
+        } else if (cv.ndeps == 0 && !cv.has_se) {  // leaf: number in place, no frame
+          if (cv.op == OP_BINDING) {
+            if (!cv.array) fail(VKJIT_ERR_INVALID, "Binding without an array");
+            number_node(c, cv);
+            touch_binding(cv, USE_STREAM);
+          } else {
+            number_node(c, cv);
+            if (cv.op == OP_ARANGE) {  // internal.rs:722-725
+              set_num(p, cv.num);
+              if (cv.sharded) {
+                p.sharded = true;
+                if (p.have_base && p.base != cv.base) fail(VKJIT_ERR_SIZE, "sharded aranges with different bases in one kernel");
+                p.have_base = true; p.base = cv.base;
+              }
+            }
           }
-          touch_binding(c, ptr_use);
-        } else if (cv.stamp != stamp) {
+        } else {
           stack.push_back({c, 0});  // invalidates f
-        } else if (cv.op == OP_BINDING) {
-          touch_binding(c, USE_STREAM);
+          goto next_frame;
         }
-        continue;
       }
       // all children done: number this node (post-order)
       const VarId id = f.id;
       stack.pop_back();
-      if (v.stamp == stamp) continue;  // reached twice through different parents while pending
-      v.stamp = stamp; v.local = (uint32_t)p.order.size();
-      p.order.push_back(id);
+      if (v.stamp == stamp) continue;
       switch (v.op) {
         case OP_BINDING:
           if (!v.array) fail(VKJIT_ERR_INVALID, "Binding without an array");
-          v.aux = (uint32_t)p.params.size();
-          p.params.push_back({id, 0, v.local});
-          touch_binding(id, USE_STREAM);
+          number_node(id, v);
+          touch_binding(v, USE_STREAM);
           break;
-        case OP_ARANGE:  // internal.rs:722-725
+        case OP_ARANGE:
+          number_node(id, v);
           set_num(p, v.num);
           if (v.sharded) {
             p.sharded = true;
@@ -151,21 +212,23 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
           }
           break;
         case OP_GATHER: case OP_SCATTER: case OP_SCATTER_ADD: {
-          const TypeId it = ir.vars[v.deps()[1]].ty;
+          const TypeId it = vars[v.deps()[1]].ty;
           if (it != VKJIT_TY_U32 && it != VKJIT_TY_I32) fail(VKJIT_ERR_TYPE, "gather/scatter index must be U32 or I32");
-          if (v.ndeps >= 3 && ir.vars[v.deps()[2]].ty != VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "gather/scatter mask must be Bool");
+          if (v.ndeps >= 3 && vars[v.deps()[2]].ty != VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "gather/scatter mask must be Bool");
           if (!ty_is_scalar(v.ty)) fail(VKJIT_ERR_UNSUPPORTED, "gather/scatter of a struct");
-          if (v.op != OP_GATHER && ir.vars[v.side_effect].ty != v.ty) fail(VKJIT_ERR_TYPE, "scatter: source and target types differ");
+          if (v.op != OP_GATHER && vars[v.side_effect].ty != v.ty) fail(VKJIT_ERR_TYPE, "scatter: source and target types differ");
           if (v.op == OP_SCATTER_ADD && v.ty == VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "scatter_add on Bool");
+          number_node(id, v);
           break;
         }
         case OP_SELECT:
-          if (ir.vars[v.deps()[0]].ty != VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "select condition must be Bool");
+          if (vars[v.deps()[0]].ty != VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "select condition must be Bool");
+          number_node(id, v);
           break;
-        default: break;
+        default: number_node(id, v); break;
       }
     }
-    p.roots.push_back(ir.vars[root].local);
+    p.roots.push_back(vars[root].local);
   }
 
   // ALU-heavy traces (config 5: ~200 ops/lane) are bound by SM issue rate, not by HBM: 128-bit
@@ -178,32 +241,23 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   if (p.n > 0xFFFFFFFFull) fail(VKJIT_ERR_SIZE, "kernel size exceeds the 32-bit invocation index");
   if (p.params.size() + p.roots.size() > 480) fail(VKJIT_ERR_UNSUPPORTED, "too many arrays in one kernel (4 KB parameter limit)");
 
-  // canonical key: structure only — no VarIds, no addresses, no n
-  std::vector<uint32_t>& key = p.key;
-  key.push_back(0x564B4A31u);  // "VKJ1"
-  key.push_back((vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16));
-  for (uint32_t li = 0; li < p.order.size(); ++li) {
-    const Var& v = ir.vars[p.order[li]];
-    const uint32_t tycode = ty_is_struct(v.ty) ? 0xFu : v.ty;
-    key.push_back((uint32_t)v.op | ((uint32_t)v.kind << 8) | (tycode << 24) | ((uint32_t)(v.has_se ? 1u : 0u) << 28));
-    key.push_back(v.ndeps);
-    if (tycode == 0xFu) type_signature(ir, v.ty, key);
-    switch (v.op) {
-      case OP_CONST: case OP_GETATTR: case OP_SETATTR: key.push_back(v.aux); break;
-      case OP_ARANGE: key.push_back(v.sharded); break;
-      case OP_BINDING: key.push_back(v.aux | ((uint32_t)p.params[v.aux].use << 16)); break;
-      default: break;
-    }
-    const VarId* d = v.deps();
-    for (uint32_t k = 0; k < v.ndeps; ++k) key.push_back(ir.vars[d[k]].local);
-    if (v.has_se) key.push_back(ir.vars[v.side_effect].local);
+  if (kn + 4 + p.roots.size() > key.size()) { key.resize(kn + 64 + p.roots.size()); kw = key.data(); }
+  kw[1] = (vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16);
+  for (size_t k = 0; k < p.params.size(); ++k) kw[binding_pos[k]] |= (uint32_t)p.params[k].use << 16;
+  kw[kn++] = 0xFFFFFFFFu;
+  for (uint32_t r : p.roots) kw[kn++] = r;
+  if (kn & 1) kw[kn++] = 0u;
+  p.key_len = kn;
+  // 128-bit hash over 64-bit pairs (the full key is compared on every cache hit anyway)
+  uint64_t h0 = 0x243F6A8885A308D3ull, h1 = 0x13198A2E03707344ull;
+  const uint32_t* kr = key.data();
+  for (size_t i = 0; i < kn; i += 2) {
+    const uint64_t w = (uint64_t)kr[i] | ((uint64_t)kr[i + 1] << 32);
+    h0 = (h0 ^ w) * 0x9E3779B97F4A7C15ull; h0 ^= h0 >> 32;
+    h1 = (h1 + w) * 0xC2B2AE3D27D4EB4Full; h1 ^= h1 >> 29;
   }
-  key.push_back(0xFFFFFFFFu);
-  for (uint32_t r : p.roots) key.push_back(r);
-  Hash128 h{0x243F6A8885A308D3ull, 0x13198A2E03707344ull};
-  for (uint32_t w : key) mix(h, w);
-  mix(h, key.size());
-  p.hash = h;
+  p.hash.lo = h0 ^ kn;
+  p.hash.hi = h1;
 }
 
 // ---------------------------------------------------------------------------------------

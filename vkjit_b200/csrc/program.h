@@ -29,7 +29,8 @@ struct Param {
 
 // One scheduled trace, canonicalised.  Reused between evals (no allocation once warm).
 struct Program {
-  std::vector<uint32_t> key;    // canonical words (cache key, verified on hit)
+  std::vector<uint32_t> key;    // canonical words (cache key, verified on hit); only [0, key_len) is meaningful
+  size_t key_len = 0;
   std::vector<VarId> order;     // post-order of var ids; index == local node id
   std::vector<Param> params;    // pointer parameters, in kernel-signature order
   std::vector<uint32_t> roots;  // local node id per scheduled var

@@ -232,7 +232,7 @@ CachedKernel* Backend::lookup(const Program& p) {
   auto it = cache_.find(p.hash);
   if (it == cache_.end()) return nullptr;
   CachedKernel* k = it->second;
-  if (k->key.size() != p.key.size() || memcmp(k->key.data(), p.key.data(), p.key.size() * 4) != 0) return nullptr;  // 128-bit collision
+  if (k->key.size() != p.key_len || memcmp(k->key.data(), p.key.data(), p.key_len * 4) != 0) return nullptr;  // 128-bit collision
   g_counters.cache_hits += 1;
   return k;
 }
@@ -249,7 +249,7 @@ CachedKernel* Backend::compile(const Ir& ir, const Program& p) {
   CUfunction fn;
   cku(g_drv.ModuleGetFunction(&fn, mod, "vkjit_trace"), "cuModuleGetFunction");
   auto* k = new CachedKernel();
-  k->module = mod; k->function = fn; k->key = p.key;
+  k->module = mod; k->function = fn; k->key.assign(p.key.begin(), p.key.begin() + p.key_len);
   k->nparams = (uint32_t)p.params.size(); k->nroots = (uint32_t)p.roots.size(); k->vectorized = p.vectorized;
   {
     std::lock_guard<std::mutex> g(cache_mu_);

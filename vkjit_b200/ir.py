@@ -241,6 +241,12 @@ class Ir:
         self.api.call("read", self._h, id, ty, out.ctypes.data_as(C.c_void_p), out.nbytes)
         return out
 
+    def as_slice_eval(self, id: int, ty: int) -> np.ndarray:
+        """eval([id]) if needed, then as_slice."""
+        if not self.is_buffer(id):
+            self.eval([id])
+        return self.as_slice(id, ty)
+
     def read_into(self, id: int, ty: int, ptr: int, nbytes: int):
         self.api.call("read", self._h, id, ty, C.c_void_p(ptr), nbytes)
 
