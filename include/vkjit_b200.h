@@ -265,6 +265,7 @@ typedef struct vkjit_stats_t {
   uint64_t bytes_d2h;
   uint64_t pool_bytes_live; /* bytes currently handed out by the pool        */
   uint64_t collectives;     /* cross-GPU combines issued                     */
+  uint64_t disk_hits;       /* kernel-cache misses served from $VKJIT_CACHE_DIR (no NVRTC) */
 } vkjit_stats_t;
 vkjit_status vkjit_stats(vkjit_stats_t* out);
 vkjit_status vkjit_stats_reset(void);

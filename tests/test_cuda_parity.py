@@ -291,3 +291,21 @@ def test_errors_match_oracle(cir, oir):
             ir.eval([ir.scatter(a, ir.const_f32(0), ir.arange(U32, 3))])  # internal.rs:1059-1062
         # the Ir stays usable after an error
         ir.eval([ir.add(a, a)])
+
+
+def test_disk_cubin_cache(cuda_backend, cir, tmp_path, monkeypatch):
+    """$VKJIT_CACHE_DIR: a kernel-cache miss whose cubin is on disk skips NVRTC."""
+    monkeypatch.setenv("VKJIT_CACHE_DIR", str(tmp_path))
+    def run():
+        x = cir.add(cir.mul(cir.arange(F32, 777), cir.const_f32(1.25)), cir.const_f32(-3.0))
+        cir.eval([x])
+        return read(cir, x)
+    cuda_backend.cache_clear(); cuda_backend.stats_reset()
+    a = run()
+    assert cuda_backend.stats()["cache_misses"] == 1 and cuda_backend.stats()["disk_hits"] == 0
+    assert len(list(tmp_path.glob("*.cubin"))) == 1
+    cuda_backend.cache_clear(); cuda_backend.stats_reset()
+    b = run()
+    st = cuda_backend.stats()
+    assert st["cache_misses"] == 1 and st["disk_hits"] == 1
+    assert same_bits(a, b, True)

@@ -45,7 +45,7 @@ _pu32, _psz, _pi32, _pu64 = C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), C.POIN
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "cache_hits", "cache_misses", "trace_launches", "prim_launches", "last_compile_ns",
-        "last_eval_ns", "bytes_h2d", "bytes_d2h", "pool_bytes_live", "collectives")]
+        "last_eval_ns", "bytes_h2d", "bytes_d2h", "pool_bytes_live", "collectives", "disk_hits")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

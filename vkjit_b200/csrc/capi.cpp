@@ -377,14 +377,14 @@ vkjit_status vkjit_stats(vkjit_stats_t* out) {
     out->trace_launches = c.trace_launches; out->prim_launches = c.prim_launches;
     out->last_compile_ns = c.last_compile_ns; out->last_eval_ns = c.last_eval_ns;
     out->bytes_h2d = c.bytes_h2d; out->bytes_d2h = c.bytes_d2h;
-    out->pool_bytes_live = c.pool_bytes_live; out->collectives = c.collectives;
+    out->pool_bytes_live = c.pool_bytes_live; out->collectives = c.collectives; out->disk_hits = c.disk_hits;
   });
 }
 vkjit_status vkjit_stats_reset(void) {
   return guard([&] {
     Counters& c = Backend::counters();
     c.cache_hits = 0; c.cache_misses = 0; c.trace_launches = 0; c.prim_launches = 0;
-    c.last_compile_ns = 0; c.last_eval_ns = 0; c.bytes_h2d = 0; c.bytes_d2h = 0; c.collectives = 0;
+    c.last_compile_ns = 0; c.last_eval_ns = 0; c.bytes_h2d = 0; c.bytes_d2h = 0; c.collectives = 0; c.disk_hits = 0;
   });
 }
 vkjit_status vkjit_cache_clear(void) { return guard([&] { Backend::get().clear_cache(); }); }

@@ -226,6 +226,65 @@ bool nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string
   return true;
 }
 
+// ---- on-disk cubin cache --------------------------------------------------
+// $VKJIT_CACHE_DIR/<hash>.cubin = {magic, nvrtc version, key_len, key words, cubin}.  The canonical key
+// is stored and compared, so a hash collision or a stale file can never load the wrong kernel.
+namespace {
+constexpr uint32_t kDiskMagic = 0x564B4331u;  // "VKC1"
+
+std::string disk_path(const Hash128& h) {
+  const char* dir = getenv("VKJIT_CACHE_DIR");
+  if (!dir || !*dir) return std::string();
+  char name[64];
+  snprintf(name, sizeof name, "/%016llx%016llx.cubin", (unsigned long long)h.hi, (unsigned long long)h.lo);
+  return std::string(dir) + name;
+}
+
+uint32_t nvrtc_version_word() {
+  int major = 0, minor = 0;
+  nvrtcVersion(&major, &minor);
+  return (uint32_t)(major * 1000 + minor);
+}
+
+bool disk_load(const Program& p, std::vector<char>& cubin) {
+  const std::string path = disk_path(p.hash);
+  if (path.empty()) return false;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  bool ok = false;
+  uint32_t hdr[3];
+  if (fread(hdr, 4, 3, f) == 3 && hdr[0] == kDiskMagic && hdr[1] == nvrtc_version_word() && hdr[2] == p.key_len) {
+    std::vector<uint32_t> key(hdr[2]);
+    if (fread(key.data(), 4, key.size(), f) == key.size() && memcmp(key.data(), p.key.data(), key.size() * 4) == 0) {
+      const long at = ftell(f);
+      fseek(f, 0, SEEK_END);
+      const long end = ftell(f);
+      fseek(f, at, SEEK_SET);
+      if (end > at) {
+        cubin.resize((size_t)(end - at));
+        ok = fread(cubin.data(), 1, cubin.size(), f) == cubin.size();
+      }
+    }
+  }
+  fclose(f);
+  return ok;
+}
+
+void disk_store(const Program& p, const std::vector<char>& cubin) {
+  const std::string path = disk_path(p.hash);
+  if (path.empty()) return;
+  const std::string tmp = path + ".tmp" + std::to_string((unsigned long long)now_ns());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const uint32_t hdr[3] = {kDiskMagic, nvrtc_version_word(), (uint32_t)p.key_len};
+  bool ok = fwrite(hdr, 4, 3, f) == 3 && fwrite(p.key.data(), 4, p.key_len, f) == p.key_len &&
+            fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  fclose(f);
+  if (ok) rename(tmp.c_str(), path.c_str());  // atomic publish
+  else remove(tmp.c_str());
+}
+}  // namespace
+
 // ---- kernel cache ------------------------------------------------------------------------
 CachedKernel* Backend::lookup(const Program& p) {
   std::lock_guard<std::mutex> g(cache_mu_);
@@ -239,11 +298,16 @@ CachedKernel* Backend::lookup(const Program& p) {
 
 CachedKernel* Backend::compile(const Ir& ir, const Program& p) {
   const uint64_t t0 = now_ns();
-  const std::string src = generate_cuda(ir, p);
-  if (getenv("VKJIT_DUMP")) fprintf(stderr, "%s\n", src.c_str());
   std::vector<char> cubin;
-  std::string log;
-  if (!nvrtc_compile(src, cubin, log)) fail(VKJIT_ERR_COMPILE, "NVRTC rejected the generated kernel:\n" + log + "\n--- source ---\n" + src);
+  if (disk_load(p, cubin)) {
+    g_counters.disk_hits += 1;
+  } else {
+    const std::string src = generate_cuda(ir, p);
+    if (getenv("VKJIT_DUMP")) fprintf(stderr, "%s\n", src.c_str());
+    std::string log;
+    if (!nvrtc_compile(src, cubin, log)) fail(VKJIT_ERR_COMPILE, "NVRTC rejected the generated kernel:\n" + log + "\n--- source ---\n" + src);
+    disk_store(p, cubin);
+  }
   CUmodule mod;
   cku(g_drv.ModuleLoadData(&mod, cubin.data()), "cuModuleLoadData");
   CUfunction fn;

@@ -34,6 +34,7 @@ struct CachedKernel {
 struct Counters {
   std::atomic<uint64_t> cache_hits{0}, cache_misses{0}, trace_launches{0}, prim_launches{0};
   std::atomic<uint64_t> last_compile_ns{0}, last_eval_ns{0}, bytes_h2d{0}, bytes_d2h{0}, pool_bytes_live{0}, collectives{0};
+  std::atomic<uint64_t> disk_hits{0};
 };
 
 // NVRTC front door; usable without a device (the cubin is produced offline for sm_100a).
