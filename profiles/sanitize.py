@@ -1,0 +1,34 @@
+"""Small run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import vkjit_b200 as vk  # noqa: E402
+from vkjit_b200.ir import Bop, Ir, Red, VarType as T  # noqa: E402
+
+vk.init(0)
+ir = Ir()
+n = 3 * 16384 + 777            # several look-back tiles + a ragged tail
+rng = np.random.default_rng(0)
+x = ir.array_f32(rng.random(n, dtype=np.float32))
+u = ir.array_u32(rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32))
+z = ir.add(ir.mul(x, x), ir.const_f32(0.5))
+ir.eval([z])
+for r in (Red.Sum, Red.Min, Red.Max):
+    ir.reduce(r, z); ir.reduce(r, u)
+    ir.reduce(r, ir.mul(u, ir.const_u32(3)))      # fused trace -> reduce
+s = ir.prefix_sum(u, True)
+m = ir.neq(ir.bop(Bop.And, u, ir.const_u32(1)), ir.const_u32(0))
+c, k = ir.compress_values(u, m)
+i, k2 = ir.compress(m)
+idx = ir.bop(Bop.And, u, ir.const_u32(1023))
+bins = ir.array_u32(np.zeros(1024, np.uint32))
+sa = ir.scatter_add(ir.gather(u, idx), bins, idx)
+ir.eval([sa])
+ref = np.cumsum(ir.as_slice(u, T.U32).astype(np.uint64)).astype(np.uint32)
+assert ir.as_slice(s, T.U32)[-1] == ref[-2] and k == k2
+vk.sync()
+print("sanitize workload ok", k)
