@@ -469,6 +469,22 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
         tma_load_1d(ring + (size_t)stage * kScanTile, in + (size_t)t2 * kScanTile, TILE_BYTES, &full[stage]);
       }
     }
+    // compress: the values of vectors with a selected lane are requested NOW, so their HBM latency
+    // overlaps the look-back instead of following it (the mask words in x[] are dead after `flags`)
+    uint4 val[VPT];
+    if (MODE == MODE_COMPRESS_VALUE) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+        if (flags[j]) {
+          if (staged || e + 3 < n) val[j] = ld_stream(reinterpret_cast<const uint4*>(values + e));
+          else {
+            val[j].x = e + 0 < n ? values[e + 0] : 0u; val[j].y = e + 1 < n ? values[e + 1] : 0u;
+            val[j].z = e + 2 < n ? values[e + 2] : 0u; val[j].w = 0u;
+          }
+        }
+      }
+    }
     if (warp == 0) {
       uint32_t t[PER_LANE], run = 0;
 #pragma unroll
@@ -507,16 +523,10 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
           if (e + 2 < n) out[e + 2] = r.z;
         }
       } else if (flags[j]) {
-        // selected lanes are written at their rank; flags of out-of-range lanes are 0.  Values are
-        // loaded only now (once from HBM, only for vectors with a selected lane).
+        // selected lanes are written at their rank; flags of out-of-range lanes are 0
         uint4 v;
-        if (MODE == MODE_COMPRESS_VALUE) {
-          if (staged || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
-          else {
-            v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
-            v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
-          }
-        } else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
+        if (MODE == MODE_COMPRESS_VALUE) v = val[j];
+        else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
         if (flags[j] & 1u) out[p++] = v.x;
         if (flags[j] & 2u) out[p++] = v.y;
         if (flags[j] & 4u) out[p++] = v.z;

@@ -307,7 +307,27 @@ struct Gen {
   std::string body;
   std::vector<Val> vals;
 
-  Gen(const Ir& i, const Program& pr) : ir(i), p(pr) { vals.resize(pr.order.size()); }
+  std::vector<int> trig_partner;  // sin(x)/cos(x) of the same x: local id of the sibling, else -1
+
+  Gen(const Ir& i, const Program& pr) : ir(i), p(pr) {
+    vals.resize(pr.order.size());
+    // Box-Muller style traces take sin and cos of the same value: pair them so that one sincosf
+    // (one range reduction) serves both
+    trig_partner.assign(pr.order.size(), -1);
+    std::vector<int> first_sin(pr.order.size(), -1), first_cos(pr.order.size(), -1);
+    for (uint32_t li = 0; li < pr.order.size(); ++li) {
+      const Var& v = ir.vars[pr.order[li]];
+      if (v.op != OP_UOP || (v.kind != VKJIT_UOP_SIN && v.kind != VKJIT_UOP_COS)) continue;
+      const uint32_t d = ir.vars[v.deps()[0]].local;
+      std::vector<int>& mine = v.kind == VKJIT_UOP_SIN ? first_sin : first_cos;
+      std::vector<int>& other = v.kind == VKJIT_UOP_SIN ? first_cos : first_sin;
+      if (mine[d] < 0) mine[d] = (int)li;
+      if (other[d] >= 0 && trig_partner[other[d]] < 0 && trig_partner[li] < 0 && mine[d] == (int)li) {
+        trig_partner[li] = other[d];
+        trig_partner[other[d]] = (int)li;
+      }
+    }
+  }
 
   void line(const std::string& s) { body += "  " + s + "\n"; }
   void def(uint32_t li, TypeId ty, const std::string& expr) {
@@ -424,7 +444,21 @@ struct Gen {
         break;
       }
       case OP_BOP: def(li, v.ty, bop_expr(v, dep(v, 0).name, dep(v, 1).name)); break;
-      case OP_UOP: def(li, v.ty, uop_expr(v, dep(v, 0).name)); break;
+      case OP_UOP: {
+        const int partner = trig_partner[li];
+        if (partner >= 0) {
+          if (partner > (int)li) {  // first of the pair: emit both values
+            const std::string other = "v" + std::to_string(partner);
+            const bool i_am_sin = v.kind == VKJIT_UOP_SIN;
+            line("f32 " + me + ", " + other + ";");
+            line("sincosf(" + dep(v, 0).name + ", &" + (i_am_sin ? me : other) + ", &" + (i_am_sin ? other : me) + ");");
+          }
+          vals[li].name = me; vals[li].ty = v.ty;
+          break;
+        }
+        def(li, v.ty, uop_expr(v, dep(v, 0).name));
+        break;
+      }
       case OP_CAST: def(li, v.ty, cast_expr(dep(v, 0).ty, v.ty, dep(v, 0).name)); break;
       case OP_BITCAST: def(li, v.ty, from_word(v.ty, to_word(dep(v, 0).ty, dep(v, 0).name))); break;
       case OP_GETATTR: vals[li] = dep(v, 0).elems.at(v.aux); break;
