@@ -300,7 +300,7 @@ __device__ __forceinline__ void status_store(uint64_t* p, uint64_t v) {
 // the persistent grid runs its 148 CTAs in generations, so a single round (one L2 round trip)
 // spans the whole current generation plus the tail of the previous one, whose inclusive prefixes
 // are already published.
-constexpr int kLookWide = 5;
+template <int kLookWide>
 __device__ __forceinline__ uint32_t look_back(uint64_t* status, uint32_t tile, uint32_t aggregate) {
   const int lane = threadIdx.x & 31;
   if (tile == 0) {
@@ -373,13 +373,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // barrier or looking back — the three serial phases no longer starve the memory system
 // (the first version, 2 non-persistent CTAs/SM with register loads, spent 60 % of its stall
 // samples at barriers and reached 45 % DRAM utilisation).
-template <int MODE>
-__global__ void __launch_bounds__(kScanThreads, 1)
+// CFG 0: one 1024-thread CTA per SM, 16384-lane tiles.  CFG 1: two 512-thread CTAs per SM, 8192-lane
+// tiles, the second wave of CTAs delayed by half a generation so that one CTA of every SM streams
+// while the other one is in its look-back.
+template <int CFG> struct ScanCfg;
+template <> struct ScanCfg<0> { static constexpr int T = 1024, TILE = 16384, CTAS = 1, WIDE = 5; };
+template <> struct ScanCfg<1> { static constexpr int T = 512, TILE = 8192, CTAS = 2, WIDE = 10; };
+
+template <int MODE, int CFG>
+__global__ void __launch_bounds__(ScanCfg<CFG>::T, ScanCfg<CFG>::CTAS)
 scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: mask words
             const uint32_t* __restrict__ values,  // MODE_COMPRESS_VALUE only
             uint32_t* __restrict__ out, uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles,
-            uint64_t* __restrict__ state) {
-  constexpr int T = kScanThreads;
+            uint64_t* __restrict__ state, uint32_t stagger_ns) {
+  constexpr int T = ScanCfg<CFG>::T;
+  constexpr int kScanTile = ScanCfg<CFG>::TILE;
   constexpr int VPT = kScanTile / (T * 4);  // 128-bit vectors per thread
   constexpr int WARPS = T / 32;
   constexpr int NTOT = VPT * WARPS;         // (slot, warp) totals per tile
@@ -414,6 +422,8 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
       tma_load_1d(ring + (size_t)k * kScanTile, in + (size_t)t * kScanTile, TILE_BYTES, &full[k]);
     }
   }
+
+  if (CFG == 1 && blockIdx.x >= gridDim.x / 2 && my_tiles > 1) __nanosleep(stagger_ns);  // phase offset of the second wave
 
   for (uint32_t k = 0; k < my_tiles; ++k) {
     const uint32_t tile = first + k * stride;
@@ -499,7 +509,7 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
 #pragma unroll
       for (int i = 0; i < PER_LANE; ++i) { s_tot[buf][lane * PER_LANE + i] = off; off += t[i]; }
       const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
-      const uint32_t excl = look_back(status, tile, aggregate);
+      const uint32_t excl = look_back<ScanCfg<CFG>::WIDE>(status, tile, aggregate);
       if (lane == 0) {
         s_tile_excl[buf] = excl;
         if (COMPRESS && tile == num_tiles - 1) *count_out = excl + aggregate;
@@ -538,33 +548,52 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   }
 }
 
-size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (1 + (n + kScanTile - 1) / kScanTile); }
+static int scan_cfg() {
+  static int cfg = -1;
+  if (cfg < 0) { const char* e = getenv("VKJIT_SCAN_CFG"); cfg = e ? atoi(e) : 0; if (cfg != 1) cfg = 0; }
+  return cfg;
+}
+static uint32_t scan_stagger_ns() {
+  static int ns = -1;
+  if (ns < 0) { const char* e = getenv("VKJIT_SCAN_STAGGER_NS"); ns = e ? atoi(e) : 800; }
+  return (uint32_t)ns;
+}
+static size_t scan_tile() { return scan_cfg() == 1 ? ScanCfg<1>::TILE : ScanCfg<0>::TILE; }
+
+size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (1 + (n + ScanCfg<1>::TILE - 1) / ScanCfg<1>::TILE); }
 
 static uint32_t prepare_scan(size_t n, const Scratch& sc, cudaStream_t s) {
-  const size_t tiles = (n + kScanTile - 1) / kScanTile;
-  if (scan_state_words(n) > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
-  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, scan_state_words(n) * sizeof(uint64_t), s);
+  const size_t tiles = (n + scan_tile() - 1) / scan_tile();
+  const size_t words = (size_t)kStatusStride * (1 + tiles);
+  if (words > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
+  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, words * sizeof(uint64_t), s);
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
   return (uint32_t)tiles;
 }
 
-constexpr size_t kScanSmem = (size_t)kScanStages * kScanTile * 4;
+template <int MODE, int CFG>
+static void launch_scan_cfg(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n, uint32_t tiles,
+                            const Scratch& sc, int sm_count, cudaStream_t s) {
+  constexpr size_t smem = (size_t)kScanStages * ScanCfg<CFG>::TILE * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan smem attribute: ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  // persistent CTAs, all co-resident: a tile only ever waits on tiles of CTAs that are running
+  // (forward progress of the look-back does not depend on dispatch order)
+  const unsigned grid = (unsigned)std::min<uint32_t>(tiles, (uint32_t)sm_count * ScanCfg<CFG>::CTAS);
+  scan_kernel<MODE, CFG><<<grid, ScanCfg<CFG>::T, smem, s>>>(in, values, out, count_out, n, tiles, sc.tile_state, scan_stagger_ns());
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
+}
 
 template <int MODE>
 static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n, uint32_t tiles,
                         const Scratch& sc, int sm_count, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem);
-    if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan smem attribute: ") + cudaGetErrorString(e));
-    configured = true;
-  }
-  // one persistent CTA per SM: all CTAs are co-resident, so a tile only ever waits on tiles of
-  // CTAs that are running (forward progress of the look-back does not depend on dispatch order)
-  const unsigned grid = (unsigned)std::min<uint32_t>(tiles, (uint32_t)sm_count);
-  scan_kernel<MODE><<<grid, kScanThreads, kScanSmem, s>>>(in, values, out, count_out, n, tiles, sc.tile_state);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
+  if (scan_cfg() == 1) launch_scan_cfg<MODE, 1>(in, values, out, count_out, n, tiles, sc, sm_count, s);
+  else launch_scan_cfg<MODE, 0>(in, values, out, count_out, n, tiles, sc, sm_count, s);
 }
 
 void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream) {
