@@ -322,9 +322,11 @@ __device__ __forceinline__ uint32_t look_back(uint64_t* status, uint32_t tile, u
     for (int i = 0; i < kLookWide; ++i) {
       if (done) continue;
       const int idx = top - 32 * i - lane;
+      uint32_t spins = 0;
       while ((uint32_t)(s[i] >> 32) == ST_INVALID) {  // predecessor not published yet
         __nanosleep(40);
         s[i] = status_load(status + (size_t)idx * kStatusStride);
+        if (++spins > (1u << 25)) __trap();  // seconds without progress: fail loudly instead of hanging the GPU
       }
       const unsigned incl = __ballot_sync(0xFFFFFFFFu, (uint32_t)(s[i] >> 32) == ST_INCLUSIVE);
       if (incl) {
@@ -358,12 +360,13 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
+  uint32_t done, spins = 0;
   do {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(done)
                  : "r"(smem_addr(bar)), "r"(parity)
                  : "memory");
+    if (!done && ++spins > (1u << 26)) __trap();  // a bulk copy that never lands: fail loudly
   } while (!done);
 }
 
@@ -373,12 +376,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // barrier or looking back — the three serial phases no longer starve the memory system
 // (the first version, 2 non-persistent CTAs/SM with register loads, spent 60 % of its stall
 // samples at barriers and reached 45 % DRAM utilisation).
-// CFG 0: one 1024-thread CTA per SM, 16384-lane tiles.  CFG 1: two 512-thread CTAs per SM, 8192-lane
-// tiles, the second wave of CTAs delayed by half a generation so that one CTA of every SM streams
-// while the other one is in its look-back.
+// CFG 0: one 1024-thread CTA per SM, 16384-lane tiles, every warp scans and warp 0 also looks back
+// (the look-back latency, ~1 us per generation of 148 tiles, is exposed: 0.72 of peak).
 template <int CFG> struct ScanCfg;
 template <> struct ScanCfg<0> { static constexpr int T = 1024, TILE = 16384, CTAS = 1, WIDE = 5; };
-template <> struct ScanCfg<1> { static constexpr int T = 512, TILE = 8192, CTAS = 2, WIDE = 10; };
 
 template <int MODE, int CFG>
 __global__ void __launch_bounds__(ScanCfg<CFG>::T, ScanCfg<CFG>::CTAS)
@@ -422,8 +423,6 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
       tma_load_1d(ring + (size_t)k * kScanTile, in + (size_t)t * kScanTile, TILE_BYTES, &full[k]);
     }
   }
-
-  if (CFG == 1 && blockIdx.x >= gridDim.x / 2 && my_tiles > 1) __nanosleep(stagger_ns);  // phase offset of the second wave
 
   for (uint32_t k = 0; k < my_tiles; ++k) {
     const uint32_t tile = first + k * stride;
@@ -509,7 +508,8 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
 #pragma unroll
       for (int i = 0; i < PER_LANE; ++i) { s_tot[buf][lane * PER_LANE + i] = off; off += t[i]; }
       const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
-      const uint32_t excl = look_back<ScanCfg<CFG>::WIDE>(status, tile, aggregate);
+      // stagger_ns == 0xFFFFFFFF: diagnostic mode (profiles/scan_ab.py), skips the look-back — results are wrong
+      const uint32_t excl = stagger_ns == 0xFFFFFFFFu ? 0u : look_back<ScanCfg<CFG>::WIDE>(status, tile, aggregate);
       if (lane == 0) {
         s_tile_excl[buf] = excl;
         if (COMPRESS && tile == num_tiles - 1) *count_out = excl + aggregate;
@@ -548,69 +548,283 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   }
 }
 
-static int scan_cfg() {
-  static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("VKJIT_SCAN_CFG"); cfg = e ? atoi(e) : 0; if (cfg != 1) cfg = 0; }
-  return cfg;
-}
-static uint32_t scan_stagger_ns() {
-  static int ns = -1;
-  if (ns < 0) { const char* e = getenv("VKJIT_SCAN_STAGGER_NS"); ns = e ? atoi(e) : 800; }
-  return (uint32_t)ns;
-}
-static size_t scan_tile() { return scan_cfg() == 1 ? ScanCfg<1>::TILE : ScanCfg<0>::TILE; }
+// ---------------------------------------------------------------------------------------
+// warp-specialised scan: the look-back of tile j overlaps the local scan of tile j+1
+// ---------------------------------------------------------------------------------------
+// 31 data warps + 1 control warp per CTA, one CTA per SM, tiles b, b+148, ...
+//   data warps, iteration j :  wait TMA(j) -> local scan of tile j, results written back IN PLACE into
+//                              the ring stage -> arrive SCANNED[j&1] -> wait PREFIX[(j-1)&1] -> add the
+//                              tile/warp offsets to tile j-1 (from shared memory) and store it ->
+//                              arrive EMPTY[(j-1)&1]
+//   control warp, phase j   :  wait SCANNED[j&1] -> scan the (slot, warp) totals -> publish the tile
+//                              aggregate -> look back -> arrive PREFIX[j&1] -> wait EMPTY[(j-1)&1] ->
+//                              TMA-refill that ring stage
+// so the ~1 us cross-SM round trip of the look-back runs while the data warps are already scanning the
+// next tile; the tile waits in shared memory, not in registers.  Named barriers (bar.sync/bar.arrive,
+// two ids per signal, alternating with the tile parity) connect the two roles.
+constexpr int kWsThreads = 1024;
+constexpr int kWsData = 992;      // 31 data warps
+constexpr int kWsDataWarps = 31;
+enum : int { BAR_SCANNED = 1, BAR_PREFIX = 3, BAR_EMPTY = 5 };
 
-size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (1 + (n + ScanCfg<1>::TILE - 1) / ScanCfg<1>::TILE); }
+__device__ __forceinline__ void named_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kWsThreads) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(kWsThreads) : "memory"); }
 
-static uint32_t prepare_scan(size_t n, const Scratch& sc, cudaStream_t s) {
-  const size_t tiles = (n + scan_tile() - 1) / scan_tile();
+template <int MODE> struct WsCfg {  // vectors per data thread, ring depth
+  static constexpr int VPT = MODE == MODE_COMPRESS_VALUE ? 2 : 3;
+  static constexpr int STAGES = MODE == MODE_COMPRESS_VALUE ? 3 : 4;
+  static constexpr int TILE = kWsData * 4 * VPT;                                   // lanes per tile
+  static constexpr int STAGE_WORDS = TILE * (MODE == MODE_COMPRESS_VALUE ? 2 : 1); // mask (+ values) words
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_WORDS * 4;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kWsThreads, 1)
+scan_ws_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ values, uint32_t* __restrict__ out,
+               uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles, uint64_t* __restrict__ state) {
+  using C = WsCfg<MODE>;
+  constexpr int VPT = C::VPT, S = C::STAGES, TILE = C::TILE;
+  constexpr int NTOT = VPT * kWsDataWarps;
+  constexpr int PER_LANE = (NTOT + 31) / 32;
+  constexpr bool COMPRESS = MODE >= MODE_COMPRESS_INDEX;
+  constexpr bool WITH_VALUES = MODE == MODE_COMPRESS_VALUE;
+  constexpr uint32_t TILE_BYTES = TILE * 4;
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  uint32_t* ring = reinterpret_cast<uint32_t*>(ring_raw);
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ uint32_t s_tot[2][PER_LANE * 32];  // local-scan totals per (slot, warp), then their exclusive offsets
+  __shared__ uint32_t s_tile_excl[2];
+
+  uint64_t* status = state + kStatusStride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t first = blockIdx.x, stride = gridDim.x;
+  const uint32_t my_tiles = (num_tiles - first + stride - 1) / stride;  // grid <= num_tiles
+  const bool ragged = (n % TILE) != 0;  // the globally last tile is partial: loaded by the data warps with guards
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  if (threadIdx.x < 2 * PER_LANE * 32) (&s_tot[0][0])[threadIdx.x] = 0u;  // padding entries stay 0
+  __syncthreads();
+
+  auto issue_tile = [&](uint32_t k) {  // one lane of the control warp: TMA tile k of this CTA into its stage
+    const uint32_t t = first + k * stride;
+    if (ragged && t == num_tiles - 1) return;
+    uint32_t* dst = ring + (size_t)(k % S) * C::STAGE_WORDS;
+    mbar_expect_tx(&full[k % S], WITH_VALUES ? 2 * TILE_BYTES : TILE_BYTES);
+    tma_load_1d(dst, in + (size_t)t * TILE, TILE_BYTES, &full[k % S]);
+    if (WITH_VALUES) tma_load_1d(dst + TILE, values + (size_t)t * TILE, TILE_BYTES, &full[k % S]);
+  };
+
+  if (warp == kWsDataWarps) {
+    // ======================= control warp =======================
+    if (lane == 0)
+      for (uint32_t k = 0; k < (uint32_t)S && k < my_tiles; ++k) issue_tile(k);
+    for (uint32_t j = 0; j < my_tiles; ++j) {
+      const uint32_t tile = first + j * stride;
+      const int buf = j & 1;
+      named_sync(BAR_SCANNED + buf);
+      uint32_t t[PER_LANE], run = 0;
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) {  // entries >= NTOT are padding (they hold stale offsets): count as 0
+        const int idx = lane * PER_LANE + i;
+        t[i] = idx < NTOT ? s_tot[buf][idx] : 0u;
+        run += t[i];
+      }
+      uint32_t s = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, s, o);
+        if (lane >= o) s += u;
+      }
+      uint32_t off = s - run;
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) { s_tot[buf][lane * PER_LANE + i] = off; off += t[i]; }
+      const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
+      const uint32_t excl = look_back<5>(status, tile, aggregate);
+      if (lane == 0) {
+        s_tile_excl[buf] = excl;
+        if (COMPRESS && tile == num_tiles - 1) *count_out = excl + aggregate;
+      }
+      __syncwarp();
+      named_arrive(BAR_PREFIX + buf);
+      if (j >= 1) {
+        named_sync(BAR_EMPTY + ((j - 1) & 1));  // tile j-1 has left its ring stage
+        if (lane == 0 && j - 1 + S < my_tiles) issue_tile(j - 1 + S);
+      }
+    }
+    return;
+  }
+
+  // ======================= data warps =======================
+  // adds the offsets to tile `t_j` (which waits in its ring stage) and stores it
+  auto store_tile = [&](uint32_t j) {
+    const uint32_t tile = first + j * stride;
+    const int buf = j & 1;
+    const size_t tile_base = (size_t)tile * TILE;
+    const bool staged = !(ragged && tile == num_tiles - 1);
+    uint32_t* stage = ring + (size_t)(j % S) * C::STAGE_WORDS;
+    named_sync(BAR_PREFIX + buf);
+    const uint32_t tile_excl = s_tile_excl[buf];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const uint32_t q = (uint32_t)v * kWsData + threadIdx.x;
+      const size_t e = tile_base + (size_t)q * 4;
+      const uint32_t off = tile_excl + s_tot[buf][v * kWsDataWarps + warp];
+      uint4 r = reinterpret_cast<const uint4*>(stage)[q];
+      if (!COMPRESS) {
+        r.x += off; r.y += off; r.z += off; r.w += off;
+        if (staged || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
+        else {
+          if (e + 0 < n) out[e + 0] = r.x;
+          if (e + 1 < n) out[e + 1] = r.y;
+          if (e + 2 < n) out[e + 2] = r.z;
+        }
+      } else {
+        const uint32_t flags = r.x & 15u;  // meta word written by the scan phase: flags | local rank << 4
+        if (flags) {
+          uint32_t p = off + (r.x >> 4);
+          uint4 val;
+          if (WITH_VALUES) val = reinterpret_cast<const uint4*>(stage + TILE)[q];
+          else { val.x = (uint32_t)e; val.y = val.x + 1; val.z = val.x + 2; val.w = val.x + 3; }
+          if (flags & 1u) out[p++] = val.x;
+          if (flags & 2u) out[p++] = val.y;
+          if (flags & 4u) out[p++] = val.z;
+          if (flags & 8u) out[p++] = val.w;
+        }
+      }
+    }
+    named_arrive(BAR_EMPTY + buf);
+  };
+
+  for (uint32_t j = 0; j < my_tiles; ++j) {
+    const uint32_t tile = first + j * stride;
+    const int buf = j & 1;
+    const size_t tile_base = (size_t)tile * TILE;
+    const bool staged = !(ragged && tile == num_tiles - 1);
+    uint32_t* stage = ring + (size_t)(j % S) * C::STAGE_WORDS;
+
+    uint4 x[VPT];
+    if (staged) {
+      mbar_wait(&full[j % S], (j / S) & 1);
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) x[v] = reinterpret_cast<const uint4*>(stage)[v * kWsData + threadIdx.x];
+    } else {
+      // ragged last tile: guarded loads; the values (if any) are put where the TMA would have put them
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const uint32_t q = (uint32_t)v * kWsData + threadIdx.x;
+        const size_t e = tile_base + (size_t)q * 4;
+        x[v].x = e + 0 < n ? in[e + 0] : 0u; x[v].y = e + 1 < n ? in[e + 1] : 0u;
+        x[v].z = e + 2 < n ? in[e + 2] : 0u; x[v].w = e + 3 < n ? in[e + 3] : 0u;
+        if (WITH_VALUES) {
+          uint4 val;
+          val.x = e + 0 < n ? values[e + 0] : 0u; val.y = e + 1 < n ? values[e + 1] : 0u;
+          val.z = e + 2 < n ? values[e + 2] : 0u; val.w = e + 3 < n ? values[e + 3] : 0u;
+          reinterpret_cast<uint4*>(stage + TILE)[q] = val;
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const uint32_t q = (uint32_t)v * kWsData + threadIdx.x;
+      uint32_t flags = 0, vsum;
+      if (COMPRESS) {
+        flags = (x[v].x != 0u ? 1u : 0u) | (x[v].y != 0u ? 2u : 0u) | (x[v].z != 0u ? 4u : 0u) | (x[v].w != 0u ? 8u : 0u);
+        vsum = (uint32_t)__popc(flags);
+      } else {
+        vsum = x[v].x + x[v].y + x[v].z + x[v].w;
+      }
+      uint32_t s = vsum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, s, o);
+        if (lane >= o) s += u;
+      }
+      if (lane == 31) s_tot[buf][v * kWsDataWarps + warp] = s;
+      const uint32_t base = s - vsum;  // exclusive prefix of this vector inside its (slot, warp) group
+      uint4 r;
+      if (COMPRESS) { r.x = flags | (base << 4); r.y = r.z = r.w = 0u; }
+      else if (MODE == MODE_EXCLUSIVE) { r.x = base; r.y = base + x[v].x; r.z = r.y + x[v].y; r.w = r.z + x[v].z; }
+      else { r.x = base + x[v].x; r.y = r.x + x[v].y; r.z = r.y + x[v].z; r.w = r.z + x[v].w; }
+      reinterpret_cast<uint4*>(stage)[q] = r;  // the tile waits in place for its global offset
+    }
+    named_arrive(BAR_SCANNED + buf);
+    if (j >= 1) store_tile(j - 1);
+  }
+  store_tile(my_tiles - 1);
+}
+
+template <int MODE>
+static void launch_scan_ws(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
+                           const Scratch& sc, int sm_count, cudaStream_t s) {
+  using C = WsCfg<MODE>;
+  const size_t tiles = (n + C::TILE - 1) / C::TILE;
   const size_t words = (size_t)kStatusStride * (1 + tiles);
   if (words > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
   cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, words * sizeof(uint64_t), s);
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
-  return (uint32_t)tiles;
-}
-
-template <int MODE, int CFG>
-static void launch_scan_cfg(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n, uint32_t tiles,
-                            const Scratch& sc, int sm_count, cudaStream_t s) {
-  constexpr size_t smem = (size_t)kScanStages * ScanCfg<CFG>::TILE * 4;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(scan_ws_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan smem attribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  // persistent CTAs, all co-resident: a tile only ever waits on tiles of CTAs that are running
-  // (forward progress of the look-back does not depend on dispatch order)
-  const unsigned grid = (unsigned)std::min<uint32_t>(tiles, (uint32_t)sm_count * ScanCfg<CFG>::CTAS);
-  scan_kernel<MODE, CFG><<<grid, ScanCfg<CFG>::T, smem, s>>>(in, values, out, count_out, n, tiles, sc.tile_state, scan_stagger_ns());
-  cudaError_t e = cudaGetLastError();
+  const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);  // persistent, all CTAs co-resident
+  scan_ws_kernel<MODE><<<grid, kWsThreads, C::SMEM, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state);
+  e = cudaGetLastError();
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
 }
 
+static int scan_cfg() {  // 1 (default): warp-specialised kernel; 0: the earlier all-warps-scan kernel (kept for A/B)
+  static int cfg = -1;
+  if (cfg < 0) { const char* e = getenv("VKJIT_SCAN_CFG"); cfg = e ? atoi(e) : 1; if (cfg != 0) cfg = 1; }
+  return cfg;
+}
+static uint32_t scan_debug_flag() {  // VKJIT_SCAN_STAGGER_NS=-1: diagnostic mode of the cfg-0 kernel (no look-back)
+  static long v = -2;
+  if (v == -2) { const char* e = getenv("VKJIT_SCAN_STAGGER_NS"); v = e ? atol(e) : 0; }
+  return v < 0 ? 0xFFFFFFFFu : 0u;
+}
+
+// smallest tile of any configuration: sizes the status array
+size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (2 + n / WsCfg<MODE_COMPRESS_VALUE>::TILE); }
+
 template <int MODE>
-static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n, uint32_t tiles,
+static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
                         const Scratch& sc, int sm_count, cudaStream_t s) {
-  if (scan_cfg() == 1) launch_scan_cfg<MODE, 1>(in, values, out, count_out, n, tiles, sc, sm_count, s);
-  else launch_scan_cfg<MODE, 0>(in, values, out, count_out, n, tiles, sc, sm_count, s);
+  if (scan_cfg() == 1) { launch_scan_ws<MODE>(in, values, out, count_out, n, sc, sm_count, s); return; }
+  constexpr size_t smem = (size_t)kScanStages * ScanCfg<0>::TILE * 4;
+  const size_t tiles = (n + ScanCfg<0>::TILE - 1) / ScanCfg<0>::TILE;
+  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, (size_t)kStatusStride * (1 + tiles) * sizeof(uint64_t), s);
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(scan_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan smem attribute: ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);
+  scan_kernel<MODE, 0><<<grid, ScanCfg<0>::T, smem, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state, scan_debug_flag());
+  e = cudaGetLastError();
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
 }
 
 void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream) {
   if (n == 0) return;
   cudaStream_t s = (cudaStream_t)stream;
-  const uint32_t tiles = prepare_scan(n, sc, s);
-  if (exclusive) launch_scan<MODE_EXCLUSIVE>(in, nullptr, out, nullptr, n, tiles, sc, sm_count, s);
-  else launch_scan<MODE_INCLUSIVE>(in, nullptr, out, nullptr, n, tiles, sc, sm_count, s);
+  if (exclusive) launch_scan<MODE_EXCLUSIVE>(in, nullptr, out, nullptr, n, sc, sm_count, s);
+  else launch_scan<MODE_INCLUSIVE>(in, nullptr, out, nullptr, n, sc, sm_count, s);
 }
 
 void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
               const Scratch& sc, int sm_count, void* stream) {
   if (n == 0) return;
   cudaStream_t s = (cudaStream_t)stream;
-  const uint32_t tiles = prepare_scan(n, sc, s);
-  if (values) launch_scan<MODE_COMPRESS_VALUE>(mask, values, out, count_out, n, tiles, sc, sm_count, s);
-  else launch_scan<MODE_COMPRESS_INDEX>(mask, nullptr, out, count_out, n, tiles, sc, sm_count, s);
+  if (values) launch_scan<MODE_COMPRESS_VALUE>(mask, values, out, count_out, n, sc, sm_count, s);
+  else launch_scan<MODE_COMPRESS_INDEX>(mask, nullptr, out, count_out, n, sc, sm_count, s);
 }
 
 __global__ void fill_kernel(uint32_t* out, uint32_t value, size_t n) {
