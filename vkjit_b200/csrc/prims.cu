@@ -552,20 +552,19 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
 // warp-specialised scan: the look-back of tile j overlaps the local scan of tile j+1
 // ---------------------------------------------------------------------------------------
 // 31 data warps + 1 control warp per CTA, one CTA per SM, tiles b, b+148, ...
-//   data warps, iteration j :  wait TMA(j) -> local scan of tile j, results written back IN PLACE into
-//                              the ring stage -> arrive SCANNED[j&1] -> wait PREFIX[(j-1)&1] -> add the
-//                              tile/warp offsets to tile j-1 (from shared memory) and store it ->
-//                              arrive EMPTY[(j-1)&1]
-//   control warp, phase j   :  wait SCANNED[j&1] -> scan the (slot, warp) totals -> publish the tile
-//                              aggregate -> look back -> arrive PREFIX[j&1] -> wait EMPTY[(j-1)&1] ->
-//                              TMA-refill that ring stage
+//   data warps, iteration j :  wait TMA(j) -> read tile j from the ring -> local scan in registers ->
+//                              arrive SCANNED[j&1] -> wait PREFIX[(j-1)&1] -> add the tile/warp offsets
+//                              to the HELD tile j-1 and store it -> hold tile j
+//   control warp, phase j   :  wait SCANNED[j&1] -> TMA-refill the ring stage tile j just left ->
+//                              scan the (slot, warp) totals -> publish the tile aggregate -> look back
+//                              -> arrive PREFIX[j&1]
 // so the ~1 us cross-SM round trip of the look-back runs while the data warps are already scanning the
-// next tile; the tile waits in shared memory, not in registers.  Named barriers (bar.sync/bar.arrive,
+// next tile; 3 of the 4 ring stages are always in flight.  Named barriers (bar.sync/bar.arrive,
 // two ids per signal, alternating with the tile parity) connect the two roles.
 constexpr int kWsThreads = 1024;
 constexpr int kWsData = 992;      // 31 data warps
 constexpr int kWsDataWarps = 31;
-enum : int { BAR_SCANNED = 1, BAR_PREFIX = 3, BAR_EMPTY = 5 };
+enum : int { BAR_SCANNED = 1, BAR_PREFIX = 3 };
 
 __device__ __forceinline__ void named_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kWsThreads) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(kWsThreads) : "memory"); }
@@ -625,7 +624,8 @@ scan_ws_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ val
     for (uint32_t j = 0; j < my_tiles; ++j) {
       const uint32_t tile = first + j * stride;
       const int buf = j & 1;
-      named_sync(BAR_SCANNED + buf);
+      named_sync(BAR_SCANNED + buf);  // the data warps hold tile j in registers: its ring stage is free again
+      if (lane == 0 && j + S < my_tiles) issue_tile(j + S);
       uint32_t t[PER_LANE], run = 0;
 #pragma unroll
       for (int i = 0; i < PER_LANE; ++i) {  // entries >= NTOT are padding (they hold stale offsets): count as 0
@@ -650,22 +650,20 @@ scan_ws_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ val
       }
       __syncwarp();
       named_arrive(BAR_PREFIX + buf);
-      if (j >= 1) {
-        named_sync(BAR_EMPTY + ((j - 1) & 1));  // tile j-1 has left its ring stage
-        if (lane == 0 && j - 1 + S < my_tiles) issue_tile(j - 1 + S);
-      }
     }
     return;
   }
 
   // ======================= data warps =======================
-  // adds the offsets to tile `t_j` (which waits in its ring stage) and stores it
-  auto store_tile = [&](uint32_t j) {
+  uint4 held[VPT];      // tile j-1: locally scanned values (scan) / {flags | rank << 4} in .x (compress)
+  uint4 held_val[WITH_VALUES ? VPT : 1];
+
+  // adds the tile/warp offsets to the held tile j and stores it
+  auto store_held = [&](uint32_t j) {
     const uint32_t tile = first + j * stride;
     const int buf = j & 1;
     const size_t tile_base = (size_t)tile * TILE;
     const bool staged = !(ragged && tile == num_tiles - 1);
-    uint32_t* stage = ring + (size_t)(j % S) * C::STAGE_WORDS;
     named_sync(BAR_PREFIX + buf);
     const uint32_t tile_excl = s_tile_excl[buf];
 #pragma unroll
@@ -673,7 +671,7 @@ scan_ws_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ val
       const uint32_t q = (uint32_t)v * kWsData + threadIdx.x;
       const size_t e = tile_base + (size_t)q * 4;
       const uint32_t off = tile_excl + s_tot[buf][v * kWsDataWarps + warp];
-      uint4 r = reinterpret_cast<const uint4*>(stage)[q];
+      uint4 r = held[v];
       if (!COMPRESS) {
         r.x += off; r.y += off; r.z += off; r.w += off;
         if (staged || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
@@ -683,11 +681,11 @@ scan_ws_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ val
           if (e + 2 < n) out[e + 2] = r.z;
         }
       } else {
-        const uint32_t flags = r.x & 15u;  // meta word written by the scan phase: flags | local rank << 4
+        const uint32_t flags = r.x & 15u;
         if (flags) {
           uint32_t p = off + (r.x >> 4);
           uint4 val;
-          if (WITH_VALUES) val = reinterpret_cast<const uint4*>(stage + TILE)[q];
+          if (WITH_VALUES) val = held_val[WITH_VALUES ? v : 0];
           else { val.x = (uint32_t)e; val.y = val.x + 1; val.z = val.x + 2; val.w = val.x + 3; }
           if (flags & 1u) out[p++] = val.x;
           if (flags & 2u) out[p++] = val.y;
@@ -696,7 +694,6 @@ scan_ws_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ val
         }
       }
     }
-    named_arrive(BAR_EMPTY + buf);
   };
 
   for (uint32_t j = 0; j < my_tiles; ++j) {
@@ -704,32 +701,32 @@ scan_ws_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ val
     const int buf = j & 1;
     const size_t tile_base = (size_t)tile * TILE;
     const bool staged = !(ragged && tile == num_tiles - 1);
-    uint32_t* stage = ring + (size_t)(j % S) * C::STAGE_WORDS;
+    const uint32_t* stage = ring + (size_t)(j % S) * C::STAGE_WORDS;
 
-    uint4 x[VPT];
+    uint4 x[VPT], xv[WITH_VALUES ? VPT : 1];
     if (staged) {
       mbar_wait(&full[j % S], (j / S) & 1);
 #pragma unroll
-      for (int v = 0; v < VPT; ++v) x[v] = reinterpret_cast<const uint4*>(stage)[v * kWsData + threadIdx.x];
-    } else {
-      // ragged last tile: guarded loads; the values (if any) are put where the TMA would have put them
+      for (int v = 0; v < VPT; ++v) {
+        x[v] = reinterpret_cast<const uint4*>(stage)[v * kWsData + threadIdx.x];
+        if (WITH_VALUES) xv[WITH_VALUES ? v : 0] = reinterpret_cast<const uint4*>(stage + TILE)[v * kWsData + threadIdx.x];
+      }
+    } else {  // ragged last tile: guarded loads
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
-        const uint32_t q = (uint32_t)v * kWsData + threadIdx.x;
-        const size_t e = tile_base + (size_t)q * 4;
+        const size_t e = tile_base + ((size_t)v * kWsData + threadIdx.x) * 4;
         x[v].x = e + 0 < n ? in[e + 0] : 0u; x[v].y = e + 1 < n ? in[e + 1] : 0u;
         x[v].z = e + 2 < n ? in[e + 2] : 0u; x[v].w = e + 3 < n ? in[e + 3] : 0u;
         if (WITH_VALUES) {
-          uint4 val;
+          uint4& val = xv[WITH_VALUES ? v : 0];
           val.x = e + 0 < n ? values[e + 0] : 0u; val.y = e + 1 < n ? values[e + 1] : 0u;
           val.z = e + 2 < n ? values[e + 2] : 0u; val.w = e + 3 < n ? values[e + 3] : 0u;
-          reinterpret_cast<uint4*>(stage + TILE)[q] = val;
         }
       }
     }
+    uint4 cur[VPT];
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
-      const uint32_t q = (uint32_t)v * kWsData + threadIdx.x;
       uint32_t flags = 0, vsum;
       if (COMPRESS) {
         flags = (x[v].x != 0u ? 1u : 0u) | (x[v].y != 0u ? 2u : 0u) | (x[v].z != 0u ? 4u : 0u) | (x[v].w != 0u ? 8u : 0u);
@@ -749,12 +746,17 @@ scan_ws_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ val
       if (COMPRESS) { r.x = flags | (base << 4); r.y = r.z = r.w = 0u; }
       else if (MODE == MODE_EXCLUSIVE) { r.x = base; r.y = base + x[v].x; r.z = r.y + x[v].y; r.w = r.z + x[v].z; }
       else { r.x = base + x[v].x; r.y = r.x + x[v].y; r.z = r.y + x[v].z; r.w = r.z + x[v].w; }
-      reinterpret_cast<uint4*>(stage)[q] = r;  // the tile waits in place for its global offset
+      cur[v] = r;
     }
-    named_arrive(BAR_SCANNED + buf);
-    if (j >= 1) store_tile(j - 1);
+    named_arrive(BAR_SCANNED + buf);  // totals published; everything this thread needs from the stage is in registers
+    if (j >= 1) store_held(j - 1);    // tile j-1's prefix was looked up while tile j was being scanned
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      held[v] = cur[v];
+      if (WITH_VALUES) held_val[WITH_VALUES ? v : 0] = xv[WITH_VALUES ? v : 0];
+    }
   }
-  store_tile(my_tiles - 1);
+  store_held(my_tiles - 1);
 }
 
 template <int MODE>
