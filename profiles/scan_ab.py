@@ -1,4 +1,4 @@
-"""A/B timing of the scan configurations (env VKJIT_SCAN_CFG / VKJIT_SCAN_STAGGER_NS), 2^28 u32."""
+"""Timing of prefix sum / compress at 2^28 u32 (VKJIT_SCAN_DIAG=nolookback: pipeline-only diagnostic)."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,4 +29,4 @@ def scan():
 def comp():
     r, k = ir.compress_values(vals, mask); ir.dec_ref_count(r)
 ms, mc = timed(scan), timed(comp)
-print(f"cfg={os.environ.get('VKJIT_SCAN_CFG','0')} stagger={os.environ.get('VKJIT_SCAN_STAGGER_NS','800')}  prefix_sum {ms:.4f} ms ({8*n/ms/1e6:.0f} GB/s, {8*n/ms/1e6/6450:.3f})  compress {mc:.4f} ms ({10*n/mc/1e6:.0f} GB/s, {10*n/mc/1e6/6450:.3f})")
+print(f"diag={os.environ.get('VKJIT_SCAN_DIAG','-')}  prefix_sum {ms:.4f} ms ({8*n/ms/1e6:.0f} GB/s, {8*n/ms/1e6/6450:.3f})  compress {mc:.4f} ms ({10*n/mc/1e6:.0f} GB/s, {10*n/mc/1e6/6450:.3f})")

@@ -300,7 +300,7 @@ __device__ __forceinline__ void status_store(uint64_t* p, uint64_t v) {
 // the persistent grid runs its 148 CTAs in generations, so a single round (one L2 round trip)
 // spans the whole current generation plus the tail of the previous one, whose inclusive prefixes
 // are already published.
-template <int kLookWide>
+constexpr int kLookWide = 5;
 __device__ __forceinline__ uint32_t look_back(uint64_t* status, uint32_t tile, uint32_t aggregate) {
   const int lane = threadIdx.x & 31;
   if (tile == 0) {
@@ -376,19 +376,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // barrier or looking back — the three serial phases no longer starve the memory system
 // (the first version, 2 non-persistent CTAs/SM with register loads, spent 60 % of its stall
 // samples at barriers and reached 45 % DRAM utilisation).
-// CFG 0: one 1024-thread CTA per SM, 16384-lane tiles, every warp scans and warp 0 also looks back
-// (the look-back latency, ~1 us per generation of 148 tiles, is exposed: 0.72 of peak).
-template <int CFG> struct ScanCfg;
-template <> struct ScanCfg<0> { static constexpr int T = 1024, TILE = 16384, CTAS = 1, WIDE = 5; };
-
-template <int MODE, int CFG>
-__global__ void __launch_bounds__(ScanCfg<CFG>::T, ScanCfg<CFG>::CTAS)
+template <int MODE>
+__global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: mask words
             const uint32_t* __restrict__ values,  // MODE_COMPRESS_VALUE only
             uint32_t* __restrict__ out, uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles,
-            uint64_t* __restrict__ state, uint32_t stagger_ns) {
-  constexpr int T = ScanCfg<CFG>::T;
-  constexpr int kScanTile = ScanCfg<CFG>::TILE;
+            uint64_t* __restrict__ state, uint32_t diag_skip_lookback) {
+  constexpr int T = kScanThreads;
   constexpr int VPT = kScanTile / (T * 4);  // 128-bit vectors per thread
   constexpr int WARPS = T / 32;
   constexpr int NTOT = VPT * WARPS;         // (slot, warp) totals per tile
@@ -508,8 +502,8 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
 #pragma unroll
       for (int i = 0; i < PER_LANE; ++i) { s_tot[buf][lane * PER_LANE + i] = off; off += t[i]; }
       const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
-      // stagger_ns == 0xFFFFFFFF: diagnostic mode (profiles/scan_ab.py), skips the look-back — results are wrong
-      const uint32_t excl = stagger_ns == 0xFFFFFFFFu ? 0u : look_back<ScanCfg<CFG>::WIDE>(status, tile, aggregate);
+      // diag_skip_lookback: timing-only diagnostic (VKJIT_SCAN_DIAG=nolookback), results are wrong
+      const uint32_t excl = diag_skip_lookback ? 0u : look_back(status, tile, aggregate);
       if (lane == 0) {
         s_tile_excl[buf] = excl;
         if (COMPRESS && tile == num_tiles - 1) *count_out = excl + aggregate;
@@ -548,285 +542,52 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// warp-specialised scan: the look-back of tile j overlaps the local scan of tile j+1
-// ---------------------------------------------------------------------------------------
-// 31 data warps + 1 control warp per CTA, one CTA per SM, tiles b, b+148, ...
-//   data warps, iteration j :  wait TMA(j) -> read tile j from the ring -> local scan in registers ->
-//                              arrive SCANNED[j&1] -> wait PREFIX[(j-1)&1] -> add the tile/warp offsets
-//                              to the HELD tile j-1 and store it -> hold tile j
-//   control warp, phase j   :  wait SCANNED[j&1] -> TMA-refill the ring stage tile j just left ->
-//                              scan the (slot, warp) totals -> publish the tile aggregate -> look back
-//                              -> arrive PREFIX[j&1]
-// so the ~1 us cross-SM round trip of the look-back runs while the data warps are already scanning the
-// next tile; 3 of the 4 ring stages are always in flight.  Named barriers (bar.sync/bar.arrive,
-// two ids per signal, alternating with the tile parity) connect the two roles.
-constexpr int kWsThreads = 1024;
-constexpr int kWsData = 992;      // 31 data warps
-constexpr int kWsDataWarps = 31;
-enum : int { BAR_SCANNED = 1, BAR_PREFIX = 3 };
+size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (1 + (n + kScanTile - 1) / kScanTile); }
 
-__device__ __forceinline__ void named_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kWsThreads) : "memory"); }
-__device__ __forceinline__ void named_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(kWsThreads) : "memory"); }
-
-template <int MODE> struct WsCfg {  // vectors per data thread, ring depth
-  static constexpr int VPT = MODE == MODE_COMPRESS_VALUE ? 2 : 3;
-  static constexpr int STAGES = MODE == MODE_COMPRESS_VALUE ? 3 : 4;
-  static constexpr int TILE = kWsData * 4 * VPT;                                   // lanes per tile
-  static constexpr int STAGE_WORDS = TILE * (MODE == MODE_COMPRESS_VALUE ? 2 : 1); // mask (+ values) words
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_WORDS * 4;
-};
-
-template <int MODE>
-__global__ void __launch_bounds__(kWsThreads, 1)
-scan_ws_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ values, uint32_t* __restrict__ out,
-               uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles, uint64_t* __restrict__ state) {
-  using C = WsCfg<MODE>;
-  constexpr int VPT = C::VPT, S = C::STAGES, TILE = C::TILE;
-  constexpr int NTOT = VPT * kWsDataWarps;
-  constexpr int PER_LANE = (NTOT + 31) / 32;
-  constexpr bool COMPRESS = MODE >= MODE_COMPRESS_INDEX;
-  constexpr bool WITH_VALUES = MODE == MODE_COMPRESS_VALUE;
-  constexpr uint32_t TILE_BYTES = TILE * 4;
-  extern __shared__ __align__(128) unsigned char ring_raw[];
-  uint32_t* ring = reinterpret_cast<uint32_t*>(ring_raw);
-  __shared__ __align__(8) uint64_t full[S];
-  __shared__ uint32_t s_tot[2][PER_LANE * 32];  // local-scan totals per (slot, warp), then their exclusive offsets
-  __shared__ uint32_t s_tile_excl[2];
-
-  uint64_t* status = state + kStatusStride;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t first = blockIdx.x, stride = gridDim.x;
-  const uint32_t my_tiles = (num_tiles - first + stride - 1) / stride;  // grid <= num_tiles
-  const bool ragged = (n % TILE) != 0;  // the globally last tile is partial: loaded by the data warps with guards
-
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
-    mbar_fence_init();
-  }
-  if (threadIdx.x < 2 * PER_LANE * 32) (&s_tot[0][0])[threadIdx.x] = 0u;  // padding entries stay 0
-  __syncthreads();
-
-  auto issue_tile = [&](uint32_t k) {  // one lane of the control warp: TMA tile k of this CTA into its stage
-    const uint32_t t = first + k * stride;
-    if (ragged && t == num_tiles - 1) return;
-    uint32_t* dst = ring + (size_t)(k % S) * C::STAGE_WORDS;
-    mbar_expect_tx(&full[k % S], WITH_VALUES ? 2 * TILE_BYTES : TILE_BYTES);
-    tma_load_1d(dst, in + (size_t)t * TILE, TILE_BYTES, &full[k % S]);
-    if (WITH_VALUES) tma_load_1d(dst + TILE, values + (size_t)t * TILE, TILE_BYTES, &full[k % S]);
-  };
-
-  if (warp == kWsDataWarps) {
-    // ======================= control warp =======================
-    if (lane == 0)
-      for (uint32_t k = 0; k < (uint32_t)S && k < my_tiles; ++k) issue_tile(k);
-    for (uint32_t j = 0; j < my_tiles; ++j) {
-      const uint32_t tile = first + j * stride;
-      const int buf = j & 1;
-      named_sync(BAR_SCANNED + buf);  // the data warps hold tile j in registers: its ring stage is free again
-      if (lane == 0 && j + S < my_tiles) issue_tile(j + S);
-      uint32_t t[PER_LANE], run = 0;
-#pragma unroll
-      for (int i = 0; i < PER_LANE; ++i) {  // entries >= NTOT are padding (they hold stale offsets): count as 0
-        const int idx = lane * PER_LANE + i;
-        t[i] = idx < NTOT ? s_tot[buf][idx] : 0u;
-        run += t[i];
-      }
-      uint32_t s = run;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, s, o);
-        if (lane >= o) s += u;
-      }
-      uint32_t off = s - run;
-#pragma unroll
-      for (int i = 0; i < PER_LANE; ++i) { s_tot[buf][lane * PER_LANE + i] = off; off += t[i]; }
-      const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
-      const uint32_t excl = look_back<5>(status, tile, aggregate);
-      if (lane == 0) {
-        s_tile_excl[buf] = excl;
-        if (COMPRESS && tile == num_tiles - 1) *count_out = excl + aggregate;
-      }
-      __syncwarp();
-      named_arrive(BAR_PREFIX + buf);
-    }
-    return;
-  }
-
-  // ======================= data warps =======================
-  uint4 held[VPT];      // tile j-1: locally scanned values (scan) / {flags | rank << 4} in .x (compress)
-  uint4 held_val[WITH_VALUES ? VPT : 1];
-
-  // adds the tile/warp offsets to the held tile j and stores it
-  auto store_held = [&](uint32_t j) {
-    const uint32_t tile = first + j * stride;
-    const int buf = j & 1;
-    const size_t tile_base = (size_t)tile * TILE;
-    const bool staged = !(ragged && tile == num_tiles - 1);
-    named_sync(BAR_PREFIX + buf);
-    const uint32_t tile_excl = s_tile_excl[buf];
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-      const uint32_t q = (uint32_t)v * kWsData + threadIdx.x;
-      const size_t e = tile_base + (size_t)q * 4;
-      const uint32_t off = tile_excl + s_tot[buf][v * kWsDataWarps + warp];
-      uint4 r = held[v];
-      if (!COMPRESS) {
-        r.x += off; r.y += off; r.z += off; r.w += off;
-        if (staged || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
-        else {
-          if (e + 0 < n) out[e + 0] = r.x;
-          if (e + 1 < n) out[e + 1] = r.y;
-          if (e + 2 < n) out[e + 2] = r.z;
-        }
-      } else {
-        const uint32_t flags = r.x & 15u;
-        if (flags) {
-          uint32_t p = off + (r.x >> 4);
-          uint4 val;
-          if (WITH_VALUES) val = held_val[WITH_VALUES ? v : 0];
-          else { val.x = (uint32_t)e; val.y = val.x + 1; val.z = val.x + 2; val.w = val.x + 3; }
-          if (flags & 1u) out[p++] = val.x;
-          if (flags & 2u) out[p++] = val.y;
-          if (flags & 4u) out[p++] = val.z;
-          if (flags & 8u) out[p++] = val.w;
-        }
-      }
-    }
-  };
-
-  for (uint32_t j = 0; j < my_tiles; ++j) {
-    const uint32_t tile = first + j * stride;
-    const int buf = j & 1;
-    const size_t tile_base = (size_t)tile * TILE;
-    const bool staged = !(ragged && tile == num_tiles - 1);
-    const uint32_t* stage = ring + (size_t)(j % S) * C::STAGE_WORDS;
-
-    uint4 x[VPT], xv[WITH_VALUES ? VPT : 1];
-    if (staged) {
-      mbar_wait(&full[j % S], (j / S) & 1);
-#pragma unroll
-      for (int v = 0; v < VPT; ++v) {
-        x[v] = reinterpret_cast<const uint4*>(stage)[v * kWsData + threadIdx.x];
-        if (WITH_VALUES) xv[WITH_VALUES ? v : 0] = reinterpret_cast<const uint4*>(stage + TILE)[v * kWsData + threadIdx.x];
-      }
-    } else {  // ragged last tile: guarded loads
-#pragma unroll
-      for (int v = 0; v < VPT; ++v) {
-        const size_t e = tile_base + ((size_t)v * kWsData + threadIdx.x) * 4;
-        x[v].x = e + 0 < n ? in[e + 0] : 0u; x[v].y = e + 1 < n ? in[e + 1] : 0u;
-        x[v].z = e + 2 < n ? in[e + 2] : 0u; x[v].w = e + 3 < n ? in[e + 3] : 0u;
-        if (WITH_VALUES) {
-          uint4& val = xv[WITH_VALUES ? v : 0];
-          val.x = e + 0 < n ? values[e + 0] : 0u; val.y = e + 1 < n ? values[e + 1] : 0u;
-          val.z = e + 2 < n ? values[e + 2] : 0u; val.w = e + 3 < n ? values[e + 3] : 0u;
-        }
-      }
-    }
-    uint4 cur[VPT];
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-      uint32_t flags = 0, vsum;
-      if (COMPRESS) {
-        flags = (x[v].x != 0u ? 1u : 0u) | (x[v].y != 0u ? 2u : 0u) | (x[v].z != 0u ? 4u : 0u) | (x[v].w != 0u ? 8u : 0u);
-        vsum = (uint32_t)__popc(flags);
-      } else {
-        vsum = x[v].x + x[v].y + x[v].z + x[v].w;
-      }
-      uint32_t s = vsum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, s, o);
-        if (lane >= o) s += u;
-      }
-      if (lane == 31) s_tot[buf][v * kWsDataWarps + warp] = s;
-      const uint32_t base = s - vsum;  // exclusive prefix of this vector inside its (slot, warp) group
-      uint4 r;
-      if (COMPRESS) { r.x = flags | (base << 4); r.y = r.z = r.w = 0u; }
-      else if (MODE == MODE_EXCLUSIVE) { r.x = base; r.y = base + x[v].x; r.z = r.y + x[v].y; r.w = r.z + x[v].z; }
-      else { r.x = base + x[v].x; r.y = r.x + x[v].y; r.z = r.y + x[v].z; r.w = r.z + x[v].w; }
-      cur[v] = r;
-    }
-    named_arrive(BAR_SCANNED + buf);  // totals published; everything this thread needs from the stage is in registers
-    if (j >= 1) store_held(j - 1);    // tile j-1's prefix was looked up while tile j was being scanned
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-      held[v] = cur[v];
-      if (WITH_VALUES) held_val[WITH_VALUES ? v : 0] = xv[WITH_VALUES ? v : 0];
-    }
-  }
-  store_held(my_tiles - 1);
-}
-
-template <int MODE>
-static void launch_scan_ws(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
-                           const Scratch& sc, int sm_count, cudaStream_t s) {
-  using C = WsCfg<MODE>;
-  const size_t tiles = (n + C::TILE - 1) / C::TILE;
-  const size_t words = (size_t)kStatusStride * (1 + tiles);
-  if (words > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
-  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, words * sizeof(uint64_t), s);
+static uint32_t prepare_scan(size_t n, const Scratch& sc, cudaStream_t s) {
+  const size_t tiles = (n + kScanTile - 1) / kScanTile;
+  if (scan_state_words(n) > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
+  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, scan_state_words(n) * sizeof(uint64_t), s);
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
-  static bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(scan_ws_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan smem attribute: ") + cudaGetErrorString(e));
-    configured = true;
-  }
-  const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);  // persistent, all CTAs co-resident
-  scan_ws_kernel<MODE><<<grid, kWsThreads, C::SMEM, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
+  return (uint32_t)tiles;
 }
 
-static int scan_cfg() {  // 1 (default): warp-specialised kernel; 0: the earlier all-warps-scan kernel (kept for A/B)
-  static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("VKJIT_SCAN_CFG"); cfg = e ? atoi(e) : 1; if (cfg != 0) cfg = 1; }
-  return cfg;
-}
-static uint32_t scan_debug_flag() {  // VKJIT_SCAN_STAGGER_NS=-1: diagnostic mode of the cfg-0 kernel (no look-back)
-  static long v = -2;
-  if (v == -2) { const char* e = getenv("VKJIT_SCAN_STAGGER_NS"); v = e ? atol(e) : 0; }
-  return v < 0 ? 0xFFFFFFFFu : 0u;
-}
-
-// smallest tile of any configuration: sizes the status array
-size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (2 + n / WsCfg<MODE_COMPRESS_VALUE>::TILE); }
+constexpr size_t kScanSmem = (size_t)kScanStages * kScanTile * 4;
 
 template <int MODE>
-static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
+static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n, uint32_t tiles,
                         const Scratch& sc, int sm_count, cudaStream_t s) {
-  if (scan_cfg() == 1) { launch_scan_ws<MODE>(in, values, out, count_out, n, sc, sm_count, s); return; }
-  constexpr size_t smem = (size_t)kScanStages * ScanCfg<0>::TILE * 4;
-  const size_t tiles = (n + ScanCfg<0>::TILE - 1) / ScanCfg<0>::TILE;
-  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, (size_t)kStatusStride * (1 + tiles) * sizeof(uint64_t), s);
-  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
   static bool configured = false;
   if (!configured) {
-    e = cudaFuncSetAttribute(scan_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem);
     if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan smem attribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);
-  scan_kernel<MODE, 0><<<grid, ScanCfg<0>::T, smem, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state, scan_debug_flag());
-  e = cudaGetLastError();
+  // one persistent CTA per SM: all CTAs are co-resident, so a tile only ever waits on tiles of
+  // CTAs that are running (forward progress of the look-back does not depend on dispatch order)
+  const unsigned grid = (unsigned)std::min<uint32_t>(tiles, (uint32_t)sm_count);
+  static int diag = -1;
+  if (diag < 0) { const char* e = getenv("VKJIT_SCAN_DIAG"); diag = (e && std::string(e) == "nolookback") ? 1 : 0; }
+  scan_kernel<MODE><<<grid, kScanThreads, kScanSmem, s>>>(in, values, out, count_out, n, tiles, sc.tile_state, (uint32_t)diag);
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
 }
 
 void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream) {
   if (n == 0) return;
   cudaStream_t s = (cudaStream_t)stream;
-  if (exclusive) launch_scan<MODE_EXCLUSIVE>(in, nullptr, out, nullptr, n, sc, sm_count, s);
-  else launch_scan<MODE_INCLUSIVE>(in, nullptr, out, nullptr, n, sc, sm_count, s);
+  const uint32_t tiles = prepare_scan(n, sc, s);
+  if (exclusive) launch_scan<MODE_EXCLUSIVE>(in, nullptr, out, nullptr, n, tiles, sc, sm_count, s);
+  else launch_scan<MODE_INCLUSIVE>(in, nullptr, out, nullptr, n, tiles, sc, sm_count, s);
 }
 
 void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
               const Scratch& sc, int sm_count, void* stream) {
   if (n == 0) return;
   cudaStream_t s = (cudaStream_t)stream;
-  if (values) launch_scan<MODE_COMPRESS_VALUE>(mask, values, out, count_out, n, sc, sm_count, s);
-  else launch_scan<MODE_COMPRESS_INDEX>(mask, nullptr, out, count_out, n, sc, sm_count, s);
+  const uint32_t tiles = prepare_scan(n, sc, s);
+  if (values) launch_scan<MODE_COMPRESS_VALUE>(mask, values, out, count_out, n, tiles, sc, sm_count, s);
+  else launch_scan<MODE_COMPRESS_INDEX>(mask, nullptr, out, count_out, n, tiles, sc, sm_count, s);
 }
 
 __global__ void fill_kernel(uint32_t* out, uint32_t value, size_t n) {

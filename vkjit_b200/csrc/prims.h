@@ -33,7 +33,9 @@ struct Mailbox {
 
 constexpr int kReduceThreads = 512;
 constexpr int kReduceMaxCtas = 2048;
-constexpr int kScanStages = 3;    // TMA-fed shared-memory ring (3 x tile bytes per CTA); tile geometry: ScanCfg in prims.cu
+constexpr int kScanThreads = 1024;
+constexpr int kScanTile = 16384;  // lanes per look-back tile (1024 threads x 4 x uint4 = 64 KiB)
+constexpr int kScanStages = 3;    // TMA-fed shared-memory ring: 3 x 64 KiB per CTA, one CTA per SM
 
 // number of 8-byte words `tile_state` must hold for n lanes
 size_t scan_state_words(size_t n);
