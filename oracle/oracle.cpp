@@ -713,24 +713,54 @@ static std::vector<std::shared_ptr<Words>> run_schedule(Ir& ir, const std::vecto
   return outs;
 }
 
+// internal.rs:492-521 for one group of roots: drop the refs held on deps, rewrite the roots into Bindings
+static void commit_group(Ir& ir, const std::vector<VarId>& sched, std::vector<std::shared_ptr<Words>>& outs) {
+  for (VarId id : sched) {
+    std::vector<VarId> refs(ir.var(id).deps);
+    refs.insert(refs.end(), ir.var(id).side_effects.begin(), ir.var(id).side_effects.end());
+    for (VarId r : refs) ir.dec_ref_count(r);
+  }
+  for (size_t i = 0; i < sched.size(); ++i) {
+    Var& v = ir.var(sched[i]);
+    Var nv; nv.op = OP_BINDING; nv.ty = v.ty; nv.ref_count = v.ref_count;
+    v = nv;
+    ir.arrays[sched[i]] = outs[i];
+  }
+}
+
+static size_t kernel_size_of(Ir& ir, const std::vector<VarId>& sched) {
+  bool have = false; size_t n = 0;
+  record_kernel_size(ir, sched, have, n);
+  if (!have) throw Error(E_SIZE, "schedule has no Binding/Arange: kernel size unknown (internal.rs:1202 num.unwrap())");
+  return n;
+}
+
 // internal.rs:482-525
 void Ir::eval(const VarId* ids, size_t nids) {
   do_schedule(ids, nids);
   try {
-    std::vector<std::shared_ptr<Words>> outs = run_schedule(*this, schedule);
-    // internal.rs:492-503
-    std::vector<VarId> sched = schedule;
-    for (VarId id : sched) {
-      std::vector<VarId> refs(var(id).deps);
-      refs.insert(refs.end(), var(id).side_effects.begin(), var(id).side_effects.end());
-      for (VarId r : refs) dec_ref_count(r);
-    }
-    // internal.rs:505-521
-    for (size_t i = 0; i < sched.size(); ++i) {
-      Var& v = var(sched[i]);
-      Var nv; nv.op = OP_BINDING; nv.ty = v.ty; nv.ref_count = v.ref_count;
-      v = nv;
-      arrays[sched[i]] = outs[i];
+    bool mixed = false;
+    try { kernel_size_of(*this, schedule); } catch (const Error& e) { if (e.code != E_SIZE || schedule.size() < 2) throw; mixed = true; }
+    if (!mixed) {
+      std::vector<std::shared_ptr<Words>> outs = run_schedule(*this, schedule);
+      std::vector<VarId> sched = schedule;
+      commit_group(*this, sched, outs);
+    } else {
+      // SPEC: the reference asserts on a mixed-size schedule (internal.rs:697-706); here the
+      // roots are evaluated in groups of equal kernel size, in schedule order.
+      std::vector<VarId> pending = schedule;
+      while (!pending.empty()) {
+        const size_t size = kernel_size_of(*this, {pending[0]});
+        std::vector<VarId> group{pending[0]}, rest;
+        for (size_t i = 1; i < pending.size(); ++i) {
+          bool same = false;
+          try { same = kernel_size_of(*this, {pending[i]}) == size; } catch (const Error&) { same = false; }
+          (same ? group : rest).push_back(pending[i]);
+        }
+        std::vector<std::shared_ptr<Words>> outs = run_schedule(*this, group);
+        commit_group(*this, group, outs);
+        pending.swap(rest);
+      }
     }
   } catch (...) {
     // the reference panics here; leave the Ir usable: undo the schedule

@@ -309,3 +309,26 @@ def test_disk_cubin_cache(cuda_backend, cir, tmp_path, monkeypatch):
     st = cuda_backend.stats()
     assert st["cache_misses"] == 1 and st["disk_hits"] == 1
     assert same_bits(a, b, True)
+
+
+def test_mixed_size_schedule_splits_into_kernels(cuda_backend, cir, oir):
+    """one eval with roots of different sizes runs one kernel per size group (the reference
+    asserts, internal.rs:697-706); a conflict inside a single root's expression is still an error."""
+    from vkjit_b200 import VkjitSizeError
+    res = []
+    for ir in (cir, oir):
+        a = ir.add(ir.arange(U32, 1000), ir.const_u32(1))
+        b = ir.mul(ir.arange(F32, 77), ir.const_f32(0.5))
+        c = ir.bop(Bop.Xor, ir.arange(U32, 1000), ir.const_u32(0xFFFF))
+        d = ir.add(ir.arange(I32, 5), ir.const_i32(-2))
+        if ir is cir:
+            cuda_backend.stats_reset()
+        ir.eval([a, b, c, d])
+        if ir is cir:
+            assert cuda_backend.stats()["trace_launches"] == 3       # sizes 1000 (a, c), 77, 5
+        res.append([read(ir, v) for v in (a, b, c, d)])
+        with pytest.raises(VkjitSizeError):
+            ir.eval([ir.add(ir.arange(U32, 3), ir.arange(U32, 4)), ir.arange(U32, 9)])
+        ir.eval([ir.arange(U32, 9)])                                 # still usable
+    for x, y in zip(*res):
+        assert x.tobytes() == y.tobytes()

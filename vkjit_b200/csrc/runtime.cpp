@@ -346,23 +346,22 @@ void Backend::launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args
 }
 
 // ---- Ir::eval (internal.rs:482-525) ---------------------------------------------------------
-void eval(Ir& ir, const VarId* ids, size_t n) {
-  const uint64_t t0 = now_ns();
-  Backend& be = Backend::get();
-  ir.do_schedule(ids, n);
-  if (ir.schedule.empty()) return;
+namespace {
+
+// Compile-or-lookup + launch of one group of roots that share a kernel size; the roots become Bindings.
+void eval_group(Ir& ir, Backend& be, const std::vector<VarId>& roots) {
   static thread_local Program prog;
   static thread_local std::vector<Array*> outs;
   static thread_local std::vector<void*> argv;
   static thread_local std::vector<uint64_t> ptrs;
   outs.clear();
   try {
-    build_program(ir, ir.schedule, true, prog);
+    build_program(ir, roots, true, prog);
     if (prog.n == 0) fail(VKJIT_ERR_SIZE, "zero-sized kernel");
     bool aligned = true;
     for (const Param& pr : prog.params)
       if ((pr.use & USE_STREAM) && ((uintptr_t)ir.vars[pr.var].array->ptr & 15u)) aligned = false;
-    if (!aligned) build_program(ir, ir.schedule, false, prog);  // scalar ld/st variant for foreign pointers
+    if (!aligned) build_program(ir, roots, false, prog);  // scalar ld/st variant for foreign pointers
 
     CachedKernel* k = be.lookup(prog);
     if (!k) k = be.compile(ir, prog);
@@ -384,18 +383,58 @@ void eval(Ir& ir, const VarId* ids, size_t n) {
     if (grid > cap) grid = cap;
     be.launch(k, (uint32_t)grid, 256, argv.data());
 
-    ir.commit_roots(ir.schedule, outs);
+    ir.commit_roots(roots, outs);
     outs.clear();
   } catch (...) {
     for (Array* a : outs) release_array(a);
     outs.clear();
+    throw;
+  }
+}
+
+}  // namespace
+
+void eval(Ir& ir, const VarId* ids, size_t n) {
+  const uint64_t t0 = now_ns();
+  Backend& be = Backend::get();
+  ir.do_schedule(ids, n);
+  if (ir.schedule.empty()) return;
+  try {
+    try {
+      eval_group(ir, be, ir.schedule);  // the common case: one kernel for the whole schedule
+    } catch (const Error& e) {
+      if (e.code != VKJIT_ERR_SIZE || ir.schedule.size() < 2) throw;
+      // Mixed-size schedule.  The reference asserts here (internal.rs:697-706); instead the
+      // roots are evaluated in groups of equal kernel size, in schedule order.  A size conflict INSIDE one
+      // root's expression still fails below.
+      std::vector<VarId> pending(ir.schedule);
+      Program probe;
+      while (!pending.empty()) {
+        std::vector<VarId> one{pending[0]};
+        build_program(ir, one, true, probe);  // throws for an intrinsically inconsistent root
+        const uint64_t size = probe.n;
+        const bool sharded = probe.sharded;
+        std::vector<VarId> group{pending[0]}, rest;
+        for (size_t i = 1; i < pending.size(); ++i) {
+          std::vector<VarId> r{pending[i]};
+          bool same = false;
+          try {
+            build_program(ir, r, true, probe);
+            same = probe.n == size && probe.sharded == sharded;
+          } catch (const Error&) { same = false; }  // reported when its own turn comes
+          (same ? group : rest).push_back(pending[i]);
+        }
+        eval_group(ir, be, group);
+        pending.swap(rest);
+      }
+    }
+  } catch (...) {
     ir.clear_schedule();
     throw;
   }
   ir.clear_schedule();
   g_counters.last_eval_ns = now_ns() - t0;
 }
-
 
 // Fused trace -> reduce: evaluates the unevaluated var `id` lane by lane and reduces it in the same
 // kernel (8 B/lane for sum(x*y+c) instead of 16 B/lane when z is materialised first).  `id` stays
