@@ -211,13 +211,24 @@ def ours(args):
     n_local = ir.size(x)
     vk.sync()
 
+    # N>1: the L2-eviction kernels take a different time on every GPU; without re-alignment that spread
+    # (~10 us) would be charged to the collective of the next timed reduction (each rank waits for the slowest).
+    # An UNTIMED tiny all-reduce after each eviction lines the streams up again (measured: 11.5 us, 8 GPUs).
+    tiny = ir.cast(ir.arange_sharded(T.U32, 4096 * world), T.F32) if world > 1 else None
+    if tiny is not None:
+        ir.eval([tiny])
+
+    def align():
+        if tiny is not None:
+            ir.dec_ref_count(ir.reduce(Red.Sum, tiny))
+
     def step(timed):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
-        flush_l2()
+        flush_l2(); align()
         if timed: ev[0].record(stream)
         s = ir.reduce(Red.Sum, x)
         if timed: ev[1].record(stream)
-        flush_l2()
+        flush_l2(); align()
         if timed: ev[2].record(stream)
         m = ir.reduce(Red.Max, x)
         if timed: ev[3].record(stream)
@@ -253,7 +264,7 @@ def ours(args):
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
     gpu_sum = float(ir.as_slice(results[0], T.F32)[0])
     gpu_max = float(ir.as_slice(results[1], T.F32)[0])
-    launches = st["trace_launches"] + st["prim_launches"]
+    launches = st["trace_launches"] + st["prim_launches"]  # includes the untimed alignment reductions at N>1
 
     # ---- roofline of the dominant kernel (reduce_kernel<float,SUM>): kernel-only, no collective
     peak, peak_src = peaks()
@@ -364,7 +375,8 @@ def ours(args):
             "config": {"workload": "R28: sum+max over 2^28 f32 (BASELINE.json configs[1])", "n": N_TOTAL, "n_per_gpu": n_local,
                        "parallelism": (f"contiguous 1-D shards x{world}, per-GPU partial + " + ("all-reduce fused into the reduce kernel's last CTA over NVLink peer memory (P2P mailbox)" if args.collective == "p2p" else "NCCL all-reduce")) if world > 1 else "single GPU",
                        "l2": "evicted before every timed reduction by streaming a 256 MiB read through L2 (clean lines: no write-back inside the timed kernel); inputs are 1 GiB/N per GPU, larger than the 126 MB L2",
-                       "timing": "CUDA events on the backend stream per reduction, mean over steps, max over ranks"},
+                       "timing": "CUDA events on the backend stream per reduction, mean over steps, max over ranks" +
+                                 ("; ranks re-aligned by an untimed tiny all-reduce after each L2 eviction (outside the events)" if world > 1 else "")},
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "wall_s_timed_region": t_wall, "result": {"sum": gpu_sum, "max": gpu_max},
             "hbm_frac_whole_job": value / (peak * world),
