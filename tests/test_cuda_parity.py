@@ -221,8 +221,8 @@ def test_fused_trace_reduce(cuda_backend, cir, oir, n):
 
 
 # ---------------------------------------------------------------- prefix sum / compress
-SCAN_SIZES = [1, 2, 3, 4, 5, 1023, 4095, 4096, 4097, 16383, 16384, 16385, 16387, 32768, 5 * 16384 + 3, (1 << 20) + 1,
-              3 * (1 << 20) + 7]
+SCAN_SIZES = [1, 2, 3, 4, 5, 1023, 4095, 4096, 4097, 16383, 16384, 16385, 16387, 24575, 24576, 24577, 32768, 49153,
+              5 * 16384 + 3, 5 * 24576 + 3, (1 << 20) + 1, 3 * (1 << 20) + 7]
 
 
 @pytest.mark.parametrize("n", SCAN_SIZES)

@@ -266,7 +266,7 @@ void p2p_allreduce(int red, uint32_t ty, void* out, const Mailbox& mb, void* str
 // ---------------------------------------------------------------------------------------
 // decoupled look-back scan (Merrill & Garland) — prefix sum and stream compaction
 // ---------------------------------------------------------------------------------------
-// Tile = 1024 threads x 4 vectors x 4 lanes = 16384 lanes (64 KiB in, 64 KiB out).  Vector
+// Tile = 1024 threads x VPT vectors x 4 lanes (24576 lanes = 96 KiB for the scans, see ScanGeom).  Vector
 // q = j*1024 + t of a tile is held by thread t in register slot j, so every shared-memory read
 // and every global store of a warp covers 512 contiguous bytes.  Tile status words pack
 // {flag:32 | value:32} into one 64-bit word so flag and value travel in a single (volatile,
@@ -376,6 +376,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // barrier or looking back — the three serial phases no longer starve the memory system
 // (the first version, 2 non-persistent CTAs/SM with register loads, spent 60 % of its stall
 // samples at barriers and reached 45 % DRAM utilisation).
+// Tile geometry per mode.  Fewer, larger generations amortise the per-generation look-back cost (measured,
+// prefix sum at 2^28: 16384-lane tiles / 3 stages 0.46 ms, 24576-lane tiles / 2 stages 0.40 ms); the
+// compress-with-values variant also holds the values of a tile in registers and keeps the smaller tile
+// (the larger one spills).
+template <int MODE> struct ScanGeom {
+  static constexpr int TILE = MODE == MODE_COMPRESS_VALUE ? 16384 : 24576;
+  static constexpr int STAGES = MODE == MODE_COMPRESS_VALUE ? 3 : 2;
+  static constexpr size_t SMEM = (size_t)STAGES * TILE * 4;
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: mask words
@@ -383,6 +393,8 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
             uint32_t* __restrict__ out, uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles,
             uint64_t* __restrict__ state, uint32_t diag_skip_lookback) {
   constexpr int T = kScanThreads;
+  constexpr int kScanTile = ScanGeom<MODE>::TILE;
+  constexpr int kScanStages = ScanGeom<MODE>::STAGES;
   constexpr int VPT = kScanTile / (T * 4);  // 128-bit vectors per thread
   constexpr int WARPS = T / 32;
   constexpr int NTOT = VPT * WARPS;         // (slot, warp) totals per tile
@@ -542,52 +554,46 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   }
 }
 
-size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (1 + (n + kScanTile - 1) / kScanTile); }
-
-static uint32_t prepare_scan(size_t n, const Scratch& sc, cudaStream_t s) {
-  const size_t tiles = (n + kScanTile - 1) / kScanTile;
-  if (scan_state_words(n) > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
-  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, scan_state_words(n) * sizeof(uint64_t), s);
-  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
-  return (uint32_t)tiles;
-}
-
-constexpr size_t kScanSmem = (size_t)kScanStages * kScanTile * 4;
+size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (2 + n / kScanMinTile); }
 
 template <int MODE>
-static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n, uint32_t tiles,
+static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
                         const Scratch& sc, int sm_count, cudaStream_t s) {
+  using G = ScanGeom<MODE>;
+  const size_t tiles = (n + G::TILE - 1) / G::TILE;
+  const size_t words = (size_t)kStatusStride * (1 + tiles);
+  if (words > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
+  cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, words * sizeof(uint64_t), s);
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem);
+    e = cudaFuncSetAttribute(scan_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan smem attribute: ") + cudaGetErrorString(e));
     configured = true;
   }
   // one persistent CTA per SM: all CTAs are co-resident, so a tile only ever waits on tiles of
   // CTAs that are running (forward progress of the look-back does not depend on dispatch order)
-  const unsigned grid = (unsigned)std::min<uint32_t>(tiles, (uint32_t)sm_count);
+  const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);
   static int diag = -1;
-  if (diag < 0) { const char* e = getenv("VKJIT_SCAN_DIAG"); diag = (e && std::string(e) == "nolookback") ? 1 : 0; }
-  scan_kernel<MODE><<<grid, kScanThreads, kScanSmem, s>>>(in, values, out, count_out, n, tiles, sc.tile_state, (uint32_t)diag);
-  cudaError_t e = cudaGetLastError();
+  if (diag < 0) { const char* d = getenv("VKJIT_SCAN_DIAG"); diag = (d && std::string(d) == "nolookback") ? 1 : 0; }
+  scan_kernel<MODE><<<grid, kScanThreads, G::SMEM, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state, (uint32_t)diag);
+  e = cudaGetLastError();
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
 }
 
 void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream) {
   if (n == 0) return;
   cudaStream_t s = (cudaStream_t)stream;
-  const uint32_t tiles = prepare_scan(n, sc, s);
-  if (exclusive) launch_scan<MODE_EXCLUSIVE>(in, nullptr, out, nullptr, n, tiles, sc, sm_count, s);
-  else launch_scan<MODE_INCLUSIVE>(in, nullptr, out, nullptr, n, tiles, sc, sm_count, s);
+  if (exclusive) launch_scan<MODE_EXCLUSIVE>(in, nullptr, out, nullptr, n, sc, sm_count, s);
+  else launch_scan<MODE_INCLUSIVE>(in, nullptr, out, nullptr, n, sc, sm_count, s);
 }
 
 void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
               const Scratch& sc, int sm_count, void* stream) {
   if (n == 0) return;
   cudaStream_t s = (cudaStream_t)stream;
-  const uint32_t tiles = prepare_scan(n, sc, s);
-  if (values) launch_scan<MODE_COMPRESS_VALUE>(mask, values, out, count_out, n, tiles, sc, sm_count, s);
-  else launch_scan<MODE_COMPRESS_INDEX>(mask, nullptr, out, count_out, n, tiles, sc, sm_count, s);
+  if (values) launch_scan<MODE_COMPRESS_VALUE>(mask, values, out, count_out, n, sc, sm_count, s);
+  else launch_scan<MODE_COMPRESS_INDEX>(mask, nullptr, out, count_out, n, sc, sm_count, s);
 }
 
 __global__ void fill_kernel(uint32_t* out, uint32_t value, size_t n) {

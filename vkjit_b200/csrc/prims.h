@@ -34,8 +34,8 @@ struct Mailbox {
 constexpr int kReduceThreads = 512;
 constexpr int kReduceMaxCtas = 2048;
 constexpr int kScanThreads = 1024;
-constexpr int kScanTile = 16384;  // lanes per look-back tile (1024 threads x 4 x uint4 = 64 KiB)
-constexpr int kScanStages = 3;    // TMA-fed shared-memory ring: 3 x 64 KiB per CTA, one CTA per SM
+// look-back tile geometry is per mode (ScanGeom in prims.cu); the smallest tile sizes the status array
+constexpr int kScanMinTile = 16384;
 
 // number of 8-byte words `tile_state` must hold for n lanes
 size_t scan_state_words(size_t n);
