@@ -195,7 +195,7 @@ def ours(args):
         vk.sync()
         torch.cuda.synchronize()
 
-    flush_buf = torch.zeros(64 << 20, dtype=torch.int32, device=dev)  # 256 MiB = 2x the 126 MB L2
+    flush_buf = torch.zeros(64 << 20, dtype=torch.float32, device=dev)  # 256 MiB = 2x the 126 MB L2 (f32: summed in place, no upcast copy)
 
     def flush_l2():
         # Evict the inputs by streaming a 256 MiB READ through L2.  A write-flush would leave ~126 MB

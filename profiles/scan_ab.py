@@ -9,7 +9,7 @@ from vkjit_b200.ir import Bop, Ir, VarType as T
 vk.init(0)
 stream = torch.cuda.ExternalStream(vk.stream_ptr())
 ir = Ir()
-fb = torch.zeros(64 << 20, dtype=torch.int32, device="cuda")
+fb = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
 n = 1 << 28
 lanes = ir.arange(T.U32, n)
 vals = hash_trace(ir, lanes, 3)

@@ -9,7 +9,7 @@ from vkjit_b200.ir import Ir, Red, VarType as T
 vk.init(0)
 stream = torch.cuda.ExternalStream(vk.stream_ptr())
 ir = Ir()
-fb = torch.zeros(64 << 20, dtype=torch.int32, device="cuda")
+fb = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
 def flush():
     with torch.cuda.stream(stream):
         fb.sum()
