@@ -376,13 +376,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // barrier or looking back — the three serial phases no longer starve the memory system
 // (the first version, 2 non-persistent CTAs/SM with register loads, spent 60 % of its stall
 // samples at barriers and reached 45 % DRAM utilisation).
-// Tile geometry per mode.  Fewer, larger generations amortise the per-generation look-back cost (measured,
-// prefix sum at 2^28: 16384-lane tiles / 3 stages 0.46 ms, 24576-lane tiles / 2 stages 0.40 ms); the
-// compress-with-values variant also holds the values of a tile in registers and keeps the smaller tile
-// (the larger one spills).
+// Tile geometry.  Fewer, larger generations amortise the per-generation look-back cost (measured at 2^28:
+// prefix sum 0.46 ms with 16384-lane tiles / 3 stages, 0.39 ms with 24576-lane tiles / 2 stages; compress
+// 0.65 -> 0.59 ms).  1024 threads x 6 vectors is the largest tile that stays within 64 registers.
 template <int MODE> struct ScanGeom {
-  static constexpr int TILE = MODE == MODE_COMPRESS_VALUE ? 16384 : 24576;
-  static constexpr int STAGES = MODE == MODE_COMPRESS_VALUE ? 3 : 2;
+  static constexpr int TILE = 24576;
+  static constexpr int STAGES = 2;
   static constexpr size_t SMEM = (size_t)STAGES * TILE * 4;
 };
 
@@ -484,22 +483,6 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
         tma_load_1d(ring + (size_t)stage * kScanTile, in + (size_t)t2 * kScanTile, TILE_BYTES, &full[stage]);
       }
     }
-    // compress: the values of vectors with a selected lane are requested NOW, so their HBM latency
-    // overlaps the look-back instead of following it (the mask words in x[] are dead after `flags`)
-    uint4 val[VPT];
-    if (MODE == MODE_COMPRESS_VALUE) {
-#pragma unroll
-      for (int j = 0; j < VPT; ++j) {
-        const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
-        if (flags[j]) {
-          if (staged || e + 3 < n) val[j] = ld_stream(reinterpret_cast<const uint4*>(values + e));
-          else {
-            val[j].x = e + 0 < n ? values[e + 0] : 0u; val[j].y = e + 1 < n ? values[e + 1] : 0u;
-            val[j].z = e + 2 < n ? values[e + 2] : 0u; val[j].w = 0u;
-          }
-        }
-      }
-    }
     if (warp == 0) {
       uint32_t t[PER_LANE], run = 0;
 #pragma unroll
@@ -541,8 +524,13 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
       } else if (flags[j]) {
         // selected lanes are written at their rank; flags of out-of-range lanes are 0
         uint4 v;
-        if (MODE == MODE_COMPRESS_VALUE) v = val[j];
-        else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
+        if (MODE == MODE_COMPRESS_VALUE) {  // values are read once, only for vectors with a selected lane
+          if (staged || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
+          else {
+            v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
+            v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
+          }
+        } else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
         if (flags[j] & 1u) out[p++] = v.x;
         if (flags[j] & 2u) out[p++] = v.y;
         if (flags[j] & 4u) out[p++] = v.z;
