@@ -269,12 +269,11 @@ void p2p_allreduce(int red, uint32_t ty, void* out, const Mailbox& mb, void* str
 // Tile = 1024 threads x VPT vectors x 4 lanes (24576 lanes = 96 KiB for the scans, see ScanGeom).  Vector
 // q = j*1024 + t of a tile is held by thread t in register slot j, so every shared-memory read
 // and every global store of a warp covers 512 contiguous bytes.  Tile status words pack
-// {flag:32 | value:32} into one 64-bit word so flag and value travel in a single (volatile,
+// {flag:32 | value:32} into one 64-bit word so flag and value travel in a single (relaxed,
 // L2-coherent) access and no fence is needed between them.
-// Why the tile is this large: the look-back frontier advances by at most 32 tiles (one warp-wide
-// window) per L2 round trip (~0.2 us), i.e. ~150 tiles/us; with 4096-lane tiles that caps the
-// kernel near 4 TB/s of traffic (measured: 2.9 TB/s), with 16384-lane tiles the cap is ~4x the
-// HBM rate.
+// Why the tile is this large: every generation of 148 tiles pays one cross-SM aggregate exchange, and
+// with strided persistent tiles each generation runs at the pace of its slowest SM; fewer, larger
+// generations pay that less often (history: profiles/r01_scan_history.md).
 enum : uint32_t { ST_INVALID = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2 };
 enum ScanMode { MODE_EXCLUSIVE = 0, MODE_INCLUSIVE = 1, MODE_COMPRESS_INDEX = 2, MODE_COMPRESS_VALUE = 3 };
 
@@ -371,8 +370,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Persistent kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The input
-// tiles arrive through a kScanStages-deep shared-memory ring filled by TMA bulk copies, so up to
-// (stages-1) x 64 KiB of loads per SM stay in flight while the CTA is scanning, waiting at a
+// tiles arrive through a 2-stage shared-memory ring filled by TMA bulk copies, so up to
+// 2 x 96 KiB of loads per SM stay in flight while the CTA is scanning, waiting at a
 // barrier or looking back — the three serial phases no longer starve the memory system
 // (the first version, 2 non-persistent CTAs/SM with register loads, spent 60 % of its stall
 // samples at barriers and reached 45 % DRAM utilisation).
