@@ -332,3 +332,26 @@ def test_mixed_size_schedule_splits_into_kernels(cuda_backend, cir, oir):
         ir.eval([ir.arange(U32, 9)])                                 # still usable
     for x, y in zip(*res):
         assert x.tobytes() == y.tobytes()
+
+
+@pytest.mark.parametrize("bins", [16, 65536, 100000])
+def test_scatter_add_privatised_in_shared_memory(cuda_backend, cir, oir, bins):
+    """Launches of >= 2^22 lanes keep up to 49152 bins of the scatter_add target in shared memory (the rest
+    go to L2 as before) and flush them once per CTA: u32 bit-exact, f32 within the sum tolerance."""
+    n = (1 << 22) + 5
+    rng = np.random.default_rng(bins)
+    idx = rng.integers(0, bins, n).astype(np.uint32)
+    vals = rng.random(n, dtype=np.float32)
+    res = []
+    for ir in (cir, oir):
+        i = ir.array_u32(idx)
+        b1 = ir.array_u32(np.full(bins, 7, np.uint32))           # non-zero start: the flush must ADD
+        b2 = ir.array_f32(np.zeros(bins, np.float32))
+        s1 = ir.scatter_add(ir.mul(i, ir.const_u32(2654435761)), b1, i, ir.neq(ir.bop(Bop.And, i, ir.const_u32(3)), ir.const_u32(0)))
+        s2 = ir.scatter_add(ir.array_f32(vals), b2, i)
+        ir.eval([s1])
+        ir.eval([s2])
+        res.append((read(ir, b1), read(ir, b2)))
+    assert same_bits(res[0][0], res[1][0], False)
+    tol = 1e-6 * 22
+    assert np.all(np.abs(res[0][1] - res[1][1]) <= tol * np.abs(res[1][1]) + 1e-30)

@@ -398,10 +398,10 @@ vkjit_status vkjit_debug_codegen(vkjit_ir* h, const vkjit_var* ids, size_t n, in
       if (std::find(sched.begin(), sched.end(), ids[i]) == sched.end()) sched.push_back(ids[i]);
     }
     Program p;
-    build_program(ir, sched, true, p);
+    build_program(ir, sched, true, p, -1, (compile & 2) != 0);  // compile bit 1: privatised scatter_add variant
     const std::string src = generate_cuda(ir, p);
     if (out_cubin) *out_cubin = 0;
-    if (compile) {
+    if (compile & 1) {
       std::vector<char> cubin;
       std::string log;
       if (!nvrtc_compile(src, cubin, log)) fail(VKJIT_ERR_COMPILE, "NVRTC rejected the generated kernel:\n" + log + "\n--- source ---\n" + src);

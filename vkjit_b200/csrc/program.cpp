@@ -11,6 +11,7 @@ namespace vkjit {
 void Program::clear() {
   key_len = 0; order.clear(); params.clear(); roots.clear();
   n = 0; have_n = false; base = 0; have_base = false; sharded = false; vectorized = true; reduce = -1;
+  privatize = false; sadd_param = -1;
   hash = Hash128();
 }
 
@@ -68,10 +69,11 @@ int unroll_factor() {
 
 }  // namespace
 
-void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce) {
+void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce, bool privatize) {
   p.clear();
   p.vectorized = vectorized;
   p.reduce = reduce;
+  p.privatize = privatize;
   const uint32_t stamp = ir.next_stamp();
   static thread_local std::vector<Frame> stack;
   stack.clear();
@@ -218,6 +220,7 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
           if (!ty_is_scalar(v.ty)) fail(VKJIT_ERR_UNSUPPORTED, "gather/scatter of a struct");
           if (v.op != OP_GATHER && vars[v.side_effect].ty != v.ty) fail(VKJIT_ERR_TYPE, "scatter: source and target types differ");
           if (v.op == OP_SCATTER_ADD && v.ty == VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "scatter_add on Bool");
+          if (v.op == OP_SCATTER_ADD && p.sadd_param < 0) p.sadd_param = (int)vars[v.side_effect].aux;
           number_node(id, v);
           break;
         }
@@ -242,7 +245,8 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   if (p.params.size() + p.roots.size() > 480) fail(VKJIT_ERR_UNSUPPORTED, "too many arrays in one kernel (4 KB parameter limit)");
 
   if (kn + 4 + p.roots.size() > key.size()) { key.resize(kn + 64 + p.roots.size()); kw = key.data(); }
-  kw[1] = (vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16);
+  if (p.sadd_param < 0 || reduce >= 0) p.privatize = false;
+  kw[1] = (vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16) | (p.privatize ? 1u << 24 : 0u);
   for (size_t k = 0; k < p.params.size(); ++k) kw[binding_pos[k]] |= (uint32_t)p.params[k].use << 16;
   kw[kn++] = 0xFFFFFFFFu;
   for (uint32_t r : p.roots) kw[kn++] = r;
@@ -492,6 +496,17 @@ struct Gen {
         const std::string at = "g" + std::to_string(pd) + " + (u32)" + dep(v, 1).name;
         std::string stmt;
         if (v.op == OP_SCATTER) stmt = "*(" + at + ") = " + to_word(v.ty, src.name) + ";";
+        else if (p.privatize && (int)pd == p.sadd_param) {
+          // bins [0, kbins) live in this CTA's shared memory (flushed once at the end of the kernel),
+          // the rest go to L2 as before: shared-memory atomics and L2 REDs run side by side
+          const std::string ix = "(u32)" + dep(v, 1).name;
+          if (v.ty == VKJIT_TY_F32)
+            stmt = "{ const u32 ix_ = " + ix + "; if (ix_ < kbins) atomicAdd(reinterpret_cast<f32*>(vk_sbins + ix_), " + src.name +
+                   "); else atomicAdd(reinterpret_cast<f32*>(g" + std::to_string(pd) + " + ix_), " + src.name + "); }";
+          else
+            stmt = "{ const u32 ix_ = " + ix + "; if (ix_ < kbins) atomicAdd(vk_sbins + ix_, " + to_word(v.ty, src.name) +
+                   "); else atomicAdd(g" + std::to_string(pd) + " + ix_, " + to_word(v.ty, src.name) + "); }";
+        }
         else if (v.ty == VKJIT_TY_F32) stmt = "atomicAdd(reinterpret_cast<f32*>(" + at + "), " + src.name + ");";
         else stmt = "atomicAdd(" + at + ", " + to_word(v.ty, src.name) + ");";  // mod 2^32 for U32 and I32 alike
         if (v.ndeps >= 3) stmt = "if (" + dep(v, 2).name + ") { " + stmt + " }";
@@ -602,8 +617,16 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
     s += reduce_defines(p.reduce, g.vals[p.roots[0]].ty) + kReduceEpilogue + "\n";
   }
 
+  const bool priv = p.privatize;
+  bool priv_f32 = false;
+  if (priv) {
+    priv_f32 = ir.vars[p.params[p.sadd_param].var].ty == VKJIT_TY_F32;
+    s += "extern __shared__ u32 vk_sbins[];  // privatised scatter_add bins [0, kbins)\n\n";
+  }
+
   // per-lane body
   s += "__device__ __forceinline__ void vk_lane(const u32 gi, const u32 li";
+  if (priv) s += ", const u32 kbins";
   for (uint32_t k : streams) s += ", const u32 in" + std::to_string(k);
   for (size_t r = 0; r < nroots; ++r) s += ", u32& out" + std::to_string(r);
   for (uint32_t k : ptrs) {
@@ -614,13 +637,15 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
 
   auto call = [&](const std::string& gi, const std::string& li, const char* comp, bool vec) {
     std::string c = "vk_lane(" + gi + ", " + li;
+    if (priv) c += ", kbins";
     for (uint32_t k : streams) c += ", a" + std::to_string(k) + (vec ? std::string(".") + comp : "");
     for (size_t r = 0; r < nroots; ++r) c += ", r" + std::to_string(r) + (vec ? std::string(".") + comp : "");
     for (uint32_t k : ptrs) c += ", p" + std::to_string(k);
     return c + ");";
   };
 
-  s += "extern \"C\" __global__ void __launch_bounds__(256) vkjit_trace(const u32 n, const u32 base";
+  s += std::string("extern \"C\" __global__ void __launch_bounds__(") + (priv ? "1024" : "256") + ") vkjit_trace(const u32 n, const u32 base";
+  if (priv) s += ", const u32 kbins";
   for (uint32_t k = 0; k < p.params.size(); ++k) {
     const bool w = p.params[k].use & USE_SCATTER;
     s += std::string(",\n    ") + (w ? "u32* " : "const u32* __restrict__ ") + "p" + std::to_string(k);
@@ -629,6 +654,7 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   else for (size_t r = 0; r < nroots; ++r) s += ",\n    u32* __restrict__ o" + std::to_string(r);
   s += ") {\n";
   if (reduce) s += "  acc_t c0 = VK_IDENTITY, c1 = VK_IDENTITY, c2 = VK_IDENTITY, c3 = VK_IDENTITY;\n";
+  if (priv) s += "  for (u32 i = threadIdx.x; i < kbins; i += blockDim.x) vk_sbins[i] = 0u;\n  __syncthreads();\n";
   s += "  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;\n";
   s += "  const u32 nthreads = gridDim.x * blockDim.x;\n";
   if (p.vectorized) {
@@ -661,6 +687,13 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   else for (size_t r = 0; r < nroots; ++r) s += "    o" + std::to_string(r) + "[i] = r" + std::to_string(r) + ";\n";
   s += "  }\n";
   if (reduce) s += "  vk_finish(VK_APPLY(VK_APPLY(c0, c1), VK_APPLY(c2, c3)), partials, ticket, o0);\n";
+  if (priv) {
+    const std::string g = "p" + std::to_string(p.sadd_param);
+    s += "  __syncthreads();\n  for (u32 i = threadIdx.x; i < kbins; i += blockDim.x) {\n    const u32 w = vk_sbins[i];\n";
+    if (priv_f32) s += "    if (w != 0u) atomicAdd(reinterpret_cast<f32*>(" + g + " + i), __uint_as_float(w));\n";
+    else s += "    if (w != 0u) atomicAdd(" + g + " + i, w);\n";
+    s += "  }\n";
+  }
   s += "}\n";
   return s;
 }

@@ -41,6 +41,8 @@ struct Program {
   bool sharded = false;
   bool vectorized = true;       // 128-bit ld/st variant
   int reduce = -1;              // >= 0: fused trace -> reduce kernel (VKJIT_RED_*), the single root is not stored
+  bool privatize = false;       // variant: the first scatter_add target is partly privatised in shared memory
+  int sadd_param = -1;          // param index of the first scatter_add target (-1: none)
   Hash128 hash;
 
   void clear();
@@ -49,7 +51,8 @@ struct Program {
 // Walks the schedule, fills `p` (key, order, params, n) and hashes it.  Throws Error on the
 // reference's panics: size mismatch (internal.rs:699-702), size-less schedule (:1202),
 // gather from a non-buffer (:1054), scatter into a non-buffer (:1059-1062), struct roots.
-void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce = -1);
+void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce = -1,
+                   bool privatize = false);
 
 // CUDA C source of the kernel for `p` (entry point "vkjit_trace").
 std::string generate_cuda(const Ir& ir, const Program& p);

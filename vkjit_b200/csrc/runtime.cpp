@@ -27,6 +27,7 @@ struct Driver {
   CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   bool load(std::string& why) {
     if (handle) return true;
     handle = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
@@ -37,7 +38,8 @@ struct Driver {
     ModuleGetFunction = (decltype(ModuleGetFunction))sym("cuModuleGetFunction");
     LaunchKernel = (decltype(LaunchKernel))sym("cuLaunchKernel");
     GetErrorString = (decltype(GetErrorString))sym("cuGetErrorString");
-    if (!ModuleLoadData || !ModuleUnload || !ModuleGetFunction || !LaunchKernel || !GetErrorString) {
+    FuncSetAttribute = (decltype(FuncSetAttribute))sym("cuFuncSetAttribute");
+    if (!ModuleLoadData || !ModuleUnload || !ModuleGetFunction || !LaunchKernel || !GetErrorString || !FuncSetAttribute) {
       why = "libcuda.so.1 lacks required entry points";
       return false;
     }
@@ -312,6 +314,8 @@ CachedKernel* Backend::compile(const Ir& ir, const Program& p) {
   cku(g_drv.ModuleLoadData(&mod, cubin.data()), "cuModuleLoadData");
   CUfunction fn;
   cku(g_drv.ModuleGetFunction(&fn, mod, "vkjit_trace"), "cuModuleGetFunction");
+  if (p.privatize)
+    cku(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kPrivatizeMaxBytes), "cuFuncSetAttribute");
   auto* k = new CachedKernel();
   k->module = mod; k->function = fn; k->key.assign(p.key.begin(), p.key.begin() + p.key_len);
   k->nparams = (uint32_t)p.params.size(); k->nroots = (uint32_t)p.roots.size(); k->vectorized = p.vectorized;
@@ -340,8 +344,8 @@ void Backend::clear_cache() {
   cache_.clear();
 }
 
-void Backend::launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args) {
-  cku(g_drv.LaunchKernel((CUfunction)k->function, grid, 1, 1, block, 1, 1, 0, (CUstream)stream, args, nullptr), "cuLaunchKernel");
+void Backend::launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args, uint32_t smem_bytes) {
+  cku(g_drv.LaunchKernel((CUfunction)k->function, grid, 1, 1, block, 1, 1, smem_bytes, (CUstream)stream, args, nullptr), "cuLaunchKernel");
   g_counters.trace_launches += 1;
 }
 
@@ -361,7 +365,14 @@ void eval_group(Ir& ir, Backend& be, const std::vector<VarId>& roots) {
     bool aligned = true;
     for (const Param& pr : prog.params)
       if ((pr.use & USE_STREAM) && ((uintptr_t)ir.vars[pr.var].array->ptr & 15u)) aligned = false;
-    if (!aligned) build_program(ir, roots, false, prog);  // scalar ld/st variant for foreign pointers
+    // scatter_add with many lanes: keep as many bins of the target as fit in shared memory (zeroing and
+    // flushing them costs ~2 x kbins atomics per CTA, so small launches keep the plain L2 path)
+    uint32_t kbins = 0;
+    if (prog.sadd_param >= 0 && prog.n >= kPrivatizeMinLanes && !getenv("VKJIT_NO_PRIVATIZE")) {
+      const size_t bins = ir.vars[prog.params[prog.sadd_param].var].array->bytes / 4;
+      kbins = (uint32_t)std::min<size_t>(bins, kPrivatizeMaxBytes / 4);
+    }
+    if (!aligned || kbins) build_program(ir, roots, aligned, prog, -1, kbins != 0);  // variant rebuild
 
     CachedKernel* k = be.lookup(prog);
     if (!k) k = be.compile(ir, prog);
@@ -374,14 +385,22 @@ void eval_group(Ir& ir, Backend& be, const std::vector<VarId>& roots) {
     for (const Param& pr : prog.params) ptrs.push_back((uint64_t)(uintptr_t)ir.vars[pr.var].array->ptr);
     for (Array* a : outs) ptrs.push_back((uint64_t)(uintptr_t)a->ptr);
     argv.push_back(&n32); argv.push_back(&base32);
+    if (prog.privatize) argv.push_back(&kbins);
     for (uint64_t& p : ptrs) argv.push_back(&p);
 
-    // grid-stride launch: enough CTAs of 256 threads to fill every SM (8 x 256 = 2048 threads/SM)
     const uint64_t items = prog.vectorized ? std::max<uint64_t>(prog.n >> 2, 1) : prog.n;
-    uint64_t grid = (items + 255) / 256;
-    const uint64_t cap = (uint64_t)be.sm_count * 8;
-    if (grid > cap) grid = cap;
-    be.launch(k, (uint32_t)grid, 256, argv.data());
+    if (prog.privatize) {
+      // persistent CTAs of 1024 threads, each with its own copy of the privatised bins
+      const uint32_t smem = kbins * 4;
+      const uint32_t per_sm = smem <= 100 * 1024 ? 2 : 1;
+      be.launch(k, (uint32_t)be.sm_count * per_sm, 1024, argv.data(), smem);
+    } else {
+      // grid-stride launch: enough CTAs of 256 threads to fill every SM (8 x 256 = 2048 threads/SM)
+      uint64_t grid = (items + 255) / 256;
+      const uint64_t cap = (uint64_t)be.sm_count * 8;
+      if (grid > cap) grid = cap;
+      be.launch(k, (uint32_t)grid, 256, argv.data());
+    }
 
     ir.commit_roots(roots, outs);
     outs.clear();

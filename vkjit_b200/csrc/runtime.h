@@ -19,6 +19,10 @@
 
 namespace vkjit {
 
+// scatter_add privatisation: bins kept in shared memory per CTA, and the launch size from which it pays
+constexpr size_t kPrivatizeMaxBytes = 192 * 1024;
+constexpr uint64_t kPrivatizeMinLanes = 1ull << 22;
+
 struct HashOf {
   size_t operator()(const Hash128& h) const { return (size_t)(h.lo ^ (h.hi * 0x9E3779B97F4A7C15ull)); }
 };
@@ -67,7 +71,7 @@ class Backend {
   // kernel cache keyed by trace hash
   CachedKernel* lookup(const Program& p);
   CachedKernel* compile(const Ir& ir, const Program& p);
-  void launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args);
+  void launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args, uint32_t smem_bytes = 0);
   void clear_cache();
 
  private:

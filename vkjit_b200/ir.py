@@ -296,13 +296,13 @@ class Ir:
         self.api.call("var_is_sharded", self._h, id, C.byref(o))
         return bool(o.value)
 
-    def debug_codegen(self, ids: Sequence[int], compile: bool = False):
+    def debug_codegen(self, ids: Sequence[int], compile: bool = False, privatize: bool = False):
         ids = list(ids)
         n, cub = C.c_size_t(), C.c_size_t()
-        self.api.call("debug_codegen", self._h, _u32arr(ids), len(ids), 0, None, 0, C.byref(n), C.byref(cub))
+        self.api.call("debug_codegen", self._h, _u32arr(ids), len(ids), 2 if privatize else 0, None, 0, C.byref(n), C.byref(cub))
         buf = C.create_string_buffer(n.value + 1)
-        self.api.call("debug_codegen", self._h, _u32arr(ids), len(ids), 1 if compile else 0, buf, n.value + 1,
-                      C.byref(n), C.byref(cub))
+        self.api.call("debug_codegen", self._h, _u32arr(ids), len(ids), (1 if compile else 0) | (2 if privatize else 0), buf,
+                      n.value + 1, C.byref(n), C.byref(cub))
         return buf.value.decode(), cub.value
 
 
