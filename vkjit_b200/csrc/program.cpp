@@ -11,7 +11,7 @@ namespace vkjit {
 void Program::clear() {
   key_len = 0; order.clear(); params.clear(); roots.clear();
   n = 0; have_n = false; base = 0; have_base = false; sharded = false; vectorized = true; reduce = -1;
-  privatize = false; sadd_param = -1;
+  privatize = false; sadd_param = -1; has_gather = false;
   hash = Hash128();
 }
 
@@ -221,6 +221,7 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
           if (v.op != OP_GATHER && vars[v.side_effect].ty != v.ty) fail(VKJIT_ERR_TYPE, "scatter: source and target types differ");
           if (v.op == OP_SCATTER_ADD && v.ty == VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "scatter_add on Bool");
           if (v.op == OP_SCATTER_ADD && p.sadd_param < 0) p.sadd_param = (int)vars[v.side_effect].aux;
+          if (v.op == OP_GATHER) p.has_gather = true;
           number_node(id, v);
           break;
         }

@@ -43,6 +43,7 @@ struct Program {
   int reduce = -1;              // >= 0: fused trace -> reduce kernel (VKJIT_RED_*), the single root is not stored
   bool privatize = false;       // variant: the first scatter_add target is partly privatised in shared memory
   int sadd_param = -1;          // param index of the first scatter_add target (-1: none)
+  bool has_gather = false;      // the trace gathers (wants L1 for its table)
   Hash128 hash;
 
   void clear();

@@ -315,7 +315,7 @@ CachedKernel* Backend::compile(const Ir& ir, const Program& p) {
   CUfunction fn;
   cku(g_drv.ModuleGetFunction(&fn, mod, "vkjit_trace"), "cuModuleGetFunction");
   if (p.privatize)
-    cku(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kPrivatizeMaxBytes), "cuFuncSetAttribute");
+    cku(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kPrivatizeMaxBytesNoGather), "cuFuncSetAttribute");
   auto* k = new CachedKernel();
   k->module = mod; k->function = fn; k->key.assign(p.key.begin(), p.key.begin() + p.key_len);
   k->nparams = (uint32_t)p.params.size(); k->nroots = (uint32_t)p.roots.size(); k->vectorized = p.vectorized;
@@ -370,7 +370,12 @@ void eval_group(Ir& ir, Backend& be, const std::vector<VarId>& roots) {
     uint32_t kbins = 0;
     if (prog.sadd_param >= 0 && prog.n >= kPrivatizeMinLanes && !getenv("VKJIT_NO_PRIVATIZE")) {
       const size_t bins = ir.vars[prog.params[prog.sadd_param].var].array->bytes / 4;
-      kbins = (uint32_t)std::min<size_t>(bins, kPrivatizeMaxBytes / 4);
+      // measured on H26 (profiles/hist_ab.py): with a gather in the trace 192 KB of bins is the optimum (more
+      // shared memory leaves too little L1 for the gather table: 0.41 ms at 192 KB, 0.55 ms at 224 KB); without
+      // one, more is better (counting histogram: 0.25 ms at 192 KB, 0.19 ms at 224 KB)
+      size_t max_bytes = prog.has_gather ? kPrivatizeMaxBytes : kPrivatizeMaxBytesNoGather;
+      if (const char* e = getenv("VKJIT_PRIV_KB")) max_bytes = std::min<size_t>((size_t)atoi(e) * 1024, kPrivatizeMaxBytesNoGather);
+      kbins = (uint32_t)std::min<size_t>(bins, max_bytes / 4);
     }
     if (!aligned || kbins) build_program(ir, roots, aligned, prog, -1, kbins != 0);  // variant rebuild
 

@@ -21,6 +21,7 @@ namespace vkjit {
 
 // scatter_add privatisation: bins kept in shared memory per CTA, and the launch size from which it pays
 constexpr size_t kPrivatizeMaxBytes = 192 * 1024;
+constexpr size_t kPrivatizeMaxBytesNoGather = 224 * 1024;
 constexpr uint64_t kPrivatizeMinLanes = 1ull << 22;
 
 struct HashOf {
