@@ -30,5 +30,11 @@ sa = ir.scatter_add(ir.gather(u, idx), bins, idx)
 ir.eval([sa])
 ref = np.cumsum(ir.as_slice(u, T.U32).astype(np.uint64)).astype(np.uint32)
 assert ir.as_slice(s, T.U32)[-1] == ref[-2] and k == k2
+# shared-memory-privatised scatter_add variant (launches of >= 2^22 lanes)
+big = (1 << 22) + 3
+bi = ir.bop(Bop.And, ir.mul(ir.arange(T.U32, big), ir.const_u32(2654435761)), ir.const_u32(0xFFFF))
+bb = ir.array_u32(np.zeros(1 << 16, np.uint32))
+ir.eval([ir.scatter_add(ir.const_u32(1), bb, bi)])
+assert int(ir.as_slice(bb, T.U32).astype(np.uint64).sum()) == big
 vk.sync()
 print("sanitize workload ok", k)
