@@ -376,23 +376,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // (the first version, 2 non-persistent CTAs/SM with register loads, spent 60 % of its stall
 // samples at barriers and reached 45 % DRAM utilisation).
 // Tile geometry.  Fewer, larger generations amortise the per-generation look-back cost (measured at 2^28:
-// prefix sum 0.46 ms with 16384-lane tiles / 3 stages, 0.39 ms with 24576-lane tiles / 2 stages).
-// 1024 threads x 6 vectors is the largest tile that stays within 64 registers.  Compress-with-values uses
-// 16384-lane tiles: 2 x 64 KiB of mask ring plus a 64 KiB shared-memory buffer into which the selected value
-// vectors are cp.async-copied while the look-back is in flight (no registers held across it).
+// prefix sum 0.46 ms with 16384-lane tiles / 3 stages, 0.39 ms with 24576-lane tiles / 2 stages; compress
+// 0.65 -> 0.59 ms).  1024 threads x 6 vectors is the largest tile that stays within 64 registers.
 template <int MODE> struct ScanGeom {
-  static constexpr bool STAGE_VALUES = MODE == MODE_COMPRESS_VALUE;
-  static constexpr int TILE = STAGE_VALUES ? 16384 : 24576;
+  static constexpr int TILE = 24576;
   static constexpr int STAGES = 2;
-  static constexpr size_t SMEM = (size_t)STAGES * TILE * 4 + (STAGE_VALUES ? (size_t)TILE * 4 : 0);
+  static constexpr size_t SMEM = (size_t)STAGES * TILE * 4;
 };
-
-// 16-byte asynchronous global -> shared copy (LDGSTS): no registers, completion by wait_group
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1)
@@ -492,15 +482,6 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
         tma_load_1d(ring + (size_t)stage * kScanTile, in + (size_t)t2 * kScanTile, TILE_BYTES, &full[stage]);
       }
     }
-    // compress with values: request the value vectors that hold a selected lane NOW, straight into shared
-    // memory, so their HBM latency overlaps the look-back below (read back after the second barrier)
-    uint4* vbuf = reinterpret_cast<uint4*>(ring + (size_t)S * kScanTile);
-    if (ScanGeom<MODE>::STAGE_VALUES && staged) {
-#pragma unroll
-      for (int j = 0; j < VPT; ++j)
-        if (flags[j]) cp_async16(vbuf + j * T + threadIdx.x, values + tile_base + ((size_t)j * T + threadIdx.x) * 4);
-      cp_async_commit();
-    }
     if (warp == 0) {
       uint32_t t[PER_LANE], run = 0;
 #pragma unroll
@@ -524,7 +505,6 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
     }
     __syncthreads();
     const uint32_t tile_excl = s_tile_excl[buf];
-    if (ScanGeom<MODE>::STAGE_VALUES && staged) cp_async_wait_all();  // each thread reads back only what it copied
 
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
@@ -544,8 +524,7 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
         // selected lanes are written at their rank; flags of out-of-range lanes are 0
         uint4 v;
         if (MODE == MODE_COMPRESS_VALUE) {  // values are read once, only for vectors with a selected lane
-          if (staged) v = vbuf[j * T + threadIdx.x];
-          else if (e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
+          if (staged || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
           else {
             v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
             v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;

@@ -35,7 +35,7 @@ constexpr int kReduceThreads = 512;
 constexpr int kReduceMaxCtas = 2048;
 constexpr int kScanThreads = 1024;
 // look-back tile geometry is per mode (ScanGeom in prims.cu); the smallest tile sizes the status array
-constexpr int kScanMinTile = 16384;
+constexpr int kScanMinTile = 24576;
 
 // number of 8-byte words `tile_state` must hold for n lanes
 size_t scan_state_words(size_t n);
