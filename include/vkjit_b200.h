@@ -213,7 +213,8 @@ vkjit_status vkjit_read(vkjit_ir* ir, vkjit_var id, vkjit_type ty, void* dst, si
  * of the same type.  With vkjit_dist_init active and a sharded operand the
  * per-GPU partial is combined across ranks (result replicated). */
 vkjit_status vkjit_reduce(vkjit_ir* ir, int32_t red, vkjit_var id, vkjit_var* out);
-/* prefix sum of a U32/I32 var (mod 2^32); exclusive != 0 -> exclusive scan. */
+/* prefix sum of a U32/I32 var (mod 2^32); exclusive != 0 -> exclusive scan.  A sharded operand (multi-GPU) is
+ * scanned over the GLOBAL range: per-rank totals are exchanged and each rank's result is its slice. */
 vkjit_status vkjit_prefix_sum(vkjit_ir* ir, vkjit_var id, int32_t exclusive, vkjit_var* out);
 /* compress(mask): stable list of lane indices whose mask is set (U32[count]). */
 vkjit_status vkjit_compress(vkjit_ir* ir, vkjit_var mask, vkjit_var* out_indices, size_t* out_count);

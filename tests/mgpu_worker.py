@@ -60,6 +60,13 @@ def main():
             assert abs(float(got[("f", Red.Sum)]) - es) <= 1e-6 * max(1.0, math.log2(n)) * abs(es)
             for r in (Red.Min, Red.Max):
                 assert got[("f", r)] == o.as_slice(o.reduce(r, of), T.F32)[0]
+        # sharded prefix sum: every rank's result is its slice of the scan over the GLOBAL range
+        for excl in (True, False):
+            ps = ir.prefix_sum(xu, excl)
+            assert ir.is_sharded(ps) and ir.size(ps) == hi - lo
+            want = o.as_slice(o.prefix_sum(ou, excl), T.U32)[lo:hi]
+            if hi > lo:
+                assert ir.as_slice(ps, T.U32).tobytes() == want.tobytes(), (n, p2p, excl)
         ir.close(); o.close()
     st = vk.stats()
     assert st["collectives"] > 0 or world == 1

@@ -276,17 +276,47 @@ vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkji
     const TypeId ty = ir.var(id).ty;
     if (ty != VKJIT_TY_U32 && ty != VKJIT_TY_I32) fail(VKJIT_ERR_TYPE, "prefix_sum needs U32/I32");
     Backend& be = Backend::get();
-    ensure_buffer(ir, id);
-    const Var& v = ir.var(id);
-    if (v.sharded && dist::active() && dist::world() > 1) fail(VKJIT_ERR_UNSUPPORTED, "prefix_sum of a sharded array (single-GPU primitive, SURVEY.md §8e)");
-    const size_t n = v.array->bytes / 4;
+    const bool sharded = ir.var(id).sharded && dist::active() && dist::world() > 1;
+    // a rank whose shard is empty cannot evaluate it, but still has to take part in the exchange
+    bool empty;
+    if (ir.is_buffer(id)) empty = ir.var(id).array->bytes == 0;
+    else {
+      Program p;
+      std::vector<VarId> roots{id};
+      build_program(ir, roots, true, p);
+      empty = p.n == 0;
+    }
+    if (!empty) ensure_buffer(ir, id);
+    const size_t n = empty ? 0 : ir.var(id).array->bytes / 4;
+    const uint32_t* in = empty ? nullptr : (const uint32_t*)ir.var(id).array->ptr;
     be.ensure_scan_scratch(n);
     Array* o = be.new_array(n * 4);
+    void* tmp = nullptr;  // sharded: [0] local total, [1] offset of this rank, [2..2+world) totals (NCCL path)
     try {
-      prims::prefix_sum((const uint32_t*)v.array->ptr, (uint32_t*)o->ptr, n, exclusive != 0, be.scratch, be.sm_count, be.stream);
+      const uint32_t* initial = nullptr;
+      if (sharded) {
+        // Sharded scan: local total -> exchange of the per-rank totals -> single-pass scan whose
+        // tile 0 starts from the sum of the lower ranks' totals.  12 B/lane per GPU, one small exchange.
+        const int world = dist::world(), rank = dist::rank();
+        tmp = be.alloc((size_t)(2 + world) * 4);
+        uint32_t* w = (uint32_t*)tmp;
+        if (empty) prims::fill_u32(w, 0u, 1, be.stream);
+        else prims::reduce(VKJIT_RED_SUM, VKJIT_TY_U32, in, n, w, be.scratch, be.sm_count, be.stream);
+        if (dist::p2p_enabled()) {
+          prims::p2p_exscan_u32(w, w + 1, dist::next_mailbox(), be.stream);
+        } else {
+          prims::one_hot_u32(w, rank, world, w + 2, be.stream);
+          dist::allreduce(w + 2, VKJIT_TY_U32, VKJIT_RED_SUM, (size_t)world);
+          prims::prefix_of_rank_u32(w + 2, rank, w + 1, be.stream);
+        }
+        initial = w + 1;
+        Backend::counters().prim_launches += 2;
+      }
+      prims::prefix_sum(in, (uint32_t*)o->ptr, n, exclusive != 0, be.scratch, be.sm_count, be.stream, initial);
       Backend::counters().prim_launches += 1;
-    } catch (...) { release_array(o); throw; }
-    *out = ir.binding(ty, o, false);
+    } catch (...) { if (tmp) be.free_async(tmp, (size_t)(2 + dist::world()) * 4); release_array(o); throw; }
+    if (tmp) be.free_async(tmp, (size_t)(2 + dist::world()) * 4);
+    *out = ir.binding(ty, o, sharded);
   });
 }
 

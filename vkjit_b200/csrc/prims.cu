@@ -137,6 +137,38 @@ __device__ __forceinline__ T mailbox_allreduce(T mine, const Mailbox& mb) {
   return acc;
 }
 
+// Exclusive scan over ranks of one u32 per GPU (mod 2^32): out[0] = sum of `mine` over all ranks below this one.
+__global__ void p2p_exscan_kernel(const uint32_t* mine, uint32_t* out, Mailbox mb) {
+  if (threadIdx.x != 0) return;
+  const size_t slot = (size_t)(mb.seq % kMailSlots) * kMailRanks;
+  const uint64_t word = ((uint64_t)mb.seq << 32) | mine[0];
+  for (int p = 0; p < mb.world; ++p) sys_store(mb.peers[p] + slot + mb.rank, word);
+  const uint64_t* local = mb.local + slot;
+  uint32_t acc = 0;
+  const unsigned long long t0 = global_ns();
+  for (int r = 0; r < mb.rank; ++r) {
+    uint64_t w = sys_load(local + r);
+    while ((uint32_t)(w >> 32) != mb.seq) {
+      if (global_ns() - t0 > 5000000000ull) __trap();
+      w = sys_load(local + r);
+    }
+    acc += (uint32_t)w;
+  }
+  out[0] = acc;
+}
+
+// out[0] = sum of v[0..rank) — the NCCL path all-reduces a one-hot vector of the per-rank totals first
+__global__ void prefix_of_rank_kernel(const uint32_t* v, int rank, uint32_t* out) {
+  if (threadIdx.x != 0) return;
+  uint32_t acc = 0;
+  for (int r = 0; r < rank; ++r) acc += v[r];
+  out[0] = acc;
+}
+
+__global__ void one_hot_kernel(const uint32_t* mine, int rank, int world, uint32_t* v) {
+  if ((int)threadIdx.x < world) v[threadIdx.x] = (int)threadIdx.x == rank ? mine[0] : 0u;
+}
+
 template <typename T, int RED>
 __global__ void p2p_allreduce_kernel(uint32_t* out, Mailbox mb) {
   if (threadIdx.x == 0) out[0] = to_bits(mailbox_allreduce<T, RED>(from_bits<T>(out[0]), mb));
@@ -263,6 +295,18 @@ void p2p_allreduce(int red, uint32_t ty, void* out, const Mailbox& mb, void* str
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("p2p all-reduce launch: ") + cudaGetErrorString(e));
 }
 
+void p2p_exscan_u32(const uint32_t* mine, uint32_t* out, const Mailbox& mb, void* stream) {
+  p2p_exscan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mine, out, mb);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("p2p exscan launch: ") + cudaGetErrorString(e));
+}
+void one_hot_u32(const uint32_t* mine, int rank, int world, uint32_t* v, void* stream) {
+  one_hot_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mine, rank, world, v);
+}
+void prefix_of_rank_u32(const uint32_t* v, int rank, uint32_t* out, void* stream) {
+  prefix_of_rank_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(v, rank, out);
+}
+
 // ---------------------------------------------------------------------------------------
 // decoupled look-back scan (Merrill & Garland) — prefix sum and stream compaction
 // ---------------------------------------------------------------------------------------
@@ -300,11 +344,11 @@ __device__ __forceinline__ void status_store(uint64_t* p, uint64_t v) {
 // spans the whole current generation plus the tail of the previous one, whose inclusive prefixes
 // are already published.
 constexpr int kLookWide = 5;
-__device__ __forceinline__ uint32_t look_back(uint64_t* status, uint32_t tile, uint32_t aggregate) {
+__device__ __forceinline__ uint32_t look_back(uint64_t* status, uint32_t tile, uint32_t aggregate, uint32_t initial) {
   const int lane = threadIdx.x & 31;
-  if (tile == 0) {
-    if (lane == 0) status_store(status, ((uint64_t)ST_INCLUSIVE << 32) | aggregate);
-    return 0u;
+  if (tile == 0) {  // `initial`: prefix carried in from outside (sharded scan: the totals of the lower ranks)
+    if (lane == 0) status_store(status, ((uint64_t)ST_INCLUSIVE << 32) | (initial + aggregate));
+    return initial;
   }
   if (lane == 0) status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_AGGREGATE << 32) | aggregate);
   uint32_t exclusive = 0;
@@ -389,7 +433,7 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: mask words
             const uint32_t* __restrict__ values,  // MODE_COMPRESS_VALUE only
             uint32_t* __restrict__ out, uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles,
-            uint64_t* __restrict__ state, uint32_t diag_skip_lookback) {
+            uint64_t* __restrict__ state, uint32_t diag_skip_lookback, const uint32_t* __restrict__ initial_ptr) {
   constexpr int T = kScanThreads;
   constexpr int kScanTile = ScanGeom<MODE>::TILE;
   constexpr int kScanStages = ScanGeom<MODE>::STAGES;
@@ -497,7 +541,8 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
       for (int i = 0; i < PER_LANE; ++i) { s_tot[buf][lane * PER_LANE + i] = off; off += t[i]; }
       const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
       // diag_skip_lookback: timing-only diagnostic (VKJIT_SCAN_DIAG=nolookback), results are wrong
-      const uint32_t excl = diag_skip_lookback ? 0u : look_back(status, tile, aggregate);
+      const uint32_t initial = (tile == 0 && initial_ptr) ? __ldcg(initial_ptr) : 0u;
+      const uint32_t excl = diag_skip_lookback ? 0u : look_back(status, tile, aggregate, initial);
       if (lane == 0) {
         s_tile_excl[buf] = excl;
         if (COMPRESS && tile == num_tiles - 1) *count_out = excl + aggregate;
@@ -545,7 +590,7 @@ size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (2 + n / kSca
 
 template <int MODE>
 static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
-                        const Scratch& sc, int sm_count, cudaStream_t s) {
+                        const Scratch& sc, int sm_count, cudaStream_t s, const uint32_t* initial = nullptr) {
   using G = ScanGeom<MODE>;
   const size_t tiles = (n + G::TILE - 1) / G::TILE;
   const size_t words = (size_t)kStatusStride * (1 + tiles);
@@ -563,16 +608,17 @@ static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* ou
   const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);
   static int diag = -1;
   if (diag < 0) { const char* d = getenv("VKJIT_SCAN_DIAG"); diag = (d && std::string(d) == "nolookback") ? 1 : 0; }
-  scan_kernel<MODE><<<grid, kScanThreads, G::SMEM, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state, (uint32_t)diag);
+  scan_kernel<MODE><<<grid, kScanThreads, G::SMEM, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state, (uint32_t)diag, initial);
   e = cudaGetLastError();
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
 }
 
-void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream) {
+void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream,
+                const uint32_t* initial) {
   if (n == 0) return;
   cudaStream_t s = (cudaStream_t)stream;
-  if (exclusive) launch_scan<MODE_EXCLUSIVE>(in, nullptr, out, nullptr, n, sc, sm_count, s);
-  else launch_scan<MODE_INCLUSIVE>(in, nullptr, out, nullptr, n, sc, sm_count, s);
+  if (exclusive) launch_scan<MODE_EXCLUSIVE>(in, nullptr, out, nullptr, n, sc, sm_count, s, initial);
+  else launch_scan<MODE_INCLUSIVE>(in, nullptr, out, nullptr, n, sc, sm_count, s, initial);
 }
 
 void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,

@@ -11,7 +11,7 @@ namespace prims {
 struct Scratch {
   void* partials = nullptr;       // reduce: one 4-byte partial per CTA
   unsigned int* ticket = nullptr; // reduce: last-CTA election (self-resetting)
-  uint64_t* tile_state = nullptr; // scan: [0] = reserved, [1..] = look-back status words
+  uint64_t* tile_state = nullptr; // scan: look-back status, one 128-byte slot per tile (slot 0 reserved)
   size_t tile_state_words = 0;
 };
 
@@ -34,8 +34,7 @@ struct Mailbox {
 constexpr int kReduceThreads = 512;
 constexpr int kReduceMaxCtas = 2048;
 constexpr int kScanThreads = 1024;
-// look-back tile geometry is per mode (ScanGeom in prims.cu); the smallest tile sizes the status array
-constexpr int kScanMinTile = 24576;
+constexpr int kScanMinTile = 24576;  // look-back tile (ScanGeom in prims.cu); sizes the status array
 
 // number of 8-byte words `tile_state` must hold for n lanes
 size_t scan_state_words(size_t n);
@@ -43,14 +42,23 @@ size_t scan_state_words(size_t n);
 // out[0] = reduce(in[0..n)).  ty: VKJIT_TY_{U32,I32,F32}; red: VKJIT_RED_*.  One launch:
 // vectorised grid-stride partials -> warp shuffle -> shared-memory tree -> last CTA folds the
 // per-CTA partials in a fixed order (deterministic for a given n and grid).
-// `mailbox` (optional): the last CTA additionally stores the result there (peer-mapped slot).
+// `mailbox` (optional, multi-GPU): the last CTA also performs the all-reduce — it publishes the per-GPU
+// partial into every peer's mailbox over NVLink and folds all ranks' partials in rank order.
 void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream,
             const Mailbox* mailbox = nullptr);
 // Stand-alone exchange: out[0] = combine over ranks of out[0] (used when a rank's shard is empty).
 void p2p_allreduce(int red, uint32_t ty, void* out, const Mailbox& mailbox, void* stream);
 
 // Single-pass decoupled look-back prefix sum (mod 2^32) over u32 words.
-void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream);
+// `initial` (optional, device): prefix carried in from outside — the sharded scan passes the sum of the lower
+// ranks' totals, which becomes the predecessor of tile 0.
+void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, const Scratch& sc, int sm_count, void* stream,
+                const uint32_t* initial = nullptr);
+// Sharded scan support: exclusive scan over ranks of one u32 per GPU through the peer mailboxes, and the two
+// tiny kernels of the NCCL path (one-hot vector of totals -> all-reduce -> prefix of this rank).
+void p2p_exscan_u32(const uint32_t* mine, uint32_t* out, const Mailbox& mailbox, void* stream);
+void one_hot_u32(const uint32_t* mine, int rank, int world, uint32_t* v, void* stream);
+void prefix_of_rank_u32(const uint32_t* v, int rank, uint32_t* out, void* stream);
 
 // Stream compaction: lanes whose mask word is non-zero, stable order.  values == nullptr writes the
 // lane index.  *count_out (device) receives the number of selected lanes.
