@@ -50,8 +50,8 @@ def main():
         o.eval([ou, of])
         if hi > lo:
             # elementwise: this rank's lanes equal the global lanes [lo, hi) bit for bit, no collective
-            assert ir.as_slice(xu, T.U32).tobytes() == o.as_slice(ou, T.U32)[lo:hi].tobytes()
-            assert ir.as_slice(xf, T.F32).tobytes() == o.as_slice(of, T.F32)[lo:hi].tobytes()
+            assert ir.as_slice_eval(xu, T.U32).tobytes() == o.as_slice(ou, T.U32)[lo:hi].tobytes()
+            assert ir.as_slice_eval(xf, T.F32).tobytes() == o.as_slice(of, T.F32)[lo:hi].tobytes()
         if True:
             for r in (Red.Sum, Red.Min, Red.Max):
                 e = o.as_slice(o.reduce(r, ou), T.U32)[0]
