@@ -133,7 +133,22 @@ def run(ir, vk, stream, flush_l2, peak):
         ir.read_into(z, T.F32, host.ctypes.data, host.nbytes)
         t.append(time.perf_counter() - t0)
         ir.dec_ref_count(z)
-    out["E20_eval_plus_readback_us"] = {"median": 1e6 * sorted(t[2:])[len(t[2:]) // 2], "n": n20, "readback_bytes": 4 * n20}
+    out["E20_eval_plus_readback_us"] = {"median": 1e6 * sorted(t[2:])[len(t[2:]) // 2], "n": n20, "readback_bytes": 4 * n20,
+                                        "host_buffer": "pageable (numpy)"}
+    import ctypes as C
+    hp = C.c_void_p()
+    vk.product_api().call("host_alloc", 4 * n20, C.byref(hp))   # pinned staging (vkjit_host_alloc)
+    t = []
+    for i in range(12):
+        t0 = time.perf_counter()
+        z = ir.add(ir.mul(ir.arange(T.F32, n20), y20), half)
+        ir.eval([z])
+        ir.read_into(z, T.F32, hp.value, 4 * n20)
+        t.append(time.perf_counter() - t0)
+        ir.dec_ref_count(z)
+    vk.product_api().call("host_free", hp)
+    out["E20_eval_plus_readback_pinned_us"] = {"median": 1e6 * sorted(t[2:])[len(t[2:]) // 2], "n": n20, "readback_bytes": 4 * n20,
+                                               "host_buffer": "pinned (vkjit_host_alloc)"}
 
     a1k = ir.arange(T.F32, 1024)
     sync()

@@ -18,6 +18,7 @@ import threading
 import numpy as np
 
 from . import ir as _ir
+from ._capi import VkjitNoDeviceError
 from .ir import Bop, Red, Uop, VarType
 
 _lock = threading.RLock()
@@ -29,6 +30,13 @@ def _global_ir() -> _ir.Ir:
     global _IR
     with _lock:
         if _IR is None:
+            # `Ir::new()` creates the backend (internal.rs:168-182 -> VulkanBackend::create); here the device is
+            # bound on first use.  Without a B200 traces can still be built and printed; uploads and eval then
+            # fail loudly with VkjitNoDeviceError (there is no CPU path).
+            try:
+                _ir.init(-1)
+            except VkjitNoDeviceError:
+                pass
             _IR = _ir.Ir()
         return _IR
 
