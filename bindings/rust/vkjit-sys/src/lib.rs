@@ -70,6 +70,7 @@ extern "C" {
     pub fn vkjit_array_u32(ir: *mut vkjit_ir, data: *const u32, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_array_bool(ir: *mut vkjit_ir, data: *const u32, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_array_empty(ir: *mut vkjit_ir, ty: vkjit_type, n: usize, out_: *mut vkjit_var) -> vkjit_status;
+    pub fn vkjit_array_wrap_device(ir: *mut vkjit_ir, ty: vkjit_type, device_ptr: u64, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_arange(ir: *mut vkjit_ir, ty: vkjit_type, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_linspace(ir: *mut vkjit_ir, ty: vkjit_type, start: vkjit_var, stop: vkjit_var, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_zeros(ir: *mut vkjit_ir, ty: vkjit_type, out_: *mut vkjit_var) -> vkjit_status;

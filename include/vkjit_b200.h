@@ -137,6 +137,10 @@ vkjit_status vkjit_array_bool(vkjit_ir* ir, const uint32_t* data, size_t n, vkji
 /* Extension: uninitialised device array of n elements — Backend::create_array
  * (backend/mod.rs:22) exposed as a Binding var. */
 vkjit_status vkjit_array_empty(vkjit_ir* ir, vkjit_type ty, size_t n, vkjit_var* out);
+/* Extension: zero-copy view of FOREIGN device memory (n 4-byte elements at device_ptr) as a Binding var.
+ * Not owned: never freed here; the caller keeps it alive while the var lives and orders its producer before
+ * the backend stream (vkjit_stream).  Pointers that are not 16-byte aligned select the scalar kernel variant. */
+vkjit_status vkjit_array_wrap_device(vkjit_ir* ir, vkjit_type ty, uint64_t device_ptr, size_t n, vkjit_var* out);
 /* Ir::arange, internal.rs:235-237 */
 vkjit_status vkjit_arange(vkjit_ir* ir, vkjit_type ty, size_t n, vkjit_var* out);
 /* Ir::linspace, internal.rs:238-246 (endpoint excluded) */

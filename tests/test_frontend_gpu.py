@@ -97,3 +97,27 @@ def test_monte_carlo_mega_trace_matches_oracle(vkjit, oir, cuda_backend):
     vkjit.eval([y2])
     st = cuda_backend.stats()
     assert st["cache_hits"] == 1 and st["cache_misses"] == 0
+
+
+def test_zero_copy_interop_and_unaligned_views(vkjit, cuda_backend):
+    """Foreign device memory is wrapped without a copy (CUDA Array Interface); a view that is only 4-byte
+    aligned takes the scalar kernel variant and still matches; results export back to torch zero-copy."""
+    import torch
+    t = torch.arange(0, 4099, device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    x = vkjit.from_cuda_array(t)
+    y = x * 2.0 + 1.0
+    assert np.array_equal(y.numpy(), (t * 2 + 1).cpu().numpy())
+    view = t[1:]                                  # base + 4 bytes: not 16-byte aligned
+    assert view.data_ptr() % 16 != 0
+    z = vkjit.from_cuda_array(view) * 0.5
+    assert np.array_equal(z.numpy(), (view * 0.5).cpu().numpy())
+    assert vkjit.from_cuda_array(view).sum().tolist() == [float(view.sum().item())]
+    cuda_backend.sync()
+    back = torch.as_tensor(y, device="cuda")      # zero-copy export
+    assert back.data_ptr() == y.__cuda_array_interface__["data"][0]
+    assert torch.equal(back, t * 2 + 1)
+    # dropping the Var does not free the foreign memory
+    del x, z
+    import gc; gc.collect()
+    assert float(t[5].item()) == 5.0

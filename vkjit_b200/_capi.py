@@ -119,6 +119,7 @@ _PRODUCT_SIGS = {
     "dist_shutdown": [],
     "dist_info": [_pi32, _pi32],
     "arange_sharded": [_p, _u32, _sz, _pu32],
+    "array_wrap_device": [_p, _u32, _u64, _sz, _pu32],
     "array_sharded": [_p, _u32, _p, _sz, _pu32],
     "array_shard_local": [_p, _u32, _p, _sz, _pu32],
     "var_is_sharded": [_p, _u32, _pi32],

@@ -65,8 +65,15 @@ VarId upload(Ir& ir, TypeId ty, const void* data, size_t n, bool sharded) {
   return ir.binding(ty, a, sharded);
 }
 
+bool misaligned(const Ir& ir, VarId id) {
+  return ir.is_buffer(id) && (((uintptr_t)ir.var(id).array->ptr) & 15u) != 0;
+}
+
+// The hand-written primitives use 128-bit / TMA accesses: an unevaluated var is evaluated, and a view of foreign
+// memory that is not 16-byte aligned is first copied into pool memory (eval of a Binding root copies it,
+// internal.rs:1192-1205; the scalar kernel variant does the copy).
 void ensure_buffer(Ir& ir, VarId id) {
-  if (!ir.is_buffer(id)) eval(ir, &id, 1);
+  if (!ir.is_buffer(id) || misaligned(ir, id)) eval(ir, &id, 1);
 }
 
 // Buffer::str (internal.rs:404-422) through a D2H copy
@@ -146,6 +153,17 @@ vkjit_status vkjit_array_empty(vkjit_ir* h, vkjit_type ty, size_t n, vkjit_var* 
   return with_ir(h, [&](Ir& ir) {
     if (!ty_is_scalar(ty)) fail(VKJIT_ERR_TYPE, "array of a non-scalar type");
     *out = ir.binding(ty, Backend::get().new_array(n * 4), false);
+  });
+}
+vkjit_status vkjit_array_wrap_device(vkjit_ir* h, vkjit_type ty, uint64_t device_ptr, size_t n, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) {
+    if (!ty_is_scalar(ty)) fail(VKJIT_ERR_TYPE, "array of a non-scalar type");
+    if (!device_ptr && n) fail(VKJIT_ERR_INVALID, "null device pointer");
+    if (device_ptr & 3u) fail(VKJIT_ERR_INVALID, "device pointer must be 4-byte aligned");
+    Backend::get();
+    Array* a = new Array();
+    a->ptr = (void*)(uintptr_t)device_ptr; a->bytes = n * 4; a->capacity = n * 4; a->owned = false;
+    *out = ir.binding(ty, a, false);
   });
 }
 vkjit_status vkjit_arange(vkjit_ir* h, vkjit_type ty, size_t n, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.arange(ty, n, 0, false); }); }
@@ -253,9 +271,9 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
         o = be.new_array(4);
         prims::fill_u32((uint32_t*)o->ptr, reduce_identity(red, ty), 1, be.stream);
         if (p2p) prims::p2p_allreduce(red, ty, o->ptr, mb, be.stream);
-      } else if (!ir.is_buffer(id)) {
-        // unevaluated operand: ONE generated kernel evaluates the trace and reduces it; the operand
-        // is not materialised and stays unevaluated
+      } else if (!ir.is_buffer(id) || misaligned(ir, id)) {
+        // unevaluated operand (or a misaligned foreign view): ONE generated kernel evaluates the trace and reduces
+        // it; the operand is not materialised and stays as it is
         o = eval_reduce(ir, id, red);
         if (p2p) prims::p2p_allreduce(red, ty, o->ptr, mb, be.stream);
       } else {

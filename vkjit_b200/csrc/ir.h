@@ -29,6 +29,7 @@ struct Array {
   void* ptr = nullptr;
   size_t bytes = 0;     // logical size (Array::size)
   size_t capacity = 0;  // allocation size (compress over-allocates)
+  bool owned = true;    // false: view of foreign device memory (vkjit_array_wrap_device), never freed here
 };
 
 struct Var {  // internal.rs:105-114

@@ -156,7 +156,7 @@ Array* Backend::new_array(size_t bytes) {
 
 void release_array(Array* a) {
   if (!a) return;
-  if (g_backend) g_backend->free_async(a->ptr, a->capacity);
+  if (g_backend && a->owned) g_backend->free_async(a->ptr, a->capacity);
   delete a;
 }
 

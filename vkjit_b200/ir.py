@@ -117,6 +117,10 @@ class Ir:
     def array_empty(self, ty: int, n: int) -> int:
         return self._new("array_empty", ty, n)
 
+    def array_wrap_device(self, ty: int, device_ptr: int, n: int) -> int:
+        """Zero-copy view of foreign device memory (not owned)."""
+        return self._new("array_wrap_device", ty, C.c_uint64(device_ptr), n)
+
     def arange(self, ty: int, num: int) -> int:
         return self._new("arange", ty, num)
 

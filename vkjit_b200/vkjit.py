@@ -216,6 +216,18 @@ class Var:
             g.eval([self._id])
         return g.to_numpy(self._id)
 
+    @property
+    def __cuda_array_interface__(self):
+        """Zero-copy export (CUDA Array Interface v3) of the evaluated device array; consumers must order their
+        work after the backend stream (`vkjit_b200.stream_ptr()`), which is what `stream` advertises."""
+        g = _global_ir()
+        if not g.is_buffer(self._id):
+            g.eval([self._id])
+        ty = g.ty(self._id)
+        typestr = {VarType.F32: "<f4", VarType.U32: "<u4", VarType.I32: "<i4", VarType.Bool: "<u4"}[ty]
+        return {"shape": (g.size(self._id),), "typestr": typestr, "data": (g.device_ptr(self._id), False), "version": 3,
+                "strides": None, "stream": _ir.stream_ptr() or None}
+
     def sum(self): return Var._own(_global_ir().reduce(Red.Sum, self._id))
     def min(self): return Var._own(_global_ir().reduce(Red.Min, self._id))
     def max(self): return Var._own(_global_ir().reduce(Red.Max, self._id))
@@ -290,6 +302,19 @@ def maximum(a, b) -> Var:
 def compress(values: Var, mask: Var):
     out, n = _global_ir().compress_values(values._id, mask._id)
     return Var._own(out), n
+
+
+def from_cuda_array(obj) -> Var:
+    """Zero-copy import of any object exposing `__cuda_array_interface__` (torch tensors, CuPy arrays): 1-D,
+    contiguous, f32/u32/i32.  The object must stay alive while the returned Var is used, and its producer must be
+    ordered before the backend stream."""
+    cai = obj.__cuda_array_interface__
+    if len(cai["shape"]) != 1 or cai.get("strides") not in (None, (4,)):
+        raise TypeError("Not a valid argument!")
+    ty = {"<f4": VarType.F32, "<u4": VarType.U32, "<i4": VarType.I32}.get(cai["typestr"])
+    if ty is None:
+        raise TypeError("Not a valid argument!")
+    return Var._own(_global_ir().array_wrap_device(ty, int(cai["data"][0]), int(cai["shape"][0])))
 
 
 def sync():
