@@ -28,5 +28,7 @@ def scan():
     ir.dec_ref_count(ir.prefix_sum(vals, True))
 def comp():
     r, k = ir.compress_values(vals, mask); ir.dec_ref_count(r)
-ms, mc = timed(scan), timed(comp)
-print(f"diag={os.environ.get('VKJIT_SCAN_DIAG','-')}  prefix_sum {ms:.4f} ms ({8*n/ms/1e6:.0f} GB/s, {8*n/ms/1e6/6450:.3f})  compress {mc:.4f} ms ({10*n/mc/1e6:.0f} GB/s, {10*n/mc/1e6/6450:.3f})")
+def compi():
+    r, k = ir.compress(mask); ir.dec_ref_count(r)
+ms, mc, mi = timed(scan), timed(comp), timed(compi)
+print(f"diag={os.environ.get('VKJIT_SCAN_DIAG','-')}  prefix_sum {ms:.4f} ms ({8*n/ms/1e6:.0f} GB/s, {8*n/ms/1e6/6450:.3f})  compress {mc:.4f} ms ({10*n/mc/1e6:.0f} GB/s, {10*n/mc/1e6/6450:.3f})  compress_index {mi:.4f} ms ({6*n/mi/1e6:.0f} GB/s of 6 B/lane, {6*n/mi/1e6/6450:.3f})")
