@@ -425,7 +425,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template <int MODE> struct ScanGeom {
   static constexpr int TILE = 24576;
   static constexpr int STAGES = 2;
-  static constexpr size_t SMEM = (size_t)STAGES * TILE * 4 + (MODE >= MODE_COMPRESS_INDEX ? (kScanThreads / 32) * 128 * 4 : 0);
+  static constexpr size_t SMEM = (size_t)STAGES * TILE * 4;
 };
 
 template <int MODE>
@@ -447,7 +447,6 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   static_assert(NTOT % 32 == 0, "tile totals must fill whole warp rows");
   extern __shared__ __align__(128) unsigned char ring_raw[];
   uint32_t* ring = reinterpret_cast<uint32_t*>(ring_raw);  // S stages x kScanTile words
-  uint32_t* stage_buf = ring + (size_t)kScanStages * kScanTile;  // compress: 128 words per warp (see below)
   __shared__ __align__(8) uint64_t full[S];
   __shared__ uint32_t s_tot[2][NTOT];
   __shared__ uint32_t s_tile_excl[2];
@@ -566,34 +565,20 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
           if (e + 1 < n) out[e + 1] = r.y;
           if (e + 2 < n) out[e + 2] = r.z;
         }
-      } else {
-        // Warp-staged compaction: the selected lanes of this warp's slot j are contiguous in the output
-        // ([p0, p0 + wcount)); they are first packed into a 128-word shared-memory buffer per warp and then
-        // written with coalesced 128-byte stores (scattered 4-byte stores made index-compress slower per byte
-        // than the scan: 0.43 ms for 1.5 GiB).  Flags of out-of-range lanes are 0.
-        const uint32_t wcount = __shfl_sync(0xFFFFFFFFu, wincl[j], 31);
-        const uint32_t p0 = tile_excl + s_tot[buf][j * WARPS + warp];  // output position of the warp's first selected lane
-        if (wcount) {
-          uint32_t* wbuf = stage_buf + warp * 128;
-          if (flags[j]) {
-            uint4 v;
-            if (MODE == MODE_COMPRESS_VALUE) {  // values are read once, only for vectors with a selected lane
-              if (staged || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
-              else {
-                v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
-                v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
-              }
-            } else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
-            uint32_t r = wincl[j] - vsum[j];  // rank of this thread's first selected lane inside the warp's slot
-            if (flags[j] & 1u) wbuf[r++] = v.x;
-            if (flags[j] & 2u) wbuf[r++] = v.y;
-            if (flags[j] & 4u) wbuf[r++] = v.z;
-            if (flags[j] & 8u) wbuf[r++] = v.w;
+      } else if (flags[j]) {
+        // selected lanes are written at their rank; flags of out-of-range lanes are 0
+        uint4 v;
+        if (MODE == MODE_COMPRESS_VALUE) {  // values are read once, only for vectors with a selected lane
+          if (staged || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
+          else {
+            v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
+            v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
           }
-          __syncwarp();
-          for (uint32_t i = lane; i < wcount; i += 32) out[p0 + i] = wbuf[i];
-          __syncwarp();
-        }
+        } else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
+        if (flags[j] & 1u) out[p++] = v.x;
+        if (flags[j] & 2u) out[p++] = v.y;
+        if (flags[j] & 4u) out[p++] = v.z;
+        if (flags[j] & 8u) out[p++] = v.w;
       }
     }
     // s_tot/s_tile_excl are double-buffered: iteration k+2 rewrites buffer `buf` only after every
