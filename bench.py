@@ -48,34 +48,48 @@ def peaks():
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock and throttle reasons through NVML (what nvidia-smi reads) every ~1 ms in a
-    background thread DURING the timed region (the region is only tens of ms long, too short for
-    `nvidia-smi -lms`)."""
+    """Samples SM clock and throttle reasons through NVML (what nvidia-smi reads) every ~1 ms in a background
+    thread DURING the timed region (the region is only tens of ms long, too short for `nvidia-smi -lms`).
+    NVML is initialised up front (prepare) so that the thread samples from the first millisecond; one sample is
+    also taken synchronously at start and at stop."""
 
     def __init__(self, device):
         self.device, self.samples, self.reasons, self.max_mhz = device, [], set(), None
         self._stop = threading.Event()
-        self._thr = None
+        self._thr, self._nv, self._h, self.error = None, None, None, None
 
-    def _run(self):
+    def prepare(self):
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.device)
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
-                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(self.device)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
+            self._bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                          "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        except Exception as ex:  # pragma: no cover
+            self.error = repr(ex)
+
+    def _sample(self):
+        nv = self._nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        for k, b in self._bits.items():
+            if r & b:
+                self.reasons.add(k)
+
+    def _run(self):
+        try:
             while not self._stop.is_set():
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for k, b in bits.items():
-                    if r & b:
-                        self.reasons.add(k)
+                self._sample()
                 time.sleep(0.001)
         except Exception as ex:  # pragma: no cover
             self.error = repr(ex)
 
     def start(self):
+        if self._nv is None:
+            self.prepare()
+        if self._nv is None:
+            return
         self._thr = threading.Thread(target=self._run, daemon=True)
         self._thr.start()
 
@@ -83,9 +97,14 @@ class ClockSampler:
         self._stop.set()
         if self._thr:
             self._thr.join(timeout=5)
+        try:
+            if self._nv is not None:
+                self._sample()   # one more sample right at the end of the region (GPU still warm)
+        except Exception as ex:  # pragma: no cover
+            self.error = repr(ex)
         out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
                "reasons": sorted(self.reasons), "samples": len(self.samples), "how": "NVML, 1 ms period, during the timed region"}
-        if getattr(self, "error", None):
+        if self.error:
             out["error"] = self.error
         return out
 
@@ -237,8 +256,10 @@ def ours(args):
     for _ in range(max(3, args.warmup)):
         s, m, _ = step(False)
         ir.dec_ref_count(s); ir.dec_ref_count(m)
-    barrier()
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.prepare()   # NVML init outside the timed region
+    barrier()
     if rank == 0:
         sampler.start()
     vk.stats_reset()
