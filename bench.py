@@ -416,6 +416,8 @@ def ours(args):
             try:
                 import bench_extras
                 line["extras"] = bench_extras.run(ir, vk, stream, flush_l2, peak)
+                lc = line["extras"].get("LAUNCH_cached_trace", {})
+                line["cached_trace_launch_us"] = lc.get("vkjit_eval_us_median")   # second half of BASELINE.json's metric
             except Exception as ex:  # extras never take the headline down
                 line["extras"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)

@@ -218,16 +218,17 @@ reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ 
   T acc = O::apply(O::apply(a0, a1), O::apply(a2, a3));
   acc = block_reduce<T, RED, THREADS>(acc, smem);
 
-  // publish the CTA partial; the last CTA to arrive folds all partials in a fixed order
+  // publish the CTA partial; the last CTA to arrive folds all partials in a fixed order.  One acquire-release
+  // atomic on the ticket orders the partial store before it and the partial loads of the last CTA after it
+  // (no separate __threadfence round trips on the critical path of small launches).
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = to_bits(acc);
-    __threadfence();
-    const unsigned int t = atomicAdd(ticket, 1u);
+    unsigned int t;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
   if (is_last) {
-    __threadfence();
     T f = O::identity();
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) f = O::apply(f, from_bits<T>(__ldcg(partials + i)));
     f = block_reduce<T, RED, THREADS>(f, smem);

@@ -554,12 +554,12 @@ __device__ __forceinline__ void vk_finish(acc_t acc, u32* partials, unsigned int
   acc = vk_block_reduce(acc, smem);
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = VK_TO_WORD(acc);
-    __threadfence();
-    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    u32 t;  // acquire-release: orders the partial store before it and the last CTA's partial loads after it
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
+    is_last = t == gridDim.x - 1;
   }
   __syncthreads();
   if (is_last) {
-    __threadfence();
     acc_t f = VK_IDENTITY;
     for (u32 i = threadIdx.x; i < gridDim.x; i += blockDim.x) f = VK_APPLY(f, VK_FROM_WORD(__ldcg(partials + i)));
     f = vk_block_reduce(f, smem);
