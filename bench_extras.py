@@ -87,6 +87,41 @@ def run(ir, vk, stream, flush_l2, peak):
     bpl = 8 + 4 * cnt[0] / n
     gbs = bpl * n / (ms * 1e-3) / 1e9
     out["C28_compress"] = {"ms_incl_count_readback": ms, "GBps": gbs, "hbm_frac": gbs / peak, "bytes_per_lane": bpl, "selected": cnt[0]}
+    # fused-mask variant: the mask is a trace, computed inside the compaction kernel
+    # (scan_fused.cuh): 4 B read (values) + 4p B written per lane; no mask array, no kernel that writes one
+    def comp_fused():
+        mk = ir.neq(ir.bop(Bop.And, hash_trace(ir, lanes, 0xB2000001 + 4 * 16 + 1), c(1)), c(0))
+        r, k = ir.compress_values(vals, mk)
+        cnt[0] = k
+        ir.dec_ref_count(r); ir.dec_ref_count(mk)
+
+    ms, best, _ = _timed(stream, flush_l2, sync, comp_fused, reps=3)
+    bpl = 4 + 4 * cnt[0] / n
+    gbs = bpl * n / (ms * 1e-3) / 1e9
+    out["C28_compress_fused_mask"] = {"ms_incl_count_readback": ms, "GBps": gbs, "hbm_frac": gbs / peak, "bytes_per_lane": bpl,
+                                      "selected": cnt[0], "vs_unfused_ms": out["C28_compress"]["ms_incl_count_readback"]}
+
+    # threshold filter: compress_values(v, v > t) — the mask depends on the values themselves, which are streamed once
+    def comp_thresh():
+        mk = ir.gt(vals, c(0x80000000))
+        r, k = ir.compress_values(vals, mk)
+        cnt[0] = k
+        ir.dec_ref_count(r); ir.dec_ref_count(mk)
+
+    ms, best, _ = _timed(stream, flush_l2, sync, comp_thresh, reps=3)
+    bpl = 4 + 4 * cnt[0] / n
+    gbs = bpl * n / (ms * 1e-3) / 1e9
+    out["C28_filter_gt_threshold"] = {"ms_incl_count_readback": ms, "GBps": gbs, "hbm_frac": gbs / peak, "bytes_per_lane": bpl, "selected": cnt[0]}
+
+    # prefix sum of an unevaluated trace: nothing is read, 4 B/lane written
+    def scan_fused():
+        h = hash_trace(ir, lanes, 0xB2000001 + 4 * 16 + 0)
+        r = ir.prefix_sum(h, True)
+        ir.dec_ref_count(r); ir.dec_ref_count(h)
+
+    ms, best, _ = _timed(stream, flush_l2, sync, scan_fused, reps=3)
+    gbs = 4 * n / (ms * 1e-3) / 1e9
+    out["C28_prefix_sum_of_trace"] = {"ms": ms, "GBps": gbs, "hbm_frac": gbs / peak, "bytes_per_lane": 4}
     ir.dec_ref_count(mask); ir.dec_ref_count(vals); ir.dec_ref_count(x)
 
     # ---------------- H26: gather + scatter-add histogram
@@ -119,6 +154,22 @@ def run(ir, vk, stream, flush_l2, peak):
     out["H26_count_histogram"] = {"ms": ms, "best_ms": best, "Gelem_per_s": m / (ms * 1e-3) / 1e9, "bins": 1 << 16,
                                   "bound": "shared-memory + L2 atomics"}
     ir.dec_ref_count(idx)
+
+    # skewed indices: min of two uniform draws — low bins are hit about twice as often
+    hh = hash_trace(ir, lanes26, 0xB2000001 + 3 * 16 + 0)
+    idx_s = ir.bop(Bop.Min, ir.bop(Bop.And, hh, c(0xFFFF)), ir.shr(hh, c(16)))
+    ir.eval([idx_s])
+
+    def hist_skew():
+        w = ir.gather(table, idx_s)
+        s = ir.scatter_add(w, bins, idx_s)
+        ir.eval([s])
+        ir.dec_ref_count(s)
+
+    ms, best, _ = _timed(stream, flush_l2, sync, hist_skew)
+    out["H26_skewed_gather_scatter_add"] = {"ms": ms, "best_ms": best, "Gelem_per_s": m / (ms * 1e-3) / 1e9, "bins": 1 << 16,
+                                            "indices": "min(h & 0xFFFF, h >> 16)"}
+    ir.dec_ref_count(idx_s); ir.dec_ref_count(hh)
 
     # ---------------- E20 with readback + cached launch overhead
     n20 = 1 << 20

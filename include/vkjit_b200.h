@@ -289,6 +289,11 @@ vkjit_status vkjit_debug_walk_ns(vkjit_ir* ir, const vkjit_var* ids, size_t n, u
 /* Same for the fused trace -> reduce kernel of vkjit_reduce(red, id). */
 vkjit_status vkjit_debug_codegen_reduce(vkjit_ir* ir, vkjit_var id, int32_t red, int32_t compile,
                                         char* buf, size_t cap, size_t* out_len, size_t* out_cubin_bytes);
+/* Same for the fused trace -> scan kernel that vkjit_prefix_sum / vkjit_compress / vkjit_compress_values launch when
+ * an operand is unevaluated.  mode: 0 exclusive sum, 1 inclusive sum, 2 compress -> indices (ids = {mask}),
+ * 3 compress -> values (ids = {mask, values}). */
+vkjit_status vkjit_debug_codegen_scan(vkjit_ir* ir, const vkjit_var* ids, size_t n, int32_t mode, int32_t compile,
+                                      char* buf, size_t cap, size_t* out_len, size_t* out_cubin_bytes);
 
 #ifdef __cplusplus
 }

@@ -771,17 +771,17 @@ void Ir::eval(const VarId* ids, size_t nids) {
 }
 
 // ---- eager primitives (SPEC) ----------------------------------
-static void ensure_buffer(Ir& ir, VarId id) {
-  if (!ir.is_buffer(id)) { VarId ids[1] = {id}; ir.eval(ids, 1); }
+// SPEC: an unevaluated operand of an eager primitive is evaluated on the fly and is NOT turned into a buffer
+// (the device fuses the trace into the primitive's kernel instead of materialising the operand)
+static std::shared_ptr<Words> operand_words(Ir& ir, VarId id) {
+  return ir.is_buffer(id) ? ir.arrays.at(id) : run_schedule(ir, std::vector<VarId>{id})[0];
 }
 
 static VarId reduce(Ir& ir, int red, VarId id) {
   const VarType ty = ir.var(id).ty;
   if (ty.k != K_U32 && ty.k != K_I32 && ty.k != K_F32) throw Error(E_TYPE, "reduce needs U32/I32/F32");
   if (red < 0 || red > 2) throw Error(E_INVALID, "unknown reduction");
-  // SPEC: reducing an unevaluated var evaluates it on the fly and does NOT turn it into a buffer
-  // (the device fuses the trace with the reduction instead of materialising the operand)
-  std::shared_ptr<Words> held = ir.is_buffer(id) ? ir.arrays.at(id) : run_schedule(ir, std::vector<VarId>{id})[0];
+  std::shared_ptr<Words> held = operand_words(ir, id);
   const Words& w = *held;
   const size_t n = w.size();
   if (n == 0) throw Error(E_SIZE, "reduce of an empty array");
@@ -819,8 +819,7 @@ static VarId reduce(Ir& ir, int red, VarId id) {
 static VarId prefix_sum(Ir& ir, VarId id, bool exclusive) {
   const VarType ty = ir.var(id).ty;
   if (ty.k != K_U32 && ty.k != K_I32) throw Error(E_TYPE, "prefix_sum needs U32/I32");
-  ensure_buffer(ir, id);
-  auto src = ir.arrays.at(id);
+  auto src = operand_words(ir, id);
   const size_t n = src->size();
   VarId out = ir.array(ty.k, nullptr, n);
   Words& o = *ir.arrays.at(out);
@@ -846,14 +845,12 @@ static VarId compress(Ir& ir, VarId mask, bool with_values, VarId values, size_t
     const VarType vt = ir.var(values).ty;
     if (!vt.scalar()) throw Error(E_TYPE, "compress values must be scalar");
     vk = vt.k;
-    ensure_buffer(ir, values);
   }
-  ensure_buffer(ir, mask);
-  auto m = ir.arrays.at(mask);
+  auto m = operand_words(ir, mask);
   const size_t n = m->size();
   std::shared_ptr<Words> vals;
   if (with_values) {
-    vals = ir.arrays.at(values);
+    vals = operand_words(ir, values);
     if (vals->size() != n) throw Error(E_SIZE, "compress: values and mask sizes differ");
   }
   int T = std::max(1, g_threads);

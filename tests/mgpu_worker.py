@@ -67,6 +67,14 @@ def main():
             want = o.as_slice(o.prefix_sum(ou, excl), T.U32)[lo:hi]
             if hi > lo:
                 assert ir.as_slice(ps, T.U32).tobytes() == want.tobytes(), (n, p2p, excl)
+        # the same on an UNEVALUATED sharded trace: local total from the fused trace -> reduce kernel, then the
+        # fused trace -> scan kernel seeded with the lower ranks' totals; the operand is never materialised
+        xu2 = ir.add(trace_u32(ir, lanes), ir.const_u32(7))
+        ps = ir.prefix_sum(xu2, True)
+        assert not ir.is_buffer(xu2) and ir.is_sharded(ps) and ir.size(ps) == hi - lo
+        want = o.as_slice(o.prefix_sum(o.add(ou, o.const_u32(7)), True), T.U32)[lo:hi]
+        if hi > lo:
+            assert ir.as_slice(ps, T.U32).tobytes() == want.tobytes(), (n, p2p, "fused")
         ir.close(); o.close()
     st = vk.stats()
     assert st["collectives"] > 0 or world == 1

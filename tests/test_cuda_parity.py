@@ -270,6 +270,87 @@ def test_compress_of_traced_mask(cir, oir):
     assert res[0][0] == res[1][0] and same_bits(res[0][1], res[1][1], False)
 
 
+# ---------------------------------------------------------------- fused trace -> scan / compress
+FUSED_SIZES = [1, 3, 4, 5, 4095, 4096, 4097, 8191, 12288, 12289, 24575, 24576, 24577, 49153, 5 * 24576 + 3, (1 << 20) + 1,
+               3 * (1 << 20) + 7]
+
+
+@pytest.mark.parametrize("n", FUSED_SIZES)
+@pytest.mark.parametrize("streams", [0, 1, 2, 3, 4, 6])
+def test_fused_scan_and_compress(cuda_backend, cir, oir, n, streams):
+    """Unevaluated operands: ONE generated kernel evaluates the trace and scans / compacts it (scan_fused.cuh).
+    `streams` arrays are staged through the TMA ring (the tile shrinks as their number grows).  Nothing is
+    materialised, the operands stay unevaluated, and every word equals the oracle's."""
+    rng = np.random.default_rng(1000 * streams + n)
+    data = [special_u32(rng, n) for _ in range(streams)]
+    res = []
+    for ir in (cir, oir):
+        acc = ir.mul(ir.arange(U32, n), ir.const_u32(2654435761))
+        for d in data:
+            acc = ir.bop(Bop.Xor, ir.add(acc, ir.array_u32(d)), ir.shr(acc, ir.const_u32(7)))
+        mask = ir.neq(ir.bop(Bop.And, acc, ir.const_u32(5)), ir.const_u32(0))
+        vals = ir.mul(acc, ir.const_u32(3))
+        if ir is cir:
+            cuda_backend.stats_reset()
+        ex, inc = ir.prefix_sum(acc, True), ir.prefix_sum(acc, False)
+        idx, c1 = ir.compress(mask)
+        out, c2 = ir.compress_values(vals, mask)
+        if ir is cir:
+            st = cuda_backend.stats()
+            assert st["trace_launches"] == 4, st          # four fused kernels and nothing else
+        assert not ir.is_buffer(acc) and not ir.is_buffer(mask) and not ir.is_buffer(vals)
+        res.append((c1, c2, read(ir, ex), read(ir, inc), read(ir, idx), read(ir, out), ir.as_slice_eval(acc, U32)))
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1] == res[0][0]
+    for k in range(2, 7):
+        assert same_bits(res[0][k], res[1][k], False), (n, streams, k)
+    acc_np = res[1][6]
+    assert np.array_equal(res[0][3], np.cumsum(acc_np.astype(np.uint64)).astype(np.uint32))
+    assert np.array_equal(res[0][4], np.nonzero(acc_np & 5)[0].astype(np.uint32))
+
+
+def test_fused_compress_values_of_a_bound_array(cuda_backend, cir, oir):
+    """compress_values(x, x > t): the C28 "fused-mask" shape — x is streamed once (4 B/lane), the mask never exists."""
+    n = 5 * 24576 + 1234
+    x = np.random.default_rng(5).random(n, dtype=np.float32)
+    res = []
+    for ir in (cir, oir):
+        xv = ir.array_f32(x)
+        m = ir.gt(xv, ir.const_f32(0.75))
+        if ir is cir:
+            cuda_backend.stats_reset()
+        out, c = ir.compress_values(xv, m)
+        if ir is cir:
+            assert cuda_backend.stats()["trace_launches"] == 1
+        res.append((c, read(ir, out)))
+    assert res[0][0] == res[1][0] == int((x > 0.75).sum())
+    assert same_bits(res[0][1], res[1][1], True) and np.array_equal(res[0][1], x[x > 0.75])
+
+
+def test_fused_scan_with_gather_and_fallbacks(cuda_backend, cir, oir, monkeypatch):
+    """A gather inside the scanned trace (pointer parameter next to the streamed arrays); traces the fused kernel
+    does not take (side effects, > 6 streamed arrays) go through temporaries and give the same words."""
+    n, m = 70001, 997
+    rng = np.random.default_rng(11)
+    table, idx = special_u32(rng, m), rng.integers(0, m, n).astype(np.uint32)
+    many = [rng.integers(0, 1 << 20, n).astype(np.uint32) for _ in range(8)]
+    res = []
+    for ir in (cir, oir):
+        g = ir.gather(ir.array_u32(table), ir.array_u32(idx))
+        a = ir.prefix_sum(g, True)
+        wide = ir.array_u32(many[0])
+        for d in many[1:]:
+            wide = ir.add(wide, ir.array_u32(d))
+        b = ir.prefix_sum(wide, False)                         # 8 streamed arrays: not fused
+        tgt = ir.array_u32(np.zeros(n, np.uint32))
+        sc = ir.scatter(ir.arange(U32, n), tgt, ir.arange(U32, n))   # value of a scatter var = its source
+        c, cnt = ir.compress(ir.neq(ir.bop(Bop.And, sc, ir.const_u32(1)), ir.const_u32(0)))
+        assert not ir.is_buffer(g) and not ir.is_buffer(wide) and not ir.is_buffer(sc)
+        res.append((read(ir, a), read(ir, b), read(ir, c), cnt, read(ir, tgt)))
+    for k in (0, 1, 2, 4):
+        assert same_bits(res[0][k], res[1][k], False), k
+    assert res[0][3] == res[1][3] == n // 2
+
+
 # ---------------------------------------------------------------- errors (reference panics -> status)
 def test_errors_match_oracle(cir, oir):
     from vkjit_b200 import VkjitError, VkjitSizeError, VkjitTypeError

@@ -161,6 +161,33 @@ def test_fused_reduce_kernel_compiles_for_sm100a(red):
         assert cubin > 1000 and "vk_finish" in src and "o0[" not in src.split("vk_finish(VK_APPLY")[0].split("extern")[1]
 
 
+@pytest.mark.parametrize("streams", [0, 1, 2, 3, 6])
+def test_fused_scan_kernels_compile_for_sm100a(streams):
+    """The fused trace -> prefix-sum / compress kernels (scan_fused.cuh + scan_common.cuh, embedded in the library as
+    text) go through NVRTC for sm_100a without a device; streamed arrays are views of (fake) device memory."""
+    ir = Ir()
+    n = 1 << 20
+    acc = ir.mul(ir.arange(U32, n), ir.const_u32(3))
+    for k in range(streams):
+        acc = ir.add(acc, ir.array_wrap_device(U32, 0x7F0000000000 + k * 4 * n, n))
+    mask = ir.neq(ir.bop(Bop.And, acc, ir.const_u32(1)), ir.const_u32(0))
+    keys = set()
+    for mode, ids in ((0, [acc]), (1, [acc]), (2, [mask]), (3, [mask, acc])):
+        src, cubin = ir.debug_codegen_scan(ids, mode, compile=True)
+        assert cubin > 1000 and f"#define VK_SCAN_MODE {mode}" in src and f"#define VK_NS {streams}" in src
+        assert "look_back(" in src and ("cp.async.bulk" in src)
+        keys.add(src.splitlines()[0])
+    assert len(keys) == 4                                  # the scan mode is part of the cache key
+    with pytest.raises(VkjitError):
+        ir.debug_codegen_scan([mask], 3)                   # mode 3 takes {mask, values}
+    wide = acc
+    for k in range(7):
+        wide = ir.add(wide, ir.array_wrap_device(U32, 0x7E0000000000 + k * 4 * n, n))
+    if streams == 0:
+        with pytest.raises(VkjitError):
+            ir.debug_codegen_scan([wide], 0)               # 7 streamed arrays: not fused (the runtime materialises)
+
+
 def test_privatised_scatter_add_kernel_compiles_for_sm100a():
     """The shared-memory-privatised scatter_add variant (trace construction needs no device: the target is
     an unevaluated... no: targets must be buffers, so this is checked on codegen text of a plain trace only)."""

@@ -160,7 +160,8 @@ vkjit_status vkjit_array_wrap_device(vkjit_ir* h, vkjit_type ty, uint64_t device
     if (!ty_is_scalar(ty)) fail(VKJIT_ERR_TYPE, "array of a non-scalar type");
     if (!device_ptr && n) fail(VKJIT_ERR_INVALID, "null device pointer");
     if (device_ptr & 3u) fail(VKJIT_ERR_INVALID, "device pointer must be 4-byte aligned");
-    Backend::get();
+    // no backend needed: the view is only dereferenced by kernels (trace construction and code generation
+    // over views work without a device; eval fails loudly there)
     Array* a = new Array();
     a->ptr = (void*)(uintptr_t)device_ptr; a->bytes = n * 4; a->capacity = n * 4; a->owned = false;
     *out = ir.binding(ty, a, false);
@@ -289,6 +290,28 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
   });
 }
 
+// Operand of an eager primitive as a 16-byte aligned device array: the var's own array, or — for an unevaluated
+// var or a misaligned foreign view — a temporary evaluated on the fly.  The var itself is never changed: like
+// reduce, the primitives do not turn an unevaluated operand into a buffer (oracle.cpp ditto).
+struct Operand {
+  const uint32_t* ptr = nullptr;
+  size_t n = 0;
+  Array* temp = nullptr;
+  Operand() = default;
+  Operand(const Operand&) = delete;
+  Operand& operator=(const Operand&) = delete;
+  ~Operand() { if (temp) release_array(temp); }  // stream-ordered: kernels already enqueued still see the memory
+  void bind(Ir& ir, VarId id) {
+    if (ir.is_buffer(id) && !misaligned(ir, id)) {
+      const Array* a = ir.var(id).array;
+      ptr = (const uint32_t*)a->ptr; n = a->bytes / 4;
+    } else {
+      temp = eval_temp(ir, id);
+      ptr = (const uint32_t*)temp->ptr; n = temp->bytes / 4;
+    }
+  }
+};
+
 vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkjit_var* out) {
   return with_ir(h, [&](Ir& ir) {
     const TypeId ty = ir.var(id).ty;
@@ -304,36 +327,55 @@ vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkji
       build_program(ir, roots, true, p);
       empty = p.n == 0;
     }
-    if (!empty) ensure_buffer(ir, id);
-    const size_t n = empty ? 0 : ir.var(id).array->bytes / 4;
-    const uint32_t* in = empty ? nullptr : (const uint32_t*)ir.var(id).array->ptr;
-    be.ensure_scan_scratch(n);
-    Array* o = be.new_array(n * 4);
-    void* tmp = nullptr;  // sharded: [0] local total, [1] offset of this rank, [2..2+world) totals (NCCL path)
+    const bool direct = !empty && ir.is_buffer(id) && !misaligned(ir, id);  // the hand-written kernel reads the var's array
+    Operand in;
+    if (direct) in.bind(ir, id);
+    Array* o = nullptr;
+    Array* total = nullptr;  // sharded, unevaluated operand: local total from the fused trace -> reduce kernel
+    void* tmp = nullptr;     // sharded: [0] local total, [1] offset of this rank, [2..2+world) totals (NCCL path)
+    const size_t tmp_bytes = (size_t)(2 + (sharded ? dist::world() : 0)) * 4;
     try {
       const uint32_t* initial = nullptr;
       if (sharded) {
         // Sharded scan: local total -> exchange of the per-rank totals -> single-pass scan whose
         // tile 0 starts from the sum of the lower ranks' totals.  12 B/lane per GPU, one small exchange.
         const int world = dist::world(), rank = dist::rank();
-        tmp = be.alloc((size_t)(2 + world) * 4);
+        tmp = be.alloc(tmp_bytes);
         uint32_t* w = (uint32_t*)tmp;
+        const uint32_t* tot = w;
         if (empty) prims::fill_u32(w, 0u, 1, be.stream);
-        else prims::reduce(VKJIT_RED_SUM, VKJIT_TY_U32, in, n, w, be.scratch, be.sm_count, be.stream);
+        else if (direct) prims::reduce(VKJIT_RED_SUM, VKJIT_TY_U32, in.ptr, in.n, w, be.scratch, be.sm_count, be.stream);
+        else { total = eval_reduce(ir, id, VKJIT_RED_SUM); tot = (const uint32_t*)total->ptr; }
         if (dist::p2p_enabled()) {
-          prims::p2p_exscan_u32(w, w + 1, dist::next_mailbox(), be.stream);
+          prims::p2p_exscan_u32(tot, w + 1, dist::next_mailbox(), be.stream);
         } else {
-          prims::one_hot_u32(w, rank, world, w + 2, be.stream);
+          prims::one_hot_u32(tot, rank, world, w + 2, be.stream);
           dist::allreduce(w + 2, VKJIT_TY_U32, VKJIT_RED_SUM, (size_t)world);
           prims::prefix_of_rank_u32(w + 2, rank, w + 1, be.stream);
         }
         initial = w + 1;
         Backend::counters().prim_launches += 2;
       }
-      prims::prefix_sum(in, (uint32_t*)o->ptr, n, exclusive != 0, be.scratch, be.sm_count, be.stream, initial);
+      bool done = false;
+      if (!empty && !direct) {  // ONE generated kernel evaluates the trace and scans it: the addends never reach memory
+        std::vector<VarId> roots{id};
+        uint64_t n = 0;
+        done = eval_scan(ir, exclusive ? SCAN_EXCLUSIVE : SCAN_INCLUSIVE, roots, initial, nullptr, &o, &n);
+        if (!done) in.bind(ir, id);
+      }
+      if (!done) {
+        be.ensure_scan_scratch(in.n);
+        o = be.new_array(in.n * 4);
+        prims::prefix_sum(in.ptr, (uint32_t*)o->ptr, in.n, exclusive != 0, be.scratch, be.sm_count, be.stream, initial);
+      }
       Backend::counters().prim_launches += 1;
-    } catch (...) { if (tmp) be.free_async(tmp, (size_t)(2 + dist::world()) * 4); release_array(o); throw; }
-    if (tmp) be.free_async(tmp, (size_t)(2 + dist::world()) * 4);
+    } catch (...) {
+      if (tmp) be.free_async(tmp, tmp_bytes);
+      release_array(total); release_array(o);
+      throw;
+    }
+    if (tmp) be.free_async(tmp, tmp_bytes);
+    release_array(total);
     *out = ir.binding(ty, o, sharded);
   });
 }
@@ -346,24 +388,38 @@ static void do_compress(Ir& ir, bool with_values, VarId values, VarId mask, vkji
     if (!ty_is_scalar(oty)) fail(VKJIT_ERR_TYPE, "compress values must be scalar");
   }
   Backend& be = Backend::get();
-  if (with_values) ensure_buffer(ir, values);
-  ensure_buffer(ir, mask);
-  const Var& m = ir.var(mask);
-  if (m.sharded && dist::active() && dist::world() > 1) fail(VKJIT_ERR_UNSUPPORTED, "compress of a sharded array (single-GPU primitive, SURVEY.md §8e)");
-  const size_t n = m.array->bytes / 4;
-  const uint32_t* vals = nullptr;
-  if (with_values) {
-    const Var& vv = ir.var(values);
-    if (vv.array->bytes / 4 != n) fail(VKJIT_ERR_SIZE, "compress: values and mask sizes differ");
-    vals = (const uint32_t*)vv.array->ptr;
-  }
-  be.ensure_scan_scratch(n);
-  Array* o = be.new_array(n * 4);  // worst case; logical size is trimmed to the count below
+  if (ir.var(mask).sharded && dist::active() && dist::world() > 1)
+    fail(VKJIT_ERR_UNSUPPORTED, "compress of a sharded array (single-GPU primitive, SURVEY.md §8e)");
+  const bool direct = ir.is_buffer(mask) && !misaligned(ir, mask) && (!with_values || (ir.is_buffer(values) && !misaligned(ir, values)));
+  Array* o = nullptr;
   void* cnt = be.alloc(4);
   uint32_t c = 0;
   try {
+    uint64_t n = 0;
+    bool done = false;
+    if (!direct) {  // fused: the mask (and the values) are computed inside the compaction kernel
+      std::vector<VarId> roots{mask};
+      if (with_values) roots.push_back(values);
+      try {
+        done = eval_scan(ir, with_values ? SCAN_COMPRESS_VALUE : SCAN_COMPRESS_INDEX, roots, nullptr, (uint32_t*)cnt, &o, &n);
+      } catch (const Error& e) {
+        if (e.code == VKJIT_ERR_SIZE && with_values) fail(VKJIT_ERR_SIZE, "compress: values and mask sizes differ");
+        throw;
+      }
+    }
+    if (!done) {
+      Operand m, v;
+      m.bind(ir, mask);
+      if (with_values) {
+        v.bind(ir, values);
+        if (v.n != m.n) fail(VKJIT_ERR_SIZE, "compress: values and mask sizes differ");
+      }
+      n = m.n;
+      be.ensure_scan_scratch(n);
+      o = be.new_array(n * 4);  // worst case; logical size is trimmed to the count below
+      if (n) prims::compress(m.ptr, with_values ? v.ptr : nullptr, (uint32_t*)o->ptr, (uint32_t*)cnt, n, be.scratch, be.sm_count, be.stream);
+    }
     if (n) {
-      prims::compress((const uint32_t*)m.array->ptr, vals, (uint32_t*)o->ptr, (uint32_t*)cnt, n, be.scratch, be.sm_count, be.stream);
       Backend::counters().prim_launches += 1;
       be.d2h(&c, cnt, 4);  // the size of the result is data dependent: one 4-byte readback
     }
@@ -479,6 +535,26 @@ vkjit_status vkjit_debug_codegen_reduce(vkjit_ir* h, vkjit_var id, int32_t red, 
     Program p;
     std::vector<VarId> roots{id};
     build_program(ir, roots, true, p, red);
+    const std::string src = generate_cuda(ir, p);
+    if (out_cubin) *out_cubin = 0;
+    if (compile) {
+      std::vector<char> cubin;
+      std::string log;
+      if (!nvrtc_compile(src, cubin, log)) fail(VKJIT_ERR_COMPILE, "NVRTC rejected the generated kernel:\n" + log + "\n--- source ---\n" + src);
+      if (out_cubin) *out_cubin = cubin.size();
+    }
+    copy_out(src, buf, cap, out_len);
+  });
+}
+
+vkjit_status vkjit_debug_codegen_scan(vkjit_ir* h, const vkjit_var* ids, size_t n, int32_t mode, int32_t compile, char* buf,
+                                      size_t cap, size_t* out_len, size_t* out_cubin) {
+  return with_ir(h, [&](Ir& ir) {
+    if (mode < SCAN_EXCLUSIVE || mode > SCAN_COMPRESS_VALUE) fail(VKJIT_ERR_INVALID, "unknown scan mode");
+    if (n != (mode == SCAN_COMPRESS_VALUE ? 2u : 1u)) fail(VKJIT_ERR_INVALID, "scan modes 0-2 take one var, mode 3 takes {mask, values}");
+    Program p;
+    std::vector<VarId> roots(ids, ids + n);
+    build_program(ir, roots, true, p, -1, false, mode);
     const std::string src = generate_cuda(ir, p);
     if (out_cubin) *out_cubin = 0;
     if (compile) {

@@ -18,18 +18,7 @@ namespace prims {
 // ---------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------
-// Streaming 128-bit load: read-only path, do not allocate in L1 (every byte is used once).
-__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
-  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
-}
+#include "scan_common.cuh"  // streaming ld/st, tile status words + look-back, TMA/mbarrier (shared with the NVRTC kernels)
 
 template <typename T> __device__ __forceinline__ T from_bits(uint32_t w);
 template <> __device__ __forceinline__ uint32_t from_bits<uint32_t>(uint32_t w) { return w; }
@@ -319,100 +308,7 @@ void prefix_of_rank_u32(const uint32_t* v, int rank, uint32_t* out, void* stream
 // Why the tile is this large: every generation of 148 tiles pays one cross-SM aggregate exchange, and
 // with strided persistent tiles each generation runs at the pace of its slowest SM; fewer, larger
 // generations pay that less often (history: profiles/r01_scan_history.md).
-enum : uint32_t { ST_INVALID = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2 };
 enum ScanMode { MODE_EXCLUSIVE = 0, MODE_INCLUSIVE = 1, MODE_COMPRESS_INDEX = 2, MODE_COMPRESS_VALUE = 3 };
-
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
-
-// Status words are read and written with gpu-scope relaxed accesses (L2 is the coherence point;
-// `volatile` would compile to system-scope STRONG.SYS) and every tile owns a full 128-byte line:
-// a window of predecessors then maps to many L2 slices instead of hammering the one or two
-// slices that hold a packed status array (the packed layout made every poll round take ~0.7 us
-// and the nearest window was polled 6.6 times per tile — ncu source page, profiles/).
-constexpr int kStatusStride = 16;  // 64-bit words per tile status slot (128 bytes)
-__device__ __forceinline__ uint64_t status_load(const uint64_t* p) {
-  uint64_t v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void status_store(uint64_t* p, uint64_t v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Executed by warp 0 of the CTA owning `tile`.  Returns the exclusive prefix of the tile.
-// One round inspects kLookWide x 32 = 160 predecessors with all status loads in flight together:
-// the persistent grid runs its 148 CTAs in generations, so a single round (one L2 round trip)
-// spans the whole current generation plus the tail of the previous one, whose inclusive prefixes
-// are already published.
-constexpr int kLookWide = 5;
-__device__ __forceinline__ uint32_t look_back(uint64_t* status, uint32_t tile, uint32_t aggregate, uint32_t initial) {
-  const int lane = threadIdx.x & 31;
-  if (tile == 0) {  // `initial`: prefix carried in from outside (sharded scan: the totals of the lower ranks)
-    if (lane == 0) status_store(status, ((uint64_t)ST_INCLUSIVE << 32) | (initial + aggregate));
-    return initial;
-  }
-  if (lane == 0) status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_AGGREGATE << 32) | aggregate);
-  uint32_t exclusive = 0;
-  int top = (int)tile - 1;  // nearest predecessor examined by lane 0
-  for (;;) {
-    uint64_t s[kLookWide];
-#pragma unroll
-    for (int i = 0; i < kLookWide; ++i) {
-      const int idx = top - 32 * i - lane;
-      s[i] = idx >= 0 ? status_load(status + (size_t)idx * kStatusStride) : ((uint64_t)ST_INCLUSIVE << 32);  // before tile 0: prefix 0
-    }
-    bool done = false;
-#pragma unroll
-    for (int i = 0; i < kLookWide; ++i) {
-      if (done) continue;
-      const int idx = top - 32 * i - lane;
-      uint32_t spins = 0;
-      while ((uint32_t)(s[i] >> 32) == ST_INVALID) {  // predecessor not published yet
-        __nanosleep(40);
-        s[i] = status_load(status + (size_t)idx * kStatusStride);
-        if (++spins > (1u << 25)) __trap();  // seconds without progress: fail loudly instead of hanging the GPU
-      }
-      const unsigned incl = __ballot_sync(0xFFFFFFFFu, (uint32_t)(s[i] >> 32) == ST_INCLUSIVE);
-      if (incl) {
-        const int first = __ffs(incl) - 1;  // nearest tile that already knows its inclusive prefix
-        exclusive += warp_sum(lane <= first ? (uint32_t)s[i] : 0u);
-        done = true;
-      } else {
-        exclusive += warp_sum((uint32_t)s[i]);
-      }
-    }
-    if (done) break;
-    top -= 32 * kLookWide;
-  }
-  if (lane == 0) status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_INCLUSIVE << 32) | (exclusive + aggregate));
-  return exclusive;
-}
-
-// ---- TMA bulk-copy / mbarrier helpers (sm_90+; SASS: UBLKCP + SYNCS) -----------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-// global -> shared bulk copy performed by the TMA unit; completion is signalled on `bar`
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done, spins = 0;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done)
-                 : "r"(smem_addr(bar)), "r"(parity)
-                 : "memory");
-    if (!done && ++spins > (1u << 26)) __trap();  // a bulk copy that never lands: fail loudly
-  } while (!done);
-}
 
 // Persistent kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The input
 // tiles arrive through a 2-stage shared-memory ring filled by TMA bulk copies, so up to
@@ -587,7 +483,8 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   }
 }
 
-size_t scan_state_words(size_t n) { return (size_t)kStatusStride * (2 + n / kScanMinTile); }
+static_assert(kStatusWordsPerTile == kStatusStride, "host and device disagree on the status slot size");
+size_t scan_state_words(size_t n, size_t tile) { return (size_t)kStatusStride * (2 + n / tile); }
 
 template <int MODE>
 static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,

@@ -37,7 +37,8 @@ constexpr int kScanThreads = 1024;
 constexpr int kScanMinTile = 24576;  // look-back tile (ScanGeom in prims.cu); sizes the status array
 
 // number of 8-byte words `tile_state` must hold for n lanes
-size_t scan_state_words(size_t n);
+constexpr int kStatusWordsPerTile = 16;  // one 128-byte line of 64-bit words per tile (kStatusStride in scan_common.cuh)
+size_t scan_state_words(size_t n, size_t tile = kScanMinTile);
 
 // out[0] = reduce(in[0..n)).  ty: VKJIT_TY_{U32,I32,F32}; red: VKJIT_RED_*.  One launch:
 // vectorised grid-stride partials -> warp shuffle -> shared-memory tree -> last CTA folds the

@@ -10,7 +10,7 @@ namespace vkjit {
 
 void Program::clear() {
   key_len = 0; order.clear(); params.clear(); roots.clear();
-  n = 0; have_n = false; base = 0; have_base = false; sharded = false; vectorized = true; reduce = -1;
+  n = 0; have_n = false; base = 0; have_base = false; sharded = false; vectorized = true; reduce = -1; scan = -1;
   privatize = false; sadd_param = -1; has_gather = false;
   hash = Hash128();
 }
@@ -69,10 +69,26 @@ int unroll_factor() {
 
 }  // namespace
 
-void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce, bool privatize) {
+int scan_fused_threads() {
+  static int t = 0;
+  if (!t) {
+    const char* s = getenv("VKJIT_SCAN_T");
+    t = (s && atoi(s) == 512) ? 512 : 1024;
+  }
+  return t;
+}
+
+size_t stream_count(const Program& p) {
+  size_t k = 0;
+  for (const Param& pr : p.params) k += (pr.use & USE_STREAM) ? 1 : 0;
+  return k;
+}
+
+void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce, bool privatize, int scan) {
   p.clear();
   p.vectorized = vectorized;
   p.reduce = reduce;
+  p.scan = scan;
   p.privatize = privatize;
   const uint32_t stamp = ir.next_stamp();
   static thread_local std::vector<Frame> stack;
@@ -246,8 +262,9 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   if (p.params.size() + p.roots.size() > 480) fail(VKJIT_ERR_UNSUPPORTED, "too many arrays in one kernel (4 KB parameter limit)");
 
   if (kn + 4 + p.roots.size() > key.size()) { key.resize(kn + 64 + p.roots.size()); kw = key.data(); }
-  if (p.sadd_param < 0 || reduce >= 0) p.privatize = false;
-  kw[1] = (vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16) | (p.privatize ? 1u << 24 : 0u);
+  if (p.sadd_param < 0 || reduce >= 0 || scan >= 0) p.privatize = false;
+  kw[1] = (vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16) | (p.privatize ? 1u << 24 : 0u) |
+          ((uint32_t)(scan + 1) << 25) | (scan >= 0 && scan_fused_threads() == 512 ? 1u << 28 : 0u);
   for (size_t k = 0; k < p.params.size(); ++k) kw[binding_pos[k]] |= (uint32_t)p.params[k].use << 16;
   kw[kn++] = 0xFFFFFFFFu;
   for (uint32_t r : p.roots) kw[kn++] = r;
@@ -568,6 +585,36 @@ __device__ __forceinline__ void vk_finish(acc_t acc, u32* partials, unsigned int
 }
 )CUDA";
 
+// scan_common.cuh / scan_fused.cuh as text (generated by the Makefile)
+#include "build/scan_src.inc"
+
+// Shell of a fused trace -> scan kernel: the pointer block, the adapter from the ring's words to vk_lane, and
+// the hand-written kernel text specialised through three macros.
+std::string scan_shell(const Program& p, const std::vector<uint32_t>& streams, const std::vector<uint32_t>& ptrs, size_t nroots) {
+  const size_t ns = streams.size();
+  if (ns > (size_t)kScanFusedMaxStreams) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: too many streamed arrays");
+  if (nroots != (p.scan == SCAN_COMPRESS_VALUE ? 2u : 1u)) fail(VKJIT_ERR_INVALID, "fused scan: wrong number of roots");
+  std::string s;
+  s += "#define VK_SCAN_MODE " + std::to_string(p.scan) + "\n#define VK_NS " + std::to_string(ns) + "\n#define VK_VPT " +
+       std::to_string(scan_fused_vpt(ns)) + "\n#define VK_T " + std::to_string(scan_fused_threads()) +
+       "\n#define VK_LOOK_WIDE " + std::to_string(scan_fused_threads() == 512 ? 10 : 5) + "  // one look-back round spans a generation of CTAs\n";
+  s += "struct VkPtrs {\n  const u32* s[" + std::to_string(std::max<size_t>(ns, 1)) + "];  // streamed arrays (staged by TMA)\n";
+  for (uint32_t k : ptrs) {
+    if (p.params[k].use & USE_SCATTER) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: the trace has side effects");
+    s += "  const u32* g" + std::to_string(k) + ";\n";
+  }
+  s += "};\n";
+  s += "__device__ __forceinline__ void vk_eval(const VkPtrs& P, const u32 gi, const u32 li, const u32* in, u32& o0, u32& o1) {\n  vk_lane(gi, li";
+  for (size_t i = 0; i < ns; ++i) s += ", in[" + std::to_string(i) + "]";
+  s += ", o0";
+  if (nroots == 2) s += ", o1";
+  for (uint32_t k : ptrs) s += ", P.g" + std::to_string(k);
+  s += ");\n}\n\n";
+  s += kScanCommonSrc;
+  s += kScanFusedSrc;
+  return s;
+}
+
 std::string reduce_defines(int red, TypeId ty) {
   std::string d = std::string("typedef ") + ctype(ty) + " acc_t;\n";
   d += "#define VK_FROM_WORD(w) (" + from_word(ty, "(w)") + ")\n";
@@ -613,6 +660,8 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   std::string s;
   s += "// vkjit-b200 fused trace kernel; key " + std::to_string(p.hash.lo) + ":" + std::to_string(p.hash.hi) + "\n";
   s += "typedef unsigned int u32;\ntypedef int i32;\ntypedef float f32;\n\n";
+  const bool scan = p.scan >= 0;
+  if (scan) s += "typedef unsigned int uint32_t;\ntypedef unsigned long long uint64_t;\n\n";
   if (reduce) {
     if (nroots != 1) fail(VKJIT_ERR_INVALID, "a fused reduction has exactly one root");
     s += reduce_defines(p.reduce, g.vals[p.roots[0]].ty) + kReduceEpilogue + "\n";
@@ -635,6 +684,7 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
     s += std::string(", ") + (w ? "u32* " : "const u32* __restrict__ ") + "g" + std::to_string(k);
   }
   s += ") {\n" + g.body + "}\n\n";
+  if (scan) return s + scan_shell(p, streams, ptrs, nroots);
 
   auto call = [&](const std::string& gi, const std::string& li, const char* comp, bool vec) {
     std::string c = "vk_lane(" + gi + ", " + li;

@@ -21,6 +21,15 @@ struct Hash128 {
 
 enum ParamUse : uint8_t { USE_STREAM = 1, USE_GATHER = 2, USE_SCATTER = 4 };
 
+// fused trace -> scan kernels (scan_fused.cuh); numbering = prims.cu's ScanMode
+enum ScanKind : int { SCAN_EXCLUSIVE = 0, SCAN_INCLUSIVE = 1, SCAN_COMPRESS_INDEX = 2, SCAN_COMPRESS_VALUE = 3 };
+constexpr int kScanFusedMaxStreams = 6;
+// tile geometry of a fused scan: T threads x vpt 128-bit vectors; the TMA ring holds 2 stages x streams x tile
+int scan_fused_threads();  // threads per CTA: 1024 (one CTA per SM); $VKJIT_SCAN_T=512 runs two 512-thread CTAs per SM (measured slower, profiles/r01_fused_scan.md)
+inline int scan_fused_vpt(size_t streams) { return streams <= 1 ? 6 : (int)(6 / streams); }
+inline size_t scan_fused_tile(size_t streams) { return (size_t)scan_fused_threads() * 4 * scan_fused_vpt(streams); }
+inline size_t scan_fused_smem(size_t streams) { return 2 * streams * scan_fused_tile(streams) * 4; }
+
 struct Param {
   VarId var;     // the Binding var whose array is passed
   uint8_t use;   // ParamUse bits
@@ -41,6 +50,7 @@ struct Program {
   bool sharded = false;
   bool vectorized = true;       // 128-bit ld/st variant
   int reduce = -1;              // >= 0: fused trace -> reduce kernel (VKJIT_RED_*), the single root is not stored
+  int scan = -1;                // >= 0: fused trace -> scan kernel (SCAN_*): root 0 is scanned / is the compress mask
   bool privatize = false;       // variant: the first scatter_add target is partly privatised in shared memory
   int sadd_param = -1;          // param index of the first scatter_add target (-1: none)
   bool has_gather = false;      // the trace gathers (wants L1 for its table)
@@ -53,7 +63,10 @@ struct Program {
 // reference's panics: size mismatch (internal.rs:699-702), size-less schedule (:1202),
 // gather from a non-buffer (:1054), scatter into a non-buffer (:1059-1062), struct roots.
 void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce = -1,
-                   bool privatize = false);
+                   bool privatize = false, int scan = -1);
+
+// number of params the kernel streams (one word per lane)
+size_t stream_count(const Program& p);
 
 // CUDA C source of the kernel for `p` (entry point "vkjit_trace").
 std::string generate_cuda(const Ir& ir, const Program& p);

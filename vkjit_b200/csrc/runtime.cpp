@@ -28,6 +28,7 @@ struct Driver {
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocks)(int*, CUfunction, int, size_t) = nullptr;
   bool load(std::string& why) {
     if (handle) return true;
     handle = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
@@ -39,7 +40,8 @@ struct Driver {
     LaunchKernel = (decltype(LaunchKernel))sym("cuLaunchKernel");
     GetErrorString = (decltype(GetErrorString))sym("cuGetErrorString");
     FuncSetAttribute = (decltype(FuncSetAttribute))sym("cuFuncSetAttribute");
-    if (!ModuleLoadData || !ModuleUnload || !ModuleGetFunction || !LaunchKernel || !GetErrorString || !FuncSetAttribute) {
+    OccupancyMaxActiveBlocks = (decltype(OccupancyMaxActiveBlocks))sym("cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (!OccupancyMaxActiveBlocks || !ModuleLoadData || !ModuleUnload || !ModuleGetFunction || !LaunchKernel || !GetErrorString || !FuncSetAttribute) {
       why = "libcuda.so.1 lacks required entry points";
       return false;
     }
@@ -181,8 +183,8 @@ void Backend::d2d(void* dst, const void* src, size_t bytes) {
 
 void Backend::sync() { ck(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
 
-void Backend::ensure_scan_scratch(size_t n) {
-  const size_t need = prims::scan_state_words(n);
+void Backend::ensure_scan_scratch(size_t n, size_t tile) {
+  const size_t need = prims::scan_state_words(n, tile);
   if (need <= scratch.tile_state_words) return;
   if (scratch.tile_state) {
     ck(cudaStreamSynchronize((cudaStream_t)stream), "sync");
@@ -316,7 +318,17 @@ CachedKernel* Backend::compile(const Ir& ir, const Program& p) {
   cku(g_drv.ModuleGetFunction(&fn, mod, "vkjit_trace"), "cuModuleGetFunction");
   if (p.privatize)
     cku(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kPrivatizeMaxBytesNoGather), "cuFuncSetAttribute");
+  int ctas_per_sm = 0;
+  if (p.scan >= 0) {
+    const size_t smem = scan_fused_smem(stream_count(p));
+    if (smem) cku(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem), "cuFuncSetAttribute");
+    // the look-back needs every CTA of the grid co-resident: the grid is sized from the real occupancy
+    cku(g_drv.OccupancyMaxActiveBlocks(&ctas_per_sm, fn, scan_fused_threads(), smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (ctas_per_sm < 1) fail(VKJIT_ERR_CUDA, "fused scan kernel does not fit on an SM");
+    ctas_per_sm = std::min(ctas_per_sm, 1024 / scan_fused_threads());
+  }
   auto* k = new CachedKernel();
+  k->ctas_per_sm = (uint32_t)ctas_per_sm;
   k->module = mod; k->function = fn; k->key.assign(p.key.begin(), p.key.begin() + p.key_len);
   k->nparams = (uint32_t)p.params.size(); k->nroots = (uint32_t)p.roots.size(); k->vectorized = p.vectorized;
   {
@@ -352,8 +364,9 @@ void Backend::launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args
 // ---- Ir::eval (internal.rs:482-525) ---------------------------------------------------------
 namespace {
 
-// Compile-or-lookup + launch of one group of roots that share a kernel size; the roots become Bindings.
-void eval_group(Ir& ir, Backend& be, const std::vector<VarId>& roots) {
+// Compile-or-lookup + launch of one group of roots that share a kernel size.  commit: the roots become
+// Bindings (Ir::eval); otherwise the fresh arrays are handed to the caller and the vars stay as they are.
+void run_group(Ir& ir, Backend& be, const std::vector<VarId>& roots, bool commit, std::vector<Array*>* result) {
   static thread_local Program prog;
   static thread_local std::vector<Array*> outs;
   static thread_local std::vector<void*> argv;
@@ -407,7 +420,8 @@ void eval_group(Ir& ir, Backend& be, const std::vector<VarId>& roots) {
       be.launch(k, (uint32_t)grid, 256, argv.data());
     }
 
-    ir.commit_roots(roots, outs);
+    if (commit) ir.commit_roots(roots, outs);
+    else *result = outs;
     outs.clear();
   } catch (...) {
     for (Array* a : outs) release_array(a);
@@ -416,7 +430,19 @@ void eval_group(Ir& ir, Backend& be, const std::vector<VarId>& roots) {
   }
 }
 
+void eval_group(Ir& ir, Backend& be, const std::vector<VarId>& roots) { run_group(ir, be, roots, true, nullptr); }
+
 }  // namespace
+
+// Evaluates `id` into a fresh array WITHOUT turning the var into a Binding (operands of the eager primitives
+// that cannot be fused into the primitive's kernel).  A Binding is copied (the scalar variant handles
+// misaligned foreign views).
+Array* eval_temp(Ir& ir, VarId id) {
+  std::vector<VarId> roots{id};
+  std::vector<Array*> outs;
+  run_group(ir, Backend::get(), roots, false, &outs);
+  return outs.at(0);
+}
 
 void eval(Ir& ir, const VarId* ids, size_t n) {
   const uint64_t t0 = now_ns();
@@ -494,6 +520,54 @@ Array* eval_reduce(Ir& ir, VarId id, int red) {
     be.launch(k, (uint32_t)grid, 256, argv.data());
   } catch (...) { release_array(out); throw; }
   return out;
+}
+
+// Fused trace -> prefix-sum / compress (scan_fused.cuh): root 0 is scanned (or is the compress mask), root 1
+// (SCAN_COMPRESS_VALUE) supplies the compacted values.  None of the roots is materialised or committed.
+// Returns false when this trace is not fused (side effects, > 6 streamed arrays, a misaligned streamed
+// array, or a body so large that evaluating it twice / inlining it 24 times does not pay): the caller then
+// evaluates the operands into temporaries and runs the hand-written primitive.
+bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t* initial, uint32_t* count_dev, Array** out,
+               uint64_t* n_out) {
+  Backend& be = Backend::get();
+  static thread_local Program prog;
+  build_program(ir, roots, true, prog, -1, false, mode);
+  *n_out = prog.n;
+  if (!prog.vectorized) return false;  // > kMaxVectorNodes nodes
+  if (getenv("VKJIT_NO_FUSED_SCAN")) return false;
+  size_t ns = 0;
+  for (const Param& pr : prog.params) {
+    if (pr.use & USE_SCATTER) return false;
+    if (pr.use & USE_STREAM) {
+      ++ns;
+      if ((uintptr_t)ir.vars[pr.var].array->ptr & 15u) return false;
+    }
+  }
+  if (ns > (size_t)kScanFusedMaxStreams) return false;
+  if (prog.n == 0) { *out = be.new_array(0); return true; }  // nothing to scan: empty result, no launch
+  CachedKernel* k = be.lookup(prog);
+  if (!k) k = be.compile(ir, prog);
+
+  const size_t tile = scan_fused_tile(ns);
+  const size_t tiles = (prog.n + tile - 1) / tile;
+  be.ensure_scan_scratch(prog.n, tile);
+  ck(cudaMemsetAsync(be.scratch.tile_state, 0, (size_t)prims::kStatusWordsPerTile * (1 + tiles) * 8, (cudaStream_t)be.stream), "scan status memset");
+  Array* o = be.new_array((size_t)prog.n * 4);  // compress: worst case, trimmed by the caller
+  // VkPtrs: streamed arrays (at least one slot), then the gather pointers in parameter order
+  std::vector<uint64_t> block;
+  for (const Param& pr : prog.params) if (pr.use & USE_STREAM) block.push_back((uint64_t)(uintptr_t)ir.vars[pr.var].array->ptr);
+  if (block.empty()) block.push_back(0);
+  for (const Param& pr : prog.params) if (pr.use & (USE_GATHER | USE_SCATTER)) block.push_back((uint64_t)(uintptr_t)ir.vars[pr.var].array->ptr);
+  uint32_t n32 = (uint32_t)prog.n, base32 = (uint32_t)prog.base, tiles32 = (uint32_t)tiles;
+  uint64_t outp = (uint64_t)(uintptr_t)o->ptr, cntp = (uint64_t)(uintptr_t)count_dev, statep = (uint64_t)(uintptr_t)be.scratch.tile_state,
+           initp = (uint64_t)(uintptr_t)initial;
+  void* argv[] = {&n32, &base32, block.data(), &outp, &cntp, &tiles32, &statep, &initp};
+  try {
+    be.launch(k, (uint32_t)std::min<size_t>(tiles, (size_t)be.sm_count * k->ctas_per_sm), (uint32_t)scan_fused_threads(), argv,
+              (uint32_t)scan_fused_smem(ns));
+  } catch (...) { release_array(o); throw; }
+  *out = o;
+  return true;
 }
 
 }  // namespace vkjit

@@ -34,6 +34,7 @@ struct CachedKernel {
   std::vector<uint32_t> key; // verified on every hit
   uint32_t nparams = 0, nroots = 0;
   bool vectorized = true;
+  uint32_t ctas_per_sm = 0;  // fused scan kernels: co-resident CTAs per SM (sizes the persistent grid)
 };
 
 struct Counters {
@@ -67,7 +68,7 @@ class Backend {
   void d2h(void* dst, const void* src, size_t bytes);  // synchronises
   void d2d(void* dst, const void* src, size_t bytes);
   void sync();
-  void ensure_scan_scratch(size_t n);
+  void ensure_scan_scratch(size_t n, size_t tile = prims::kScanMinTile);
 
   // kernel cache keyed by trace hash
   CachedKernel* lookup(const Program& p);
@@ -86,5 +87,8 @@ void eval(Ir& ir, const VarId* ids, size_t n);
 
 // Fused trace -> reduce kernel for an unevaluated var (see runtime.cpp).
 Array* eval_reduce(Ir& ir, VarId id, int red);
+Array* eval_temp(Ir& ir, VarId id);
+bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t* initial, uint32_t* count_dev, Array** out,
+               uint64_t* n_out);
 
 }  // namespace vkjit

@@ -1,0 +1,187 @@
+// scan_fused.cuh — fused trace -> prefix-sum / compress kernel (NVRTC only; the Makefile embeds this text).
+//
+// Same single-pass decoupled look-back scan as prims.cu's scan_kernel (persistent CTAs walking tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...; all CTAs co-resident), but the scanned words are not loaded: they are
+// computed lane by lane by the generated trace body.  The arrays the trace STREAMS (one word per lane) are
+// staged through the same 2-stage TMA ring, one ring slot per streamed array, so a mask such as `x > t`
+// costs 4 B/lane of HBM reads and the mask itself never exists in memory (SURVEY.md §8d C28 "fused-mask
+// variant": 4 B read + 4p B written instead of 8 + 4p, and no kernel that materialises the mask first).
+//
+// The generated prelude provides:
+//   VK_SCAN_MODE  0 exclusive sum, 1 inclusive sum, 2 compress -> lane indices, 3 compress -> values (root 1)
+//   VK_NS         number of streamed arrays (0..6);  VK_VPT  128-bit vectors per thread and tile (6 / max(NS,1))
+//   VK_T          threads per CTA (1024 / VK_T CTAs per SM: with two CTAs one computes while the other looks back)
+//   struct VkPtrs { const u32* s[max(NS,1)]; <gather/scatter pointers> };
+//   vk_eval(P, gi, li, in[max(NS,1)], o0, o1)   root words of global lane gi / local lane li
+extern "C" __global__ void __launch_bounds__(VK_T, 1024 / VK_T)
+vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, u32* __restrict__ count_out,
+            const u32 num_tiles, uint64_t* __restrict__ state, const u32* __restrict__ initial_ptr) {
+  constexpr int T = VK_T, VPT = VK_VPT, TILE = T * 4 * VPT, NS = VK_NS, NSA = NS > 0 ? NS : 1, S = 2;
+  constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = (NTOT + 31) / 32;
+  constexpr u32 TILE_BYTES = TILE * 4;
+  constexpr bool COMPRESS = VK_SCAN_MODE >= 2, VALUES = VK_SCAN_MODE == 3;
+  // compress -> values re-evaluates the selected lanes when it writes them, so the ring slot is kept
+  // until the tile's output phase is over (the other slot is still being filled meanwhile)
+  constexpr bool LATE_RELEASE = VALUES && NS > 0;
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  u32* ring = reinterpret_cast<u32*>(ring_raw);  // [stage][stream][TILE]
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ u32 s_tot[2][NTOT];
+  __shared__ u32 s_tile_excl[2];
+
+  uint64_t* status = state + kStatusStride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 first = blockIdx.x, stride = gridDim.x;
+  const u32 my_tiles = first < num_tiles ? (num_tiles - first + stride - 1) / stride : 0;
+  const bool ragged = (n % TILE) != 0;  // the globally last tile is partial: guarded loads, no TMA
+
+  auto fill = [&](u32 t, int stage) {  // thread 0: one bulk copy per streamed array, all on the stage's barrier
+    if (ragged && t == num_tiles - 1) return;
+    mbar_expect_tx(&full[stage], (u32)NS * TILE_BYTES);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      tma_load_1d(ring + ((size_t)stage * NS + s) * TILE, P.s[s] + (size_t)t * TILE, TILE_BYTES, &full[stage]);
+  };
+  // words of vector j of the current tile, per streamed array
+  auto fetch = [&](int j, bool staged, int stage, size_t e, u32 (&w)[NSA][4]) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (staged) {
+        const uint4 a = reinterpret_cast<const uint4*>(ring + ((size_t)stage * NS + s) * TILE)[j * T + threadIdx.x];
+        w[s][0] = a.x; w[s][1] = a.y; w[s][2] = a.z; w[s][3] = a.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w[s][c] = e + c < n ? P.s[s][e + c] : 0u;
+      }
+    }
+  };
+
+  if (NS > 0) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (u32 k = 0; k < (u32)S && k < my_tiles; ++k) fill(first + k * stride, (int)k);
+  }
+
+  for (u32 k = 0; k < my_tiles; ++k) {
+    const u32 tile = first + k * stride;
+    const int stage = k % S;
+    const int buf = k & 1;
+    const size_t tile_base = (size_t)tile * TILE;
+    const bool whole = !(ragged && tile == num_tiles - 1);
+    const bool staged = whole && NS > 0;
+
+    if (staged) mbar_wait(&full[stage], (k / S) & 1);
+    uint4 x[VPT];     // sums: the addends
+    u32 flags[VPT];   // compress: 4 selection bits per vector
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+      u32 w[NSA][4];
+      fetch(j, staged, stage, e, w);
+      u32 r[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        u32 o0 = 0u, o1 = 0u;
+        if (whole || e + c < n) {  // lanes past the end are never evaluated (their gathers would be out of range)
+          u32 in[NSA];
+#pragma unroll
+          for (int s = 0; s < NS; ++s) in[s] = w[s][c];
+          vk_eval(P, base + (u32)(e + c), (u32)(e + c), in, o0, o1);
+        }
+        r[c] = o0;
+      }
+      if (COMPRESS) flags[j] = (r[0] != 0u ? 1u : 0u) | (r[1] != 0u ? 2u : 0u) | (r[2] != 0u ? 4u : 0u) | (r[3] != 0u ? 8u : 0u);
+      else { x[j].x = r[0]; x[j].y = r[1]; x[j].z = r[2]; x[j].w = r[3]; }
+    }
+
+    // 1) per-vector sums, 2) inclusive warp scan per register slot, 3) one warp scans the
+    // (slot, warp) totals in tile order, 4) look-back gives the tile's global offset.
+    u32 vsum[VPT], wincl[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      vsum[j] = COMPRESS ? (u32)__popc(flags[j]) : x[j].x + x[j].y + x[j].z + x[j].w;
+      u32 s = vsum[j];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+        if (lane >= o) s += t;
+      }
+      wincl[j] = s;
+      if (lane == 31) s_tot[buf][j * WARPS + warp] = s;
+    }
+    __syncthreads();  // every thread has consumed its part of ring[stage]
+    if (NS > 0 && !LATE_RELEASE && threadIdx.x == 0 && k + S < my_tiles) fill(first + (k + S) * stride, stage);
+    if (warp == 0) {
+      u32 t[PER_LANE], run = 0;
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) { t[i] = lane * PER_LANE + i < NTOT ? s_tot[buf][lane * PER_LANE + i] : 0u; run += t[i]; }
+      u32 s = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 u = __shfl_up_sync(0xFFFFFFFFu, s, o);
+        if (lane >= o) s += u;
+      }
+      u32 off = s - run;  // exclusive offset of this lane's first entry
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) { if (lane * PER_LANE + i < NTOT) s_tot[buf][lane * PER_LANE + i] = off; off += t[i]; }
+      const u32 aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
+      const u32 initial = (tile == 0 && initial_ptr) ? __ldcg(initial_ptr) : 0u;
+      const u32 excl = look_back(status, tile, aggregate, initial);
+      if (lane == 0) {
+        s_tile_excl[buf] = excl;
+        if (COMPRESS && tile == num_tiles - 1) *count_out = excl + aggregate;
+      }
+    }
+    __syncthreads();
+    const u32 tile_excl = s_tile_excl[buf];
+
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+      u32 p = tile_excl + s_tot[buf][j * WARPS + warp] + (wincl[j] - vsum[j]);  // exclusive prefix of lane e
+      if (!COMPRESS) {
+        uint4 r;
+        if (VK_SCAN_MODE == 0) { r.x = p; r.y = p + x[j].x; r.z = r.y + x[j].y; r.w = r.z + x[j].z; }
+        else { r.x = p + x[j].x; r.y = r.x + x[j].y; r.z = r.y + x[j].z; r.w = r.z + x[j].w; }
+        if (whole || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
+        else {
+          if (e + 0 < n) out[e + 0] = r.x;
+          if (e + 1 < n) out[e + 1] = r.y;
+          if (e + 2 < n) out[e + 2] = r.z;
+        }
+      } else if (flags[j]) {
+        // selected lanes are written at their rank; flags of out-of-range lanes are 0
+        if (VALUES) {
+          u32 w[NSA][4];
+          fetch(j, staged, stage, e, w);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (flags[j] & (1u << c)) {
+              u32 in[NSA];
+#pragma unroll
+              for (int s = 0; s < NS; ++s) in[s] = w[s][c];
+              u32 o0, o1 = 0u;
+              vk_eval(P, base + (u32)(e + c), (u32)(e + c), in, o0, o1);
+              out[p++] = o1;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (flags[j] & (1u << c)) out[p++] = (u32)(e + c);
+        }
+      }
+    }
+    if (LATE_RELEASE) {
+      __syncthreads();  // the output phase read ring[stage] again
+      if (threadIdx.x == 0 && k + S < my_tiles) fill(first + (k + S) * stride, stage);
+    }
+    // s_tot/s_tile_excl are double-buffered: iteration k+2 rewrites buffer `buf` only after every
+    // thread passed the first barrier of iteration k+1, i.e. after it finished reading it here.
+  }
+}

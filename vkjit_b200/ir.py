@@ -321,6 +321,19 @@ def _debug_codegen_reduce(self, id: int, red: int, compile: bool = False):
 Ir.debug_codegen_reduce = _debug_codegen_reduce
 
 
+def _debug_codegen_scan(self, ids, mode: int, compile: bool = False):
+    """Source (and cubin size) of the fused trace -> scan kernel; mode 0/1 prefix sums, 2 compress, 3 compress_values."""
+    arr = (C.c_uint32 * len(ids))(*ids)
+    n, cub = C.c_size_t(), C.c_size_t()
+    self.api.call("debug_codegen_scan", self._h, arr, len(ids), mode, 0, None, 0, C.byref(n), C.byref(cub))
+    buf = C.create_string_buffer(n.value + 1)
+    self.api.call("debug_codegen_scan", self._h, arr, len(ids), mode, 1 if compile else 0, buf, n.value + 1, C.byref(n), C.byref(cub))
+    return buf.value.decode(), cub.value
+
+
+Ir.debug_codegen_scan = _debug_codegen_scan
+
+
 # convenience: named binary ops exactly as the reference's bop! expansion (internal.rs:218-227)
 def _mk(kind):
     def f(self, lhs: int, rhs: int) -> int:
