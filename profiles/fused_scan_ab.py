@@ -40,8 +40,13 @@ def scan_trace():  # prefix sum of hash(lane): nothing read
 def scan_x2():     # prefix sum of (values >> 3): one streamed array
     h = ir.shr(vals, c(3))
     r = ir.prefix_sum(h, True); ir.dec_ref_count(r); ir.dec_ref_count(h)
+mask_arr = ir.neq(ir.bop(Bop.And, hash_trace(ir, lanes, 4), c(1)), c(0))
+ir.eval([mask_arr])
+def two_streams():  # mask array AND values array both streamed through the ring (12288-lane tiles)
+    mk = ir.bop(Bop.And, mask_arr, ir.const_bool(True))
+    r, k = ir.compress_values(vals, mk); ir.dec_ref_count(r); ir.dec_ref_count(mk)
 out = [f"T={os.environ.get('VKJIT_SCAN_T', '1024')}"]
-for name, fn, bpl in (("hash_mask", hash_mask, 6), ("thresh", thresh, 6), ("thresh_idx", thresh_idx, 6), ("scan_trace", scan_trace, 4), ("scan_stream", scan_x2, 8)):
+for name, fn, bpl in (("hash_mask", hash_mask, 6), ("thresh", thresh, 6), ("thresh_idx", thresh_idx, 6), ("scan_trace", scan_trace, 4), ("scan_stream", scan_x2, 8), ("two_streams", two_streams, 10)):
     ms = timed(fn)
     out.append(f"{name} {ms:.4f} ms ({bpl*n/ms/1e6/6450:.3f} of peak at {bpl} B/lane)")
 print("  ".join(out))

@@ -90,6 +90,41 @@ def test_C28_prefix_sum_and_compress_full_size(cir, oir_mt):
     assert cir.size(id_) == nd and np.array_equal(cir.as_slice(back, T.U32), cir.as_slice(cd2, T.U32))
 
 
+def test_C28_fused_mask_compress_full_size(cuda_backend, cir, oir_mt):
+    """configs[3], fused-mask variant: the mask is a trace (`v > 2^31`, and a bit of a hash of v)
+    evaluated inside the compaction kernel — bit-exact on the whole result; ONE kernel, nothing materialised."""
+    vd, vo = device_array(cir, N28, 0xB2000041, RAW), oracle_array(oir_mt, N28, 0xB2000041, RAW)
+    res = []
+    for ir, v in ((cir, vd), (oir_mt, vo)):
+        m1 = ir.gt(v, ir.const_u32(1 << 31))
+        m2 = ir.neq(ir.bop(Bop.And, ir.mul(v, ir.const_u32(2654435761)), ir.const_u32(1 << 19)), ir.const_u32(0))
+        if ir is cir:
+            cuda_backend.stats_reset()
+        (a, na), (b, nb) = ir.compress_values(v, m1), ir.compress(m2)
+        if ir is cir:
+            assert cuda_backend.stats()["trace_launches"] == 2 and not ir.is_buffer(m1) and not ir.is_buffer(m2)
+        res.append((na, nb, ir.as_slice(a, T.U32), ir.as_slice(b, T.U32)))
+        ir.dec_ref_count(a); ir.dec_ref_count(b)
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+    assert np.array_equal(res[0][2], res[1][2]) and np.array_equal(res[0][3], res[1][3])
+    assert (res[0][2] > (1 << 31)).all() and (np.diff(res[0][3].astype(np.int64)) > 0).all()   # filter holds; indices ascend
+
+
+def test_H26_skewed_indices_full_size(cir, oir_mt):
+    """configs[2], skewed run: indices min(h & 0xFFFF, h >> 16) — low bins are hit more often."""
+    out = []
+    for ir, mk in ((cir, device_array), (oir_mt, oracle_array)):
+        h = mk(ir, N26, 0xB2000031, RAW)
+        idx = ir.bop(Bop.Min, ir.bop(Bop.And, h, ir.const_u32(0xFFFF)), ir.shr(h, ir.const_u32(16)))
+        ir.eval([idx])
+        table = mk(ir, 1 << 16, 0xB2000032, RAW)
+        bins = ir.array_u32(np.zeros(1 << 16, np.uint32))
+        s = ir.scatter_add(ir.gather(table, idx), bins, idx)
+        ir.eval([s])
+        out.append(ir.as_slice(bins, T.U32))
+    assert np.array_equal(out[0], out[1])
+
+
 def test_H26_gather_scatter_add_full_size(cir, oir_mt):
     """configs[2]: 2^26 indices into 2^16 bins, weighted (gather) and counting histograms — bit-exact;
     checksum: the bins of the counting histogram sum to the number of indices."""

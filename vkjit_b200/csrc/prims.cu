@@ -10,6 +10,8 @@
 
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "common.h"
 
 namespace vkjit {
@@ -393,27 +395,52 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
         }
       }
     }
-    uint32_t flags[VPT];  // compress: 4 selection bits per vector
-    if (COMPRESS) {
-#pragma unroll
-      for (int j = 0; j < VPT; ++j)
-        flags[j] = (x[j].x != 0u ? 1u : 0u) | (x[j].y != 0u ? 2u : 0u) | (x[j].z != 0u ? 4u : 0u) | (x[j].w != 0u ? 8u : 0u);
-    }
 
     // 1) per-vector sums, 2) inclusive warp scan per register slot, 3) one warp scans the
     // (slot, warp) totals in tile order, 4) look-back gives the tile's global offset.
+    // The kernel is as much instruction-issue bound as memory bound (ncu: ~830 warp instructions per warp and
+    // tile, issue slots 50 % busy at half occupancy), so the per-lane instruction count is kept down.
+    uint32_t flags[VPT];  // compress: 4 selection bits per vector
     uint32_t vsum[VPT], wincl[VPT];
+    if (COMPRESS) {
+      // a warp's inclusive count per slot is at most 32 x 4 = 128: four slots share one 32-bit word (8-bit
+      // fields, no carries between them), so VPT warp scans become ceil(VPT / 4)
+      constexpr int G = (VPT + 3) / 4;
+      uint32_t pk[G];
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) {
-      vsum[j] = COMPRESS ? (uint32_t)__popc(flags[j]) : x[j].x + x[j].y + x[j].z + x[j].w;
-      uint32_t s = vsum[j];
+      for (int g = 0; g < G; ++g) pk[g] = 0u;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
-        if (lane >= o) s += t;
+      for (int j = 0; j < VPT; ++j) {
+        flags[j] = (x[j].x != 0u ? 1u : 0u) | (x[j].y != 0u ? 2u : 0u) | (x[j].z != 0u ? 4u : 0u) | (x[j].w != 0u ? 8u : 0u);
+        vsum[j] = (uint32_t)__popc(flags[j]);
+        pk[j / 4] |= vsum[j] << (8 * (j % 4));
       }
-      wincl[j] = s;
-      if (lane == 31) s_tot[buf][j * WARPS + warp] = s;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pk[g], o);
+          if (lane >= o) pk[g] += t;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        wincl[j] = (pk[j / 4] >> (8 * (j % 4))) & 0xFFu;
+        if (lane == 31) s_tot[buf][j * WARPS + warp] = wincl[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        vsum[j] = x[j].x + x[j].y + x[j].z + x[j].w;
+        uint32_t s = vsum[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+          if (lane >= o) s += t;
+        }
+        wincl[j] = s;
+        if (lane == 31) s_tot[buf][j * WARPS + warp] = s;
+      }
     }
     __syncthreads();  // every thread has consumed its part of ring[stage]: the stage can be refilled
     if (threadIdx.x == 0 && k + S < my_tiles) {
@@ -448,36 +475,44 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
     __syncthreads();
     const uint32_t tile_excl = s_tile_excl[buf];
 
+    // W: whole tile — the common case is compiled without bounds checks
+    auto emit = [&](auto whole_c) {
+      constexpr bool W = decltype(whole_c)::value;
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) {
-      const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
-      uint32_t p = tile_excl + s_tot[buf][j * WARPS + warp] + (wincl[j] - vsum[j]);  // exclusive prefix of lane e
-      if (!COMPRESS) {
-        uint4 r;
-        if (MODE == MODE_EXCLUSIVE) { r.x = p; r.y = p + x[j].x; r.z = r.y + x[j].y; r.w = r.z + x[j].z; }
-        else { r.x = p + x[j].x; r.y = r.x + x[j].y; r.z = r.y + x[j].z; r.w = r.z + x[j].w; }
-        if (staged || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
-        else {
-          if (e + 0 < n) out[e + 0] = r.x;
-          if (e + 1 < n) out[e + 1] = r.y;
-          if (e + 2 < n) out[e + 2] = r.z;
-        }
-      } else if (flags[j]) {
-        // selected lanes are written at their rank; flags of out-of-range lanes are 0
-        uint4 v;
-        if (MODE == MODE_COMPRESS_VALUE) {  // values are read once, only for vectors with a selected lane
-          if (staged || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
+      for (int j = 0; j < VPT; ++j) {
+        const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+        const uint32_t p = tile_excl + s_tot[buf][j * WARPS + warp] + (wincl[j] - vsum[j]);  // exclusive prefix of lane e
+        if (!COMPRESS) {
+          uint4 r;
+          if (MODE == MODE_EXCLUSIVE) { r.x = p; r.y = p + x[j].x; r.z = r.y + x[j].y; r.w = r.z + x[j].z; }
+          else { r.x = p + x[j].x; r.y = r.x + x[j].y; r.z = r.y + x[j].z; r.w = r.z + x[j].w; }
+          if (W || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
           else {
-            v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
-            v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
+            if (e + 0 < n) out[e + 0] = r.x;
+            if (e + 1 < n) out[e + 1] = r.y;
+            if (e + 2 < n) out[e + 2] = r.z;
           }
-        } else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
-        if (flags[j] & 1u) out[p++] = v.x;
-        if (flags[j] & 2u) out[p++] = v.y;
-        if (flags[j] & 4u) out[p++] = v.z;
-        if (flags[j] & 8u) out[p++] = v.w;
+        } else if (flags[j]) {
+          // selected lanes are written at their rank; flags of out-of-range lanes are 0
+          const uint32_t f = flags[j];
+          uint4 v;
+          if (MODE == MODE_COMPRESS_VALUE) {  // values are read once, only for vectors with a selected lane
+            if (W || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
+            else {
+              v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
+              v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
+            }
+          } else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
+          uint32_t* q = out + p;  // one 64-bit address per vector; the slots of its lanes follow from the flag bits
+          const uint32_t s1 = f & 1u, s2 = s1 + ((f >> 1) & 1u), s3 = s2 + ((f >> 2) & 1u);
+          if (f & 1u) q[0] = v.x;
+          if (f & 2u) q[s1] = v.y;
+          if (f & 4u) q[s2] = v.z;
+          if (f & 8u) q[s3] = v.w;
+        }
       }
-    }
+    };
+    if (staged) emit(std::true_type{}); else emit(std::false_type{});
     // s_tot/s_tile_excl are double-buffered: iteration k+2 rewrites buffer `buf` only after every
     // thread passed the first barrier of iteration k+1, i.e. after it finished reading it here.
   }

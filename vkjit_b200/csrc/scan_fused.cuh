@@ -13,6 +13,8 @@
 //   VK_T          threads per CTA (1024 / VK_T CTAs per SM: with two CTAs one computes while the other looks back)
 //   struct VkPtrs { const u32* s[max(NS,1)]; <gather/scatter pointers> };
 //   vk_eval(P, gi, li, in[max(NS,1)], o0, o1)   root words of global lane gi / local lane li
+template <bool B> struct VkBool { static constexpr bool value = B; };
+
 extern "C" __global__ void __launch_bounds__(VK_T, 1024 / VK_T)
 vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, u32* __restrict__ count_out,
             const u32 num_tiles, uint64_t* __restrict__ state, const u32* __restrict__ initial_ptr) {
@@ -78,41 +80,71 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
     if (staged) mbar_wait(&full[stage], (k / S) & 1);
     uint4 x[VPT];     // sums: the addends
     u32 flags[VPT];   // compress: 4 selection bits per vector
+    // W: whole tile (no bounds checks; the common case is compiled without them)
+    auto evaluate = [&](auto whole_c) {
+      constexpr bool W = decltype(whole_c)::value;
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) {
-      const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
-      u32 w[NSA][4];
-      fetch(j, staged, stage, e, w);
-      u32 r[4];
+      for (int j = 0; j < VPT; ++j) {
+        const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+        u32 w[NSA][4];
+        fetch(j, W && NS > 0, stage, e, w);
+        u32 r[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        u32 o0 = 0u, o1 = 0u;
-        if (whole || e + c < n) {  // lanes past the end are never evaluated (their gathers would be out of range)
-          u32 in[NSA];
+        for (int c = 0; c < 4; ++c) {
+          u32 o0 = 0u, o1 = 0u;
+          if (W || e + c < n) {  // lanes past the end are never evaluated (their gathers would be out of range)
+            u32 in[NSA];
 #pragma unroll
-          for (int s = 0; s < NS; ++s) in[s] = w[s][c];
-          vk_eval(P, base + (u32)(e + c), (u32)(e + c), in, o0, o1);
+            for (int s = 0; s < NS; ++s) in[s] = w[s][c];
+            vk_eval(P, base + (u32)(e + c), (u32)(e + c), in, o0, o1);
+          }
+          r[c] = o0;
         }
-        r[c] = o0;
+        // the word of a Bool root is exactly 0 or 1
+        if (COMPRESS) flags[j] = r[0] | (r[1] << 1) | (r[2] << 2) | (r[3] << 3);
+        else { x[j].x = r[0]; x[j].y = r[1]; x[j].z = r[2]; x[j].w = r[3]; }
       }
-      if (COMPRESS) flags[j] = (r[0] != 0u ? 1u : 0u) | (r[1] != 0u ? 2u : 0u) | (r[2] != 0u ? 4u : 0u) | (r[3] != 0u ? 8u : 0u);
-      else { x[j].x = r[0]; x[j].y = r[1]; x[j].z = r[2]; x[j].w = r[3]; }
-    }
+    };
+    if (whole) evaluate(VkBool<true>{}); else evaluate(VkBool<false>{});
 
     // 1) per-vector sums, 2) inclusive warp scan per register slot, 3) one warp scans the
     // (slot, warp) totals in tile order, 4) look-back gives the tile's global offset.
     u32 vsum[VPT], wincl[VPT];
+    if (COMPRESS) {
+      // a warp's inclusive count per slot is at most 32 x 4 = 128: four slots share one 32-bit word (8-bit
+      // fields, no carries between them), so VPT warp scans become ceil(VPT / 4)
+      constexpr int G = (VPT + 3) / 4;
+      u32 pk[G];
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) {
-      vsum[j] = COMPRESS ? (u32)__popc(flags[j]) : x[j].x + x[j].y + x[j].z + x[j].w;
-      u32 s = vsum[j];
+      for (int g = 0; g < G; ++g) pk[g] = 0u;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 t = __shfl_up_sync(0xFFFFFFFFu, s, o);
-        if (lane >= o) s += t;
+      for (int j = 0; j < VPT; ++j) { vsum[j] = (u32)__popc(flags[j]); pk[j / 4] |= vsum[j] << (8 * (j % 4)); }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 t = __shfl_up_sync(0xFFFFFFFFu, pk[g], o);
+          if (lane >= o) pk[g] += t;
+        }
       }
-      wincl[j] = s;
-      if (lane == 31) s_tot[buf][j * WARPS + warp] = s;
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        wincl[j] = (pk[j / 4] >> (8 * (j % 4))) & 0xFFu;
+        if (lane == 31) s_tot[buf][j * WARPS + warp] = wincl[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        vsum[j] = x[j].x + x[j].y + x[j].z + x[j].w;
+        u32 s = vsum[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+          if (lane >= o) s += t;
+        }
+        wincl[j] = s;
+        if (lane == 31) s_tot[buf][j * WARPS + warp] = s;
+      }
     }
     __syncthreads();  // every thread has consumed its part of ring[stage]
     if (NS > 0 && !LATE_RELEASE && threadIdx.x == 0 && k + S < my_tiles) fill(first + (k + S) * stride, stage);
@@ -140,43 +172,54 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
     __syncthreads();
     const u32 tile_excl = s_tile_excl[buf];
 
+    auto emit = [&](auto whole_c) {
+      constexpr bool W = decltype(whole_c)::value;
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) {
-      const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
-      u32 p = tile_excl + s_tot[buf][j * WARPS + warp] + (wincl[j] - vsum[j]);  // exclusive prefix of lane e
-      if (!COMPRESS) {
-        uint4 r;
-        if (VK_SCAN_MODE == 0) { r.x = p; r.y = p + x[j].x; r.z = r.y + x[j].y; r.w = r.z + x[j].z; }
-        else { r.x = p + x[j].x; r.y = r.x + x[j].y; r.z = r.y + x[j].z; r.w = r.z + x[j].w; }
-        if (whole || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
-        else {
-          if (e + 0 < n) out[e + 0] = r.x;
-          if (e + 1 < n) out[e + 1] = r.y;
-          if (e + 2 < n) out[e + 2] = r.z;
-        }
-      } else if (flags[j]) {
-        // selected lanes are written at their rank; flags of out-of-range lanes are 0
-        if (VALUES) {
-          u32 w[NSA][4];
-          fetch(j, staged, stage, e, w);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (flags[j] & (1u << c)) {
-              u32 in[NSA];
-#pragma unroll
-              for (int s = 0; s < NS; ++s) in[s] = w[s][c];
-              u32 o0, o1 = 0u;
-              vk_eval(P, base + (u32)(e + c), (u32)(e + c), in, o0, o1);
-              out[p++] = o1;
-            }
+      for (int j = 0; j < VPT; ++j) {
+        const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+        const u32 p = tile_excl + s_tot[buf][j * WARPS + warp] + (wincl[j] - vsum[j]);  // exclusive prefix of lane e
+        if (!COMPRESS) {
+          uint4 r;
+          if (VK_SCAN_MODE == 0) { r.x = p; r.y = p + x[j].x; r.z = r.y + x[j].y; r.w = r.z + x[j].z; }
+          else { r.x = p + x[j].x; r.y = r.x + x[j].y; r.z = r.y + x[j].z; r.w = r.z + x[j].w; }
+          if (W || e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
+          else {
+            if (e + 0 < n) out[e + 0] = r.x;
+            if (e + 1 < n) out[e + 1] = r.y;
+            if (e + 2 < n) out[e + 2] = r.z;
           }
-        } else {
+        } else if (flags[j]) {
+          // selected lanes are written at their rank; flags of out-of-range lanes are 0
+          const u32 f = flags[j];
+          u32 v[4];
+          if (VALUES) {
+            u32 w[NSA][4];
+            fetch(j, W && NS > 0, stage, e, w);
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (flags[j] & (1u << c)) out[p++] = (u32)(e + c);
+            for (int c = 0; c < 4; ++c) {
+              v[c] = 0u;
+              if (W || e + c < n) {  // all four lanes of the vector are re-evaluated (no per-lane branches)
+                u32 in[NSA];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) in[s] = w[s][c];
+                u32 o0;
+                vk_eval(P, base + (u32)(e + c), (u32)(e + c), in, o0, v[c]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = (u32)(e + c);
+          }
+          u32* q = out + p;  // one 64-bit address per vector; the slots of its lanes follow from the flag bits
+          const u32 s1 = f & 1u, s2 = s1 + ((f >> 1) & 1u), s3 = s2 + ((f >> 2) & 1u);
+          if (f & 1u) q[0] = v[0];
+          if (f & 2u) q[s1] = v[1];
+          if (f & 4u) q[s2] = v[2];
+          if (f & 8u) q[s3] = v[3];
         }
       }
-    }
+    };
+    if (whole) emit(VkBool<true>{}); else emit(VkBool<false>{});
     if (LATE_RELEASE) {
       __syncthreads();  // the output phase read ring[stage] again
       if (threadIdx.x == 0 && k + S < my_tiles) fill(first + (k + S) * stride, stage);
