@@ -116,6 +116,7 @@ extern "C" {
     pub fn vkjit_array_sharded(ir: *mut vkjit_ir, ty: vkjit_type, data: *const c_void, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_array_shard_local(ir: *mut vkjit_ir, ty: vkjit_type, data: *const c_void, n_local: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_var_is_sharded(ir: *mut vkjit_ir, id: vkjit_var, out_: *mut i32) -> vkjit_status;
+    pub fn vkjit_var_shard_base(ir: *mut vkjit_ir, id: vkjit_var, out: *mut u64) -> vkjit_status;
     pub fn vkjit_stats(out_: *mut vkjit_stats_t) -> vkjit_status;
     pub fn vkjit_stats_reset() -> vkjit_status;
     pub fn vkjit_cache_clear() -> vkjit_status;

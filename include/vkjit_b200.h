@@ -218,9 +218,14 @@ vkjit_status vkjit_read(vkjit_ir* ir, vkjit_var id, vkjit_type ty, void* dst, si
  * per-GPU partial is combined across ranks (result replicated). */
 vkjit_status vkjit_reduce(vkjit_ir* ir, int32_t red, vkjit_var id, vkjit_var* out);
 /* prefix sum of a U32/I32 var (mod 2^32); exclusive != 0 -> exclusive scan.  A sharded operand (multi-GPU) is
- * scanned over the GLOBAL range: per-rank totals are exchanged and each rank's result is its slice. */
+ * scanned over the GLOBAL range: per-rank totals are exchanged and each rank's result is its slice.
+ * prefix_sum / compress / compress_values: an UNEVALUATED operand is evaluated inside the primitive's kernel (one
+ * generated kernel: trace body + look-back scan); like reduce, the primitives never turn an operand into a buffer. */
 vkjit_status vkjit_prefix_sum(vkjit_ir* ir, vkjit_var id, int32_t exclusive, vkjit_var* out);
-/* compress(mask): stable list of lane indices whose mask is set (U32[count]). */
+/* compress(mask): stable list of lane indices whose mask is set (U32[count]).
+ * Sharded mask (multi-GPU): every rank compacts its shard; the result is a ragged sharded array (rank r holds the
+ * global elements [vkjit_var_shard_base(out), + its size)), indices are GLOBAL lane numbers and *out_count is the
+ * GLOBAL count (replicated).  All ranks must call it, also those whose shard is empty. */
 vkjit_status vkjit_compress(vkjit_ir* ir, vkjit_var mask, vkjit_var* out_indices, size_t* out_count);
 /* compress(values, mask): values of the selected lanes, stable order. */
 vkjit_status vkjit_compress_values(vkjit_ir* ir, vkjit_var values, vkjit_var mask, vkjit_var* out_values, size_t* out_count);
@@ -255,6 +260,9 @@ vkjit_status vkjit_array_sharded(vkjit_ir* ir, vkjit_type ty, const void* data, 
 /* Upload this rank's slice directly: `data` holds the n_local elements this rank owns. */
 vkjit_status vkjit_array_shard_local(vkjit_ir* ir, vkjit_type ty, const void* data, size_t n_local, vkjit_var* out);
 vkjit_status vkjit_var_is_sharded(vkjit_ir* ir, vkjit_var id, int32_t* out);
+/* Global index of the first element this rank holds of a sharded var: set for vkjit_arange_sharded,
+ * vkjit_array_sharded and the results of a sharded compress (0 otherwise). */
+vkjit_status vkjit_var_shard_base(vkjit_ir* ir, vkjit_var id, uint64_t* out);
 
 /* ------------------------------------------------------------------ */
 /* Counters (new).                                                      */

@@ -60,6 +60,20 @@ def main():
     # the shard holds exactly the global lanes [lo, hi)
     full.eval([xf])
     assert np.array_equal(ir.as_slice(x, T.U32), full.as_slice(xf, T.U32)[lo:hi])
+    # 4) sharded compress: per-shard compaction, global lane numbers = shard base + local index, ragged result
+    #    placed by an exclusive scan of the per-rank counts — the composition the device path implements
+    m = ir.neq(ir.bop(Bop.And, x, ir.const_u32(4)), ir.const_u32(0))
+    idx_local, k = ir.compress(m)
+    val_local, _ = ir.compress_values(x, m)
+    counts = [None] * world
+    td.all_gather_object(counts, k)
+    off = sum(counts[:rank])
+    mf = full.neq(full.bop(Bop.And, xf, full.const_u32(4)), full.const_u32(0))
+    idx_full, kf = full.compress(mf)
+    val_full, _ = full.compress_values(xf, mf)
+    assert sum(counts) == kf
+    assert np.array_equal(ir.as_slice(idx_local, T.U32) + np.uint32(lo), full.as_slice(idx_full, T.U32)[off:off + k])
+    assert np.array_equal(ir.as_slice(val_local, T.U32), full.as_slice(val_full, T.U32)[off:off + k])
     td.barrier()
     td.destroy_process_group()
     print(f"rank {rank} ok")

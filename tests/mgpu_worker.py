@@ -75,6 +75,29 @@ def main():
         want = o.as_slice(o.prefix_sum(o.add(ou, o.const_u32(7)), True), T.U32)[lo:hi]
         if hi > lo:
             assert ir.as_slice(ps, T.U32).tobytes() == want.tobytes(), (n, p2p, "fused")
+        # sharded compress: every rank compacts its shard; results are ragged shards of the GLOBAL result
+        for fused in (True, False):
+            m_d = ir.neq(ir.bop(Bop.And, trace_u32(ir, lanes), ir.const_u32(4)), ir.const_u32(0))
+            v_d = ir.add(trace_u32(ir, lanes), ir.const_u32(1))
+            if not fused and hi > lo:
+                ir.eval([m_d, v_d])                                 # hand-written kernel on bound arrays
+            m_o = o.neq(o.bop(Bop.And, ou, o.const_u32(4)), o.const_u32(0))
+            want_idx, cg = o.compress(m_o)
+            want_val, _ = o.compress_values(o.add(ou, o.const_u32(1)), m_o)
+            want_idx, want_val = o.as_slice(want_idx, T.U32), o.as_slice(want_val, T.U32)
+            gi, c1 = ir.compress(m_d)
+            gv, c2 = ir.compress_values(v_d, m_d)
+            assert c1 == c2 == cg, (n, p2p, fused, c1, c2, cg)         # global count, replicated
+            assert ir.is_sharded(gi) and ir.is_sharded(gv)
+            off, k = ir.shard_base(gi), ir.size(gi)
+            assert ir.shard_base(gv) == off and ir.size(gv) == k
+            counts = [None] * world
+            td.all_gather_object(counts, (off, k))
+            assert counts[0][0] == 0 and sum(c[1] for c in counts) == cg
+            assert all(a[0] + a[1] == b[0] for a, b in zip(counts, counts[1:]))
+            if k:
+                assert ir.as_slice(gi, T.U32).tobytes() == want_idx[off:off + k].tobytes(), (n, p2p, fused)   # GLOBAL lane numbers
+                assert ir.as_slice(gv, T.U32).tobytes() == want_val[off:off + k].tobytes(), (n, p2p, fused)
         ir.close(); o.close()
     st = vk.stats()
     assert st["collectives"] > 0 or world == 1

@@ -123,6 +123,7 @@ _PRODUCT_SIGS = {
     "array_sharded": [_p, _u32, _p, _sz, _pu32],
     "array_shard_local": [_p, _u32, _p, _sz, _pu32],
     "var_is_sharded": [_p, _u32, _pi32],
+    "var_shard_base": [_p, _u32, _pu64],
     "stats": [C.POINTER(Stats)],
     "stats_reset": [],
     "cache_clear": [],

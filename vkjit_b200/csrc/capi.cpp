@@ -290,6 +290,23 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
   });
 }
 
+// Exclusive scan over ranks of one u32 per GPU: out[0] = sum of *mine over the lower ranks and, with `total`,
+// out[1] = sum over all ranks.  Through the NVLink peer mailboxes, or as one-hot vector -> ncclAllReduce -> prefix.
+// `vec`: `world` words of device scratch (NCCL path).  mine may alias out.
+void rank_exscan(Backend& be, const uint32_t* mine, uint32_t* out, bool total, uint32_t* vec) {
+  const int world = dist::world(), rank = dist::rank();
+  if (dist::p2p_enabled()) {
+    if (total) prims::p2p_exscan_total_u32(mine, out, dist::next_mailbox(), be.stream);
+    else prims::p2p_exscan_u32(mine, out, dist::next_mailbox(), be.stream);
+  } else {
+    prims::one_hot_u32(mine, rank, world, vec, be.stream);
+    dist::allreduce(vec, VKJIT_TY_U32, VKJIT_RED_SUM, (size_t)world);
+    prims::prefix_of_rank_u32(vec, rank, out, be.stream);
+    if (total) prims::prefix_of_rank_u32(vec, world, out + 1, be.stream);
+  }
+  Backend::counters().prim_launches += 1;
+}
+
 // Operand of an eager primitive as a 16-byte aligned device array: the var's own array, or — for an unevaluated
 // var or a misaligned foreign view — a temporary evaluated on the fly.  The var itself is never changed: like
 // reduce, the primitives do not turn an unevaluated operand into a buffer (oracle.cpp ditto).
@@ -339,22 +356,15 @@ vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkji
       if (sharded) {
         // Sharded scan: local total -> exchange of the per-rank totals -> single-pass scan whose
         // tile 0 starts from the sum of the lower ranks' totals.  12 B/lane per GPU, one small exchange.
-        const int world = dist::world(), rank = dist::rank();
         tmp = be.alloc(tmp_bytes);
         uint32_t* w = (uint32_t*)tmp;
         const uint32_t* tot = w;
         if (empty) prims::fill_u32(w, 0u, 1, be.stream);
         else if (direct) prims::reduce(VKJIT_RED_SUM, VKJIT_TY_U32, in.ptr, in.n, w, be.scratch, be.sm_count, be.stream);
         else { total = eval_reduce(ir, id, VKJIT_RED_SUM); tot = (const uint32_t*)total->ptr; }
-        if (dist::p2p_enabled()) {
-          prims::p2p_exscan_u32(tot, w + 1, dist::next_mailbox(), be.stream);
-        } else {
-          prims::one_hot_u32(tot, rank, world, w + 2, be.stream);
-          dist::allreduce(w + 2, VKJIT_TY_U32, VKJIT_RED_SUM, (size_t)world);
-          prims::prefix_of_rank_u32(w + 2, rank, w + 1, be.stream);
-        }
+        rank_exscan(be, tot, w + 1, false, w + 2);
         initial = w + 1;
-        Backend::counters().prim_launches += 2;
+        Backend::counters().prim_launches += 1;
       }
       bool done = false;
       if (!empty && !direct) {  // ONE generated kernel evaluates the trace and scans it: the addends never reach memory
@@ -388,20 +398,45 @@ static void do_compress(Ir& ir, bool with_values, VarId values, VarId mask, vkji
     if (!ty_is_scalar(oty)) fail(VKJIT_ERR_TYPE, "compress values must be scalar");
   }
   Backend& be = Backend::get();
-  if (ir.var(mask).sharded && dist::active() && dist::world() > 1)
-    fail(VKJIT_ERR_UNSUPPORTED, "compress of a sharded array (single-GPU primitive, SURVEY.md §8e)");
+  // Sharded compress: every rank compacts its own shard; the result is a ragged sharded array —
+  // rank r holds the global elements [offset_r, offset_r + count_r), `count` is the GLOBAL number of selected lanes,
+  // index results are global lane numbers.  Two small exchanges: exscan of the shard sizes (index base) and
+  // exscan + total of the counts.
+  const bool sharded = ir.var(mask).sharded && dist::active() && dist::world() > 1;
+  if (sharded && with_values && !ir.var(values).sharded) fail(VKJIT_ERR_SIZE, "compress: sharded mask with unsharded values");
+  size_t n_local = 0;
+  if (sharded) {  // a rank whose shard is empty cannot evaluate it, but still has to take part in the exchanges
+    if (ir.is_buffer(mask)) n_local = ir.var(mask).array->bytes / 4;
+    else {
+      Program p;
+      std::vector<VarId> roots{mask};
+      build_program(ir, roots, true, p);
+      n_local = p.n;
+    }
+  }
   const bool direct = ir.is_buffer(mask) && !misaligned(ir, mask) && (!with_values || (ir.is_buffer(values) && !misaligned(ir, values)));
   Array* o = nullptr;
-  void* cnt = be.alloc(4);
-  uint32_t c = 0;
+  // device words: [0] local count, [1] offset of this rank, [2] global count, [3] index base, [4..4+world) NCCL scratch
+  const size_t cnt_bytes = (size_t)(4 + (sharded ? dist::world() : 0)) * 4;
+  uint32_t* w = (uint32_t*)be.alloc(cnt_bytes);
+  uint32_t host[3] = {0, 0, 0};
   try {
+    const uint32_t* index_base = nullptr;
+    if (sharded && !with_values) {
+      prims::fill_u32(w + 3, (uint32_t)n_local, 1, be.stream);
+      rank_exscan(be, w + 3, w + 3, false, w + 4);
+      index_base = w + 3;
+    }
     uint64_t n = 0;
     bool done = false;
-    if (!direct) {  // fused: the mask (and the values) are computed inside the compaction kernel
+    if (sharded && n_local == 0) {
+      o = be.new_array(0);
+      done = true;
+    } else if (!direct) {  // fused: the mask (and the values) are computed inside the compaction kernel
       std::vector<VarId> roots{mask};
       if (with_values) roots.push_back(values);
       try {
-        done = eval_scan(ir, with_values ? SCAN_COMPRESS_VALUE : SCAN_COMPRESS_INDEX, roots, nullptr, (uint32_t*)cnt, &o, &n);
+        done = eval_scan(ir, with_values ? SCAN_COMPRESS_VALUE : SCAN_COMPRESS_INDEX, roots, nullptr, w, &o, &n, index_base);
       } catch (const Error& e) {
         if (e.code == VKJIT_ERR_SIZE && with_values) fail(VKJIT_ERR_SIZE, "compress: values and mask sizes differ");
         throw;
@@ -417,17 +452,19 @@ static void do_compress(Ir& ir, bool with_values, VarId values, VarId mask, vkji
       n = m.n;
       be.ensure_scan_scratch(n);
       o = be.new_array(n * 4);  // worst case; logical size is trimmed to the count below
-      if (n) prims::compress(m.ptr, with_values ? v.ptr : nullptr, (uint32_t*)o->ptr, (uint32_t*)cnt, n, be.scratch, be.sm_count, be.stream);
+      if (n) prims::compress(m.ptr, with_values ? v.ptr : nullptr, (uint32_t*)o->ptr, w, n, be.scratch, be.sm_count, be.stream, index_base);
     }
-    if (n) {
-      Backend::counters().prim_launches += 1;
-      be.d2h(&c, cnt, 4);  // the size of the result is data dependent: one 4-byte readback
-    }
-  } catch (...) { be.free_async(cnt, 4); release_array(o); throw; }
-  be.free_async(cnt, 4);
-  o->bytes = (size_t)c * 4;
-  *count = c;
-  *out = ir.binding(oty, o, false);
+    if (n) Backend::counters().prim_launches += 1;
+    else if (sharded) prims::fill_u32(w, 0u, 1, be.stream);
+    if (sharded) rank_exscan(be, w, w + 1, true, w + 4);
+    // the size of the result is data dependent: one small readback
+    if (n || sharded) be.d2h(host, w, sharded ? 12 : 4);
+  } catch (...) { be.free_async(w, cnt_bytes); release_array(o); throw; }
+  be.free_async(w, cnt_bytes);
+  o->bytes = (size_t)host[0] * 4;
+  *count = sharded ? host[2] : host[0];
+  *out = ir.binding(oty, o, sharded);
+  if (sharded) ir.var(*out).base = host[1];
 }
 
 vkjit_status vkjit_compress(vkjit_ir* h, vkjit_var mask, vkjit_var* out, size_t* count) {
@@ -463,6 +500,7 @@ vkjit_status vkjit_array_sharded(vkjit_ir* h, vkjit_type ty, const void* data, s
     size_t lo, hi;
     dist::shard_range(n, dist::rank(), dist::world(), lo, hi);
     *out = upload(ir, ty, (const char*)data + lo * 4, hi - lo, true);
+    ir.var(*out).base = lo;
   });
 }
 vkjit_status vkjit_array_shard_local(vkjit_ir* h, vkjit_type ty, const void* data, size_t n_local, vkjit_var* out) {
@@ -472,6 +510,7 @@ vkjit_status vkjit_array_shard_local(vkjit_ir* h, vkjit_type ty, const void* dat
   });
 }
 vkjit_status vkjit_var_is_sharded(vkjit_ir* h, vkjit_var id, int32_t* out) { return with_ir(h, [&](Ir& ir) { *out = ir.var(id).sharded; }); }
+vkjit_status vkjit_var_shard_base(vkjit_ir* h, vkjit_var id, uint64_t* out) { return with_ir(h, [&](Ir& ir) { *out = ir.var(id).base; }); }
 
 // ---- counters ----------------------------------------------------------------------------------------------------
 vkjit_status vkjit_stats(vkjit_stats_t* out) {

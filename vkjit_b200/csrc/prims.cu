@@ -129,6 +129,8 @@ __device__ __forceinline__ T mailbox_allreduce(T mine, const Mailbox& mb) {
 }
 
 // Exclusive scan over ranks of one u32 per GPU (mod 2^32): out[0] = sum of `mine` over all ranks below this one.
+// TOTAL: additionally out[1] = sum over all ranks (waits for every rank, not only the lower ones).
+template <bool TOTAL>
 __global__ void p2p_exscan_kernel(const uint32_t* mine, uint32_t* out, Mailbox mb) {
   if (threadIdx.x != 0) return;
   const size_t slot = (size_t)(mb.seq % kMailSlots) * kMailRanks;
@@ -137,15 +139,19 @@ __global__ void p2p_exscan_kernel(const uint32_t* mine, uint32_t* out, Mailbox m
   const uint64_t* local = mb.local + slot;
   uint32_t acc = 0;
   const unsigned long long t0 = global_ns();
-  for (int r = 0; r < mb.rank; ++r) {
+  uint32_t below = 0;
+  const int upto = TOTAL ? mb.world : mb.rank;
+  for (int r = 0; r < upto; ++r) {
     uint64_t w = sys_load(local + r);
     while ((uint32_t)(w >> 32) != mb.seq) {
       if (global_ns() - t0 > 5000000000ull) __trap();
       w = sys_load(local + r);
     }
+    if (r == mb.rank) below = acc;
     acc += (uint32_t)w;
   }
-  out[0] = acc;
+  if (TOTAL) { out[0] = below; out[1] = acc; }
+  else out[0] = acc;
 }
 
 // out[0] = sum of v[0..rank) — the NCCL path all-reduces a one-hot vector of the per-rank totals first
@@ -288,7 +294,12 @@ void p2p_allreduce(int red, uint32_t ty, void* out, const Mailbox& mb, void* str
 }
 
 void p2p_exscan_u32(const uint32_t* mine, uint32_t* out, const Mailbox& mb, void* stream) {
-  p2p_exscan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mine, out, mb);
+  p2p_exscan_kernel<false><<<1, 32, 0, (cudaStream_t)stream>>>(mine, out, mb);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("p2p exscan launch: ") + cudaGetErrorString(e));
+}
+void p2p_exscan_total_u32(const uint32_t* mine, uint32_t* out2, const Mailbox& mb, void* stream) {
+  p2p_exscan_kernel<true><<<1, 32, 0, (cudaStream_t)stream>>>(mine, out2, mb);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("p2p exscan launch: ") + cudaGetErrorString(e));
 }
@@ -332,7 +343,8 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: mask words
             const uint32_t* __restrict__ values,  // MODE_COMPRESS_VALUE only
             uint32_t* __restrict__ out, uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles,
-            uint64_t* __restrict__ state, uint32_t diag_skip_lookback, const uint32_t* __restrict__ initial_ptr) {
+            uint64_t* __restrict__ state, uint32_t diag_skip_lookback, const uint32_t* __restrict__ initial_ptr,
+            const uint32_t* __restrict__ index_base_ptr) {  // MODE_COMPRESS_INDEX: global index of lane 0 (sharded masks)
   constexpr int T = kScanThreads;
   constexpr int kScanTile = ScanGeom<MODE>::TILE;
   constexpr int kScanStages = ScanGeom<MODE>::STAGES;
@@ -355,6 +367,7 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   const uint32_t first = blockIdx.x, stride = gridDim.x;
   const uint32_t my_tiles = first < num_tiles ? (num_tiles - first + stride - 1) / stride : 0;
   const bool ragged = (n % kScanTile) != 0;  // the globally last tile is partial: plain guarded loads
+  const uint32_t index_base = (MODE == MODE_COMPRESS_INDEX && index_base_ptr) ? __ldcg(index_base_ptr) : 0u;
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -502,7 +515,7 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
               v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
               v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
             }
-          } else { v.x = (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
+          } else { v.x = index_base + (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
           uint32_t* q = out + p;  // one 64-bit address per vector; the slots of its lanes follow from the flag bits
           const uint32_t s1 = f & 1u, s2 = s1 + ((f >> 1) & 1u), s3 = s2 + ((f >> 2) & 1u);
           if (f & 1u) q[0] = v.x;
@@ -523,7 +536,8 @@ size_t scan_state_words(size_t n, size_t tile) { return (size_t)kStatusStride * 
 
 template <int MODE>
 static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
-                        const Scratch& sc, int sm_count, cudaStream_t s, const uint32_t* initial = nullptr) {
+                        const Scratch& sc, int sm_count, cudaStream_t s, const uint32_t* initial = nullptr,
+                        const uint32_t* index_base = nullptr) {
   using G = ScanGeom<MODE>;
   const size_t tiles = (n + G::TILE - 1) / G::TILE;
   const size_t words = (size_t)kStatusStride * (1 + tiles);
@@ -541,7 +555,7 @@ static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* ou
   const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);
   static int diag = -1;
   if (diag < 0) { const char* d = getenv("VKJIT_SCAN_DIAG"); diag = (d && std::string(d) == "nolookback") ? 1 : 0; }
-  scan_kernel<MODE><<<grid, kScanThreads, G::SMEM, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state, (uint32_t)diag, initial);
+  scan_kernel<MODE><<<grid, kScanThreads, G::SMEM, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state, (uint32_t)diag, initial, index_base);
   e = cudaGetLastError();
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
 }
@@ -555,11 +569,11 @@ void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, con
 }
 
 void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
-              const Scratch& sc, int sm_count, void* stream) {
+              const Scratch& sc, int sm_count, void* stream, const uint32_t* index_base) {
   if (n == 0) return;
   cudaStream_t s = (cudaStream_t)stream;
   if (values) launch_scan<MODE_COMPRESS_VALUE>(mask, values, out, count_out, n, sc, sm_count, s);
-  else launch_scan<MODE_COMPRESS_INDEX>(mask, nullptr, out, count_out, n, sc, sm_count, s);
+  else launch_scan<MODE_COMPRESS_INDEX>(mask, nullptr, out, count_out, n, sc, sm_count, s, nullptr, index_base);
 }
 
 __global__ void fill_kernel(uint32_t* out, uint32_t value, size_t n) {

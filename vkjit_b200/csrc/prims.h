@@ -58,13 +58,15 @@ void prefix_sum(const uint32_t* in, uint32_t* out, size_t n, bool exclusive, con
 // Sharded scan support: exclusive scan over ranks of one u32 per GPU through the peer mailboxes, and the two
 // tiny kernels of the NCCL path (one-hot vector of totals -> all-reduce -> prefix of this rank).
 void p2p_exscan_u32(const uint32_t* mine, uint32_t* out, const Mailbox& mailbox, void* stream);
+void p2p_exscan_total_u32(const uint32_t* mine, uint32_t* out2, const Mailbox& mailbox, void* stream);  // out2 = {below, total}
 void one_hot_u32(const uint32_t* mine, int rank, int world, uint32_t* v, void* stream);
 void prefix_of_rank_u32(const uint32_t* v, int rank, uint32_t* out, void* stream);
 
 // Stream compaction: lanes whose mask word is non-zero, stable order.  values == nullptr writes the
-// lane index.  *count_out (device) receives the number of selected lanes.
+// lane index (+ *index_base when given: the global index of lane 0 of a sharded mask).  *count_out (device)
+// receives the number of selected lanes.
 void compress(const uint32_t* mask, const uint32_t* values, uint32_t* out, uint32_t* count_out, size_t n,
-              const Scratch& sc, int sm_count, void* stream);
+              const Scratch& sc, int sm_count, void* stream, const uint32_t* index_base = nullptr);
 
 // out[i] = value for i in [0, n)
 void fill_u32(uint32_t* out, uint32_t value, size_t n, void* stream);

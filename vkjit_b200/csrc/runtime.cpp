@@ -528,7 +528,7 @@ Array* eval_reduce(Ir& ir, VarId id, int red) {
 // array, or a body so large that evaluating it twice / inlining it 24 times does not pay): the caller then
 // evaluates the operands into temporaries and runs the hand-written primitive.
 bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t* initial, uint32_t* count_dev, Array** out,
-               uint64_t* n_out) {
+               uint64_t* n_out, const uint32_t* index_base) {
   Backend& be = Backend::get();
   static thread_local Program prog;
   build_program(ir, roots, true, prog, -1, false, mode);
@@ -560,8 +560,8 @@ bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t
   for (const Param& pr : prog.params) if (pr.use & (USE_GATHER | USE_SCATTER)) block.push_back((uint64_t)(uintptr_t)ir.vars[pr.var].array->ptr);
   uint32_t n32 = (uint32_t)prog.n, base32 = (uint32_t)prog.base, tiles32 = (uint32_t)tiles;
   uint64_t outp = (uint64_t)(uintptr_t)o->ptr, cntp = (uint64_t)(uintptr_t)count_dev, statep = (uint64_t)(uintptr_t)be.scratch.tile_state,
-           initp = (uint64_t)(uintptr_t)initial;
-  void* argv[] = {&n32, &base32, block.data(), &outp, &cntp, &tiles32, &statep, &initp};
+           initp = (uint64_t)(uintptr_t)initial, ibasep = (uint64_t)(uintptr_t)index_base;
+  void* argv[] = {&n32, &base32, block.data(), &outp, &cntp, &tiles32, &statep, &initp, &ibasep};
   try {
     be.launch(k, (uint32_t)std::min<size_t>(tiles, (size_t)be.sm_count * k->ctas_per_sm), (uint32_t)scan_fused_threads(), argv,
               (uint32_t)scan_fused_smem(ns));

@@ -89,6 +89,6 @@ void eval(Ir& ir, const VarId* ids, size_t n);
 Array* eval_reduce(Ir& ir, VarId id, int red);
 Array* eval_temp(Ir& ir, VarId id);
 bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t* initial, uint32_t* count_dev, Array** out,
-               uint64_t* n_out);
+               uint64_t* n_out, const uint32_t* index_base = nullptr);
 
 }  // namespace vkjit

@@ -17,7 +17,8 @@ template <bool B> struct VkBool { static constexpr bool value = B; };
 
 extern "C" __global__ void __launch_bounds__(VK_T, 1024 / VK_T)
 vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, u32* __restrict__ count_out,
-            const u32 num_tiles, uint64_t* __restrict__ state, const u32* __restrict__ initial_ptr) {
+            const u32 num_tiles, uint64_t* __restrict__ state, const u32* __restrict__ initial_ptr,
+            const u32* __restrict__ index_base_ptr) {  // mode 2: global index of lane 0 (sharded masks)
   constexpr int T = VK_T, VPT = VK_VPT, TILE = T * 4 * VPT, NS = VK_NS, NSA = NS > 0 ? NS : 1, S = 2;
   constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = (NTOT + 31) / 32;
   constexpr u32 TILE_BYTES = TILE * 4;
@@ -36,6 +37,7 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
   const u32 first = blockIdx.x, stride = gridDim.x;
   const u32 my_tiles = first < num_tiles ? (num_tiles - first + stride - 1) / stride : 0;
   const bool ragged = (n % TILE) != 0;  // the globally last tile is partial: guarded loads, no TMA
+  const u32 index_base = (VK_SCAN_MODE == 2 && index_base_ptr) ? __ldcg(index_base_ptr) : 0u;
 
   auto fill = [&](u32 t, int stage) {  // thread 0: one bulk copy per streamed array, all on the stage's barrier
     if (ragged && t == num_tiles - 1) return;
@@ -208,7 +210,7 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
             }
           } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) v[c] = (u32)(e + c);
+            for (int c = 0; c < 4; ++c) v[c] = index_base + (u32)(e + c);
           }
           u32* q = out + p;  // one 64-bit address per vector; the slots of its lanes follow from the flag bits
           const u32 s1 = f & 1u, s2 = s1 + ((f >> 1) & 1u), s3 = s2 + ((f >> 2) & 1u);

@@ -300,6 +300,12 @@ class Ir:
         self.api.call("var_is_sharded", self._h, id, C.byref(o))
         return bool(o.value)
 
+    def shard_base(self, id: int) -> int:
+        """Global index of the first element this rank holds (sharded aranges / arrays / compress results)."""
+        o = C.c_uint64()
+        self.api.call("var_shard_base", self._h, id, C.byref(o))
+        return int(o.value)
+
     def debug_codegen(self, ids: Sequence[int], compile: bool = False, privatize: bool = False):
         ids = list(ids)
         n, cub = C.c_size_t(), C.c_size_t()
