@@ -53,6 +53,7 @@ extern "C" {
     pub fn vkjit_last_error() -> *const c_char;
     pub fn vkjit_abi_version() -> u32;
     pub fn vkjit_stream(out_stream: *mut *mut c_void) -> vkjit_status;
+    pub fn vkjit_device(out_device: *mut i32) -> vkjit_status;
     pub fn vkjit_sync() -> vkjit_status;
     pub fn vkjit_host_alloc(bytes: usize, out_ptr: *mut *mut c_void) -> vkjit_status;
     pub fn vkjit_host_free(ptr: *mut c_void) -> vkjit_status;
@@ -71,6 +72,10 @@ extern "C" {
     pub fn vkjit_array_bool(ir: *mut vkjit_ir, data: *const u32, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_array_empty(ir: *mut vkjit_ir, ty: vkjit_type, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_array_wrap_device(ir: *mut vkjit_ir, ty: vkjit_type, device_ptr: u64, n: usize, out_: *mut vkjit_var) -> vkjit_status;
+    pub fn vkjit_array_wrap_device_owned(ir: *mut vkjit_ir, ty: vkjit_type, device_ptr: u64, n: usize, release: Option<unsafe extern "C" fn(*mut c_void)>, ctx: *mut c_void, out_: *mut vkjit_var) -> vkjit_status;
+    pub fn vkjit_var_to_dlpack(ir: *mut vkjit_ir, id: vkjit_var, out_managed_tensor: *mut *mut c_void) -> vkjit_status;
+    pub fn vkjit_var_from_dlpack(ir: *mut vkjit_ir, managed_tensor: *mut c_void, out_: *mut vkjit_var) -> vkjit_status;
+    pub fn vkjit_dlpack_delete(managed_tensor: *mut c_void);
     pub fn vkjit_arange(ir: *mut vkjit_ir, ty: vkjit_type, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_linspace(ir: *mut vkjit_ir, ty: vkjit_type, start: vkjit_var, stop: vkjit_var, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_zeros(ir: *mut vkjit_ir, ty: vkjit_type, out_: *mut vkjit_var) -> vkjit_status;

@@ -96,6 +96,8 @@ const char* vkjit_last_error(void);
 uint32_t vkjit_abi_version(void);
 /* The CUstream/cudaStream_t every launch and copy is ordered on. */
 vkjit_status vkjit_stream(void** out_stream);
+/* CUDA device ordinal the backend was initialised on. */
+vkjit_status vkjit_device(int32_t* out_device);
 /* cudaStreamSynchronize on the backend stream (reference: vkWaitForFences +
  * vkDeviceWaitIdle inside every execute, backend/vulkan/mod.rs:185-190; here
  * eval is asynchronous and only readback/sync waits). */
@@ -142,6 +144,18 @@ vkjit_status vkjit_array_empty(vkjit_ir* ir, vkjit_type ty, size_t n, vkjit_var*
  * the backend stream (vkjit_stream).  Pointers that are not 16-byte aligned select the scalar kernel variant. */
 vkjit_status vkjit_array_wrap_device(vkjit_ir* ir, vkjit_type ty, uint64_t device_ptr, size_t n, vkjit_var* out);
 /* Ir::arange, internal.rs:235-237 */
+/* Same, with an owner: release(ctx) is called exactly once when the view's array is dropped (the var is freed or
+ * re-evaluated), after the library has synchronised its stream and released the Ir lock. */
+vkjit_status vkjit_array_wrap_device_owned(vkjit_ir* ir, vkjit_type ty, uint64_t device_ptr, size_t n,
+                                           void (*release)(void*), void* ctx, vkjit_var* out);
+/* DLPack ("dltensor" ABI, DLManagedTensor*).  to_dlpack: zero-copy export of an evaluated var — the tensor holds
+ * one reference on the var until its deleter runs (the Ir must outlive it); the backend stream is synchronised
+ * first.  from_dlpack: zero-copy import of a 1-D contiguous f32/i32/u32 CUDA tensor; on success the library owns
+ * the tensor and calls its deleter when the var's array is dropped; on failure the caller keeps ownership.
+ * vkjit_dlpack_delete runs a tensor's deleter (for an exported tensor nobody consumed). */
+vkjit_status vkjit_var_to_dlpack(vkjit_ir* ir, vkjit_var id, void** out_managed_tensor);
+vkjit_status vkjit_var_from_dlpack(vkjit_ir* ir, void* managed_tensor, vkjit_var* out);
+void vkjit_dlpack_delete(void* managed_tensor);
 vkjit_status vkjit_arange(vkjit_ir* ir, vkjit_type ty, size_t n, vkjit_var* out);
 /* Ir::linspace, internal.rs:238-246 (endpoint excluded) */
 vkjit_status vkjit_linspace(vkjit_ir* ir, vkjit_type ty, vkjit_var start, vkjit_var stop, size_t n, vkjit_var* out);

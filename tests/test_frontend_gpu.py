@@ -121,3 +121,41 @@ def test_zero_copy_interop_and_unaligned_views(vkjit, cuda_backend):
     del x, z
     import gc; gc.collect()
     assert float(t[5].item()) == 5.0
+
+
+def test_dlpack_round_trip_with_torch(vkjit, cuda_backend):
+    """DLPack in and out, zero-copy, with correct ownership in both directions."""
+    import gc
+    import torch
+    # export: torch sees the Var's memory; the tensor keeps the array alive after the Var is gone
+    y = vkjit.arange(np.uint32, 5000) * 3 + 1 if hasattr(vkjit, "arange") else None
+    if y is None:
+        pytest.skip("no arange in this surface")
+    t = torch.from_dlpack(y)
+    assert t.device.type == "cuda" and t.shape == (5000,) and t.data_ptr() == y.__cuda_array_interface__["data"][0]
+    expect = np.arange(5000, dtype=np.uint32) * 3 + 1
+    assert np.array_equal(t.cpu().numpy().view(np.uint32), expect)
+    live = cuda_backend.stats()["pool_bytes_live"]
+    del y; gc.collect()
+    assert cuda_backend.stats()["pool_bytes_live"] == live            # still referenced by the exported tensor
+    assert np.array_equal(t.cpu().numpy().view(np.uint32), expect)
+    del t; gc.collect()
+    assert cuda_backend.stats()["pool_bytes_live"] < live             # deleter ran: the var and its array are gone
+    # import: a Var over torch memory; the torch tensor object may die, the memory must not
+    src = torch.arange(0, 4096, device="cuda", dtype=torch.float32)
+    ptr = src.data_ptr()
+    torch.cuda.synchronize()
+    x = vkjit.from_dlpack(src)
+    assert x.__cuda_array_interface__["data"][0] == ptr
+    del src; gc.collect()
+    junk = [torch.empty(4096, device="cuda") for _ in range(8)]      # would reuse the block if it had been freed
+    assert all(j.data_ptr() != ptr for j in junk)
+    assert np.array_equal((x + 1.0).numpy(), np.arange(4096, dtype=np.float32) + 1)
+    del x; gc.collect()
+    # unsupported tensors are rejected and stay usable by their owner
+    with pytest.raises(Exception):
+        vkjit.from_dlpack(torch.zeros(4, 4, device="cuda"))
+    with pytest.raises(Exception):
+        vkjit.from_dlpack(torch.zeros(8, device="cuda", dtype=torch.float64))
+    with pytest.raises(Exception):
+        vkjit.from_dlpack(torch.zeros(8, dtype=torch.float32))       # host memory

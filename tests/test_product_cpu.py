@@ -188,6 +188,37 @@ def test_fused_scan_kernels_compile_for_sm100a(streams):
             ir.debug_codegen_scan([wide], 0)               # 7 streamed arrays: not fused (the runtime materialises)
 
 
+def test_dlpack_export_import_without_a_device():
+    """DLPack ABI on a view of (fake) device memory: struct layout, capsule protocol, ownership."""
+    import gc
+    ir = Ir()
+    v = ir.array_wrap_device(F32, 0x7F0000001000, 1000)
+    cap = ir.to_dlpack(v)
+    mt = ctypes.pythonapi.PyCapsule_GetPointer(ctypes.py_object(cap), b"dltensor")
+
+    class DLManaged(ctypes.Structure):
+        _fields_ = [("data", ctypes.c_void_p), ("device_type", ctypes.c_int32), ("device_id", ctypes.c_int32), ("ndim", ctypes.c_int32),
+                    ("code", ctypes.c_uint8), ("bits", ctypes.c_uint8), ("lanes", ctypes.c_uint16), ("shape", ctypes.POINTER(ctypes.c_int64)),
+                    ("strides", ctypes.c_void_p), ("byte_offset", ctypes.c_uint64), ("ctx", ctypes.c_void_p), ("deleter", ctypes.c_void_p)]
+    t = DLManaged.from_address(mt)
+    assert (t.data, t.device_type, t.ndim, t.code, t.bits, t.lanes, t.shape[0], t.strides, t.byte_offset) == \
+        (0x7F0000001000, 2, 1, 2, 32, 1, 1000, None, 0) and t.deleter
+    w = ir.from_dlpack(cap)                       # our own export comes back as a view whose owner is that tensor
+    assert ir.size(w) == 1000 and ir.ty(w) == F32 and ir.is_buffer(w)
+    with pytest.raises(TypeError):
+        ir.from_dlpack(cap)                       # a consumed capsule ("used_dltensor") is refused
+    assert ir.ref_count(v) == 2                   # ours + the exported tensor's
+    ir.dec_ref_count(v)
+    assert ir.ref_count(v) == 1 and ir.is_buffer(v)
+    ir.dec_ref_count(w)                           # view dropped -> deleter -> last reference on v released (outside the Ir lock)
+    with pytest.raises(VkjitError):
+        ir.is_buffer(v)                           # freed
+    cap2 = ir.to_dlpack(ir.array_wrap_device(U32, 0x7F0000002000, 8))
+    del cap2; gc.collect()                        # never consumed: the capsule destructor runs the deleter
+    with pytest.raises(VkjitError):
+        ir.to_dlpack(ir.arange(U32, 4))           # unevaluated
+
+
 def test_privatised_scatter_add_kernel_compiles_for_sm100a():
     """The shared-memory-privatised scatter_add variant (trace construction needs no device: the target is
     an unevaluated... no: targets must be buffers, so this is checked on codegen text of a plain trace only)."""

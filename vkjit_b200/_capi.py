@@ -107,6 +107,7 @@ _PRODUCT_SIGS = {
     "init": [_i32],
     "shutdown": [],
     "stream": [C.POINTER(_p)],
+    "device": [_pi32],
     "sync": [],
     "host_alloc": [_sz, C.POINTER(_p)],
     "host_free": [_p],
@@ -120,6 +121,9 @@ _PRODUCT_SIGS = {
     "dist_info": [_pi32, _pi32],
     "arange_sharded": [_p, _u32, _sz, _pu32],
     "array_wrap_device": [_p, _u32, _u64, _sz, _pu32],
+    "array_wrap_device_owned": [_p, _u32, _u64, _sz, _p, _p, _pu32],
+    "var_to_dlpack": [_p, _u32, C.POINTER(_p)],
+    "var_from_dlpack": [_p, _p, _pu32],
     "array_sharded": [_p, _u32, _p, _sz, _pu32],
     "array_shard_local": [_p, _u32, _p, _sz, _pu32],
     "var_is_sharded": [_p, _u32, _pi32],

@@ -39,10 +39,12 @@ vkjit_status guard(F&& f) {
 template <class F>
 vkjit_status with_ir(vkjit_ir* h, F&& f) {
   if (!h) { g_last_error = "null vkjit_ir"; return VKJIT_ERR_INVALID; }
-  return guard([&] {
+  const vkjit_status st = guard([&] {
     std::lock_guard<std::mutex> lock(h->ir.mu);
     f(h->ir);
   });
+  drain_foreign_releases();  // owners of dropped foreign views, outside the lock
+  return st;
 }
 
 vkjit_status copy_out(const std::string& s, char* buf, size_t cap, size_t* out_len) {
@@ -110,6 +112,7 @@ int32_t vkjit_is_initialized(void) { return Backend::initialized() ? 1 : 0; }
 const char* vkjit_last_error(void) { return g_last_error.c_str(); }
 uint32_t vkjit_abi_version(void) { return VKJIT_B200_ABI_VERSION; }
 vkjit_status vkjit_stream(void** out) { return guard([&] { *out = Backend::get().stream; }); }
+vkjit_status vkjit_device(int32_t* out) { return guard([&] { *out = Backend::get().device; }); }
 vkjit_status vkjit_sync(void) { return guard([&] { Backend::get().sync(); }); }
 vkjit_status vkjit_host_alloc(size_t bytes, void** out) {
   return guard([&] {
@@ -123,7 +126,11 @@ vkjit_status vkjit_host_free(void* p) {
 }
 
 vkjit_status vkjit_ir_create(vkjit_ir** out) { return guard([&] { *out = new vkjit_ir(); }); }
-vkjit_status vkjit_ir_destroy(vkjit_ir* h) { return guard([&] { delete h; }); }
+vkjit_status vkjit_ir_destroy(vkjit_ir* h) {
+  const vkjit_status st = guard([&] { delete h; });
+  drain_foreign_releases();
+  return st;
+}
 
 // ---- types ------------------------------------------------------------------------------------
 vkjit_status vkjit_type_struct(vkjit_ir* h, const vkjit_type* e, size_t n, vkjit_type* out) {
@@ -167,6 +174,90 @@ vkjit_status vkjit_array_wrap_device(vkjit_ir* h, vkjit_type ty, uint64_t device
     *out = ir.binding(ty, a, false);
   });
 }
+vkjit_status vkjit_array_wrap_device_owned(vkjit_ir* h, vkjit_type ty, uint64_t device_ptr, size_t n, void (*release)(void*),
+                                           void* ctx, vkjit_var* out) {
+  return with_ir(h, [&](Ir& ir) {
+    if (!ty_is_scalar(ty)) fail(VKJIT_ERR_TYPE, "array of a non-scalar type");
+    if (!device_ptr && n) fail(VKJIT_ERR_INVALID, "null device pointer");
+    if (device_ptr & 3u) fail(VKJIT_ERR_INVALID, "device pointer must be 4-byte aligned");
+    Array* a = new Array();
+    a->ptr = (void*)(uintptr_t)device_ptr; a->bytes = n * 4; a->capacity = n * 4; a->owned = false;
+    try { *out = ir.binding(ty, a, false); } catch (...) { delete a; throw; }
+    a->release = release; a->release_ctx = ctx;  // only now: on failure the caller still owns ctx
+  });
+}
+
+// ---- DLPack (dlpack.h v0.8 "dltensor" ABI) ---------------------------------------------------------
+namespace {
+struct DLDevice { int32_t device_type, device_id; };
+struct DLDataType { uint8_t code, bits; uint16_t lanes; };
+struct DLTensor { void* data; DLDevice device; int32_t ndim; DLDataType dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset; };
+struct DLManagedTensor { DLTensor dl_tensor; void* manager_ctx; void (*deleter)(DLManagedTensor*); };
+enum { kDLCUDA = 2, kDLInt = 0, kDLUInt = 1, kDLFloat = 2 };
+
+struct ExportCtx { vkjit_ir* ir; vkjit_var id; int64_t shape; };
+void export_deleter(DLManagedTensor* t) {
+  ExportCtx* c = (ExportCtx*)t->manager_ctx;
+  vkjit_dec_ref(c->ir, c->id);  // the reference taken at export
+  delete c;
+  delete t;
+}
+void import_release(void* p) {
+  DLManagedTensor* t = (DLManagedTensor*)p;
+  if (t->deleter) t->deleter(t);
+}
+}  // namespace
+
+vkjit_status vkjit_var_to_dlpack(vkjit_ir* h, vkjit_var id, void** out) {
+  return with_ir(h, [&](Ir& ir) {
+    if (!ir.is_buffer(id)) fail(VKJIT_ERR_INVALID, "to_dlpack: the var is not evaluated");
+    const Var& v = ir.var(id);
+    DLDataType dt{};
+    switch (v.ty) {
+      case VKJIT_TY_F32: dt = {kDLFloat, 32, 1}; break;
+      case VKJIT_TY_I32: dt = {kDLInt, 32, 1}; break;
+      case VKJIT_TY_U32: case VKJIT_TY_BOOL: dt = {kDLUInt, 32, 1}; break;  // Bool arrays hold 0/1 words (vartype.rs:45-64)
+      default: fail(VKJIT_ERR_TYPE, "to_dlpack: scalar arrays only");
+    }
+    if (Backend::initialized()) Backend::get().sync();  // the consumer may use any stream
+    auto* c = new ExportCtx{h, id, (int64_t)(v.array->bytes / 4)};
+    auto* t = new DLManagedTensor();
+    t->dl_tensor.data = v.array->ptr;
+    t->dl_tensor.device = {kDLCUDA, Backend::initialized() ? Backend::get().device : 0};
+    t->dl_tensor.ndim = 1;
+    t->dl_tensor.dtype = dt;
+    t->dl_tensor.shape = &c->shape;
+    t->dl_tensor.strides = nullptr;
+    t->dl_tensor.byte_offset = 0;
+    t->manager_ctx = c;
+    t->deleter = export_deleter;
+    ir.inc_ref(id);  // the tensor keeps the array alive until the consumer calls the deleter
+    *out = t;
+  });
+}
+
+vkjit_status vkjit_var_from_dlpack(vkjit_ir* h, void* managed, vkjit_var* out) {
+  if (!managed) { g_last_error = "null DLManagedTensor"; return VKJIT_ERR_INVALID; }
+  DLManagedTensor* t = (DLManagedTensor*)managed;
+  const DLTensor& d = t->dl_tensor;
+  vkjit_type ty = VKJIT_TY_VOID;
+  const vkjit_status st = guard([&] {
+    if (d.device.device_type != kDLCUDA) fail(VKJIT_ERR_INVALID, "from_dlpack: not CUDA device memory");
+    if (Backend::initialized() && d.device.device_id != Backend::get().device) fail(VKJIT_ERR_INVALID, "from_dlpack: tensor lives on another GPU");
+    if (d.dtype.lanes != 1 || d.dtype.bits != 32) fail(VKJIT_ERR_TYPE, "from_dlpack: 32-bit f32/i32/u32 elements only");
+    ty = d.dtype.code == kDLFloat ? VKJIT_TY_F32 : d.dtype.code == kDLInt ? VKJIT_TY_I32 : d.dtype.code == kDLUInt ? VKJIT_TY_U32 : VKJIT_TY_VOID;
+    if (ty == VKJIT_TY_VOID) fail(VKJIT_ERR_TYPE, "from_dlpack: 32-bit f32/i32/u32 elements only");
+    if (d.ndim != 1) fail(VKJIT_ERR_INVALID, "from_dlpack: 1-D tensors only");
+    if (d.strides && d.shape[0] > 1 && d.strides[0] != 1) fail(VKJIT_ERR_INVALID, "from_dlpack: the tensor is not contiguous");
+  });
+  if (st != VKJIT_OK) return st;  // the caller keeps ownership of the capsule
+  return vkjit_array_wrap_device_owned(h, ty, (uint64_t)(uintptr_t)d.data + d.byte_offset, (size_t)d.shape[0], import_release, t, out);
+}
+void vkjit_dlpack_delete(void* managed) {
+  DLManagedTensor* t = (DLManagedTensor*)managed;
+  if (t && t->deleter) t->deleter(t);
+}
+
 vkjit_status vkjit_arange(vkjit_ir* h, vkjit_type ty, size_t n, vkjit_var* out) { return with_ir(h, [&](Ir& ir) { *out = ir.arange(ty, n, 0, false); }); }
 vkjit_status vkjit_linspace(vkjit_ir* h, vkjit_type ty, vkjit_var a, vkjit_var b, size_t n, vkjit_var* out) {
   return with_ir(h, [&](Ir& ir) { *out = ir.linspace(ty, a, b, n); });

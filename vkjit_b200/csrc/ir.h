@@ -30,6 +30,8 @@ struct Array {
   size_t bytes = 0;     // logical size (Array::size)
   size_t capacity = 0;  // allocation size (compress over-allocates)
   bool owned = true;    // false: view of foreign device memory (vkjit_array_wrap_device), never freed here
+  void (*release)(void*) = nullptr;  // view with an owner (DLPack import): called once, after the Ir lock is dropped
+  void* release_ctx = nullptr;
 };
 
 struct Var {  // internal.rs:105-114
@@ -121,7 +123,10 @@ class Ir {
 // Rust `{:?}` text of an f32 (shortest round-trip digits, always a fractional part).
 std::string format_f32(float f);
 
-// Implemented by the runtime: returns the memory of a dying Binding to the pool.
+// Implemented by the runtime: returns the memory of a dying Binding to the pool.  Owner callbacks of foreign
+// views are queued per thread and run by drain_foreign_releases() once the caller holds no Ir lock (an owner
+// may be one of our own exported DLPack tensors, whose deleter takes that lock).
 void release_array(Array* a);
+void drain_foreign_releases();
 
 }  // namespace vkjit

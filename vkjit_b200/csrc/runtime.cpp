@@ -156,10 +156,25 @@ Array* Backend::new_array(size_t bytes) {
   return a;
 }
 
+namespace {
+thread_local std::vector<std::pair<void (*)(void*), void*>> g_pending_release;
+}
+
 void release_array(Array* a) {
   if (!a) return;
   if (g_backend && a->owned) g_backend->free_async(a->ptr, a->capacity);
+  if (a->release) g_pending_release.emplace_back(a->release, a->release_ctx);
   delete a;
+}
+
+void drain_foreign_releases() {
+  while (!g_pending_release.empty()) {
+    auto pr = g_pending_release.back();
+    g_pending_release.pop_back();
+    // the consumer may still have work queued on our stream that reads the memory
+    if (g_backend) cudaStreamSynchronize((cudaStream_t)g_backend->stream);
+    pr.first(pr.second);
+  }
 }
 
 void Backend::h2d(void* dst, const void* src, size_t bytes) {

@@ -121,6 +121,24 @@ class Ir:
         """Zero-copy view of foreign device memory (not owned)."""
         return self._new("array_wrap_device", ty, C.c_uint64(device_ptr), n)
 
+    # ---- DLPack (SURVEY.md §8f N2): capsules named "dltensor" holding a DLManagedTensor*
+    def to_dlpack(self, id: int):
+        """Zero-copy export of an evaluated var as a DLPack capsule (the capsule holds one reference on the var)."""
+        mt = C.c_void_p()
+        self.api.call("var_to_dlpack", self._h, id, C.byref(mt))
+        return _dl_capsule_new(self.api, mt.value)
+
+    def from_dlpack(self, capsule) -> int:
+        """Zero-copy import of a DLPack capsule (1-D contiguous f32/i32/u32 CUDA tensor); the capsule is consumed."""
+        py = C.pythonapi
+        if not py.PyCapsule_IsValid(C.py_object(capsule), b"dltensor"):
+            raise TypeError("Not a valid argument!")   # not a capsule, or already consumed
+        mt = py.PyCapsule_GetPointer(C.py_object(capsule), b"dltensor")
+        out = C.c_uint32()
+        self.api.call("var_from_dlpack", self._h, C.c_void_p(mt), C.byref(out))   # raises: the capsule stays valid
+        py.PyCapsule_SetName(C.py_object(capsule), b"used_dltensor")              # ownership moved to the library
+        return out.value
+
     def arange(self, ty: int, num: int) -> int:
         return self._new("arange", ty, num)
 
@@ -316,6 +334,33 @@ class Ir:
         return buf.value.decode(), cub.value
 
 
+C.pythonapi.PyCapsule_New.restype = C.py_object
+C.pythonapi.PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+C.pythonapi.PyCapsule_IsValid.restype = C.c_int
+C.pythonapi.PyCapsule_IsValid.argtypes = [C.py_object, C.c_char_p]
+C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
+C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+C.pythonapi.PyCapsule_SetName.restype = C.c_int
+C.pythonapi.PyCapsule_SetName.argtypes = [C.py_object, C.c_char_p]
+_DL_DESTRUCTOR = C.CFUNCTYPE(None, C.c_void_p)
+_dl_destructors = {}
+
+
+def _dl_capsule_new(api, managed_ptr: int):
+    """PyCapsule("dltensor") whose destructor runs the tensor's deleter unless a consumer renamed (= took) it."""
+    key = id(api)
+    if key not in _dl_destructors:
+        delete = getattr(api.lib, "vkjit_dlpack_delete")
+        delete.argtypes, delete.restype = [C.c_void_p], None
+
+        def destroy(capsule_ptr):
+            cap = C.cast(capsule_ptr, C.py_object)
+            if C.pythonapi.PyCapsule_IsValid(cap, b"dltensor"):
+                delete(C.pythonapi.PyCapsule_GetPointer(cap, b"dltensor"))
+        _dl_destructors[key] = _DL_DESTRUCTOR(destroy)
+    return C.pythonapi.PyCapsule_New(managed_ptr, b"dltensor", C.cast(_dl_destructors[key], C.c_void_p))
+
+
 def _debug_codegen_reduce(self, id: int, red: int, compile: bool = False):
     n, cub = C.c_size_t(), C.c_size_t()
     self.api.call("debug_codegen_reduce", self._h, id, red, 0, None, 0, C.byref(n), C.byref(cub))
@@ -371,6 +416,12 @@ def stream_ptr() -> int:
     p = C.c_void_p()
     product_api().call("stream", C.byref(p))
     return p.value or 0
+
+
+def device_index() -> int:
+    d = C.c_int32()
+    product_api().call("device", C.byref(d))
+    return d.value
 
 
 def stats() -> dict:

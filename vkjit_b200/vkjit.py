@@ -228,6 +228,19 @@ class Var:
         return {"shape": (g.size(self._id),), "typestr": typestr, "data": (g.device_ptr(self._id), False), "version": 3,
                 "strides": None, "stream": _ir.stream_ptr() or None}
 
+    def __dlpack__(self, *, stream=None, max_version=None, dl_device=None, copy=None):
+        """DLPack export (zero-copy; evaluates first; the backend stream is synchronised, so any consumer stream
+        is safe).  `torch.from_dlpack(v)` / `cupy.from_dlpack(v)` work on a Var."""
+        if copy:
+            raise BufferError("vkjit_b200 exports views only")
+        g = _global_ir()
+        if not g.is_buffer(self._id):
+            g.eval([self._id])
+        return g.to_dlpack(self._id)
+
+    def __dlpack_device__(self):
+        return (2, _ir.device_index())   # kDLCUDA
+
     def sum(self): return Var._own(_global_ir().reduce(Red.Sum, self._id))
     def min(self): return Var._own(_global_ir().reduce(Red.Min, self._id))
     def max(self): return Var._own(_global_ir().reduce(Red.Max, self._id))
@@ -315,6 +328,14 @@ def from_cuda_array(obj) -> Var:
     if ty is None:
         raise TypeError("Not a valid argument!")
     return Var._own(_global_ir().array_wrap_device(ty, int(cai["data"][0]), int(cai["shape"][0])))
+
+
+def from_dlpack(obj) -> Var:
+    """Zero-copy import of a DLPack capsule or of any object with `__dlpack__` (torch / CuPy / JAX arrays): 1-D,
+    contiguous, f32/u32/i32, on this GPU.  The tensor is kept alive by the returned Var's array and released
+    when that array is dropped; its producer must be ordered before the backend stream."""
+    cap = obj.__dlpack__() if hasattr(obj, "__dlpack__") else obj
+    return Var._own(_global_ir().from_dlpack(cap))
 
 
 def sync():
