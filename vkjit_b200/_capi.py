@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIB = os.path.join(_HERE, "libvkjit_b200.so")
+PRODUCT_LIB = os.environ.get("VKJIT_B200_LIB") or os.path.join(_HERE, "libvkjit_b200.so")   # override: A/B of builds
 
 # status codes (include/vkjit_b200.h)
 OK, ERR_INVALID, ERR_TYPE, ERR_SIZE, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_COMPILE, ERR_DIST = range(9)
