@@ -321,6 +321,7 @@ void prefix_of_rank_u32(const uint32_t* v, int rank, uint32_t* out, void* stream
 // Why the tile is this large: every generation of 148 tiles pays one cross-SM aggregate exchange, and
 // with strided persistent tiles each generation runs at the pace of its slowest SM; fewer, larger
 // generations pay that less often (history: profiles/r01_scan_history.md).
+constexpr uint32_t kValueStageDensity = 16;  // compress -> values: TMA-stage the values of tiles selecting >= 1/16 of their lanes
 enum ScanMode { MODE_EXCLUSIVE = 0, MODE_INCLUSIVE = 1, MODE_COMPRESS_INDEX = 2, MODE_COMPRESS_VALUE = 3 };
 
 // Persistent kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The input
@@ -361,6 +362,12 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   __shared__ __align__(8) uint64_t full[S];
   __shared__ uint32_t s_tot[2][NTOT];
   __shared__ uint32_t s_tile_excl[2];
+  __shared__ uint32_t s_vstaged[2];
+  // compress -> values: when a tile selects enough lanes, its VALUES are fetched by TMA into the ring slot its mask
+  // words just left, during the look-back, instead of by register loads after it (whose latency is exposed once
+  // per tile).  The slot's barrier then completes twice for that tile, so its parity is tracked, not derived.
+  constexpr bool VSTAGE = MODE == MODE_COMPRESS_VALUE;
+  uint32_t parity = 0;  // bit s: parity of the next completion of full[s]
 
   uint64_t* status = state + kStatusStride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -393,7 +400,8 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
 
     uint4 x[VPT];  // scan: addends; compress: mask words
     if (staged) {
-      mbar_wait(&full[stage], (k / S) & 1);
+      mbar_wait(&full[stage], (parity >> stage) & 1u);
+      parity ^= 1u << stage;
       const uint4* src = reinterpret_cast<const uint4*>(ring + (size_t)stage * kScanTile);
 #pragma unroll
       for (int j = 0; j < VPT; ++j) x[j] = src[j * T + threadIdx.x];  // conflict-free 128-bit shared loads
@@ -456,13 +464,16 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
       }
     }
     __syncthreads();  // every thread has consumed its part of ring[stage]: the stage can be refilled
-    if (threadIdx.x == 0 && k + S < my_tiles) {
-      const uint32_t t2 = first + (k + S) * stride;
-      if (!(ragged && t2 == num_tiles - 1)) {
-        mbar_expect_tx(&full[stage], TILE_BYTES);
-        tma_load_1d(ring + (size_t)stage * kScanTile, in + (size_t)t2 * kScanTile, TILE_BYTES, &full[stage]);
+    auto refill = [&]() {  // thread 0: next mask / addend tile of this slot
+      if (k + S < my_tiles) {
+        const uint32_t t2 = first + (k + S) * stride;
+        if (!(ragged && t2 == num_tiles - 1)) {
+          mbar_expect_tx(&full[stage], TILE_BYTES);
+          tma_load_1d(ring + (size_t)stage * kScanTile, in + (size_t)t2 * kScanTile, TILE_BYTES, &full[stage]);
+        }
       }
-    }
+    };
+    if (!VSTAGE && threadIdx.x == 0) refill();
     if (warp == 0) {
       uint32_t t[PER_LANE], run = 0;
 #pragma unroll
@@ -477,6 +488,16 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
 #pragma unroll
       for (int i = 0; i < PER_LANE; ++i) { s_tot[buf][lane * PER_LANE + i] = off; off += t[i]; }
       const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, s, 31);
+      if (VSTAGE && lane == 0) {
+        const bool vs = staged && aggregate * kValueStageDensity >= (uint32_t)kScanTile;
+        s_vstaged[buf] = vs ? 1u : 0u;
+        if (vs) {
+          mbar_expect_tx(&full[stage], TILE_BYTES);
+          tma_load_1d(ring + (size_t)stage * kScanTile, values + tile_base, TILE_BYTES, &full[stage]);
+        } else {
+          refill();
+        }
+      }
       // diag_skip_lookback: timing-only diagnostic (VKJIT_SCAN_DIAG=nolookback), results are wrong
       const uint32_t initial = (tile == 0 && initial_ptr) ? __ldcg(initial_ptr) : 0u;
       const uint32_t excl = diag_skip_lookback ? 0u : look_back(status, tile, aggregate, initial);
@@ -487,6 +508,12 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
     }
     __syncthreads();
     const uint32_t tile_excl = s_tile_excl[buf];
+    const bool vstaged = VSTAGE && s_vstaged[buf] != 0u;
+    if (vstaged) {
+      mbar_wait(&full[stage], (parity >> stage) & 1u);
+      parity ^= 1u << stage;
+    }
+    const uint4* vsrc = reinterpret_cast<const uint4*>(ring + (size_t)stage * kScanTile);
 
     // W: whole tile — the common case is compiled without bounds checks
     auto emit = [&](auto whole_c) {
@@ -510,7 +537,8 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
           const uint32_t f = flags[j];
           uint4 v;
           if (MODE == MODE_COMPRESS_VALUE) {  // values are read once, only for vectors with a selected lane
-            if (W || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
+            if (W && vstaged) v = vsrc[j * T + threadIdx.x];
+            else if (W || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
             else {
               v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
               v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
@@ -526,6 +554,10 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
       }
     };
     if (staged) emit(std::true_type{}); else emit(std::false_type{});
+    if (vstaged) {  // the slot held the values until now
+      __syncthreads();
+      if (threadIdx.x == 0) refill();
+    }
     // s_tot/s_tile_excl are double-buffered: iteration k+2 rewrites buffer `buf` only after every
     // thread passed the first barrier of iteration k+1, i.e. after it finished reading it here.
   }

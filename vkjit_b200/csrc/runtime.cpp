@@ -124,6 +124,7 @@ void Backend::shutdown() {
   std::lock_guard<std::mutex> g(g_init_mu);
   if (!g_backend) return;
   Backend* b = g_backend;
+  b->trim();
   cudaStreamSynchronize((cudaStream_t)b->stream);
   b->clear_cache();
   cudaFree(b->scratch.partials);
@@ -134,18 +135,53 @@ void Backend::shutdown() {
   delete b;
 }
 
+// Small blocks are recycled by exact size in front of the CUDA pool.  Every kernel, copy and collective of this
+// backend runs on the ONE backend stream, so a block released after its last user was enqueued may be handed to
+// the next request at once — the same guarantee cudaFreeAsync/cudaMallocAsync give, minus two driver calls
+// (~1 us of the ~3.3 us a cached trace launch costs).  Bounded: blocks <= 4 MiB, <= 8 per size, <= 64 MiB in all.
+namespace {
+constexpr size_t kRecycleMaxBlock = 4u << 20, kRecycleMaxPerSize = 8, kRecycleMaxTotal = 64u << 20;
+}
+
 void* Backend::alloc(size_t bytes) {
   void* p = nullptr;
   const size_t sz = bytes ? bytes : 16;
-  ck(cudaMallocAsync(&p, sz, (cudaStream_t)stream), "cudaMallocAsync");
+  if (sz <= kRecycleMaxBlock) {
+    std::lock_guard<std::mutex> g(recycle_mu_);
+    auto it = recycle_.find(sz);
+    if (it != recycle_.end() && !it->second.empty()) {
+      p = it->second.back();
+      it->second.pop_back();
+      recycle_bytes_ -= sz;
+    }
+  }
+  if (!p) ck(cudaMallocAsync(&p, sz, (cudaStream_t)stream), "cudaMallocAsync");
   g_counters.pool_bytes_live += sz;
   return p;
 }
 
 void Backend::free_async(void* p, size_t bytes) {
   if (!p) return;
+  const size_t sz = bytes ? bytes : 16;
+  g_counters.pool_bytes_live -= sz;
+  if (sz <= kRecycleMaxBlock) {
+    std::lock_guard<std::mutex> g(recycle_mu_);
+    std::vector<void*>& slot = recycle_[sz];
+    if (slot.size() < kRecycleMaxPerSize && recycle_bytes_ + sz <= kRecycleMaxTotal) {
+      slot.push_back(p);
+      recycle_bytes_ += sz;
+      return;
+    }
+  }
   cudaFreeAsync(p, (cudaStream_t)stream);
-  g_counters.pool_bytes_live -= bytes ? bytes : 16;
+}
+
+void Backend::trim() {
+  std::lock_guard<std::mutex> g(recycle_mu_);
+  for (auto& kv : recycle_)
+    for (void* p : kv.second) cudaFreeAsync(p, (cudaStream_t)stream);
+  recycle_.clear();
+  recycle_bytes_ = 0;
 }
 
 Array* Backend::new_array(size_t bytes) {

@@ -64,6 +64,7 @@ class Backend {
   Array* new_array(size_t bytes);
   void* alloc(size_t bytes);
   void free_async(void* p, size_t bytes);
+  void trim();                      // return the recycled blocks to the CUDA pool
   void h2d(void* dst, const void* src, size_t bytes);
   void d2h(void* dst, const void* src, size_t bytes);  // synchronises
   void d2d(void* dst, const void* src, size_t bytes);
@@ -80,6 +81,9 @@ class Backend {
   std::mutex cache_mu_;
   std::unordered_map<Hash128, CachedKernel*, HashOf> cache_;
   void* pool_ = nullptr;            // cudaMemPool_t
+  std::mutex recycle_mu_;
+  std::unordered_map<size_t, std::vector<void*>> recycle_;  // exact size -> released blocks
+  size_t recycle_bytes_ = 0;
 };
 
 // Evaluate the Ir's schedule (+ ids): the body of Ir::eval (internal.rs:482-525).
