@@ -157,3 +157,35 @@ def test_dlpack_round_trip_with_torch(vkjit, cuda_backend):
         vkjit.from_dlpack(torch.zeros(8, device="cuda", dtype=torch.float64))
     with pytest.raises(Exception):
         vkjit.from_dlpack(torch.zeros(8, dtype=torch.float32))       # host memory
+
+
+def test_rust_front_end_surface(vkjit):
+    """The names vkjit-rust exposes (types.rs:142-197, functions.rs:5-82) exist with the same meaning; the two
+    front-end tests of the reference run as written: `setattr` (types.rs:214-228) and `test_scatter` (:230-242)."""
+    F32, U32 = vkjit.VarType.F32, vkjit.VarType.U32
+    st = vkjit.zeros(vkjit._global_ir().struct_type([F32, F32]))
+    x = vkjit.var([1.0, 2.0, 3.0])
+    st.setattr(x, 0)
+    a, b = st.getattr(0), st.getattr(1)
+    vkjit.eval([a, b])
+    assert a.to_vec() == [1.0, 2.0, 3.0] and b.to_vec() == [0.0, 0.0, 0.0]
+    y = vkjit.var(7.0)
+    target = vkjit.var([1.0, 2.0, 3.0])
+    y.scatter(target, vkjit.arange(U32, 3))
+    vkjit.eval([y])
+    assert target.to_vec() == [7.0, 7.0, 7.0]
+    # scatter_with / gather_with: masked forms
+    src = vkjit.var([10, 20, 30, 40])
+    idx = vkjit.arange(U32, 4)
+    keep = idx.lt(2)
+    g = vkjit.gather_with(src, idx, keep)
+    dst = vkjit.var([0, 0, 0, 0])
+    s = vkjit.var([5, 6, 7, 8])
+    s.scatter_with(dst, idx, keep)
+    vkjit.schedule([g])                       # schedule! then eval! of another var evaluates both
+    vkjit.eval([s])
+    assert g.to_vec() == [10, 20, 0, 0] and dst.to_vec() == [5, 6, 0, 0]
+    p = vkjit.struct(src, vkjit.var(2.5))     # Var::from(&[Var])
+    q = p.getattr(0) + vkjit.ones(U32)
+    assert q.tolist() == [11, 21, 31, 41]
+    assert vkjit.repr_ir() == vkjit.ir() and vkjit.repr_ir().startswith("Ir {")

@@ -194,6 +194,23 @@ class Var:
     def get(self, idx) -> "Var":  # vkjit-rust types.rs:190-192
         return gather(self, idx)
 
+    def getattr(self, idx: int) -> "Var":  # vkjit-rust types.rs:149-151
+        return Var._own(_global_ir().getattr(self._id, idx))
+
+    def setattr(self, var, idx: int):  # vkjit-rust types.rs:152-159: `*self = ret`
+        v = _coerce(var)
+        g = _global_ir()
+        new = g.setattr(self._id, v._id, idx)
+        g.dec_ref_count(self._id)
+        self._id = new
+
+    def scatter_with(self, to: "Var", idx, condition=None):  # vkjit-rust types.rs:172-189
+        self.scatter(to, idx, condition)
+
+    def to_vec(self):  # vkjit-rust types.rs:193-196 (as_slice: the var must be evaluated)
+        g = _global_ir()
+        return g.as_slice(self._id, g.ty(self._id)).tolist()
+
     def scatter(self, to: "Var", idx, condition=None):  # vkjit-rust types.rs:169-189
         i = _coerce(idx)
         c = None if condition is None else _coerce(condition)
@@ -273,6 +290,30 @@ def linspace(start, stop, num: int) -> Var:
     a, b = _coerce(start), _coerce(stop)
     assert a.ty() == b.ty()
     return Var._own(_global_ir().linspace(a.ty(), a._id, b._id, num))
+
+
+# -- the Rust front-end's free functions (vkjit-rust/src/functions.rs) -------------------------
+def schedule(vars_):
+    """`schedule!(a, b, ...)` / schedule_internal (functions.rs:72-82): queue vars for the next eval."""
+    _global_ir().schedule([v.id() for v in vars_])
+
+
+def repr_ir() -> str:  # functions.rs:54-56
+    return _global_ir().repr()
+
+
+def struct(*members) -> Var:
+    """`Var::from(&[Var])` (vkjit-rust types.rs:99-105): a struct-typed var from its members."""
+    vs = [_coerce(m) for m in members]
+    return Var._own(_global_ir().struct_init([v._id for v in vs]))
+
+
+def gather_with(src: Var, idx, condition=None) -> Var:  # functions.rs:39-52
+    return gather(src, idx, condition)
+
+
+def ones(ty: int) -> Var:  # Ir::ones (internal.rs:265-282; not re-exported by the reference front-ends)
+    return Var._own(_global_ir().ones(ty))
 
 
 # -- additions -------------------------------------------------------------------------------
