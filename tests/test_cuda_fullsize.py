@@ -158,3 +158,31 @@ def test_M26_monte_carlo_full_size(cuda_backend, oir_mt):
     exp = oir_mt.as_slice(yo.id, T.F32)
     assert np.allclose(got[:w], exp, rtol=2e-5, atol=1e-5)
     assert abs(float(got.mean()) - float(exp.mean())) < 0.05 * float(exp.mean())
+
+
+def test_lane_indices_beyond_2_to_31(cuda_backend, cir):
+    """Maximum sizes: n = 2^31 + 5 lanes (the reference's invocation index is 32-bit; so is ours, and nothing may
+    wrap at 2^31).  No oracle here (8 GiB per array on the host): every result has a closed form."""
+    n = (1 << 31) + 5
+    M = 1 << 32
+    i = cir.arange(T.U32, n)
+    x = cir.add(cir.mul(i, cir.const_u32(3)), cir.const_u32(1))                 # x_i = 3 i + 1 (mod 2^32)
+    want_sum = (3 * (n * (n - 1) // 2) + n) % M
+    assert int(cir.as_slice(cir.reduce(Red.Sum, x), T.U32)[0]) == want_sum     # fused trace -> reduce, nothing stored
+    assert int(cir.as_slice(cir.reduce(Red.Max, i), T.U32)[0]) == n - 1
+    probe = np.array([0, 1, (1 << 31) - 1, 1 << 31, (1 << 31) + 1, n - 1], dtype=np.uint32)
+    pv = cir.array_u32(probe)
+    cir.eval([x])                                                              # 8 GiB elementwise store (vector + scalar tail)
+    got = cir.as_slice_eval(cir.gather(x, pv), T.U32)
+    assert np.array_equal(got, ((3 * probe.astype(np.uint64) + 1) % M).astype(np.uint32))
+    assert int(cir.as_slice(cir.reduce(Red.Sum, x), T.U32)[0]) == want_sum     # hand-written reduce over 8 GiB
+    s = cir.prefix_sum(x, True)                                                # look-back scan over 87382 tiles
+    got = cir.as_slice_eval(cir.gather(s, pv), T.U32)
+    p64 = probe.astype(object)
+    assert [int(v) for v in got] == [int((3 * (p * (p - 1) // 2) + p) % M) for p in p64]
+    cir.dec_ref_count(s)
+    m = cir.eq(cir.bop(Bop.And, i, cir.const_u32(1023)), cir.const_u32(3))     # every 1024th lane, computed in-kernel
+    idx, cnt = cir.compress(m)
+    assert cnt == (n - 4) // 1024 + 1 and cir.size(idx) == cnt
+    tail = cir.as_slice_eval(cir.gather(idx, cir.array_u32(np.array([0, cnt // 2, cnt - 1], dtype=np.uint32))), T.U32)
+    assert [int(v) for v in tail] == [3, 3 + 1024 * (cnt // 2), 3 + 1024 * (cnt - 1)] and int(tail[-1]) == (1 << 31) + 3
