@@ -73,4 +73,8 @@ def bench(vk, stream, flush_l2, log2n=26, rounds=5):
     return {"lanes": n, "rounds": rounds, "ir_nodes_live_after_build": nodes, "trace_build_ms_python": t_trace * 1e3,
             "compile_ms_cold": compile_ms, "first_eval_wall_ms": t_cold * 1e3, "kernel_ms": ms, "Glanes_per_s": n / (ms * 1e-3) / 1e9,
             "cache_hit_eval_us": sorted(evals[1:])[len(evals[1:]) // 2] / 1e3, "cache_hits": st2["cache_hits"], "cache_misses": st2["cache_misses"],
-            "GBps_written": 4 * n / (ms * 1e-3) / 1e9}
+            "GBps_written": 4 * n / (ms * 1e-3) / 1e9,
+            # lane-ops/s against 148 SMs x 128 FP32/INT32 lanes x clock.  One IR node is one lane-op here,
+            # although sin/cos/log/sqrt/div expand to tens of instructions each, so the fraction understates ALU use.
+            "T_ir_ops_per_s": nodes * n / (ms * 1e-3) / 1e12, "alu_peak_T_lane_ops_per_s": 148 * 128 * 1.965e9 / 1e12,
+            "alu_frac_by_ir_ops": nodes * n / (ms * 1e-3) / (148 * 128 * 1.965e9)}
