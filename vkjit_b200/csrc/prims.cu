@@ -10,7 +10,9 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <type_traits>
+#include <vector>
 
 #include "common.h"
 
@@ -322,6 +324,7 @@ void prefix_of_rank_u32(const uint32_t* v, int rank, uint32_t* out, void* stream
 // with strided persistent tiles each generation runs at the pace of its slowest SM; fewer, larger
 // generations pay that less often (history: profiles/r01_scan_history.md).
 constexpr uint32_t kValueStageDensity = 16;  // compress -> values: TMA-stage the values of tiles selecting >= 1/16 of their lanes
+constexpr int kScanLagVpt = 4;  // lagged variant: 16384-lane tiles, 3 ring slots
 enum ScanMode { MODE_EXCLUSIVE = 0, MODE_INCLUSIVE = 1, MODE_COMPRESS_INDEX = 2, MODE_COMPRESS_VALUE = 3 };
 
 // Persistent kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The input
@@ -473,7 +476,7 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
         }
       }
     };
-    if (!VSTAGE && threadIdx.x == 0) refill();
+    if (!VSTAGE && threadIdx.x == 32) refill();  // warp 1 issues the copy: a full TMA queue would otherwise hold up warp 0's look-back
     if (warp == 0) {
       uint32_t t[PER_LANE], run = 0;
 #pragma unroll
@@ -563,6 +566,177 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
   }
 }
 
+// Lagged prefix sum (the default for MODE_EXCLUSIVE / MODE_INCLUSIVE; VKJIT_SCAN_IMPL=classic selects scan_kernel).
+// Measured on the kernel above (globaltimer per phase, profiles/): a tile
+// costs 0.9 us local scan + 2.2-2.5 us look-back + 1.4 us stores, and the look-back time is the same at every
+// position of a generation — it is not a wait for stragglers but the store -> poll -> load visibility latency of
+// the immediate predecessor's status word, which the 148 CTAs chase around a ring.  Here tile k's aggregate is
+// published as soon as its local scan is done, but its prefix is resolved one iteration later (by then every
+// predecessor has been visible for a whole tile period: one L2 round trip), and its results are written from
+// registers then.  All three ring slots stay free for prefetching.
+template <int MODE>
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_kernel_lag(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t num_tiles,
+                uint64_t* __restrict__ state, const uint32_t* __restrict__ initial_ptr, unsigned long long* __restrict__ trace) {
+  constexpr int T = kScanThreads, VPT = kScanLagVpt, TILE = T * 4 * VPT, S = 2;
+  constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = NTOT / 32;
+  constexpr uint32_t TILE_BYTES = TILE * 4;
+  static_assert(NTOT % 32 == 0, "tile totals must fill whole warp rows");
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  uint32_t* ring = reinterpret_cast<uint32_t*>(ring_raw);  // S input slots, then one output staging tile
+  uint32_t* stage_out = ring + (size_t)S * TILE;
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ uint32_t s_tot[3][NTOT];  // tile k writes [k % 3] while tile k-1's offsets are still being read
+  __shared__ uint32_t s_tile_excl;
+  __shared__ __align__(16) uint64_t s_window[kLookWide * 32 * 2];
+
+  uint64_t* status = state + kStatusStride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t first = blockIdx.x, stride = gridDim.x;
+  const uint32_t my_tiles = first < num_tiles ? (num_tiles - first + stride - 1) / stride : 0;
+  const bool ragged = (n % TILE) != 0;
+
+  auto fill = [&](uint32_t k) {  // thread 0
+    if (k >= my_tiles) return;
+    const uint32_t t = first + k * stride;
+    if (ragged && t == num_tiles - 1) return;
+    mbar_expect_tx(&full[k % S], TILE_BYTES);
+    tma_load_1d(ring + (size_t)(k % S) * TILE, in + (size_t)t * TILE, TILE_BYTES, &full[k % S]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (uint32_t k = 0; k < (uint32_t)S; ++k) fill(k);
+
+  uint4 xp[VPT];          // previous tile: addends
+  uint32_t prep[VPT];     // previous tile: exclusive offset of each vector within its warp row
+  uint32_t agg_prev = 0u; // warp 0: aggregate of the previous tile
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) { xp[j] = make_uint4(0u, 0u, 0u, 0u); prep[j] = 0u; }
+
+  for (uint32_t k = 0; k <= my_tiles; ++k) {
+    const bool have_cur = k < my_tiles, have_prev = k > 0;
+    const uint32_t tile = first + k * stride;
+    uint4 xc[VPT];
+    uint32_t prec[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) { xc[j] = make_uint4(0u, 0u, 0u, 0u); prec[j] = 0u; }
+    // warp 0: the previous tile's predecessors published a whole iteration ago — fetch their status words now,
+    // use them after this tile's local scan
+    if (warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
+    if (have_cur) {  // ---- local scan of tile k
+      const size_t tile_base = (size_t)tile * TILE;
+      if (trace && threadIdx.x == 0) trace[(size_t)tile * 8 + 0] = global_ns();
+      if (!(ragged && tile == num_tiles - 1)) {
+        mbar_wait(&full[k % S], (k / S) & 1);
+        const uint4* src = reinterpret_cast<const uint4*>(ring + (size_t)(k % S) * TILE);
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) xc[j] = src[j * T + threadIdx.x];
+      } else {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+          const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+          if (e + 3 < n) xc[j] = ld_stream(reinterpret_cast<const uint4*>(in + e));
+          else {
+            xc[j].x = e + 0 < n ? in[e + 0] : 0u; xc[j].y = e + 1 < n ? in[e + 1] : 0u;
+            xc[j].z = e + 2 < n ? in[e + 2] : 0u; xc[j].w = 0u;
+          }
+        }
+      }
+      if (trace && threadIdx.x == 0) trace[(size_t)tile * 8 + 1] = global_ns();
+      uint32_t* tot = s_tot[k % 3];
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        const uint32_t vs = xc[j].x + xc[j].y + xc[j].z + xc[j].w;
+        uint32_t s = vs;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+          if (lane >= o) s += t;
+        }
+        prec[j] = s - vs;
+        if (lane == 31) tot[j * WARPS + warp] = s;
+      }
+    }
+    __syncthreads();  // s_tot[k % 3] complete; every thread has consumed ring slot k % S
+    if (have_cur && threadIdx.x == 32) fill(k + S);
+    if (have_cur && trace && threadIdx.x == 0) trace[(size_t)tile * 8 + 2] = global_ns();
+    if (warp == 0) {
+      uint32_t agg_cur = 0u;
+      if (have_cur) {  // (slot, warp) totals in tile order -> exclusive offsets; publish the tile aggregate
+        uint32_t* tot = s_tot[k % 3];
+        uint32_t t[PER_LANE], run = 0;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) { t[i] = tot[lane * PER_LANE + i]; run += t[i]; }
+        uint32_t s = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, s, o);
+          if (lane >= o) s += u;
+        }
+        uint32_t off = s - run;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) { tot[lane * PER_LANE + i] = off; off += t[i]; }
+        agg_cur = __shfl_sync(0xFFFFFFFFu, s, 31);
+        const uint32_t initial = (tile == 0 && initial_ptr) ? __ldcg(initial_ptr) : 0u;
+        if (lane == 0) {
+          if (tile == 0) status_store(status, ((uint64_t)ST_INCLUSIVE << 32) | (initial + agg_cur));
+          else status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_AGGREGATE << 32) | agg_cur);
+        }
+      }
+      if (have_prev) {  // the previous tile's predecessors have been visible for a whole iteration
+        const uint32_t tprev = tile - stride;
+        if (trace && lane == 0) trace[(size_t)tprev * 8 + 6] = global_ns();
+        uint64_t window[kLookWide];
+        load_window(s_window, window);
+        const uint32_t excl = resolve_prefix(status, tprev, agg_prev, (tprev == 0 && initial_ptr) ? __ldcg(initial_ptr) : 0u, window);
+        if (lane == 0) {
+          s_tile_excl = excl;
+          if (trace) { trace[(size_t)tprev * 8 + 3] = global_ns(); trace[(size_t)tprev * 8 + 5] = blockIdx.x; }
+        }
+      }
+      agg_prev = agg_cur;
+    }
+    if (threadIdx.x == 0) tma_store_wait_read();  // the previous bulk store has read the staging tile
+    __syncthreads();
+    if (have_prev) {  // ---- results of tile k-1, from registers, through shared memory and ONE bulk store
+      const uint32_t tprev = tile - stride;
+      const size_t tile_base = (size_t)tprev * TILE;
+      const bool whole = !(ragged && tprev == num_tiles - 1);
+      const uint32_t tile_excl = s_tile_excl;
+      const uint32_t* tot = s_tot[(k - 1) % 3];
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+        const uint32_t p = tile_excl + tot[j * WARPS + warp] + prep[j];
+        uint4 r;
+        if (MODE == MODE_EXCLUSIVE) { r.x = p; r.y = p + xp[j].x; r.z = r.y + xp[j].y; r.w = r.z + xp[j].z; }
+        else { r.x = p + xp[j].x; r.y = r.x + xp[j].y; r.z = r.y + xp[j].z; r.w = r.z + xp[j].w; }
+        if (whole) reinterpret_cast<uint4*>(stage_out)[j * T + threadIdx.x] = r;
+        else if (e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
+        else {
+          if (e + 0 < n) out[e + 0] = r.x;
+          if (e + 1 < n) out[e + 1] = r.y;
+          if (e + 2 < n) out[e + 2] = r.z;
+        }
+      }
+      if (whole) {
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) tma_store_1d(out + tile_base, stage_out, TILE_BYTES);
+      }
+      if (trace && threadIdx.x == 0) trace[(size_t)tprev * 8 + 4] = global_ns();
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) { xp[j] = xc[j]; prep[j] = prec[j]; }
+  }
+  if (threadIdx.x == 0) tma_store_wait_all();  // shared memory must outlive the last bulk store
+}
+
 static_assert(kStatusWordsPerTile == kStatusStride, "host and device disagree on the status slot size");
 size_t scan_state_words(size_t n, size_t tile) { return (size_t)kStatusStride * (2 + n / tile); }
 
@@ -571,6 +745,40 @@ static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* ou
                         const Scratch& sc, int sm_count, cudaStream_t s, const uint32_t* initial = nullptr,
                         const uint32_t* index_base = nullptr) {
   using G = ScanGeom<MODE>;
+  static int impl = -1;
+  if (impl < 0) { const char* d = getenv("VKJIT_SCAN_IMPL"); impl = (d && std::string(d) == "classic") ? 0 : 1; }  // prefix sums: lagged kernel unless "classic"
+  if constexpr (MODE < MODE_COMPRESS_INDEX) {
+    if (impl == 1) {
+      constexpr size_t TILE = (size_t)kScanThreads * 4 * kScanLagVpt, SMEM = 3 * TILE * 4;  // 2 input slots + 1 output staging tile
+      const size_t tiles = (n + TILE - 1) / TILE;
+      const size_t words = (size_t)kStatusStride * (1 + tiles);
+      if (words > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
+      cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, words * sizeof(uint64_t), s);
+      if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
+      static bool configured_lag = false;
+      if (!configured_lag) {
+        e = cudaFuncSetAttribute(scan_kernel_lag<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan smem attribute: ") + cudaGetErrorString(e));
+        configured_lag = true;
+      }
+      static unsigned long long* d_trace = nullptr;
+      const char* tf = getenv("VKJIT_SCAN_TRACE");
+      if (tf && !d_trace) cudaMalloc(&d_trace, tiles * 64);
+      if (tf) cudaMemsetAsync(d_trace, 0, tiles * 64, s);
+      const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);
+      scan_kernel_lag<MODE><<<grid, kScanThreads, SMEM, s>>>(in, out, n, (uint32_t)tiles, sc.tile_state, initial, tf ? d_trace : nullptr);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
+      if (tf) {
+        cudaStreamSynchronize(s);
+        std::vector<unsigned long long> h(tiles * 8);
+        cudaMemcpy(h.data(), d_trace, tiles * 64, cudaMemcpyDeviceToHost);
+        FILE* fp = fopen(tf, "wb");
+        if (fp) { fwrite(h.data(), 8, h.size(), fp); fclose(fp); }
+      }
+      return;
+    }
+  }
   const size_t tiles = (n + G::TILE - 1) / G::TILE;
   const size_t words = (size_t)kStatusStride * (1 + tiles);
   if (words > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");

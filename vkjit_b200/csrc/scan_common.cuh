@@ -17,6 +17,7 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
 
 enum : uint32_t { ST_INVALID = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2 };
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 
 // Status words are read and written with gpu-scope relaxed accesses (L2 is the coherence point;
@@ -86,8 +87,74 @@ __device__ __forceinline__ uint32_t look_back(uint64_t* status, uint32_t tile, u
   return exclusive;
 }
 
+// ---- lagged look-back (scan_kernel_lag): a tile's prefix is resolved one iteration after its aggregate was published
+// First round of status words of `tile`'s look-back window, fetched EARLY and without registers: each lane copies its
+// kLookWide status slots (16 bytes each, L2 only: cp.async.cg) into its own row of a shared-memory window, so the
+// L2 round trip (1.3-1.5 us while the memory system is saturated) overlaps the local scan of the next tile.
+__device__ __forceinline__ void prefetch_window(const uint64_t* status, uint32_t tile, uint64_t* window /* [kLookWide*32][2] */) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < kLookWide; ++i) {
+    const int idx = (int)tile - 1 - 32 * i - lane;
+    uint64_t* dst = window + (size_t)(i * 32 + lane) * 2;
+    if (idx >= 0)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(status + (size_t)idx * kStatusStride) : "memory");
+    else
+      dst[0] = (uint64_t)ST_INCLUSIVE << 32;  // before tile 0: prefix 0
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void load_window(const uint64_t* window, uint64_t (&s)[kLookWide]) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < kLookWide; ++i) s[i] = window[(size_t)(i * 32 + lane) * 2];
+}
+// The look-back walk for a tile whose aggregate was published earlier; `first_round` = the prefetched window.
+__device__ __forceinline__ uint32_t resolve_prefix(uint64_t* status, uint32_t tile, uint32_t aggregate, uint32_t initial,
+                                                   uint64_t (&first_round)[kLookWide]) {
+  const int lane = threadIdx.x & 31;
+  if (tile == 0) return initial;  // tile 0 published its inclusive prefix at once
+  uint32_t exclusive = 0;
+  int top = (int)tile - 1;
+  bool preloaded = true;
+  for (;;) {
+    uint64_t s[kLookWide];
+#pragma unroll
+    for (int i = 0; i < kLookWide; ++i) {
+      const int idx = top - 32 * i - lane;
+      if (preloaded) s[i] = first_round[i];
+      else s[i] = idx >= 0 ? status_load(status + (size_t)idx * kStatusStride) : ((uint64_t)ST_INCLUSIVE << 32);
+    }
+    preloaded = false;
+    bool done = false;
+#pragma unroll
+    for (int i = 0; i < kLookWide; ++i) {
+      if (done) continue;
+      const int idx = top - 32 * i - lane;
+      uint32_t spins = 0;
+      while ((uint32_t)(s[i] >> 32) == ST_INVALID) {
+        __nanosleep(40);
+        s[i] = status_load(status + (size_t)idx * kStatusStride);
+        if (++spins > (1u << 25)) __trap();
+      }
+      const unsigned incl = __ballot_sync(0xFFFFFFFFu, (uint32_t)(s[i] >> 32) == ST_INCLUSIVE);
+      if (incl) {
+        const int first = __ffs(incl) - 1;
+        exclusive += warp_sum(lane <= first ? (uint32_t)s[i] : 0u);
+        done = true;
+      } else {
+        exclusive += warp_sum((uint32_t)s[i]);
+      }
+    }
+    if (done) break;
+    top -= 32 * kLookWide;
+  }
+  if (lane == 0) status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_INCLUSIVE << 32) | (exclusive + aggregate));
+  return exclusive;
+}
+
 // ---- TMA bulk-copy / mbarrier helpers (sm_90+; SASS: UBLKCP + SYNCS) -----------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }
@@ -101,6 +168,17 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
                : "memory");
 }
+// shared -> global bulk copy by the TMA unit (bulk async-group completion); the stores leave the SM without
+// occupying LSU store slots, so the issuing warps are not back-pressured while the memory system drains them
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (before a bulk store reads them)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done, spins = 0;
   do {
