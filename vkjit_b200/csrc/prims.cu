@@ -612,19 +612,17 @@ scan_kernel_lag(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, siz
   if (threadIdx.x == 0)
     for (uint32_t k = 0; k < (uint32_t)S; ++k) fill(k);
 
-  uint4 xp[VPT];          // previous tile: addends
-  uint32_t prep[VPT];     // previous tile: exclusive offset of each vector within its warp row
+  uint4 xp[VPT];          // previous tile: results relative to the start of the vector's warp row
   uint32_t agg_prev = 0u; // warp 0: aggregate of the previous tile
 #pragma unroll
-  for (int j = 0; j < VPT; ++j) { xp[j] = make_uint4(0u, 0u, 0u, 0u); prep[j] = 0u; }
+  for (int j = 0; j < VPT; ++j) xp[j] = make_uint4(0u, 0u, 0u, 0u);
 
   for (uint32_t k = 0; k <= my_tiles; ++k) {
     const bool have_cur = k < my_tiles, have_prev = k > 0;
     const uint32_t tile = first + k * stride;
     uint4 xc[VPT];
-    uint32_t prec[VPT];
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) { xc[j] = make_uint4(0u, 0u, 0u, 0u); prec[j] = 0u; }
+    for (int j = 0; j < VPT; ++j) xc[j] = make_uint4(0u, 0u, 0u, 0u);
     // warp 0: the previous tile's predecessors published a whole iteration ago — fetch their status words now,
     // use them after this tile's local scan
     if (warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
@@ -658,8 +656,11 @@ scan_kernel_lag(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, siz
           const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
           if (lane >= o) s += t;
         }
-        prec[j] = s - vs;
         if (lane == 31) tot[j * WARPS + warp] = s;
+        const uint32_t p = s - vs;  // exclusive offset of the vector within its warp row
+        const uint4 a = xc[j];
+        if (MODE == MODE_EXCLUSIVE) { xc[j].x = p; xc[j].y = p + a.x; xc[j].z = xc[j].y + a.y; xc[j].w = xc[j].z + a.z; }
+        else { xc[j].x = p + a.x; xc[j].y = xc[j].x + a.y; xc[j].z = xc[j].y + a.z; xc[j].w = xc[j].z + a.w; }
       }
     }
     __syncthreads();  // s_tot[k % 3] complete; every thread has consumed ring slot k % S
@@ -712,10 +713,9 @@ scan_kernel_lag(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, siz
 #pragma unroll
       for (int j = 0; j < VPT; ++j) {
         const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
-        const uint32_t p = tile_excl + tot[j * WARPS + warp] + prep[j];
+        const uint32_t p = tile_excl + tot[j * WARPS + warp];
         uint4 r;
-        if (MODE == MODE_EXCLUSIVE) { r.x = p; r.y = p + xp[j].x; r.z = r.y + xp[j].y; r.w = r.z + xp[j].z; }
-        else { r.x = p + xp[j].x; r.y = r.x + xp[j].y; r.z = r.y + xp[j].z; r.w = r.z + xp[j].w; }
+        r.x = xp[j].x + p; r.y = xp[j].y + p; r.z = xp[j].z + p; r.w = xp[j].w + p;
         if (whole) reinterpret_cast<uint4*>(stage_out)[j * T + threadIdx.x] = r;
         else if (e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
         else {
@@ -732,7 +732,7 @@ scan_kernel_lag(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, siz
       if (trace && threadIdx.x == 0) trace[(size_t)tprev * 8 + 4] = global_ns();
     }
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) { xp[j] = xc[j]; prep[j] = prec[j]; }
+    for (int j = 0; j < VPT; ++j) xp[j] = xc[j];
   }
   if (threadIdx.x == 0) tma_store_wait_all();  // shared memory must outlive the last bulk store
 }
