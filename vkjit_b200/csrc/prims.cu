@@ -324,6 +324,7 @@ void prefix_of_rank_u32(const uint32_t* v, int rank, uint32_t* out, void* stream
 // with strided persistent tiles each generation runs at the pace of its slowest SM; fewer, larger
 // generations pay that less often (history: profiles/r01_scan_history.md).
 constexpr uint32_t kValueStageDensity = 16;  // compress -> values: TMA-stage the values of tiles selecting >= 1/16 of their lanes
+constexpr int kCompressLagVptIndex = 4, kCompressLagVptValues = 3;  // lagged compaction: 16384- / 12288-lane tiles
 constexpr int kScanLagVpt = 4;  // lagged variant: 16384-lane tiles, 3 ring slots
 enum ScanMode { MODE_EXCLUSIVE = 0, MODE_INCLUSIVE = 1, MODE_COMPRESS_INDEX = 2, MODE_COMPRESS_VALUE = 3 };
 
@@ -737,6 +738,190 @@ scan_kernel_lag(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, siz
   if (threadIdx.x == 0) tma_store_wait_all();  // shared memory must outlive the last bulk store
 }
 
+// Lagged stream compaction (the default for MODE_COMPRESS_*; VKJIT_SCAN_IMPL=classic selects scan_kernel): the same
+// schedule as scan_kernel_lag.  What a tile carries into the next iteration is tiny — 4 selection bits and one
+// 8-bit row offset per vector, packed into two registers — so nothing is parked in shared memory.
+//   VALUES = false: 16384-lane tiles, 3 mask slots.
+//   VALUES = true : 12288-lane tiles, 2 mask slots + 2 value slots; the values of tile k are fetched by one TMA
+//                   bulk copy issued as soon as its count is known (dense tiles only) and read from shared memory
+//                   when the tile is written one iteration later.
+template <bool VALUES>
+__global__ void __launch_bounds__(kScanThreads, 1)
+compress_kernel_lag(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ values, uint32_t* __restrict__ out,
+                    uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles, uint64_t* __restrict__ state,
+                    const uint32_t* __restrict__ index_base_ptr) {
+  constexpr int T = kScanThreads, VPT = VALUES ? kCompressLagVptValues : kCompressLagVptIndex, TILE = T * 4 * VPT;
+  constexpr int S = VALUES ? 2 : 3;  // mask slots
+  constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = NTOT / 32;
+  constexpr uint32_t TILE_BYTES = TILE * 4;
+  static_assert(NTOT % 32 == 0 && VPT <= 4, "packed per-slot counts need VPT <= 4");
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  uint32_t* ring = reinterpret_cast<uint32_t*>(ring_raw);  // S mask slots, then (VALUES) 2 value slots
+  uint32_t* vring = ring + (size_t)S * TILE;
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ __align__(8) uint64_t vfull[2];
+  __shared__ uint32_t s_tot[3][NTOT];
+  __shared__ uint32_t s_tile_excl;
+  __shared__ uint32_t s_vstaged[2];
+  __shared__ __align__(16) uint64_t s_window[kLookWide * 32 * 2];
+
+  uint64_t* status = state + kStatusStride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t first = blockIdx.x, stride = gridDim.x;
+  const uint32_t my_tiles = first < num_tiles ? (num_tiles - first + stride - 1) / stride : 0;
+  const bool ragged = (n % TILE) != 0;
+  const uint32_t index_base = (!VALUES && index_base_ptr) ? __ldcg(index_base_ptr) : 0u;
+
+  auto fill = [&](uint32_t k) {  // next mask tile of slot k % S
+    if (k >= my_tiles) return;
+    const uint32_t t = first + k * stride;
+    if (ragged && t == num_tiles - 1) return;
+    mbar_expect_tx(&full[k % S], TILE_BYTES);
+    tma_load_1d(ring + (size_t)(k % S) * TILE, mask + (size_t)t * TILE, TILE_BYTES, &full[k % S]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_init(&vfull[0], 1); mbar_init(&vfull[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (uint32_t k = 0; k < (uint32_t)S; ++k) fill(k);
+
+  uint32_t flags_p = 0u, pre_p = 0u;  // previous tile: 4 selection bits / one 8-bit exclusive row offset per vector
+  uint32_t agg_prev = 0u;             // warp 0: aggregate of the previous tile
+  uint32_t vparity = 0u;              // bit s: parity of the next completion of vfull[s]
+
+  for (uint32_t k = 0; k <= my_tiles; ++k) {
+    const bool have_cur = k < my_tiles, have_prev = k > 0;
+    const uint32_t tile = first + k * stride;
+    const bool staged = have_cur && !(ragged && tile == num_tiles - 1);
+    uint32_t flags_c = 0u, pre_c = 0u;
+    if (warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
+    if (have_cur) {  // ---- selection bits and packed local scan of tile k
+      const size_t tile_base = (size_t)tile * TILE;
+      uint32_t pk = 0u, own = 0u;
+      if (staged) {
+        mbar_wait(&full[k % S], (k / S) & 1);
+        const uint4* src = reinterpret_cast<const uint4*>(ring + (size_t)(k % S) * TILE);
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+          const uint4 x = src[j * T + threadIdx.x];
+          const uint32_t f = (x.x != 0u ? 1u : 0u) | (x.y != 0u ? 2u : 0u) | (x.z != 0u ? 4u : 0u) | (x.w != 0u ? 8u : 0u);
+          flags_c |= f << (4 * j);
+          own |= (uint32_t)__popc(f) << (8 * j);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+          const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+          uint32_t f = 0u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) f |= (e + c < n && mask[e + c] != 0u) ? (1u << c) : 0u;
+          flags_c |= f << (4 * j);
+          own |= (uint32_t)__popc(f) << (8 * j);
+        }
+      }
+      pk = own;  // a warp's inclusive count per slot is at most 128: four 8-bit fields scan in one word
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pk, o);
+        if (lane >= o) pk += t;
+      }
+      pre_c = pk - own;
+      if (lane == 31) {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) s_tot[k % 3][j * WARPS + warp] = (pk >> (8 * j)) & 0xFFu;
+      }
+    }
+    __syncthreads();  // s_tot[k % 3] complete; every thread has consumed mask slot k % S
+    if (have_cur && threadIdx.x == 32) fill(k + S);
+    if (warp == 0) {
+      uint32_t agg_cur = 0u;
+      if (have_cur) {
+        uint32_t* tot = s_tot[k % 3];
+        uint32_t t[PER_LANE], run = 0;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) { t[i] = tot[lane * PER_LANE + i]; run += t[i]; }
+        uint32_t s = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, s, o);
+          if (lane >= o) s += u;
+        }
+        uint32_t off = s - run;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) { tot[lane * PER_LANE + i] = off; off += t[i]; }
+        agg_cur = __shfl_sync(0xFFFFFFFFu, s, 31);
+        if (lane == 0) {
+          if (tile == 0) status_store(status, ((uint64_t)ST_INCLUSIVE << 32) | agg_cur);
+          else status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_AGGREGATE << 32) | agg_cur);
+          if (VALUES) {  // dense tile: its values travel by TMA while the next tile is scanned
+            const bool vs = staged && agg_cur * kValueStageDensity >= (uint32_t)TILE;
+            s_vstaged[k % 2] = vs ? 1u : 0u;
+            if (vs) {
+              mbar_expect_tx(&vfull[k % 2], TILE_BYTES);
+              tma_load_1d(vring + (size_t)(k % 2) * TILE, values + (size_t)tile * TILE, TILE_BYTES, &vfull[k % 2]);
+            }
+          }
+        }
+      }
+      if (have_prev) {
+        const uint32_t tprev = tile - stride;
+        uint64_t window[kLookWide];
+        load_window(s_window, window);
+        const uint32_t excl = resolve_prefix(status, tprev, agg_prev, 0u, window);
+        if (lane == 0) {
+          s_tile_excl = excl;
+          if (tprev == num_tiles - 1) *count_out = excl + agg_prev;
+        }
+      }
+      agg_prev = agg_cur;
+    }
+    __syncthreads();
+    if (have_prev) {  // ---- selected lanes of tile k-1, written at their rank
+      const uint32_t kp = k - 1, tprev = tile - stride;
+      const size_t tile_base = (size_t)tprev * TILE;
+      const bool whole = !(ragged && tprev == num_tiles - 1);
+      const uint32_t tile_excl = s_tile_excl;
+      const uint32_t* tot = s_tot[kp % 3];
+      bool vstaged = false;
+      if (VALUES) {
+        vstaged = s_vstaged[kp % 2] != 0u;
+        if (vstaged) {
+          mbar_wait(&vfull[kp % 2], (vparity >> (kp % 2)) & 1u);
+          vparity ^= 1u << (kp % 2);
+        }
+      }
+      const uint4* vsrc = reinterpret_cast<const uint4*>(vring + (size_t)(kp % 2) * TILE);
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        const uint32_t f = (flags_p >> (4 * j)) & 0xFu;
+        if (f) {
+          const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+          uint4 v;
+          if (VALUES) {
+            if (vstaged) v = vsrc[j * T + threadIdx.x];
+            else if (whole || e + 3 < n) v = ld_stream(reinterpret_cast<const uint4*>(values + e));
+            else {
+              v.x = e + 0 < n ? values[e + 0] : 0u; v.y = e + 1 < n ? values[e + 1] : 0u;
+              v.z = e + 2 < n ? values[e + 2] : 0u; v.w = 0u;
+            }
+          } else { v.x = index_base + (uint32_t)e; v.y = v.x + 1; v.z = v.x + 2; v.w = v.x + 3; }
+          uint32_t* q = out + (tile_excl + tot[j * WARPS + warp] + ((pre_p >> (8 * j)) & 0xFFu));
+          const uint32_t s1 = f & 1u, s2 = s1 + ((f >> 1) & 1u), s3 = s2 + ((f >> 2) & 1u);
+          if (f & 1u) q[0] = v.x;
+          if (f & 2u) q[s1] = v.y;
+          if (f & 4u) q[s2] = v.z;
+          if (f & 8u) q[s3] = v.w;
+        }
+      }
+    }
+    flags_p = flags_c; pre_p = pre_c;
+  }
+}
+
 static_assert(kStatusWordsPerTile == kStatusStride, "host and device disagree on the status slot size");
 size_t scan_state_words(size_t n, size_t tile) { return (size_t)kStatusStride * (2 + n / tile); }
 
@@ -776,6 +961,29 @@ static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* ou
         FILE* fp = fopen(tf, "wb");
         if (fp) { fwrite(h.data(), 8, h.size(), fp); fclose(fp); }
       }
+      return;
+    }
+  }
+  if constexpr (MODE >= MODE_COMPRESS_INDEX) {
+    if (impl == 1) {
+      constexpr bool VALUES = MODE == MODE_COMPRESS_VALUE;
+      constexpr size_t TILE = (size_t)kScanThreads * 4 * (VALUES ? kCompressLagVptValues : kCompressLagVptIndex);
+      constexpr size_t SMEM = (VALUES ? 4 : 3) * TILE * 4;
+      const size_t tiles = (n + TILE - 1) / TILE;
+      const size_t words = (size_t)kStatusStride * (1 + tiles);
+      if (words > sc.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
+      cudaError_t e = cudaMemsetAsync(sc.tile_state, 0, words * sizeof(uint64_t), s);
+      if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan memset: ") + cudaGetErrorString(e));
+      static bool configured_lag = false;
+      if (!configured_lag) {
+        e = cudaFuncSetAttribute(compress_kernel_lag<VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("compress smem attribute: ") + cudaGetErrorString(e));
+        configured_lag = true;
+      }
+      const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);
+      compress_kernel_lag<VALUES><<<grid, kScanThreads, SMEM, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state, index_base);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("compress launch: ") + cudaGetErrorString(e));
       return;
     }
   }
