@@ -308,6 +308,31 @@ def test_fused_scan_and_compress(cuda_backend, cir, oir, n, streams):
     assert np.array_equal(res[0][4], np.nonzero(acc_np & 5)[0].astype(np.uint32))
 
 
+@pytest.mark.parametrize("n", FUSED_SIZES)
+def test_lagged_fused_kernels_small_traces(cuda_backend, cir, oir, n):
+    """Traces of a few nodes over at most one streamed array take the LAGGED fused kernels (look-back one tile behind,
+    16384- / 12288-lane tiles): all four modes, with and without a streamed array, every tile-boundary size."""
+    x = special_u32(np.random.default_rng(n), n)
+    res = []
+    for ir in (cir, oir):
+        xv = ir.array_u32(x)
+        lanes = ir.arange(U32, n)
+        m_x, m_l = ir.gt(xv, ir.const_u32(1 << 31)), ir.eq(ir.bop(Bop.And, lanes, ir.const_u32(3)), ir.const_u32(1))
+        sh = ir.shr(xv, ir.const_u32(3))
+        if ir is cir:
+            cuda_backend.stats_reset()
+        outs = [ir.prefix_sum(sh, True), ir.prefix_sum(sh, False), ir.prefix_sum(ir.mul(lanes, ir.const_u32(5)), True)]
+        (i1, c1), (v1, c2) = ir.compress(m_x), ir.compress_values(xv, m_x)
+        (i2, c3), (v2, c4) = ir.compress(m_l), ir.compress_values(ir.mul(lanes, ir.const_u32(7)), m_l)
+        if ir is cir:
+            assert cuda_backend.stats()["trace_launches"] == 7
+        res.append(([read(ir, o) for o in outs + [i1, v1, i2, v2]], (c1, c2, c3, c4)))
+    assert res[0][1] == res[1][1]
+    for a, b in zip(res[0][0], res[1][0]):
+        assert same_bits(a, b, False), n
+    assert np.array_equal(res[0][0][4], x[x > (1 << 31)])
+
+
 def test_fused_compress_values_of_a_bound_array(cuda_backend, cir, oir):
     """compress_values(x, x > t): the C28 "fused-mask" shape — x is streamed once (4 B/lane), the mask never exists."""
     n = 5 * 24576 + 1234

@@ -2,6 +2,7 @@
 // Reference counterparts: Kernel::record_kernel_size (internal.rs:710-729), record_ops
 // (:874-1117), compile (:1148-1305).  See program.h.
 #include "program.h"
+#include <string>
 
 #include <cstdio>
 #include <cstdlib>
@@ -69,13 +70,21 @@ int unroll_factor() {
 
 }  // namespace
 
-int scan_fused_threads() {
-  static int t = 0;
-  if (!t) {
-    const char* s = getenv("VKJIT_SCAN_T");
-    t = (s && atoi(s) == 512) ? 512 : 1024;
+ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes) {
+  static int classic = -1;
+  if (classic < 0) { const char* s = getenv("VKJIT_SCAN_IMPL"); classic = (s && std::string(s) == "classic") ? 1 : 0; }
+  ScanFusedGeom g;
+  // Lagging pays when the tile time is dominated by the look-back latency; ALU-heavy bodies (a hash per lane) are
+  // issue bound and do better with the larger tiles of the immediate look-back (measured: profiles/r01_fused_scan.md).
+  if (streams <= 1 && nodes <= kScanFusedLagMaxNodes && !classic) {
+    g.lag = true;
+    if (mode == SCAN_COMPRESS_VALUE) { g.vpt = 3; g.slots = 4; }        // the tile's slot stays resident until its output
+    else if (mode == SCAN_COMPRESS_INDEX) { g.vpt = 4; g.slots = 3; }
+    else { g.vpt = 4; g.slots = 2; g.staging = true; }
+  } else {
+    g.vpt = streams <= 1 ? 6 : (int)(6 / streams);
   }
-  return t;
+  return g;
 }
 
 size_t stream_count(const Program& p) {
@@ -264,8 +273,9 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   if (kn + 4 + p.roots.size() > key.size()) { key.resize(kn + 64 + p.roots.size()); kw = key.data(); }
   if (p.sadd_param < 0 || reduce >= 0 || scan >= 0) p.privatize = false;
   kw[1] = (vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16) | (p.privatize ? 1u << 24 : 0u) |
-          ((uint32_t)(scan + 1) << 25) | (scan >= 0 && scan_fused_threads() == 512 ? 1u << 28 : 0u);
+          ((uint32_t)(scan + 1) << 25);  // bit 28 (lagged fused scan) is patched once the streams are known
   for (size_t k = 0; k < p.params.size(); ++k) kw[binding_pos[k]] |= (uint32_t)p.params[k].use << 16;
+  if (scan >= 0 && scan_fused_geom(stream_count(p), scan, p.order.size()).lag) kw[1] |= 1u << 28;
   kw[kn++] = 0xFFFFFFFFu;
   for (uint32_t r : p.roots) kw[kn++] = r;
   if (kn & 1) kw[kn++] = 0u;
@@ -595,9 +605,10 @@ std::string scan_shell(const Program& p, const std::vector<uint32_t>& streams, c
   if (ns > (size_t)kScanFusedMaxStreams) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: too many streamed arrays");
   if (nroots != (p.scan == SCAN_COMPRESS_VALUE ? 2u : 1u)) fail(VKJIT_ERR_INVALID, "fused scan: wrong number of roots");
   std::string s;
+  const ScanFusedGeom geom = scan_fused_geom(ns, p.scan, p.order.size());
   s += "#define VK_SCAN_MODE " + std::to_string(p.scan) + "\n#define VK_NS " + std::to_string(ns) + "\n#define VK_VPT " +
-       std::to_string(scan_fused_vpt(ns)) + "\n#define VK_T " + std::to_string(scan_fused_threads()) +
-       "\n#define VK_LOOK_WIDE " + std::to_string(scan_fused_threads() == 512 ? 10 : 5) + "  // one look-back round spans a generation of CTAs\n";
+       std::to_string(geom.vpt) + "\n#define VK_LAG " + std::to_string(geom.lag ? 1 : 0) + "\n#define VK_SLOTS " +
+       std::to_string(geom.slots) + "\n";
   s += "struct VkPtrs {\n  const u32* s[" + std::to_string(std::max<size_t>(ns, 1)) + "];  // streamed arrays (staged by TMA)\n";
   for (uint32_t k : ptrs) {
     if (p.params[k].use & USE_SCATTER) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: the trace has side effects");

@@ -24,11 +24,19 @@ enum ParamUse : uint8_t { USE_STREAM = 1, USE_GATHER = 2, USE_SCATTER = 4 };
 // fused trace -> scan kernels (scan_fused.cuh); numbering = prims.cu's ScanMode
 enum ScanKind : int { SCAN_EXCLUSIVE = 0, SCAN_INCLUSIVE = 1, SCAN_COMPRESS_INDEX = 2, SCAN_COMPRESS_VALUE = 3 };
 constexpr int kScanFusedMaxStreams = 6;
-// tile geometry of a fused scan: T threads x vpt 128-bit vectors; the TMA ring holds 2 stages x streams x tile
-int scan_fused_threads();  // threads per CTA: 1024 (one CTA per SM); $VKJIT_SCAN_T=512 runs two 512-thread CTAs per SM (measured slower, profiles/r01_fused_scan.md)
-inline int scan_fused_vpt(size_t streams) { return streams <= 1 ? 6 : (int)(6 / streams); }
-inline size_t scan_fused_tile(size_t streams) { return (size_t)scan_fused_threads() * 4 * scan_fused_vpt(streams); }
-inline size_t scan_fused_smem(size_t streams) { return 2 * streams * scan_fused_tile(streams) * 4; }
+constexpr size_t kScanFusedLagMaxNodes = 8;
+// Geometry of a fused scan kernel (scan_fused.cuh): 1024 threads x vpt 128-bit vectors per tile.  Traces that stream at
+// most one array get the lagged variant (look-back one tile behind, see prims.cu: scan_kernel_lag) unless
+// $VKJIT_SCAN_IMPL=classic; the others keep the immediate look-back with a 2-slot ring per streamed array.
+struct ScanFusedGeom {
+  bool lag = false;
+  int vpt = 6;      // 128-bit vectors per thread and tile
+  int slots = 2;    // ring slots per streamed array
+  bool staging = false;  // lagged prefix sums: one output staging tile for the TMA bulk store
+  size_t tile() const { return (size_t)1024 * 4 * vpt; }
+  size_t smem(size_t streams) const { return (streams * slots + (staging ? 1 : 0)) * tile() * 4; }
+};
+ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes);
 
 struct Param {
   VarId var;     // the Binding var whose array is passed

@@ -371,12 +371,12 @@ CachedKernel* Backend::compile(const Ir& ir, const Program& p) {
     cku(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kPrivatizeMaxBytesNoGather), "cuFuncSetAttribute");
   int ctas_per_sm = 0;
   if (p.scan >= 0) {
-    const size_t smem = scan_fused_smem(stream_count(p));
+    const size_t smem = scan_fused_geom(stream_count(p), p.scan, p.order.size()).smem(stream_count(p));
     if (smem) cku(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem), "cuFuncSetAttribute");
-    // the look-back needs every CTA of the grid co-resident: the grid is sized from the real occupancy
-    cku(g_drv.OccupancyMaxActiveBlocks(&ctas_per_sm, fn, scan_fused_threads(), smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    // the look-back needs every CTA of the grid co-resident: check the real occupancy (one 1024-thread CTA per SM)
+    cku(g_drv.OccupancyMaxActiveBlocks(&ctas_per_sm, fn, 1024, smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
     if (ctas_per_sm < 1) fail(VKJIT_ERR_CUDA, "fused scan kernel does not fit on an SM");
-    ctas_per_sm = std::min(ctas_per_sm, 1024 / scan_fused_threads());
+    ctas_per_sm = 1;
   }
   auto* k = new CachedKernel();
   k->ctas_per_sm = (uint32_t)ctas_per_sm;
@@ -599,7 +599,8 @@ bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t
   CachedKernel* k = be.lookup(prog);
   if (!k) k = be.compile(ir, prog);
 
-  const size_t tile = scan_fused_tile(ns);
+  const ScanFusedGeom geom = scan_fused_geom(ns, mode, prog.order.size());
+  const size_t tile = geom.tile();
   const size_t tiles = (prog.n + tile - 1) / tile;
   be.ensure_scan_scratch(prog.n, tile);
   ck(cudaMemsetAsync(be.scratch.tile_state, 0, (size_t)prims::kStatusWordsPerTile * (1 + tiles) * 8, (cudaStream_t)be.stream), "scan status memset");
@@ -614,8 +615,7 @@ bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t
            initp = (uint64_t)(uintptr_t)initial, ibasep = (uint64_t)(uintptr_t)index_base;
   void* argv[] = {&n32, &base32, block.data(), &outp, &cntp, &tiles32, &statep, &initp, &ibasep};
   try {
-    be.launch(k, (uint32_t)std::min<size_t>(tiles, (size_t)be.sm_count * k->ctas_per_sm), (uint32_t)scan_fused_threads(), argv,
-              (uint32_t)scan_fused_smem(ns));
+    be.launch(k, (uint32_t)std::min<size_t>(tiles, (size_t)be.sm_count * k->ctas_per_sm), 1024, argv, (uint32_t)geom.smem(ns));
   } catch (...) { release_array(o); throw; }
   *out = o;
   return true;

@@ -10,16 +10,18 @@
 // The generated prelude provides:
 //   VK_SCAN_MODE  0 exclusive sum, 1 inclusive sum, 2 compress -> lane indices, 3 compress -> values (root 1)
 //   VK_NS         number of streamed arrays (0..6);  VK_VPT  128-bit vectors per thread and tile (6 / max(NS,1))
-//   VK_T          threads per CTA (1024 / VK_T CTAs per SM: with two CTAs one computes while the other looks back)
+//   VK_LAG        1: lagged look-back (traces streaming at most one array; see prims.cu: scan_kernel_lag), VK_SLOTS ring slots
 //   struct VkPtrs { const u32* s[max(NS,1)]; <gather/scatter pointers> };
 //   vk_eval(P, gi, li, in[max(NS,1)], o0, o1)   root words of global lane gi / local lane li
 template <bool B> struct VkBool { static constexpr bool value = B; };
 
-extern "C" __global__ void __launch_bounds__(VK_T, 1024 / VK_T)
+#if !VK_LAG
+
+extern "C" __global__ void __launch_bounds__(1024, 1)
 vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, u32* __restrict__ count_out,
             const u32 num_tiles, uint64_t* __restrict__ state, const u32* __restrict__ initial_ptr,
             const u32* __restrict__ index_base_ptr) {  // mode 2: global index of lane 0 (sharded masks)
-  constexpr int T = VK_T, VPT = VK_VPT, TILE = T * 4 * VPT, NS = VK_NS, NSA = NS > 0 ? NS : 1, S = 2;
+  constexpr int T = 1024, VPT = VK_VPT, TILE = T * 4 * VPT, NS = VK_NS, NSA = NS > 0 ? NS : 1, S = 2;
   constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = (NTOT + 31) / 32;
   constexpr u32 TILE_BYTES = TILE * 4;
   constexpr bool COMPRESS = VK_SCAN_MODE >= 2, VALUES = VK_SCAN_MODE == 3;
@@ -230,3 +232,257 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
     // thread passed the first barrier of iteration k+1, i.e. after it finished reading it here.
   }
 }
+
+#else  // VK_LAG
+
+// ---- lagged variant: tile k's aggregate is published right after its evaluation + local scan; its prefix is resolved and
+// its output written one iteration later (status window prefetched with cp.async before the next tile is evaluated).
+// VK_NS <= 1.  Modes 0/1: row-relative results wait in registers and leave through a staging tile + one TMA bulk store.
+// Mode 2: 4 selection bits + an 8-bit row offset per vector wait in two registers.  Mode 3: additionally the tile's ring slot
+// stays resident one more iteration (VK_SLOTS = 4) and the selected lanes' values are re-evaluated from it.
+extern "C" __global__ void __launch_bounds__(1024, 1)
+vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, u32* __restrict__ count_out,
+            const u32 num_tiles, uint64_t* __restrict__ state, const u32* __restrict__ initial_ptr,
+            const u32* __restrict__ index_base_ptr) {
+  constexpr int T = 1024, VPT = VK_VPT, TILE = T * 4 * VPT, NS = VK_NS, NSA = 1, S = VK_SLOTS;
+  constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = NTOT / 32;
+  constexpr u32 TILE_BYTES = TILE * 4;
+  constexpr bool COMPRESS = VK_SCAN_MODE >= 2, VALUES = VK_SCAN_MODE == 3;
+  static_assert(NS <= 1 && NTOT % 32 == 0 && (!COMPRESS || VPT <= 4), "lagged fused scan geometry");
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  u32* ring = reinterpret_cast<u32*>(ring_raw);          // NS * S input slots
+  u32* stage_out = ring + (size_t)NS * S * TILE;         // modes 0/1: output staging tile
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ u32 s_tot[3][NTOT];
+  __shared__ u32 s_tile_excl;
+  __shared__ __align__(16) uint64_t s_window[kLookWide * 32 * 2];
+
+  uint64_t* status = state + kStatusStride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 first = blockIdx.x, stride = gridDim.x;
+  const u32 my_tiles = first < num_tiles ? (num_tiles - first + stride - 1) / stride : 0;
+  const bool ragged = (n % TILE) != 0;
+  const u32 index_base = (VK_SCAN_MODE == 2 && index_base_ptr) ? __ldcg(index_base_ptr) : 0u;
+
+  auto fill = [&](u32 k) {  // one thread: the streamed array's tile k into slot k % S
+    if (NS == 0 || k >= my_tiles) return;
+    const u32 t = first + k * stride;
+    if (ragged && t == num_tiles - 1) return;
+    mbar_expect_tx(&full[k % S], TILE_BYTES);
+    tma_load_1d(ring + (size_t)(k % S) * TILE, P.s[0] + (size_t)t * TILE, TILE_BYTES, &full[k % S]);
+  };
+  // words of vector j of tile (slot, e) of the streamed array
+  auto fetch = [&](int j, bool staged, u32 slot, size_t e, u32 (&w)[4]) {
+    if (NS == 0) return;
+    if (staged) {
+      const uint4 a = reinterpret_cast<const uint4*>(ring + (size_t)slot * TILE)[j * T + threadIdx.x];
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) w[c] = e + c < n ? P.s[0][e + c] : 0u;
+    }
+  };
+
+  if (NS > 0) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (u32 k = 0; k < (u32)S; ++k) fill(k);
+  }
+
+  uint4 xp[VPT];                // modes 0/1, previous tile: results relative to the start of the vector's warp row
+  u32 flags_p = 0u, pre_p = 0u; // modes 2/3, previous tile: selection bits / 8-bit exclusive row offsets
+  u32 agg_prev = 0u;            // warp 0: aggregate of the previous tile
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) xp[j] = make_uint4(0u, 0u, 0u, 0u);
+
+  for (u32 k = 0; k <= my_tiles; ++k) {
+    const bool have_cur = k < my_tiles, have_prev = k > 0;
+    const u32 tile = first + k * stride;
+    uint4 xc[VPT];
+    u32 flags_c = 0u, pre_c = 0u;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) xc[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
+    if (have_cur) {  // ---- evaluate tile k and scan it locally
+      const size_t tile_base = (size_t)tile * TILE;
+      const bool whole = !(ragged && tile == num_tiles - 1);
+      if (whole && NS > 0) mbar_wait(&full[k % S], (k / S) & 1);
+      u32 own = 0u;
+      auto evaluate = [&](auto whole_c) {
+        constexpr bool W = decltype(whole_c)::value;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+          const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+          u32 w[4];
+          fetch(j, W, k % S, e, w);
+          u32 r[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            u32 o0 = 0u, o1 = 0u;
+            if (W || e + c < n) {
+              u32 in[NSA];
+              in[0] = NS > 0 ? w[c] : 0u;
+              vk_eval(P, base + (u32)(e + c), (u32)(e + c), in, o0, o1);
+            }
+            r[c] = o0;
+          }
+          if (COMPRESS) {
+            const u32 f = r[0] | (r[1] << 1) | (r[2] << 2) | (r[3] << 3);  // the word of a Bool root is exactly 0 or 1
+            flags_c |= f << (4 * j);
+            own |= (u32)__popc(f) << (8 * j);
+          } else {
+            xc[j].x = r[0]; xc[j].y = r[1]; xc[j].z = r[2]; xc[j].w = r[3];
+          }
+        }
+      };
+      if (whole) evaluate(VkBool<true>{}); else evaluate(VkBool<false>{});
+      u32* tot = s_tot[k % 3];
+      if (COMPRESS) {
+        u32 pk = own;  // four 8-bit per-slot counts, one packed warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 t = __shfl_up_sync(0xFFFFFFFFu, pk, o);
+          if (lane >= o) pk += t;
+        }
+        pre_c = pk - own;
+        if (lane == 31) {
+#pragma unroll
+          for (int j = 0; j < VPT; ++j) tot[j * WARPS + warp] = (pk >> (8 * j)) & 0xFFu;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+          const uint4 a = xc[j];
+          const u32 vs = a.x + a.y + a.z + a.w;
+          u32 s = vs;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+            if (lane >= o) s += t;
+          }
+          if (lane == 31) tot[j * WARPS + warp] = s;
+          const u32 p = s - vs;
+          if (VK_SCAN_MODE == 0) { xc[j].x = p; xc[j].y = p + a.x; xc[j].z = xc[j].y + a.y; xc[j].w = xc[j].z + a.z; }
+          else { xc[j].x = p + a.x; xc[j].y = xc[j].x + a.y; xc[j].z = xc[j].y + a.z; xc[j].w = xc[j].z + a.w; }
+        }
+      }
+    }
+    __syncthreads();  // s_tot[k % 3] complete; (modes 0-2) every thread has consumed ring slot k % S
+    if (!VALUES && have_cur && threadIdx.x == 32) fill(k + S);
+    if (warp == 0) {
+      u32 agg_cur = 0u;
+      if (have_cur) {
+        u32* tot = s_tot[k % 3];
+        u32 t[PER_LANE], run = 0;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) { t[i] = tot[lane * PER_LANE + i]; run += t[i]; }
+        u32 s = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 u = __shfl_up_sync(0xFFFFFFFFu, s, o);
+          if (lane >= o) s += u;
+        }
+        u32 off = s - run;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) { tot[lane * PER_LANE + i] = off; off += t[i]; }
+        agg_cur = __shfl_sync(0xFFFFFFFFu, s, 31);
+        const u32 initial = (tile == 0 && initial_ptr) ? __ldcg(initial_ptr) : 0u;
+        if (lane == 0) {
+          if (tile == 0) status_store(status, ((uint64_t)ST_INCLUSIVE << 32) | (initial + agg_cur));
+          else status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_AGGREGATE << 32) | agg_cur);
+        }
+      }
+      if (have_prev) {
+        const u32 tprev = tile - stride;
+        uint64_t window[kLookWide];
+        load_window(s_window, window);
+        const u32 excl = resolve_prefix(status, tprev, agg_prev, (tprev == 0 && initial_ptr) ? __ldcg(initial_ptr) : 0u, window);
+        if (lane == 0) {
+          s_tile_excl = excl;
+          if (COMPRESS && tprev == num_tiles - 1) *count_out = excl + agg_prev;
+        }
+      }
+      agg_prev = agg_cur;
+    }
+    if (!COMPRESS && threadIdx.x == 0) tma_store_wait_read();  // the previous bulk store has read the staging tile
+    __syncthreads();
+    if (have_prev) {  // ---- output of tile k-1
+      const u32 kp = k - 1, tprev = tile - stride;
+      const size_t tile_base = (size_t)tprev * TILE;
+      const bool whole = !(ragged && tprev == num_tiles - 1);
+      const u32 tile_excl = s_tile_excl;
+      const u32* tot = s_tot[kp % 3];
+      if (!COMPRESS) {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+          const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+          const u32 p = tile_excl + tot[j * WARPS + warp];
+          uint4 r;
+          r.x = xp[j].x + p; r.y = xp[j].y + p; r.z = xp[j].z + p; r.w = xp[j].w + p;
+          if (whole) reinterpret_cast<uint4*>(stage_out)[j * T + threadIdx.x] = r;
+          else if (e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
+          else {
+            if (e + 0 < n) out[e + 0] = r.x;
+            if (e + 1 < n) out[e + 1] = r.y;
+            if (e + 2 < n) out[e + 2] = r.z;
+          }
+        }
+        if (whole) {
+          fence_proxy_async();
+          __syncthreads();
+          if (threadIdx.x == 0) tma_store_1d(out + tile_base, stage_out, TILE_BYTES);
+        }
+      } else {
+        auto emit = [&](auto whole_c) {
+          constexpr bool W = decltype(whole_c)::value;
+#pragma unroll
+          for (int j = 0; j < VPT; ++j) {
+            const u32 f = (flags_p >> (4 * j)) & 0xFu;
+            if (f) {
+              const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
+              u32 v[4];
+              if (VALUES) {  // all four lanes of the vector are re-evaluated (no per-lane branches)
+                u32 w[4];
+                fetch(j, W, kp % S, e, w);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  v[c] = 0u;
+                  if (W || e + c < n) {
+                    u32 in[NSA];
+                    in[0] = NS > 0 ? w[c] : 0u;
+                    u32 o0;
+                    vk_eval(P, base + (u32)(e + c), (u32)(e + c), in, o0, v[c]);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c] = index_base + (u32)(e + c);
+              }
+              u32* q = out + (tile_excl + tot[j * WARPS + warp] + ((pre_p >> (8 * j)) & 0xFFu));
+              const u32 s1 = f & 1u, s2 = s1 + ((f >> 1) & 1u), s3 = s2 + ((f >> 2) & 1u);
+              if (f & 1u) q[0] = v[0];
+              if (f & 2u) q[s1] = v[1];
+              if (f & 4u) q[s2] = v[2];
+              if (f & 8u) q[s3] = v[3];
+            }
+          }
+        };
+        if (whole) emit(VkBool<true>{}); else emit(VkBool<false>{});
+        if (VALUES && NS > 0) {  // the slot of tile k-1 was kept for the re-evaluation: free now
+          __syncthreads();
+          if (threadIdx.x == 32) fill(kp + S);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) xp[j] = xc[j];
+    flags_p = flags_c; pre_p = pre_c;
+  }
+  if (!COMPRESS && threadIdx.x == 0) tma_store_wait_all();  // shared memory must outlive the last bulk store
+}
+#endif
