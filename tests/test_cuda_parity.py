@@ -7,6 +7,7 @@ f64 libm value rounded to f32 (CUDA's documented bound for expf; logf/sinf/cosf:
 Everything outside the reference's own golden tests is "parity unpinned": the oracle is the spec.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -461,3 +462,40 @@ def test_scatter_add_privatised_in_shared_memory(cuda_backend, cir, oir, bins):
     assert same_bits(res[0][0], res[1][0], False)
     tol = 1e-6 * 22
     assert np.all(np.abs(res[0][1] - res[1][1]) <= tol * np.abs(res[1][1]) + 1e-30)
+
+
+def test_classic_scan_kernels_still_agree(tmp_path):
+    """`VKJIT_SCAN_IMPL=classic` selects the immediate-look-back kernels that the lagged ones replaced (kept for A/B
+    measurements, profiles/r01_scan_history.md).  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    script = tmp_path / "classic.py"
+    script.write_text('''
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+import vkjit_b200 as vk
+from vkjit_b200.ir import Ir, VarType as T
+vk.init(0)
+ir = Ir()
+for n in (5, 24577, 3 * 24576 + 11, (1 << 21) + 3):
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    m = rng.random(n) < 0.4
+    xv, mv = ir.array_u32(x), ir.array_bool(m)
+    ex = ir.as_slice(ir.prefix_sum(xv, True), T.U32)
+    ref = np.cumsum(x.astype(np.uint64)).astype(np.uint32)
+    assert ex[0] == 0 and np.array_equal(ex[1:], ref[:-1]), n
+    idx, c1 = ir.compress(mv)
+    val, c2 = ir.compress_values(xv, mv)
+    assert c1 == c2 == int(m.sum())
+    assert np.array_equal(ir.as_slice(idx, T.U32), np.nonzero(m)[0].astype(np.uint32))
+    assert np.array_equal(ir.as_slice(val, T.U32), x[m])
+    fm = ir.gt(xv, ir.const_u32(1 << 31))                      # fused, immediate look-back
+    fv, c3 = ir.compress_values(xv, fm)
+    assert c3 == int((x > (1 << 31)).sum()) and np.array_equal(ir.as_slice(fv, T.U32), x[x > (1 << 31)])
+print("classic ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, VKJIT_SCAN_IMPL="classic")
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "classic ok" in r.stdout, r.stdout + r.stderr
