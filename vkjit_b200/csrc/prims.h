@@ -34,7 +34,7 @@ struct Mailbox {
 constexpr int kReduceThreads = 512;
 constexpr int kReduceMaxCtas = 2048;
 constexpr int kScanThreads = 1024;
-constexpr int kScanMinTile = 12288;  // look-back tile (ScanGeom in prims.cu); sizes the status array
+constexpr int kScanMinTile = 12288;  // look-back tile (smallest tile of the kernels in scan.cu); sizes the status array
 
 // number of 8-byte words `tile_state` must hold for n lanes
 constexpr int kStatusWordsPerTile = 16;  // one 128-byte line of 64-bit words per tile (kStatusStride in scan_common.cuh)

@@ -21,12 +21,12 @@ struct Hash128 {
 
 enum ParamUse : uint8_t { USE_STREAM = 1, USE_GATHER = 2, USE_SCATTER = 4 };
 
-// fused trace -> scan kernels (scan_fused.cuh); numbering = prims.cu's ScanMode
+// fused trace -> scan kernels (scan_fused.cuh); numbering = scan.cu's ScanMode
 enum ScanKind : int { SCAN_EXCLUSIVE = 0, SCAN_INCLUSIVE = 1, SCAN_COMPRESS_INDEX = 2, SCAN_COMPRESS_VALUE = 3 };
 constexpr int kScanFusedMaxStreams = 6;
 constexpr size_t kScanFusedLagMaxNodes = 8;
 // Geometry of a fused scan kernel (scan_fused.cuh): 1024 threads x vpt 128-bit vectors per tile.  Traces that stream at
-// most one array get the lagged variant (look-back one tile behind, see prims.cu: scan_kernel_lag) unless
+// most one array get the lagged variant (look-back one tile behind, see scan.cu: scan_kernel_lag) unless
 // $VKJIT_SCAN_IMPL=classic; the others keep the immediate look-back with a 2-slot ring per streamed array.
 struct ScanFusedGeom {
   bool lag = false;

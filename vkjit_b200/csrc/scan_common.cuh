@@ -1,4 +1,4 @@
-// scan_common.cuh — device helpers shared by the hand-written scan/compress kernel (prims.cu, compiled by
+// scan_common.cuh — device helpers shared by the hand-written scan/compress kernels (scan.cu; prims.cu uses the ld/st helpers — compiled by
 // nvcc) and the generated fused trace -> scan kernels (scan_fused.cuh, compiled by NVRTC at run time; the
 // Makefile embeds both texts into the library as strings).  No #includes: only built-in types and intrinsics.
 // uint32_t / uint64_t are typedef'd by the NVRTC prelude.
@@ -17,6 +17,11 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
 
 enum : uint32_t { ST_INVALID = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2 };
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 

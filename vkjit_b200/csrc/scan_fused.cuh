@@ -1,6 +1,6 @@
 // scan_fused.cuh — fused trace -> prefix-sum / compress kernel (NVRTC only; the Makefile embeds this text).
 //
-// Same single-pass decoupled look-back scan as prims.cu's scan_kernel (persistent CTAs walking tiles
+// Same single-pass decoupled look-back scan as scan.cu's scan_kernel (persistent CTAs walking tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ...; all CTAs co-resident), but the scanned words are not loaded: they are
 // computed lane by lane by the generated trace body.  The arrays the trace STREAMS (one word per lane) are
 // staged through the same 2-stage TMA ring, one ring slot per streamed array, so a mask such as `x > t`
@@ -10,7 +10,7 @@
 // The generated prelude provides:
 //   VK_SCAN_MODE  0 exclusive sum, 1 inclusive sum, 2 compress -> lane indices, 3 compress -> values (root 1)
 //   VK_NS         number of streamed arrays (0..6);  VK_VPT  128-bit vectors per thread and tile (6 / max(NS,1))
-//   VK_LAG        1: lagged look-back (traces streaming at most one array; see prims.cu: scan_kernel_lag), VK_SLOTS ring slots
+//   VK_LAG        1: lagged look-back (traces streaming at most one array; see scan.cu: scan_kernel_lag), VK_SLOTS ring slots
 //   struct VkPtrs { const u32* s[max(NS,1)]; <gather/scatter pointers> };
 //   vk_eval(P, gi, li, in[max(NS,1)], o0, o1)   root words of global lane gi / local lane li
 template <bool B> struct VkBool { static constexpr bool value = B; };
