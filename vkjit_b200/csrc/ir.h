@@ -7,6 +7,7 @@
 // var instead of in a side HashMap, and every var carries scratch fields so that the per-eval
 // trace walk needs no hashing or allocation (cached-launch budget: < 10 us).
 #pragma once
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -34,27 +35,37 @@ struct Array {
   void* release_ctx = nullptr;
 };
 
-struct Var {  // internal.rs:105-114
+// One cache line per var: the per-eval trace walk (program.cpp: build_program, the cache-hit critical path) touches
+// every reachable var once, and everything it reads sits in the first 40 bytes.
+struct alignas(64) Var {  // internal.rs:105-114
   Op op = OP_FREE;
   uint8_t sharded = 0;   // lanes are this rank's slice of a global 1-D range
   uint16_t kind = 0;     // Bop / Uop kind
   TypeId ty = VKJIT_TY_VOID;
-  uint32_t aux = 0;      // Const bit pattern | GetAttr/SetAttr index
-  uint32_t ref_count = 0;
-  uint64_t num = 0;      // Arange(n)
-  uint64_t base = 0;     // first global lane of a sharded Arange
+  uint32_t aux = 0;      // Const bit pattern | GetAttr/SetAttr index | (during a walk) a Binding's param index
   uint32_t ndeps = 0;
-  bool has_se = false;
-  VarId dep_inline[3] = {0, 0, 0};
-  std::vector<VarId> dep_ext;  // StructInit with more than 3 members
-  VarId side_effect = 0;       // Scatter target (side_effects[0], internal.rs:396)
-  Array* array = nullptr;      // replaces Ir.arrays: HashMap<VarId, Array> (internal.rs:130)
+  union {                // a var with dependencies is never an Arange or a Binding, so the two views share storage
+    struct {
+      VarId dep_inline[3];
+      VarId side_effect;   // Scatter target (side_effects[0], internal.rs:396)
+    };
+    struct {
+      uint64_t num;        // Arange(n)
+      uint64_t base;       // first global lane of a sharded Arange / of a ragged sharded Binding
+    };
+  };
   // scratch for trace walks
   uint32_t stamp = 0;
   uint32_t local = 0;
+  uint32_t ref_count = 0;
+  bool has_se = false;
+  std::unique_ptr<VarId[]> dep_ext;  // StructInit with more than 3 members
+  Array* array = nullptr;            // replaces Ir.arrays: HashMap<VarId, Array> (internal.rs:130)
 
-  const VarId* deps() const { return ndeps <= 3 ? dep_inline : dep_ext.data(); }
+  Var() : num(0), base(0) {}
+  const VarId* deps() const { return ndeps <= 3 ? dep_inline : dep_ext.get(); }
 };
+static_assert(sizeof(Var) == 64, "Var is meant to be exactly one cache line");
 
 class Ir {
  public:

@@ -285,7 +285,7 @@ bool nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string
 // $VKJIT_CACHE_DIR/<hash>.cubin = {magic, nvrtc version, key_len, key words, cubin}.  The canonical key
 // is stored and compared, so a hash collision or a stale file can never load the wrong kernel.
 namespace {
-constexpr uint32_t kDiskMagic = 0x564B4331u;  // "VKC1"
+constexpr uint32_t kDiskMagic = 0x564B4332u;  // "VKC2" (key format: node word carries ndeps)
 
 std::string disk_path(const Hash128& h) {
   const char* dir = getenv("VKJIT_CACHE_DIR");
