@@ -48,7 +48,8 @@ def bench(vk, stream, flush_l2, log2n=26, rounds=5):
     t0 = time.perf_counter()
     y = build(vkjit, n, rounds)
     t_trace = time.perf_counter() - t0
-    nodes = vkjit.ir().count("Var {")
+    text = vkjit.ir()
+    nodes = text.count("Var {") - text.count("op: Free")
     t0 = time.perf_counter()
     vkjit.eval([y])
     vk.sync()

@@ -18,8 +18,15 @@ import threading
 import numpy as np
 
 from . import ir as _ir
-from ._capi import VkjitNoDeviceError
+from ._capi import VkjitError, VkjitNoDeviceError, VkjitSizeError, VkjitTypeError
 from .ir import Bop, Red, Uop, VarType
+
+try:
+    from . import _native
+except ImportError as e:  # pragma: no cover - build error
+    raise ImportError(
+        "vkjit_b200/_native*.so is missing — build it first (python -c 'import __graft_entry__ as g; g.build()'). "
+        "The Python front-end is a compiled module, as the reference's (pyo3); there is no pure-Python path.") from e
 
 _lock = threading.RLock()
 _IR = None
@@ -38,6 +45,7 @@ def _global_ir() -> _ir.Ir:
             except VkjitNoDeviceError:
                 pass
             _IR = _ir.Ir()
+            _native.bind(_IR, _IR._h.value)  # the native Var records into this Ir (and keeps it alive)
         return _IR
 
 
@@ -45,11 +53,11 @@ def _is_int(x):
     return isinstance(x, (int, np.integer)) and not isinstance(x, (bool, np.bool_))
 
 
-def _coerce(value) -> "Var":
-    """TryFrom<&PyAny> for Var (types.rs:47-82): Var, u32, i32, f32, bool, [u32], [i32], [f32]."""
+def _coerce_slow(value) -> "Var":
+    """The part of `TryFrom<&PyAny> for Var` (types.rs:47-82) that needs NumPy: NumPy scalars, arrays and
+    sequences ([u32], [i32], [f32] in that order).  Var / bool / int / float are handled natively
+    (csrc/pyfront.cpp: coerce)."""
     g = _global_ir()
-    if isinstance(value, Var):
-        return value._clone()
     if isinstance(value, (bool, np.bool_)):
         # pyo3 extracts a Python bool as u32 first (bool is an int): True -> UInt32(1)
         return Var._own(g.const_u32(int(value)))
@@ -85,62 +93,21 @@ def _coerce(value) -> "Var":
     raise TypeError("Not a valid argument!")
 
 
-class Var:
+_coerce = _native.coerce   # any accepted value -> a new owned Var (a Var argument is cloned)
+
+
+class Var(_native.VarBase):
     """`#[pyclass] pub struct Var(VarId)` (types.rs:84-85).  Owns exactly one reference count:
-    cloning bumps it (types.rs:87-92), dropping releases it (types.rs:94-98)."""
+    cloning bumps it (types.rs:87-92), dropping releases it (types.rs:94-98).
 
-    __slots__ = ("_id",)
+    The base type is native (csrc/pyfront.cpp): construction from a value (`#[new]`, types.rs:117-120), `id()`,
+    `ty()`, the arithmetic / bit / comparison operators (types.rs:124-139) with their reflected forms, the named
+    comparisons `lt gt eq leq geq neq`, `cast`, `bitcast`, and the ownership helpers `_own`, `_steal`, `_clone`,
+    `_id`.  This subclass adds what is not on the trace-building path."""
 
-    def __init__(self, arg):  # #[new] __new__(args) (types.rs:117-120)
-        self._id = _coerce(arg)._steal()
+    __slots__ = ()
 
-    @classmethod
-    def _own(cls, var_id: int) -> "Var":
-        v = object.__new__(cls)
-        v._id = var_id
-        return v
-
-    def _steal(self) -> int:
-        i, self._id = self._id, None
-        return i
-
-    def _clone(self) -> "Var":
-        _global_ir().inc_ref_count(self._id)
-        return Var._own(self._id)
-
-    def __del__(self):
-        if getattr(self, "_id", None) is not None and _IR is not None:
-            try:
-                _IR.dec_ref_count(self._id)
-            except Exception:
-                pass
-            self._id = None
-
-    # -- reference methods ------------------------------------------------------
-    def id(self) -> int:
-        return self._id
-
-    def ty(self) -> int:
-        return _global_ir().ty(self._id)
-
-    def tolist(self):
-        """types.rs:121-123 reads f32 only; here every dtype is readable (evaluates if needed)."""
-        return self.numpy().tolist()
-
-    def _bop(self, kind, rhs, swap=False) -> "Var":
-        r = _coerce(rhs)
-        a, b = (r._id, self._id) if swap else (self._id, r._id)
-        return Var._own(_global_ir().bop(kind, a, b))
-
-    def __add__(self, rhs): return self._bop(Bop.Add, rhs)        # types.rs:124-127
-    def __sub__(self, rhs): return self._bop(Bop.Sub, rhs)        # types.rs:128-131
-    def __mul__(self, rhs): return self._bop(Bop.Mul, rhs)        # types.rs:132-135
-    def __div__(self, rhs): return self._bop(Bop.Div, rhs)        # types.rs:136-139
-    __truediv__ = __div__
-    def __radd__(self, lhs): return self._bop(Bop.Add, lhs, True)
-    def __rsub__(self, lhs): return self._bop(Bop.Sub, lhs, True)
-    def __rmul__(self, lhs): return self._bop(Bop.Mul, lhs, True)
-    def __rtruediv__(self, lhs): return self._bop(Bop.Div, lhs, True)
+    def __div__(self, rhs): return self._bop(Bop.Div, rhs)        # types.rs:136-139 (Python-2 name kept)
 
     def __repr__(self):  # types.rs:140-147
         g = _global_ir()
@@ -155,38 +122,9 @@ class Var:
         return g.str(self._id)
 
     # -- additions (N2) ------------------------------------------------------------
-    def lt(self, r): return self._bop(Bop.Lt, r)
-    def gt(self, r): return self._bop(Bop.Gt, r)
-    def eq(self, r): return self._bop(Bop.Eq, r)
-    def leq(self, r): return self._bop(Bop.Leq, r)
-    def geq(self, r): return self._bop(Bop.Geq, r)
-    def neq(self, r): return self._bop(Bop.Neq, r)
-    __lt__, __gt__, __le__, __ge__ = lt, gt, leq, geq
-    def __and__(self, r): return self._bop(Bop.And, r)
-    def __or__(self, r): return self._bop(Bop.Or, r)
-    def __xor__(self, r): return self._bop(Bop.Xor, r)
-    def __lshift__(self, r): return self._bop(Bop.Shl, r)
-    def __rshift__(self, r): return self._bop(Bop.Shr, r)
-    def __rand__(self, l): return self._bop(Bop.And, l, True)
-    def __ror__(self, l): return self._bop(Bop.Or, l, True)
-    def __rxor__(self, l): return self._bop(Bop.Xor, l, True)
-    def __neg__(self): return Var._own(_global_ir().uop(Uop.Neg, self._id))
-    def __invert__(self): return Var._own(_global_ir().uop(Uop.Not, self._id))
-    def __abs__(self): return Var._own(_global_ir().uop(Uop.Abs, self._id))
-
-    def cast(self, ty: int) -> "Var":
-        g = _global_ir()
-        out = g.cast(self._id, ty)
-        if out == self._id:  # Ir::cast returns the same id without a new reference
-            g.inc_ref_count(out)
-        return Var._own(out)
-
-    def bitcast(self, ty: int) -> "Var":
-        g = _global_ir()
-        out = g.bitcast(self._id, ty)
-        if out == self._id:
-            g.inc_ref_count(out)
-        return Var._own(out)
+    def tolist(self):
+        """types.rs:121-123 reads f32 only; here every dtype is readable (evaluates if needed)."""
+        return self.numpy().tolist()
 
     def then_else(self, then, other) -> "Var":  # vkjit-rust types.rs:160-168
         return select(self, then, other)
@@ -272,7 +210,7 @@ class Var:
 # -- module functions (functions.rs:9-52) ---------------------------------------------------
 def eval(schedule):  # noqa: A001 - the reference's name
     """`eval(schedule: &PyList)` (functions.rs:9-23)"""
-    _global_ir().eval([v.id() for v in schedule])
+    _native.eval(schedule)
 
 
 def var(*args) -> Var:
@@ -295,7 +233,7 @@ def linspace(start, stop, num: int) -> Var:
 # -- the Rust front-end's free functions (vkjit-rust/src/functions.rs) -------------------------
 def schedule(vars_):
     """`schedule!(a, b, ...)` / schedule_internal (functions.rs:72-82): queue vars for the next eval."""
-    _global_ir().schedule([v.id() for v in vars_])
+    _native.schedule(vars_)
 
 
 def repr_ir() -> str:  # functions.rs:54-56
@@ -318,7 +256,7 @@ def ones(ty: int) -> Var:  # Ir::ones (internal.rs:265-282; not re-exported by t
 
 # -- additions -------------------------------------------------------------------------------
 def arange(ty: int, num: int) -> Var:  # vkjit-rust functions.rs:9-11
-    return Var._own(_global_ir().arange(ty, num))
+    return _native.arange(ty, num)
 
 
 def zeros(ty: int) -> Var:  # vkjit-rust functions.rs:5-7
@@ -326,8 +264,7 @@ def zeros(ty: int) -> Var:  # vkjit-rust functions.rs:5-7
 
 
 def select(condition, x, y) -> Var:  # vkjit-rust functions.rs:24-31
-    c, a, b = _coerce(condition), _coerce(x), _coerce(y)
-    return Var._own(_global_ir().select(c._id, a._id, b._id))
+    return _native.select(condition, x, y)
 
 
 def gather(src: Var, idx, condition=None) -> Var:  # vkjit-rust functions.rs:32-52
@@ -338,7 +275,7 @@ def gather(src: Var, idx, condition=None) -> Var:  # vkjit-rust functions.rs:32-
 
 def _u(kind):
     def f(x):
-        return Var._own(_global_ir().uop(kind, _coerce(x)._id))
+        return _native.uop(kind, x)
     return f
 
 
@@ -346,11 +283,11 @@ sqrt, exp, log, sin, cos = _u(Uop.Sqrt), _u(Uop.Exp), _u(Uop.Log), _u(Uop.Sin), 
 
 
 def minimum(a, b) -> Var:
-    return _coerce(a)._bop(Bop.Min, b)
+    return _native.bop(Bop.Min, a, b)
 
 
 def maximum(a, b) -> Var:
-    return _coerce(a)._bop(Bop.Max, b)
+    return _native.bop(Bop.Max, a, b)
 
 
 def compress(values: Var, mask: Var):
@@ -381,3 +318,6 @@ def from_dlpack(obj) -> Var:
 
 def sync():
     _ir.sync()
+
+
+_native.configure(Var, _coerce_slow, _global_ir, (VkjitError, VkjitTypeError, VkjitSizeError, VkjitNoDeviceError))
