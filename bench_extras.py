@@ -225,6 +225,18 @@ def run(ir, vk, stream, flush_l2, peak):
     st = vk.stats()
     out["LAUNCH_cached_trace"] = {"python_loop_us_per_iter": host_us, "vkjit_eval_us_median": sorted(evals)[len(evals) // 2] / 1e3,
                                   "cache_hits": st["cache_hits"], "cache_misses": st["cache_misses"], "n": 1024}
+    # the same loop through the `vkjit` Python module (native Var type, csrc/pyfront.cpp): what a front-end user pays
+    from vkjit_b200 import vkjit as vj
+    b1k = vj.arange(T.F32, 1024)
+    vj.eval([b1k * 0.5 + 0.5])
+    sync()
+    t0 = time.perf_counter()
+    for i in range(reps):
+        z = b1k * 0.5 + 0.5
+        vj.eval([z])
+    out["LAUNCH_cached_trace"]["vkjit_module_loop_us_per_iter"] = (time.perf_counter() - t0) / reps * 1e6
+    sync()
+    del z, b1k
     try:
         import monte_carlo
         out["M26_monte_carlo"] = monte_carlo.bench(vk, stream, flush_l2)
