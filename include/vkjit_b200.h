@@ -306,7 +306,8 @@ vkjit_status vkjit_cache_clear(void);
 vkjit_status vkjit_debug_codegen(vkjit_ir* ir, const vkjit_var* ids, size_t n, int32_t compile,
                                  char* buf, size_t cap, size_t* out_len, size_t* out_cubin_bytes);
 /* Debug: average host time of the per-eval trace walk + hash (the cache-hit critical path) and the
- * number of trace nodes; needs no device. */
+ * number of trace nodes; needs no device.  reps = 0: time ONE walk, in whatever cache state the construction
+ * of the trace left its vars (what a fresh eval pays). */
 vkjit_status vkjit_debug_walk_ns(vkjit_ir* ir, const vkjit_var* ids, size_t n, uint32_t reps, uint64_t* out_ns, uint32_t* out_nodes);
 /* Same for the fused trace -> reduce kernel of vkjit_reduce(red, id). */
 vkjit_status vkjit_debug_codegen_reduce(vkjit_ir* ir, vkjit_var id, int32_t red, int32_t compile,

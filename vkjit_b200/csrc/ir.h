@@ -115,8 +115,9 @@ class Ir {
   void do_schedule(const VarId* ids, size_t n);
   void clear_schedule();
 
-  // after a kernel ran: roots become Bindings owning `outs` (internal.rs:492-521)
-  void commit_roots(const std::vector<VarId>& roots, const std::vector<Array*>& outs);
+  // after a kernel ran: roots become Bindings owning `outs` (internal.rs:492-521); `order` = post-order of the
+  // trace that ran (Program::order), which is what makes the release a single reverse sweep
+  void commit_roots(const std::vector<VarId>& roots, const std::vector<Array*>& outs, const std::vector<VarId>& order);
 
   // repr
   std::string repr() const;                // {:#?} of the Ir

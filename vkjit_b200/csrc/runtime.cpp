@@ -417,7 +417,16 @@ namespace {
 
 // Compile-or-lookup + launch of one group of roots that share a kernel size.  commit: the roots become
 // Bindings (Ir::eval); otherwise the fresh arrays are handed to the caller and the vars stay as they are.
+// $VKJIT_EVAL_TRACE=1: per-phase host time of every eval on stderr (walk / lookup / alloc / launch / commit)
+bool eval_trace_on() {
+  static const bool on = getenv("VKJIT_EVAL_TRACE") != nullptr;
+  return on;
+}
+
 void run_group(Ir& ir, Backend& be, const std::vector<VarId>& roots, bool commit, std::vector<Array*>* result) {
+  const bool trace = eval_trace_on();
+  uint64_t ts[6] = {0, 0, 0, 0, 0, 0};
+  if (trace) ts[0] = now_ns();
   static thread_local Program prog;
   static thread_local std::vector<Array*> outs;
   static thread_local std::vector<void*> argv;
@@ -443,12 +452,15 @@ void run_group(Ir& ir, Backend& be, const std::vector<VarId>& roots, bool commit
     }
     if (!aligned || kbins) build_program(ir, roots, aligned, prog, -1, kbins != 0);  // variant rebuild
 
+    if (trace) ts[1] = now_ns();
     CachedKernel* k = be.lookup(prog);
     if (!k) k = be.compile(ir, prog);
+    if (trace) ts[2] = now_ns();
 
     // one fresh n*stride output per scheduled var (internal.rs:1192-1205), from the stream-ordered pool
     for (size_t r = 0; r < prog.roots.size(); ++r) outs.push_back(be.new_array((size_t)prog.n * 4));
 
+    if (trace) ts[3] = now_ns();
     uint32_t n32 = (uint32_t)prog.n, base32 = (uint32_t)prog.base;
     ptrs.clear(); argv.clear();
     for (const Param& pr : prog.params) ptrs.push_back((uint64_t)(uintptr_t)ir.vars[pr.var].array->ptr);
@@ -471,9 +483,16 @@ void run_group(Ir& ir, Backend& be, const std::vector<VarId>& roots, bool commit
       be.launch(k, (uint32_t)grid, 256, argv.data());
     }
 
-    if (commit) ir.commit_roots(roots, outs);
+    if (trace) ts[4] = now_ns();
+    if (commit) ir.commit_roots(roots, outs, prog.order);
     else *result = outs;
     outs.clear();
+    if (trace) {
+      ts[5] = now_ns();
+      fprintf(stderr, "[vkjit eval] nodes=%zu walk=%llu lookup=%llu alloc=%llu launch=%llu commit=%llu ns\n", prog.order.size(),
+              (unsigned long long)(ts[1] - ts[0]), (unsigned long long)(ts[2] - ts[1]), (unsigned long long)(ts[3] - ts[2]),
+              (unsigned long long)(ts[4] - ts[3]), (unsigned long long)(ts[5] - ts[4]));
+    }
   } catch (...) {
     for (Array* a : outs) release_array(a);
     outs.clear();
