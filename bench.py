@@ -9,10 +9,14 @@ One step = sum(x) and max(x) over the whole 2^28-lane array = 2 GiB of algorithm
   python bench.py --impl reference ...                   the CPU restatement of the reference
                                                          (oracle port) on the box's host cores
 
-Timing: CUDA events on the backend stream around each reduction (L2 evicted by a 256 MiB streaming
-read between every timed interval, outside the events), max over ranks; clocks sampled with
-nvidia-smi during the timed region.  `e2e` goes through the same API with pinned HOST buffers:
-H2D of the step's input, both reductions, D2H of the two results, wall clock.
+Timing: the K steps run back to back between ONE pair of CUDA events on the backend stream (barrier +
+synchronize on both sides), max over ranks.  The steps rotate over four independent input arrays
+(4 GiB/N per GPU, far beyond the 126 MB L2; profiles/rotation_ab.py shows that 1, 2, 4 or 8 arrays give
+the same time, i.e. nothing is served from L2), so no eviction kernel sits inside the timed region.
+The per-reduction figure with an L2 eviction and an event pair around every single reduction (the
+method of the first bench lines of this round) is kept as `isolated`.  Clocks are sampled through NVML
+during the timed region.  `e2e` goes through the same API with pinned HOST buffers: H2D of the step's
+input, both reductions, D2H of the two results, wall clock.
 """
 import argparse
 import ctypes as C
@@ -223,16 +227,21 @@ def ours(args):
         with torch.cuda.stream(stream):
             flush_buf.sum()
 
-    # ---- input: 2^28 f32 uniform[0,1), this rank's contiguous shard, generated on the device
+    # ---- input: four independent arrays of 2^28 f32 uniform[0,1) (this rank's contiguous shard of each), generated
+    # on the device.  Reduction j of the run reads array j mod 4, so an array is re-read only after 3 GiB/N of other
+    # reads went through the 126 MB L2.
+    ROT = 4
     lanes = ir.arange_sharded(T.U32, N_TOTAL)
-    x = uniform_trace(ir, lanes, SEED_R28)
-    ir.eval([x])
+    xs = [uniform_trace(ir, lanes, SEED_R28 + i) for i in range(ROT)]
+    for v in xs:
+        ir.eval([v])
+    x = xs[0]
     n_local = ir.size(x)
     vk.sync()
 
-    # N>1: the L2-eviction kernels take a different time on every GPU; without re-alignment that spread
-    # (~10 us) would be charged to the collective of the next timed reduction (each rank waits for the slowest).
-    # An UNTIMED tiny all-reduce after each eviction lines the streams up again (measured: 11.5 us, 8 GPUs).
+    # N>1, isolated timing only: the L2-eviction kernels take a different time on every GPU; without re-alignment
+    # that spread (~10 us) would be charged to the collective of the next timed reduction (each rank waits for the
+    # slowest).  An UNTIMED tiny all-reduce after each eviction lines the streams up again.
     tiny = ir.cast(ir.arange_sharded(T.U32, 4096 * world), T.F32) if world > 1 else None
     if tiny is not None:
         ir.eval([tiny])
@@ -241,21 +250,19 @@ def ours(args):
         if tiny is not None:
             ir.dec_ref_count(ir.reduce(Red.Sum, tiny))
 
-    def step(timed):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
-        flush_l2(); align()
-        if timed: ev[0].record(stream)
-        s = ir.reduce(Red.Sum, x)
-        if timed: ev[1].record(stream)
-        flush_l2(); align()
-        if timed: ev[2].record(stream)
-        m = ir.reduce(Red.Max, x)
-        if timed: ev[3].record(stream)
-        return s, m, ev
+    pending = []
 
-    for _ in range(max(3, args.warmup)):
-        s, m, _ = step(False)
-        ir.dec_ref_count(s); ir.dec_ref_count(m)
+    def step(k):
+        """One step: sum over one array, max over the next (2 GiB of algorithmic reads in total over all GPUs)."""
+        s = ir.reduce(Red.Sum, xs[(2 * k) % ROT])
+        m = ir.reduce(Red.Max, xs[(2 * k + 1) % ROT])
+        pending.append((s, m))
+        if len(pending) > 2:          # results are dropped two steps later: no host round trip in the loop
+            for v in pending.pop(0):
+                ir.dec_ref_count(v)
+
+    for k in range(max(3, args.warmup)):
+        step(k)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.prepare()   # NVML init outside the timed region
@@ -263,34 +270,61 @@ def ours(args):
     if rank == 0:
         sampler.start()
     vk.stats_reset()
-    evs, results = [], None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        s, m, ev = step(True)
-        evs.append(ev)
-        if results is not None:
-            ir.dec_ref_count(results[0]); ir.dec_ref_count(results[1])
-        results = (s, m)
+    ev0.record(stream)
+    for k in range(args.steps):
+        step(k)
+    ev1.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     st = vk.stats()
     clocks = sampler.stop() if rank == 0 else None
-    ms_sum = [e[0].elapsed_time(e[1]) for e in evs]
-    ms_max = [e[2].elapsed_time(e[3]) for e in evs]
-    step_ms = torch.tensor([sum(ms_sum) / len(evs) + sum(ms_max) / len(evs)], device=dev, dtype=torch.float64)
+    step_ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev, dtype=torch.float64)
     if world > 1:
         td.all_reduce(step_ms, op=td.ReduceOp.MAX)
     ms_per_step = float(step_ms.item())
     total_bytes = 2 * N_TOTAL * 4
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
-    gpu_sum = float(ir.as_slice(results[0], T.F32)[0])
-    gpu_max = float(ir.as_slice(results[1], T.F32)[0])
-    launches = st["trace_launches"] + st["prim_launches"]  # includes the untimed alignment reductions at N>1
+    launches = st["trace_launches"] + st["prim_launches"]
+    for pr in pending:
+        for v in pr:
+            ir.dec_ref_count(v)
+    pending.clear()
+    # the result that is checked against the CPU side: sum and max of array 0 (untimed)
+    s0, m0 = ir.reduce(Red.Sum, x), ir.reduce(Red.Max, x)
+    gpu_sum = float(ir.as_slice(s0, T.F32)[0])
+    gpu_max = float(ir.as_slice(m0, T.F32)[0])
+    ir.dec_ref_count(s0); ir.dec_ref_count(m0)
+
+    # ---- the same step timed reduction by reduction: L2 evicted (and, at N>1, ranks re-aligned) before each one,
+    # one event pair per reduction.  Carries ~2.6 us of event overhead and the full launch latency per reduction.
+    iso_steps = min(args.steps, 10)
+    iso = []
+    for i in range(2 + iso_steps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        flush_l2(); align()
+        evs[0].record(stream)
+        s = ir.reduce(Red.Sum, xs[(2 * i) % ROT])
+        evs[1].record(stream)
+        flush_l2(); align()
+        evs[2].record(stream)
+        m = ir.reduce(Red.Max, xs[(2 * i + 1) % ROT])
+        evs[3].record(stream)
+        vk.sync()
+        ir.dec_ref_count(s); ir.dec_ref_count(m)
+        if i >= 2:
+            iso.append((evs[0].elapsed_time(evs[1]), evs[2].elapsed_time(evs[3])))
+    iso_ms = torch.tensor([sum(a + b for a, b in iso) / len(iso)], device=dev, dtype=torch.float64)
+    if world > 1:
+        td.all_reduce(iso_ms, op=td.ReduceOp.MAX)
+    isolated = {"ms_per_step": float(iso_ms.item()), "value": total_bytes / (float(iso_ms.item()) * 1e-3) / 1e9, "unit": UNIT, "steps": iso_steps,
+                "how": "L2 evicted by a 256 MiB read before every reduction, one CUDA-event pair per reduction (outside the headline)"}
 
     # ---- roofline of the dominant kernel (reduce_kernel<float,SUM>): kernel-only, no collective
     peak, peak_src = peaks()
     if world == 1:
-        kern_ms = sum(ms_sum) / len(ms_sum)
+        kern_ms = ms_per_step / 2          # two launches per step, timed live over the timed region
     else:
         xl = uniform_trace(ir, ir.arange(T.U32, n_local), SEED_R28)
         ir.eval([xl])
@@ -313,7 +347,7 @@ def ours(args):
             traffic, traffic_src = ent["dram_read_bytes"] + ent["dram_write_bytes"], "profiles/r01_traffic.json (ncu --set full, round 1)"
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "reduce_kernel<float, SUM, 512>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "reduce_kernel<float, SUM, 512>" + (" / <float, MAX, 512> (mean over the timed region's launches)" if world == 1 else " (kernel only, isolated)"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": kern_ms,
                 "algorithmic_bytes_per_launch": n_local * 4}
 
@@ -395,10 +429,9 @@ def ours(args):
             "data": "synthetic",
             "config": {"workload": "R28: sum+max over 2^28 f32 (BASELINE.json configs[1])", "n": N_TOTAL, "n_per_gpu": n_local,
                        "parallelism": (f"contiguous 1-D shards x{world}, per-GPU partial + " + ("all-reduce fused into the reduce kernel's last CTA over NVLink peer memory (P2P mailbox)" if args.collective == "p2p" else "NCCL all-reduce")) if world > 1 else "single GPU",
-                       "l2": "evicted before every timed reduction by streaming a 256 MiB read through L2 (clean lines: no write-back inside the timed kernel); inputs are 1 GiB/N per GPU, larger than the 126 MB L2",
-                       "timing": "CUDA events on the backend stream per reduction, mean over steps, max over ranks" +
-                                 ("; ranks re-aligned by an untimed tiny all-reduce after each L2 eviction (outside the events)" if world > 1 else "")},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                       "l2": "inputs larger than L2: the steps rotate over 4 independent arrays (4 GiB/N per GPU against 126 MB of L2), each re-read only after 3 GiB/N of other reads; no flush inside the timed region",
+                       "timing": "K steps back to back between one pair of CUDA events on the backend stream, barrier + synchronize on both sides, max over ranks"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "isolated": isolated,
             "wall_s_timed_region": t_wall, "result": {"sum": gpu_sum, "max": gpu_max},
             "hbm_frac_whole_job": value / (peak * world),
         }
