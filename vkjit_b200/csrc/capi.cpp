@@ -223,6 +223,7 @@ vkjit_status vkjit_var_to_dlpack(vkjit_ir* h, vkjit_var id, void** out) {
     auto* c = new ExportCtx{h, id, (int64_t)(v.array->bytes / 4)};
     auto* t = new DLManagedTensor();
     t->dl_tensor.data = v.array->ptr;
+    v.array->exposed = true;  // the consumer may write it on its own streams from now on
     t->dl_tensor.device = {kDLCUDA, Backend::initialized() ? Backend::get().device : 0};
     t->dl_tensor.ndim = 1;
     t->dl_tensor.dtype = dt;
@@ -302,6 +303,7 @@ vkjit_status vkjit_var_size(vkjit_ir* h, vkjit_var id, size_t* out) {
 vkjit_status vkjit_var_device_ptr(vkjit_ir* h, vkjit_var id, uint64_t* out) {
   return with_ir(h, [&](Ir& ir) {
     if (!ir.is_buffer(id)) fail(VKJIT_ERR_INVALID, "var is not a buffer");
+    ir.var(id).array->exposed = true;  // whoever holds the pointer may write the memory (CUDA Array Interface consumers)
     *out = (uint64_t)(uintptr_t)ir.var(id).array->ptr;
   });
 }
@@ -336,6 +338,12 @@ static uint32_t reduce_identity(int red, TypeId ty) {
   return red == VKJIT_RED_MIN ? 0xFFFFFFFFu : 0u;
 }
 
+// $VKJIT_REDUCE_OVERLAP=0 switches the programmatic-dependent-launch overlap of consecutive reductions off (A/B)
+static bool reduce_overlap_enabled() {
+  static const bool on = [] { const char* e = getenv("VKJIT_REDUCE_OVERLAP"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out) {
   return with_ir(h, [&](Ir& ir) {
     const TypeId ty = ir.var(id).ty;
@@ -358,6 +366,7 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
     prims::Mailbox mb;
     if (p2p) mb = dist::next_mailbox();
     Array* o = nullptr;
+    bool counted = false;
     try {
       if (empty) {
         o = be.new_array(4);
@@ -371,10 +380,27 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
       } else {
         o = be.new_array(4);
         const Var& v = ir.var(id);
+        // Back-to-back reductions overlap (prims.cu: reduce_kernel, programmatic dependent launch): the streaming
+        // phase of this one may run under the tail of the previous one if (a) that previous kernel is a reduction
+        // of this chain — nothing else went onto the stream since, (b) the input is none of the results the chain
+        // still has in flight, and (c) nobody outside this backend can be writing the input (foreign views,
+        // exported pointers).  Otherwise the kernel waits first: plain stream order.
+        Backend::ReduceChain& ch = be.reduce_chain;
+        std::lock_guard<std::mutex> chain_lock(ch.mu);
+        const void* in = v.array->ptr;
+        bool overlap = reduce_overlap_enabled() && ch.sig == Backend::counters().stream_ops && v.array->owned && !v.array->exposed &&
+                       ch.outs.size() < 32;
+        for (size_t i = 0; overlap && i < ch.outs.size(); ++i) overlap = ch.outs[i] != in;
+        if (!overlap) ch.outs.clear();
         // p2p: the last CTA of the reduction exchanges the per-GPU partial over NVLink peer memory
-        prims::reduce(red, ty, v.array->ptr, v.array->bytes / 4, o->ptr, be.scratch, be.sm_count, be.stream, p2p ? &mb : nullptr);
+        prims::reduce(red, ty, in, v.array->bytes / 4, o->ptr, be.scratch, be.sm_count, be.stream, p2p ? &mb : nullptr,
+                      overlap ? 0u : prims::kReduceWaitFirst);
+        Backend::counters().note_prim();
+        ch.outs.push_back(o->ptr);
+        ch.sig = (combine && !p2p) ? ~0ull : (uint64_t)Backend::counters().stream_ops;  // an NCCL kernel follows: chain ends
+        counted = true;
       }
-      Backend::counters().prim_launches += 1;
+      if (!counted) Backend::counters().note_prim();
       if (combine && !p2p) dist::allreduce(o->ptr, ty, red, 1);  // NCCL: per-GPU partial -> replicated result
     } catch (...) { release_array(o); throw; }
     *out = ir.binding(ty, o, false);
@@ -395,7 +421,7 @@ void rank_exscan(Backend& be, const uint32_t* mine, uint32_t* out, bool total, u
     prims::prefix_of_rank_u32(vec, rank, out, be.stream);
     if (total) prims::prefix_of_rank_u32(vec, world, out + 1, be.stream);
   }
-  Backend::counters().prim_launches += 1;
+  Backend::counters().note_prim();
 }
 
 // Operand of an eager primitive as a 16-byte aligned device array: the var's own array, or — for an unevaluated
@@ -455,7 +481,7 @@ vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkji
         else { total = eval_reduce(ir, id, VKJIT_RED_SUM); tot = (const uint32_t*)total->ptr; }
         rank_exscan(be, tot, w + 1, false, w + 2);
         initial = w + 1;
-        Backend::counters().prim_launches += 1;
+        Backend::counters().note_prim();
       }
       bool done = false;
       if (!empty && !direct) {  // ONE generated kernel evaluates the trace and scans it: the addends never reach memory
@@ -469,7 +495,7 @@ vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkji
         o = be.new_array(in.n * 4);
         prims::prefix_sum(in.ptr, (uint32_t*)o->ptr, in.n, exclusive != 0, be.scratch, be.sm_count, be.stream, initial);
       }
-      Backend::counters().prim_launches += 1;
+      Backend::counters().note_prim();
     } catch (...) {
       if (tmp) be.free_async(tmp, tmp_bytes);
       release_array(total); release_array(o);
@@ -545,7 +571,7 @@ static void do_compress(Ir& ir, bool with_values, VarId values, VarId mask, vkji
       o = be.new_array(n * 4);  // worst case; logical size is trimmed to the count below
       if (n) prims::compress(m.ptr, with_values ? v.ptr : nullptr, (uint32_t*)o->ptr, w, n, be.scratch, be.sm_count, be.stream, index_base);
     }
-    if (n) Backend::counters().prim_launches += 1;
+    if (n) Backend::counters().note_prim();
     else if (sharded) prims::fill_u32(w, 0u, 1, be.stream);
     if (sharded) rank_exscan(be, w, w + 1, true, w + 4);
     // the size of the result is data dependent: one small readback

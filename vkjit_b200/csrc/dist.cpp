@@ -137,6 +137,7 @@ prims::Mailbox next_mailbox() {
   mb.seq = ++g_seq;
   if (g_seq == 0xFFFFFFFFu) g_seq = 0;
   Backend::counters().collectives += 1;
+  Backend::counters().stream_ops += 1;
   return mb;
 }
 
@@ -161,6 +162,7 @@ void allreduce(void* buf, uint32_t ty, int red, size_t count) {
   ncclRedOp_t op = red == VKJIT_RED_SUM ? ncclSum : red == VKJIT_RED_MIN ? ncclMin : ncclMax;
   ckn(g_nccl.AllReduce(buf, buf, count, dt, op, g_comm, (cudaStream_t)Backend::get().stream), "ncclAllReduce");
   Backend::counters().collectives += 1;
+  Backend::counters().stream_ops += 1;
 }
 
 void shard_range(size_t n, int rank, int world, size_t& lo, size_t& hi) {

@@ -31,6 +31,7 @@ struct Array {
   size_t bytes = 0;     // logical size (Array::size)
   size_t capacity = 0;  // allocation size (compress over-allocates)
   bool owned = true;    // false: view of foreign device memory (vkjit_array_wrap_device), never freed here
+  bool exposed = false; // the device pointer was handed out (device_ptr / DLPack / CUDA Array Interface): others may write it
   void (*release)(void*) = nullptr;  // view with an owner (DLPack import): called once, after the Ir lock is dropped
   void* release_ctx = nullptr;
 };

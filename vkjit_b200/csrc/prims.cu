@@ -169,13 +169,24 @@ __global__ void p2p_allreduce_kernel(uint32_t* out, Mailbox mb) {
 // horizontal reduction
 // ---------------------------------------------------------------------------------------
 // Algorithmic traffic: 4 B/lane read, 4 B written in total.
+//
+// Programmatic dependent launch (PDL): the kernel is launched with programmatic stream serialization, so its CTAs may
+// start while the PREVIOUS kernel on the stream is still in its tail.  A reduction has a long streaming phase that
+// only reads its input and a short tail that touches state shared between launches (partials, ticket, result,
+// mailbox).  Each CTA therefore (1) streams, (2) signals `launch_dependents` — once every CTA has, the next
+// reduction's CTAs take over the SM slots this grid frees — and (3) executes `griddepcontrol.wait` (completion and
+// memory flush of the previous kernel) before its tail.  The last-CTA fold and, on several GPUs, the NVLink exchange
+// of reduction k thus run underneath the streaming phase of reduction k+1, while the tails stay strictly ordered.
+// flags bit 0 (kReduceWaitFirst): the input may have been written by a kernel that is still running (the host cannot
+// prove otherwise, see capi.cpp: vkjit_reduce) — wait before the first load, i.e. plain stream order.
 template <typename T, int RED, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
 reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ partials, unsigned int* __restrict__ ticket,
-              uint32_t* __restrict__ out, const Mailbox mb) {
+              uint32_t* __restrict__ out, const Mailbox mb, const uint32_t flags) {
   using O = RedOp<T, RED>;
   __shared__ T smem[THREADS / 32];
   __shared__ bool is_last;
+  if (flags & kReduceWaitFirst) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const size_t tid = (size_t)blockIdx.x * THREADS + threadIdx.x;
   const size_t nthreads = (size_t)gridDim.x * THREADS;
@@ -206,8 +217,10 @@ reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ 
   }
   for (size_t i = (n4 << 2) + tid; i < n; i += nthreads) a0 = O::apply(a0, from_bits<T>(in[i]));
 
+  asm volatile("griddepcontrol.launch_dependents;");  // this CTA's input reads are done
   T acc = O::apply(O::apply(a0, a1), O::apply(a2, a3));
   acc = block_reduce<T, RED, THREADS>(acc, smem);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous kernel on the stream has completed (no-op if it already had)
 
   // publish the CTA partial; the last CTA to arrive folds all partials in a fixed order.  One acquire-release
   // atomic on the ticket orders the partial store before it and the partial loads of the last CTA after it
@@ -234,26 +247,37 @@ reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ 
 }
 
 template <typename T, int RED>
-static void launch_reduce(const void* in, size_t n, void* out, const Scratch& sc, int sm_count, cudaStream_t s, const Mailbox& mb) {
+static void launch_reduce(const void* in, size_t n, void* out, const Scratch& sc, int sm_count, cudaStream_t s, const Mailbox& mb,
+                          uint32_t flags) {
   const size_t n4 = n >> 2;
   size_t ctas = (std::max<size_t>(n4, 1) + kReduceThreads - 1) / kReduceThreads;
   const size_t cap = (size_t)sm_count * (2048 / kReduceThreads);  // one full wave: 4 CTAs of 512 threads per SM
   if (ctas > cap) ctas = cap;
   if (ctas > (size_t)kReduceMaxCtas) ctas = kReduceMaxCtas;
-  reduce_kernel<T, RED, kReduceThreads><<<(unsigned)ctas, kReduceThreads, 0, s>>>(
-      (const uint32_t*)in, n, (uint32_t*)sc.partials, sc.ticket, (uint32_t*)out, mb);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(kReduceThreads);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, reduce_kernel<T, RED, kReduceThreads>, (const uint32_t*)in, n, (uint32_t*)sc.partials,
+                                           sc.ticket, (uint32_t*)out, mb, flags);
+  if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(e));
 }
 
 void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream,
-            const Mailbox* mailbox) {
+            const Mailbox* mailbox, uint32_t flags) {
   cudaStream_t s = (cudaStream_t)stream;
   Mailbox mb;
   if (mailbox) mb = *mailbox;
 #define VK_DISPATCH(T)                                                                          \
   switch (red) {                                                                                \
-    case VKJIT_RED_SUM: launch_reduce<T, VKJIT_RED_SUM>(in, n, out, sc, sm_count, s, mb); break;    \
-    case VKJIT_RED_MIN: launch_reduce<T, VKJIT_RED_MIN>(in, n, out, sc, sm_count, s, mb); break;    \
-    case VKJIT_RED_MAX: launch_reduce<T, VKJIT_RED_MAX>(in, n, out, sc, sm_count, s, mb); break;    \
+    case VKJIT_RED_SUM: launch_reduce<T, VKJIT_RED_SUM>(in, n, out, sc, sm_count, s, mb, flags); break;    \
+    case VKJIT_RED_MIN: launch_reduce<T, VKJIT_RED_MIN>(in, n, out, sc, sm_count, s, mb, flags); break;    \
+    case VKJIT_RED_MAX: launch_reduce<T, VKJIT_RED_MAX>(in, n, out, sc, sm_count, s, mb, flags); break;    \
     default: fail(VKJIT_ERR_INVALID, "unknown reduction");                                      \
   }
   switch (ty) {

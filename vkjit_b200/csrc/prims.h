@@ -45,8 +45,12 @@ size_t scan_state_words(size_t n, size_t tile = kScanMinTile);
 // per-CTA partials in a fixed order (deterministic for a given n and grid).
 // `mailbox` (optional, multi-GPU): the last CTA also performs the all-reduce — it publishes the per-GPU
 // partial into every peer's mailbox over NVLink and folds all ranks' partials in rank order.
+// `flags`: kReduceWaitFirst = plain stream order (the default); 0 = the streaming phase may overlap the tail of the
+// kernel launched right before on the stream (programmatic dependent launch) — only when the caller can prove that
+// `in` is not written by a kernel that may still be running (see capi.cpp: vkjit_reduce).
+constexpr uint32_t kReduceWaitFirst = 1u;
 void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream,
-            const Mailbox* mailbox = nullptr);
+            const Mailbox* mailbox = nullptr, uint32_t flags = kReduceWaitFirst);
 // Stand-alone exchange: out[0] = combine over ranks of out[0] (used when a rank's shard is empty).
 void p2p_allreduce(int red, uint32_t ty, void* out, const Mailbox& mailbox, void* stream);
 

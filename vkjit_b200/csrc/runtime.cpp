@@ -220,16 +220,19 @@ void Backend::h2d(void* dst, const void* src, size_t bytes) {
   // synchronously into mapped memory, vulkan/mod.rs:56-73)
   ck(cudaStreamSynchronize((cudaStream_t)stream), "H2D sync");
   g_counters.bytes_h2d += bytes;
+  g_counters.stream_ops += 1;
 }
 
 void Backend::d2h(void* dst, const void* src, size_t bytes) {
   if (bytes) ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H copy");
   ck(cudaStreamSynchronize((cudaStream_t)stream), "D2H sync");
   g_counters.bytes_d2h += bytes;
+  g_counters.stream_ops += 1;
 }
 
 void Backend::d2d(void* dst, const void* src, size_t bytes) {
   if (bytes) ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "D2D copy");
+  g_counters.stream_ops += 1;
 }
 
 void Backend::sync() { ck(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
@@ -410,6 +413,7 @@ void Backend::clear_cache() {
 void Backend::launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args, uint32_t smem_bytes) {
   cku(g_drv.LaunchKernel((CUfunction)k->function, grid, 1, 1, block, 1, 1, smem_bytes, (CUstream)stream, args, nullptr), "cuLaunchKernel");
   g_counters.trace_launches += 1;
+  g_counters.stream_ops += 1;
 }
 
 // ---- Ir::eval (internal.rs:482-525) ---------------------------------------------------------

@@ -41,6 +41,8 @@ struct Counters {
   std::atomic<uint64_t> cache_hits{0}, cache_misses{0}, trace_launches{0}, prim_launches{0};
   std::atomic<uint64_t> last_compile_ns{0}, last_eval_ns{0}, bytes_h2d{0}, bytes_d2h{0}, pool_bytes_live{0}, collectives{0};
   std::atomic<uint64_t> disk_hits{0};
+  std::atomic<uint64_t> stream_ops{0};  // every launch / copy / collective this backend puts on its stream (never reset)
+  void note_prim() { prim_launches += 1; stream_ops += 1; }
 };
 
 // NVRTC front door; usable without a device (the cubin is produced offline for sm_100a).
@@ -76,6 +78,16 @@ class Backend {
   CachedKernel* compile(const Ir& ir, const Program& p);
   void launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args, uint32_t smem_bytes = 0);
   void clear_cache();
+
+  // Reductions launched back to back overlap through programmatic dependent launch (prims.cu: reduce_kernel).  A
+  // reduction may skip the wait in front of its streaming phase only if nothing else was put on the stream by this
+  // backend since the previous overlapping reduction (`sig` = Counters::stream_ops right after it) and its input is
+  // none of the results the chain still has in flight (`outs`).
+  struct ReduceChain {
+    std::mutex mu;
+    uint64_t sig = ~0ull;
+    std::vector<const void*> outs;
+  } reduce_chain;
 
  private:
   std::mutex cache_mu_;
