@@ -196,6 +196,56 @@ def test_reduce_f32(cir, oir, n):
         assert abs(float(cs[0]) - float(os_[0])) <= tol, (n, cs, os_)
 
 
+def test_back_to_back_reductions_keep_stream_order(cuda_backend, cir):
+    """Consecutive reductions overlap through programmatic dependent launch (prims.cu: reduce_kernel).  Whatever a
+    reduction reads must be complete when it reads it: results of reductions still in flight, arrays rewritten by a
+    trace kernel in between, and memory someone else may write (exported pointers) all fall back to stream order."""
+    import torch
+    rng = np.random.default_rng(7)
+    n = (1 << 22) + 3
+    data = [rng.integers(0, 1 << 20, n).astype(np.uint32) for _ in range(4)]
+    xs = [cir.array_u32(d) for d in data]
+    sums = [int(d.astype(np.uint64).sum() % (1 << 32)) for d in data]
+    maxs = [int(d.max()) for d in data]
+    outs = []
+    for j in range(120):                          # a long chain, no host synchronisation inside
+        k = j % 4
+        s = cir.reduce(Red.Sum, xs[k])
+        m = cir.reduce(Red.Max, xs[k])
+        ss = cir.reduce(Red.Sum, s)               # input = the result of the reduction launched right before the last
+        mm = cir.reduce(Red.Max, cir.reduce(Red.Min, m))   # ... and of the one launched right before
+        outs.append((k, s, m, ss, mm))
+    for k, s, m, ss, mm in outs:
+        assert int(read(cir, s)[0]) == sums[k] and int(read(cir, m)[0]) == maxs[k]
+        assert int(read(cir, ss)[0]) == sums[k] and int(read(cir, mm)[0]) == maxs[k]
+    # an array rewritten by a trace kernel between two reductions of it
+    y = cir.array_u32(np.zeros(n, np.uint32))
+    idx = cir.arange(U32, n)
+    for j in range(20):
+        r0 = cir.reduce(Red.Sum, xs[0])
+        sc = cir.scatter(cir.add(idx, cir.const_u32(j)), y, idx)    # y[i] = i + j
+        cir.eval([sc])
+        r1 = cir.reduce(Red.Sum, y)
+        want = (n * (n - 1) // 2 + j * n) % (1 << 32)
+        assert int(read(cir, r1)[0]) == want and int(read(cir, r0)[0]) == sums[0]
+    # exported memory: torch writes it on the backend stream between two reductions
+    z = cir.array_u32(np.ones(n, np.uint32))
+    stream = torch.cuda.ExternalStream(cuda_backend.stream_ptr())
+    t = torch.as_tensor(_CudaView(cir.device_ptr(z), n), device="cuda")
+    for j in range(10):
+        cir.reduce(Red.Sum, xs[1])
+        with torch.cuda.stream(stream):
+            t.fill_(j + 2)
+        assert int(read(cir, cir.reduce(Red.Sum, z))[0]) == (j + 2) * n
+
+
+class _CudaView:
+    """A CUDA Array Interface view of n i32 words at a device pointer."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3, "strides": None}
+
+
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 1000, 100003, (1 << 20) + 1])
 def test_fused_trace_reduce(cuda_backend, cir, oir, n):
     """An unevaluated operand is reduced by ONE generated kernel (trace + reduction epilogue); it is
