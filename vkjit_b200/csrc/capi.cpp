@@ -388,8 +388,10 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
         Backend::ReduceChain& ch = be.reduce_chain;
         std::lock_guard<std::mutex> chain_lock(ch.mu);
         const void* in = v.array->ptr;
+        // (d) the input is large enough for the overlap to matter (>= 2^16 lanes): a reduction's own 1-element result
+        // is never an overlapped input
         bool overlap = reduce_overlap_enabled() && ch.sig == Backend::counters().stream_ops && v.array->owned && !v.array->exposed &&
-                       ch.outs.size() < 32;
+                       v.array->bytes >= (size_t(1) << 18) && ch.outs.size() < 32;
         for (size_t i = 0; overlap && i < ch.outs.size(); ++i) overlap = ch.outs[i] != in;
         if (!overlap) ch.outs.clear();
         // p2p: the last CTA of the reduction exchanges the per-GPU partial over NVLink peer memory
