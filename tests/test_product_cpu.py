@@ -241,6 +241,90 @@ def test_trace_hash_is_address_and_size_free():
     assert ir.debug_codegen([y])[0] != srcs[0]             # constants are part of the key
 
 
+def _key(ir, roots):
+    """The 128-bit trace hash, as printed in the first line of the generated source."""
+    src = ir.debug_codegen(list(roots))[0]
+    head = src.splitlines()[0]
+    assert "key " in head
+    return head.split("key ")[1].strip()
+
+
+def test_trace_key_separates_structures_and_ignores_var_ids():
+    """the key is the canonical structure.  Same DAG under different var ids / slot reuse / sizes gives
+    the same key; any structural difference (sharing, operand order, arity, constant bits, types, roots) a new one."""
+    def build(ir, variant, n=64, pad=0):
+        for _ in range(pad):                     # shifts every var id
+            ir.const_u32(7)
+        a, b = ir.arange(F32, n), ir.arange(F32, n)
+        c = ir.const_f32(1.5)
+        if variant == "a*b+c":
+            return [ir.add(ir.mul(a, b), c)]
+        if variant == "a*a+c":                   # same ops, different sharing of the leaves
+            return [ir.add(ir.mul(a, a), c)]
+        if variant == "c+a*b":                   # operand order
+            return [ir.add(c, ir.mul(a, b))]
+        if variant == "a*b-c":
+            return [ir.sub(ir.mul(a, b), c)]
+        if variant == "a*b+c'":                  # another constant
+            return [ir.add(ir.mul(a, b), ir.const_f32(1.5000001))]
+        if variant == "two roots":
+            m = ir.mul(a, b)
+            return [ir.add(m, c), m]
+        if variant == "two roots swapped":
+            m = ir.mul(a, b)
+            return [m, ir.add(m, c)]
+        if variant == "u32":
+            return [ir.add(ir.mul(ir.arange(U32, n), ir.arange(U32, n)), ir.const_u32(1))]
+        if variant == "select":
+            return [ir.select(ir.lt(a, b), a, c)]
+        raise AssertionError(variant)
+
+    variants = ["a*b+c", "a*a+c", "c+a*b", "a*b-c", "a*b+c'", "two roots", "two roots swapped", "u32", "select"]
+    keys = {}
+    for v in variants:
+        ir = Ir()
+        keys[v] = _key(ir, build(ir, v))
+        ir.close()
+    assert len(set(keys.values())) == len(variants), keys
+    for v in variants:                           # other ids, other size, recycled slots: same key
+        ir = Ir()
+        junk = [ir.const_f32(float(i)) for i in range(9)]
+        for j in junk[::2]:
+            ir.dec_ref_count(j)                  # holes in the var table that the next vars fill
+        assert _key(ir, build(ir, v, n=4099, pad=5)) == keys[v], v
+        ir.close()
+
+
+def test_trace_key_of_wide_struct_nodes():
+    """The node word of the key carries min(ndeps, 255); wider StructInit nodes spill the count into an extra word.
+    254-, 255-, 256- and 300-member structs all lower, compile and get distinct keys."""
+    keys = {}
+    for members in (3, 254, 255, 256, 300):
+        ir = Ir()
+        x = ir.arange(U32, 128)
+        st = ir.struct_init([x] + [ir.const_u32(i) for i in range(members - 1)])
+        root = ir.add(ir.getattr(st, 0), ir.getattr(st, members - 1))
+        src, cubin = ir.debug_codegen([root], compile=(members in (3, 256)))
+        if members in (3, 256):
+            assert cubin > 0
+        keys[members] = _key(ir, [root])
+        ir.close()
+    assert len(set(keys.values())) == len(keys)
+
+
+def test_trace_walk_debug_entry():
+    """vkjit_debug_walk_ns: reps = 0 times one walk, reps > 0 the mean of many; both report the node count."""
+    import ctypes as C
+    ir = Ir()
+    x = ir.add(ir.mul(ir.arange(F32, 100), ir.const_f32(2.0)), ir.const_f32(0.5))
+    ns, nodes = C.c_uint64(), C.c_uint32()
+    ids = (C.c_uint32 * 1)(x)
+    for reps in (0, 50):
+        ir.api.call("debug_walk_ns", ir._h, ids, 1, reps, C.byref(ns), C.byref(nodes))
+        assert nodes.value == 5 and 0 < ns.value < 10_000_000
+    ir.close()
+
+
 def test_size_rule_errors():
     from vkjit_b200 import VkjitSizeError
     ir = Ir()
