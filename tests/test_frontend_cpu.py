@@ -69,6 +69,10 @@ def test_operators_lower_to_the_same_nodes_as_the_ir_api():
     assert node(z) == "Var { op: Bop(Gt)"
     # autocast U32 + I32 -> I32 through an inserted Cast (internal.rs:146-166)
     assert (i + (-1)).ty() == T.I32 and (i + 1).ty() == T.U32 and (i + 1.0).ty() == T.F32
+    # NumPy scalars on the left defer to Var (no element-wise broadcasting over an opaque object)
+    w = np.float32(2.0) * x
+    assert type(w) is vkjit.Var and node(w) == "Var { op: Bop(Mul)" and w.ty() == T.F32
+    assert (np.uint32(3) + i).ty() == T.U32 and (np.int64(-3) + i).ty() == T.I32
     # `==` stays identity, so a Var is hashable and usable as a dict key
     assert (x == x) is True and (x == y) is False and len({x: 1, y: 2}) == 2
     assert node(vkjit.select(x < 1.0, x, 0.0)) == "Var { op: Select" and node(x.then_else(x, x)) == "Var { op: Select"

@@ -295,6 +295,29 @@ def test_trace_key_separates_structures_and_ignores_var_ids():
         ir.close()
 
 
+def test_trace_key_fuzz_same_program_same_key():
+    """64 seeded random programs (tests/trace_gen.py): replaying a program in another Ir — other var ids, recycled slots,
+    another n — reproduces its key and its kernel source exactly; different programs never share a key."""
+    from trace_gen import TraceBuilder
+    seen = {}
+    for seed in range(64):
+        ir = Ir()
+        roots = TraceBuilder(ir, seed, 64, n_ops=32, arrays=False).build()
+        src = ir.debug_codegen(roots)[0]
+        k = _key(ir, roots)
+        ir.close()
+        ir = Ir()
+        junk = [ir.const_u32(i) for i in range(seed % 7 + 2)]
+        for j in junk[1::2]:
+            ir.dec_ref_count(j)
+        roots2 = TraceBuilder(ir, seed, 3001, n_ops=32, arrays=False).build()
+        assert _key(ir, roots2) == k, seed
+        assert ir.debug_codegen(roots2)[0] == src, seed
+        ir.close()
+        assert k not in seen, (seed, seen.get(k))
+        seen[k] = seed
+
+
 def test_trace_key_of_wide_struct_nodes():
     """The node word of the key carries min(ndeps, 255); wider StructInit nodes spill the count into an extra word.
     254-, 255-, 256- and 300-member structs all lower, compile and get distinct keys."""

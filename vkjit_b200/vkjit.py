@@ -106,6 +106,7 @@ class Var(_native.VarBase):
     `_id`.  This subclass adds what is not on the trace-building path."""
 
     __slots__ = ()
+    __array_ufunc__ = None   # NumPy operands defer to Var's reflected operators instead of broadcasting over it
 
     def __div__(self, rhs): return self._bop(Bop.Div, rhs)        # types.rs:136-139 (Python-2 name kept)
 
