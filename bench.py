@@ -387,45 +387,48 @@ def ours(args):
     # the sharded fused elementwise trace E28 (2^28 lanes in total, no collective at all)
     mgpu_extras = None
     if world > 1 and not args.no_extras:
-        mgpu_extras = {}
-        big = uniform_trace(ir, ir.arange_sharded(T.U32, N_TOTAL * world), SEED_R28)
-        ir.eval([big])
-        ts = []
-        for i in range(3 + 10):
-            flush_l2()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            r1 = ir.reduce(Red.Sum, big); r2 = ir.reduce(Red.Max, big)
-            b.record(stream)
-            vk.sync()
-            ir.dec_ref_count(r1); ir.dec_ref_count(r2)
-            if i >= 3:
-                ts.append(a.elapsed_time(b))
-        t = torch.tensor([sum(ts) / len(ts)], device=dev, dtype=torch.float64)
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-        mgpu_extras["weak_R28_per_gpu"] = {"ms_per_step": float(t.item()), "GBps": 2 * N_TOTAL * world * 4 / (float(t.item()) * 1e-3) / 1e9,
-                                           "lanes_per_gpu": N_TOTAL, "note": "sum+max, 2^28 lanes per GPU (weak scaling), fused P2P all-reduce" if args.collective == "p2p" else "NCCL"}
-        ir.dec_ref_count(big)
-        xs = uniform_trace(ir, lanes, 0xB2000011)
-        ys = uniform_trace(ir, lanes, 0xB2000012)
-        ir.eval([xs, ys])
-        half = ir.const_f32(0.5)
-        ts = []
-        for i in range(3 + 10):
-            flush_l2()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            z = ir.add(ir.mul(xs, ys), half); ir.eval([z])
-            b.record(stream)
-            vk.sync()
-            ir.dec_ref_count(z)
-            if i >= 3:
-                ts.append(a.elapsed_time(b))
-        t = torch.tensor([sum(ts) / len(ts)], device=dev, dtype=torch.float64)
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-        mgpu_extras["E28_sharded_elementwise"] = {"ms": float(t.item()), "GBps": 12 * N_TOTAL / (float(t.item()) * 1e-3) / 1e9,
-                                                   "note": "z = x*y + c over 2^28 lanes in total, contiguous shards, no collective"}
-        ir.dec_ref_count(xs); ir.dec_ref_count(ys)
+        try:  # extras never take the headline down (an error here is the same on every rank)
+            mgpu_extras = {}
+            big = uniform_trace(ir, ir.arange_sharded(T.U32, N_TOTAL * world), SEED_R28)
+            ir.eval([big])
+            ts = []
+            for i in range(3 + 10):
+                flush_l2()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                r1 = ir.reduce(Red.Sum, big); r2 = ir.reduce(Red.Max, big)
+                b.record(stream)
+                vk.sync()
+                ir.dec_ref_count(r1); ir.dec_ref_count(r2)
+                if i >= 3:
+                    ts.append(a.elapsed_time(b))
+            t = torch.tensor([sum(ts) / len(ts)], device=dev, dtype=torch.float64)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            mgpu_extras["weak_R28_per_gpu"] = {"ms_per_step": float(t.item()), "GBps": 2 * N_TOTAL * world * 4 / (float(t.item()) * 1e-3) / 1e9,
+                                               "lanes_per_gpu": N_TOTAL, "note": "sum+max, 2^28 lanes per GPU (weak scaling), fused P2P all-reduce" if args.collective == "p2p" else "NCCL"}
+            ir.dec_ref_count(big)
+            ex_x = uniform_trace(ir, lanes, 0xB2000011)
+            ex_y = uniform_trace(ir, lanes, 0xB2000012)
+            ir.eval([ex_x, ex_y])
+            half = ir.const_f32(0.5)
+            ts = []
+            for i in range(3 + 10):
+                flush_l2()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                z = ir.add(ir.mul(ex_x, ex_y), half); ir.eval([z])
+                b.record(stream)
+                vk.sync()
+                ir.dec_ref_count(z)
+                if i >= 3:
+                    ts.append(a.elapsed_time(b))
+            t = torch.tensor([sum(ts) / len(ts)], device=dev, dtype=torch.float64)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            mgpu_extras["E28_sharded_elementwise"] = {"ms": float(t.item()), "GBps": 12 * N_TOTAL / (float(t.item()) * 1e-3) / 1e9,
+                                                       "note": "z = x*y + c over 2^28 lanes in total, contiguous shards, no collective"}
+            ir.dec_ref_count(ex_x); ir.dec_ref_count(ex_y)
+        except Exception as ex:
+            mgpu_extras = {"error": repr(ex)}
 
     line = None
     if rank == 0:
