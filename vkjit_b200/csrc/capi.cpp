@@ -629,7 +629,12 @@ vkjit_status vkjit_array_shard_local(vkjit_ir* h, vkjit_type ty, const void* dat
   });
 }
 vkjit_status vkjit_var_is_sharded(vkjit_ir* h, vkjit_var id, int32_t* out) { return with_ir(h, [&](Ir& ir) { *out = ir.var(id).sharded; }); }
-vkjit_status vkjit_var_shard_base(vkjit_ir* h, vkjit_var id, uint64_t* out) { return with_ir(h, [&](Ir& ir) { *out = ir.var(id).base; }); }
+vkjit_status vkjit_var_shard_base(vkjit_ir* h, vkjit_var id, uint64_t* out) {
+  return with_ir(h, [&](Ir& ir) {
+    const Var& v = ir.var(id);
+    *out = (v.op == OP_BINDING || v.op == OP_ARANGE) ? v.base : 0;  // the field shares storage with the dependency ids
+  });
+}
 
 // ---- counters ----------------------------------------------------------------------------------------------------
 vkjit_status vkjit_stats(vkjit_stats_t* out) {

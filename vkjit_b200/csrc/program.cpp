@@ -5,6 +5,7 @@
 #include <string>
 
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 
 namespace vkjit {
@@ -283,12 +284,14 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   // 128-bit hash: four independent multiply chains over 64-bit pairs (a single chain is latency bound: ~8 cycles
   // per pair, 2.5 us for the 364-node trace), folded at the end.  The full key is compared on every cache hit anyway.
   uint64_t a0 = 0x243F6A8885A308D3ull, a1 = 0x13198A2E03707344ull, a2 = 0xA4093822299F31D0ull, a3 = 0x082EFA98EC4E6C89ull;
-  const uint64_t* kr = reinterpret_cast<const uint64_t*>(key.data());  // vector storage is 16-byte aligned
-  for (size_t i = 0; i < kn / 2; i += 4) {
-    a0 = (a0 ^ kr[i]) * 0x9E3779B97F4A7C15ull;     a0 ^= a0 >> 32;
-    a1 = (a1 ^ kr[i + 1]) * 0xC2B2AE3D27D4EB4Full; a1 ^= a1 >> 29;
-    a2 = (a2 ^ kr[i + 2]) * 0x165667B19E3779F9ull; a2 ^= a2 >> 31;
-    a3 = (a3 ^ kr[i + 3]) * 0xD6E8FEB86659FD93ull; a3 ^= a3 >> 30;
+  const uint32_t* kr = key.data();
+  for (size_t i = 0; i < kn; i += 8) {
+    uint64_t w[4];
+    memcpy(w, kr + i, 32);  // four 64-bit pairs (memcpy: the words were written through a uint32_t pointer)
+    a0 = (a0 ^ w[0]) * 0x9E3779B97F4A7C15ull; a0 ^= a0 >> 32;
+    a1 = (a1 ^ w[1]) * 0xC2B2AE3D27D4EB4Full; a1 ^= a1 >> 29;
+    a2 = (a2 ^ w[2]) * 0x165667B19E3779F9ull; a2 ^= a2 >> 31;
+    a3 = (a3 ^ w[3]) * 0xD6E8FEB86659FD93ull; a3 ^= a3 >> 30;
   }
   uint64_t h0 = (a0 ^ (a1 * 0x9E3779B97F4A7C15ull)) * 0xC2B2AE3D27D4EB4Full; h0 ^= h0 >> 29;
   h0 = (h0 ^ a2) * 0x165667B19E3779F9ull; h0 ^= h0 >> 32;
