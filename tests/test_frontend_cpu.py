@@ -176,3 +176,25 @@ def test_threads_can_build_traces_concurrently():
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs
+
+
+def test_closing_the_global_ir_detaches_live_handles():
+    """Run last in this file: handles that outlive the global Ir must not touch it again; the next operation starts
+    a fresh Ir."""
+    x = vkjit.arange(T.U32, 8)
+    y = x + 1
+    stale = x * 3
+    old = vkjit._global_ir()
+    old.close()
+    del y, x                                   # released into nothing: no crash, no error
+    gc.collect()
+    z = vkjit.arange(T.F32, 4) * 2.0           # lazily creates and binds a new global Ir
+    assert vkjit._global_ir() is not old and z.ty() == T.F32
+    assert repr(z).startswith("Var { op: Bop(Mul)")
+    with pytest.raises(TypeError):
+        stale + 1                              # a handle of the closed Ir is not an operand of the new one
+    g = vkjit._global_ir()
+    counts = [g.ref_count(z.id())]
+    del stale                                  # ... and its release does not touch the new Ir's vars
+    gc.collect()
+    assert [g.ref_count(z.id())] == counts and "Var {" in vkjit.ir()

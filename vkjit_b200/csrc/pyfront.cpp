@@ -28,8 +28,10 @@ PyObject* g_errs[4] = {nullptr, nullptr, nullptr, nullptr};  // VkjitError, Vkji
 struct VarObject {
   PyObject_HEAD
   uint32_t id;
-  int live;  // owns one reference count of `id` (Clone / Drop, types.rs:87-98)
+  int live;      // owns one reference count of `id` (Clone / Drop, types.rs:87-98)
+  uint32_t gen;  // binding generation it was created under: a handle of a closed Ir never touches its successor
 };
+uint32_t g_gen = 0;  // bumped by every bind()
 
 extern PyTypeObject VarBase_Type;
 
@@ -63,7 +65,7 @@ PyObject* invalid_argument() {
 PyObject* wrap(PyTypeObject* cls, vkjit_var id) {
   VarObject* o = (VarObject*)cls->tp_alloc(cls, 0);
   if (!o) { vkjit_dec_ref(g_ir, id); return nullptr; }
-  o->id = id; o->live = 1;
+  o->id = id; o->live = 1; o->gen = g_gen;
   return (PyObject*)o;
 }
 inline PyObject* wrap(vkjit_var id) { return wrap(g_var_cls ? g_var_cls : &VarBase_Type, id); }
@@ -88,7 +90,7 @@ bool coerce(PyObject* v, Operand& o) {
   vkjit_status st;
   if (PyObject_TypeCheck(v, &VarBase_Type)) {
     VarObject* x = (VarObject*)v;
-    if (!x->live) { PyErr_SetString(PyExc_TypeError, "this Var no longer owns a variable"); return false; }
+    if (!x->live || x->gen != g_gen) { PyErr_SetString(PyExc_TypeError, "this Var no longer owns a variable"); return false; }
     o.id = x->id;
     return true;
   }
@@ -106,7 +108,11 @@ bool coerce(PyObject* v, Operand& o) {
     if (!g_slow_coerce) { invalid_argument(); return false; }
     PyObject* r = PyObject_CallOneArg(g_slow_coerce, v);
     if (!r) return false;
-    if (!PyObject_TypeCheck(r, &VarBase_Type) || !((VarObject*)r)->live) { Py_DECREF(r); invalid_argument(); return false; }
+    if (!PyObject_TypeCheck(r, &VarBase_Type) || !((VarObject*)r)->live || ((VarObject*)r)->gen != g_gen) {
+      Py_DECREF(r);
+      invalid_argument();
+      return false;
+    }
     o.id = ((VarObject*)r)->id;
     o.keep = r;
     return true;
@@ -203,7 +209,7 @@ PyObject* var_richcompare(PyObject* a, PyObject* b, int op) {
 // ---- Var methods ----------------------------------------------------------------------------------------------------
 inline VarObject* self_live(PyObject* self) {
   VarObject* v = (VarObject*)self;
-  if (!v->live) { PyErr_SetString(PyExc_TypeError, "this Var no longer owns a variable"); return nullptr; }
+  if (!v->live || v->gen != g_gen) { PyErr_SetString(PyExc_TypeError, "this Var no longer owns a variable"); return nullptr; }
   return v;
 }
 
@@ -300,7 +306,7 @@ int var_set_id(PyObject* self, PyObject* value, void*) {  // `*self = ret` of se
   if (!value || value == Py_None) { v->live = 0; return 0; }
   const unsigned long id = PyLong_AsUnsignedLong(value);
   if (id == (unsigned long)-1 && PyErr_Occurred()) return -1;
-  v->id = (uint32_t)id; v->live = 1;
+  v->id = (uint32_t)id; v->live = 1; v->gen = g_gen;
   return 0;
 }
 PyGetSetDef var_getset[] = {
@@ -323,14 +329,14 @@ int var_init(PyObject* self, PyObject* args, PyObject* kwds) {  // #[new] __new_
     const vkjit_status st = vkjit_inc_ref(g_ir, o.id);
     if (st != VKJIT_OK) { raise_status(st); return -1; }
   }
-  if (v->live) vkjit_dec_ref(g_ir, v->id);
-  v->id = o.id; v->live = 1;
+  if (v->live && v->gen == g_gen) vkjit_dec_ref(g_ir, v->id);
+  v->id = o.id; v->live = 1; v->gen = g_gen;
   return 0;
 }
 
 void var_dealloc(PyObject* self) {  // Drop (types.rs:94-98)
   VarObject* v = (VarObject*)self;
-  if (v->live && g_ir) vkjit_dec_ref(g_ir, v->id);
+  if (v->live && g_ir && v->gen == g_gen) vkjit_dec_ref(g_ir, v->id);
   v->live = 0;
   Py_TYPE(self)->tp_free(self);
 }
@@ -349,6 +355,7 @@ PyObject* mod_bind(PyObject*, PyObject* args) {
   Py_INCREF(owner);
   Py_XSETREF(g_ir_owner, owner);
   g_ir = (vkjit_ir*)(uintptr_t)handle;
+  ++g_gen;
   Py_RETURN_NONE;
 }
 
@@ -427,7 +434,7 @@ bool collect_ids(PyObject* seq, std::vector<vkjit_var>& ids) {
   ids.reserve((size_t)n);
   for (Py_ssize_t i = 0; i < n; ++i) {
     PyObject* it = PySequence_Fast_GET_ITEM(fast, i);
-    if (!PyObject_TypeCheck(it, &VarBase_Type) || !((VarObject*)it)->live) {
+    if (!PyObject_TypeCheck(it, &VarBase_Type) || !((VarObject*)it)->live || ((VarObject*)it)->gen != g_gen) {
       Py_DECREF(fast);
       PyErr_SetString(PyExc_TypeError, "expected a sequence of Var");
       return false;

@@ -32,6 +32,20 @@ _lock = threading.RLock()
 _IR = None
 
 
+class _GlobalIr(_ir.Ir):
+    """The process-wide Ir.  Closing it first detaches the native Var type, so handles that outlive it turn into
+    no-ops on release instead of touching a destroyed Ir."""
+
+    def close(self):
+        global _IR
+        if self._h is not None and self._h.value:
+            _native.unbind()
+            with _lock:
+                if _IR is self:
+                    _IR = None
+        super().close()
+
+
 def _global_ir() -> _ir.Ir:
     """`lazy_static! { pub static ref IR: Mutex<Ir> }` (lib.rs:14-16)"""
     global _IR
@@ -44,7 +58,7 @@ def _global_ir() -> _ir.Ir:
                 _ir.init(-1)
             except VkjitNoDeviceError:
                 pass
-            _IR = _ir.Ir()
+            _IR = _GlobalIr()
             _native.bind(_IR, _IR._h.value)  # the native Var records into this Ir (and keeps it alive)
         return _IR
 
