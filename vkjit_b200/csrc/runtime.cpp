@@ -261,8 +261,11 @@ bool nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string
   // --fmad=false: the reference's OpFMul/OpFAdd are separate roundings (no contraction); f32
   // + - * / are additionally emitted as __f*_rn intrinsics, which never contract.  IEEE
   // division/sqrt and no flush-to-zero are the NVRTC defaults and are stated explicitly.
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--prec-div=true", "--prec-sqrt=true",
-                        "--ftz=false",               "-lineinfo",    "--std=c++17",     "-default-device"};
+  // --minimal: leaves texture / surface / cudadevrt declarations out of the implicit header — 20 % less compile time
+  // (3-op trace 84 -> 66 ms, 364-node trace 256 -> 200 ms on the build container's CPU) for byte-identical cubins
+  // (checked for every kernel family the generator emits).
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
+                        "-lineinfo",                  "--std=c++17",  "-default-device", "--minimal"};
   nvrtcResult r = nvrtcCompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
   size_t ls = 0;
   nvrtcGetProgramLogSize(prog, &ls);
