@@ -229,7 +229,9 @@ vkjit_status vkjit_read(vkjit_ir* ir, vkjit_var id, vkjit_type ty, void* dst, si
  * hand-written reduction; an UNEVALUATED operand is reduced by one generated kernel that fuses the
  * trace with the reduction (the operand is not materialised and stays unevaluated).  Returns a 1-element Binding
  * of the same type.  With vkjit_dist_init active and a sharded operand the
- * per-GPU partial is combined across ranks (result replicated). */
+ * per-GPU partial is combined across ranks (result replicated).  Reductions issued back to back overlap on the
+ * device (programmatic dependent launch: the fold / exchange of one runs under the streaming phase of the next)
+ * whenever the backend can prove the operand is complete; the observable order is that of the stream. */
 vkjit_status vkjit_reduce(vkjit_ir* ir, int32_t red, vkjit_var id, vkjit_var* out);
 /* prefix sum of a U32/I32 var (mod 2^32); exclusive != 0 -> exclusive scan.  A sharded operand (multi-GPU) is
  * scanned over the GLOBAL range: per-rank totals are exchanged and each rank's result is its slice.
