@@ -127,6 +127,7 @@ extern "C" {
     pub fn vkjit_cache_clear() -> vkjit_status;
     pub fn vkjit_debug_codegen(ir: *mut vkjit_ir, ids: *const vkjit_var, n: usize, compile: i32, buf: *mut c_char, cap: usize, out_len: *mut usize, out_cubin_bytes: *mut usize) -> vkjit_status;
     pub fn vkjit_debug_walk_ns(ir: *mut vkjit_ir, ids: *const vkjit_var, n: usize, reps: u32, out_ns: *mut u64, out_nodes: *mut u32) -> vkjit_status;
+    pub fn vkjit_debug_eval_bookkeeping(ir: *mut vkjit_ir, ids: *const vkjit_var, n: usize) -> vkjit_status;
     pub fn vkjit_debug_codegen_reduce(ir: *mut vkjit_ir, id: vkjit_var, red: i32, compile: i32, buf: *mut c_char, cap: usize, out_len: *mut usize, out_cubin_bytes: *mut usize) -> vkjit_status;
     pub fn vkjit_debug_codegen_scan(ir: *mut vkjit_ir, ids: *const vkjit_var, n: usize, mode: i32, compile: i32, buf: *mut c_char, cap: usize, out_len: *mut usize, out_cubin_bytes: *mut usize) -> vkjit_status;
 }

@@ -311,6 +311,11 @@ vkjit_status vkjit_debug_codegen(vkjit_ir* ir, const vkjit_var* ids, size_t n, i
  * number of trace nodes; needs no device.  reps = 0: time ONE walk, in whatever cache state the construction
  * of the trace left its vars (what a fresh eval pays). */
 vkjit_status vkjit_debug_walk_ns(vkjit_ir* ir, const vkjit_var* ids, size_t n, uint32_t reps, uint64_t* out_ns, uint32_t* out_nodes);
+/* Debug: the bookkeeping of Ir::eval (internal.rs:482-525) WITHOUT compiling or launching anything — schedule, walk,
+ * every root rewritten into a Binding (a foreign view of the right size with NO memory behind it), the consumed trace
+ * released, schedule cleared.  Lets the ref-count contract of eval be tested without a device; never evaluate or read
+ * anything that depends on such a root. */
+vkjit_status vkjit_debug_eval_bookkeeping(vkjit_ir* ir, const vkjit_var* ids, size_t n);
 /* Same for the fused trace -> reduce kernel of vkjit_reduce(red, id). */
 vkjit_status vkjit_debug_codegen_reduce(vkjit_ir* ir, vkjit_var id, int32_t red, int32_t compile,
                                         char* buf, size_t cap, size_t* out_len, size_t* out_cubin_bytes);

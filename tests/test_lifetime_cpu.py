@@ -15,13 +15,14 @@ class Model:
     """Edge-exact reference counting over model ids (independent of the product's var ids)."""
 
     def __init__(self):
-        self.rc, self.deps = {}, {}
+        self.rc, self.deps, self.sized = {}, {}, {}
         self.next = 0
 
-    def new(self, deps=()):
+    def new(self, deps=(), lanes=False):
         i = self.next
         self.next += 1
         self.rc[i], self.deps[i] = 1, list(deps)
+        self.sized[i] = lanes or any(self.sized[d] for d in deps)   # reaches an Arange: a schedule needs a kernel size
         for d in deps:
             self.rc[d] += 1
         return i
@@ -38,6 +39,23 @@ class Model:
             if self.rc[v] == 0:
                 stack.extend(self.deps[v])
                 self.deps[v] = []
+
+    def evaluate(self, roots):
+        """Ir::eval's bookkeeping (internal.rs:482-525): +1 per scheduled root, every root gives up its dependency
+        edges and becomes a leaf (a Binding), the schedule's references are dropped again."""
+        sched = []
+        for r in roots:
+            if r not in sched:                      # duplicate roots collapse
+                sched.append(r)
+                self.rc[r] += 1
+        released = []
+        for r in sched:
+            released += self.deps[r]
+            self.deps[r] = []
+        for d in released:
+            self.dec(d)
+        for r in sched:
+            self.dec(r)
 
     def live(self):
         return sum(1 for c in self.rc.values() if c > 0)
@@ -60,7 +78,7 @@ def test_random_handle_lifetimes_match_the_model(seed):
     def leaf():
         ty = int(rng.choice([U32, I32, F32]))
         if rng.random() < 0.5:
-            add(ir.arange(ty, 16), model.new(), ty)
+            add(ir.arange(ty, 16), model.new(lanes=True), ty)
         else:
             v = int(rng.integers(1, 100))
             add({U32: ir.const_u32, I32: ir.const_i32, F32: ir.const_f32}[ty](v), model.new(), ty)
@@ -124,6 +142,16 @@ def test_random_handle_lifetimes_match_the_model(seed):
                 add(hp[k], hm[k], tys[k])
             else:
                 ir.dec_ref_count(hp[k]); model.dec(hm[k])
+        elif act == 10 and num:                                      # eval bookkeeping of up to 3 sized roots (no device)
+            import ctypes as C
+            ks = [int(x) for x in rng.choice(num, min(3, len(num)), replace=False)]
+            ks = [k for k in ks if model.sized[hm[k]]]
+            if ks:
+                ids = (C.c_uint32 * len(ks))(*[hp[k] for k in ks])
+                ir.api.call("debug_eval_bookkeeping", ir._h, ids, len(ks))
+                model.evaluate([hm[k] for k in ks])
+                for k in ks:
+                    assert ir.is_buffer(hp[k])
         elif act >= 10 and len(live) > 2:                            # drop a handle others may depend on
             k = int(rng.choice(live))
             ir.dec_ref_count(hp[k]); model.dec(hm[k])

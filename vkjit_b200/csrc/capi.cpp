@@ -697,6 +697,29 @@ vkjit_status vkjit_debug_walk_ns(vkjit_ir* h, const vkjit_var* ids, size_t n, ui
   });
 }
 
+vkjit_status vkjit_debug_eval_bookkeeping(vkjit_ir* h, const vkjit_var* ids, size_t n) {
+  return with_ir(h, [&](Ir& ir) {
+    ir.do_schedule(ids, n);
+    if (ir.schedule.empty()) return;
+    try {
+      Program p;
+      build_program(ir, ir.schedule, true, p);
+      std::vector<Array*> outs;
+      for (size_t r = 0; r < p.roots.size(); ++r) {
+        Array* a = new Array();  // a foreign view of nothing: the right size for later walks, no memory behind it
+        a->owned = false;
+        a->bytes = a->capacity = (size_t)p.n * 4;
+        outs.push_back(a);
+      }
+      ir.commit_roots(ir.schedule, outs, p.order);
+    } catch (...) {
+      ir.clear_schedule();
+      throw;
+    }
+    ir.clear_schedule();
+  });
+}
+
 vkjit_status vkjit_debug_codegen_reduce(vkjit_ir* h, vkjit_var id, int32_t red, int32_t compile, char* buf, size_t cap,
                                         size_t* out_len, size_t* out_cubin) {
   return with_ir(h, [&](Ir& ir) {
