@@ -38,6 +38,9 @@ N_TOTAL = 1 << LOG2N
 SEED_R28 = 0xB2000001 + 2 * 16  # 0xB200_0001 + config*16 + array#
 METRIC = "fused elementwise/reduce HBM GB/s (sum+max over 2^28 f32, sharded)"
 UNIT = "GB/s"
+# the SAME dict in both arms (the driver compares them); everything arm-specific lives under "setup"
+CONFIG = {"workload": "R28: sum+max over 2^28 f32 (BASELINE.json configs[1])", "n": N_TOTAL,
+          "l2": "inputs larger than L2 (every reduction reads 1 GiB / N per GPU, a different array than the one before)"}
 
 
 def peaks():
@@ -141,8 +144,11 @@ def cpu_reduce_arm(steps, warmup, log2n=LOG2N):
     from oracle_lib import oracle_api
     from vkjit_b200.ir import Ir, Red, VarType as T
     api = oracle_api()
-    cores = os.cpu_count() or 1
-    api.call("set_threads", cores)
+    try:
+        cores = len(os.sched_getaffinity(0))   # the cores this process may use (cgroup / taskset), not the box's total
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    api.call("set_threads", cores)            # worker t is pinned to the t-th allowed core (oracle.cpp: parallel_for)
     n = 1 << log2n
     ir = Ir(_api=api)
     x = ir.array_empty(T.F32, n)
@@ -172,15 +178,29 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "R28: sum+max over 2^28 f32 (BASELINE.json configs[1])", "n": N_TOTAL,
-                   "note": "CPU restatement of the reference semantics (oracle port), NOT the reference's Vulkan backend on Mesa "
-                           "lavapipe: no Rust/Vulkan toolchain exists in this image"},
+        "config": dict(CONFIG),
+        "setup": {"note": "CPU restatement of the reference semantics (oracle port), NOT the reference's Vulkan backend on Mesa "
+                          "lavapipe: no Rust/Vulkan toolchain exists in this image",
+                  "threads": r["cores"], "pinned": True},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                         "sample": "full workload: sum+max over 2^28 f32 per step, all host threads"},
+                         "sample": "full workload: sum+max over 2^28 f32 per step, all host threads (pinned)"},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "result": {"sum": r["sum"], "max": r["max"]},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_arm_subprocess(steps=5, warmup=2):
+    """The CPU leg of OUR arm is the reference arm itself, run as a child process with the same code, thread count and
+    pinning (`bench.py --impl reference`): the two figures cannot drift apart (round 1: 37.8 vs 57.3 GB/s on one box,
+    because the in-process leg shared the host with torch / NCCL helper threads and timed two passes only)."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE")}
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup)],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError("reference arm failed: " + r.stderr[-500:])
+    return json.loads(lines[-1])
 
 
 # ------------------------------------------------------------------------------------------
@@ -267,21 +287,27 @@ def ours(args):
             for v in pending.pop(0):
                 ir.dec_ref_count(v)
 
+    # Warm-up: the same back-to-back chain as the timed region.
     for k in range(max(3, args.warmup)):
         step(k)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.prepare()   # NVML init outside the timed region
-    barrier()
-    if rank == 0:
-        sampler.start()
-    vk.stats_reset()
+        sampler.start()     # the sampling thread starts BEFORE the barrier: nothing rank-specific sits between barrier and ev0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    vk.stats_reset()
+    # N>1: the ranks leave the host-side barrier up to a few hundred us apart.  Without re-alignment that skew is charged to
+    # the first exchange of the timed region (every rank's first tail waits for the last rank to arrive) — 0.4-0.6 ms
+    # against a 1.5 ms region at N = 8, --steps 20 (round 1).  Two untimed tiny sharded reductions IN THE STREAM, right
+    # before ev0, are a device-side barrier: every rank's ev0 fires within an NVLink round trip of the others'.
+    align(); align()
     t_wall0 = time.perf_counter()
     ev0.record(stream)
     for k in range(args.steps):
         step(k)
     ev1.record(stream)
+    t_issue = time.perf_counter() - t_wall0    # host time to put the K steps on the stream (no sync inside)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     st = vk.stats()
@@ -292,7 +318,7 @@ def ours(args):
     ms_per_step = float(step_ms.item())
     total_bytes = 2 * N_TOTAL * 4
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
-    launches = st["trace_launches"] + st["prim_launches"]
+    launches = st["trace_launches"] + st["prim_launches"] - (2 if world > 1 else 0)   # minus the two untimed alignment reductions
     for pr in pending:
         for v in pr:
             ir.dec_ref_count(v)
@@ -436,22 +462,28 @@ def ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "R28: sum+max over 2^28 f32 (BASELINE.json configs[1])", "n": N_TOTAL, "n_per_gpu": n_local,
-                       "parallelism": (f"contiguous 1-D shards x{world}, per-GPU partial + " + ("all-reduce fused into the reduce kernel's last CTA over NVLink peer memory (P2P mailbox)" if args.collective == "p2p" else "NCCL all-reduce")) if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: the steps rotate over 4 independent arrays (4 GiB/N per GPU against 126 MB of L2), each re-read only after 3 GiB/N of other reads; no flush inside the timed region",
-                       "timing": "K steps back to back between one pair of CUDA events on the backend stream, barrier + synchronize on both sides, max over ranks"},
+            "config": dict(CONFIG),
+            "setup": {"n_per_gpu": n_local,
+                      "parallelism": (f"contiguous 1-D shards x{world}, per-GPU partial + " + ("all-reduce fused into the reduce kernel's last CTA over NVLink peer memory (P2P mailbox)" if args.collective == "p2p" else "NCCL all-reduce")) if world > 1 else "single GPU",
+                      "l2": "the steps rotate over 4 independent arrays (4 GiB/N per GPU against 126 MB of L2), each re-read only after 3 GiB/N of other reads; no flush inside the timed region",
+                      "timing": "K steps back to back between one pair of CUDA events on the backend stream; barrier + synchronize on both sides, "
+                                "plus (N>1) an untimed in-stream device barrier right before the first event; max over ranks"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "isolated": isolated,
-            "wall_s_timed_region": t_wall, "result": {"sum": gpu_sum, "max": gpu_max},
+            "wall_s_timed_region": t_wall, "host_issue_us_per_reduction": t_issue / (2 * args.steps) * 1e6,
+            "result": {"sum": gpu_sum, "max": gpu_max},
             "hbm_frac_whole_job": value / (peak * world),
         }
-        if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reduce_arm(2, 1)
-            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
-                                    "sample": "full workload (sum+max over 2^28 f32), 2 timed passes, all host threads; CPU restatement "
-                                              "of the reference semantics, not Mesa lavapipe"}
-            tol = 1e-6 * LOG2N * abs(cb["sum"])
-            line["check"] = {"sum_abs_err": abs(gpu_sum - cb["sum"]), "sum_tol": tol, "max_equal": gpu_max == cb["max"],
-                             "ok": bool(abs(gpu_sum - cb["sum"]) <= tol and gpu_max == cb["max"])}
+        if not args.no_cpu_baseline:
+            # rank 0 has the host cores: the CPU arm runs (and checks the GPU result) at every N
+            # (cpu_baseline is REPORTED at N=1 only — at N>1 the other ranks' processes share the host; there the child runs one pass for the check)
+            cb = cpu_arm_subprocess() if world == 1 else cpu_arm_subprocess(steps=1, warmup=0)
+            if world == 1:
+                line["cpu_baseline"] = dict(cb["cpu_baseline"], steps=cb["steps"], warmup=cb["warmup"],
+                                            how="child process `bench.py --impl reference` (the reference arm itself)")
+            osum, omax = cb["result"]["sum"], cb["result"]["max"]
+            tol = 1e-6 * LOG2N * abs(osum)
+            line["check"] = {"sum_abs_err": abs(gpu_sum - osum), "sum_tol": tol, "max_equal": gpu_max == omax,
+                             "ok": bool(abs(gpu_sum - osum) <= tol and gpu_max == omax), "against": "oracle port (CPU), full 2^28 lanes"}
         if world > 1:
             line["extras"] = mgpu_extras
         if world == 1 and not args.no_extras:

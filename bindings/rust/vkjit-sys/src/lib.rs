@@ -121,7 +121,7 @@ extern "C" {
     pub fn vkjit_array_sharded(ir: *mut vkjit_ir, ty: vkjit_type, data: *const c_void, n: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_array_shard_local(ir: *mut vkjit_ir, ty: vkjit_type, data: *const c_void, n_local: usize, out_: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_var_is_sharded(ir: *mut vkjit_ir, id: vkjit_var, out_: *mut i32) -> vkjit_status;
-    pub fn vkjit_var_shard_base(ir: *mut vkjit_ir, id: vkjit_var, out: *mut u64) -> vkjit_status;
+    pub fn vkjit_var_shard_base(ir: *mut vkjit_ir, id: vkjit_var, out_: *mut u64) -> vkjit_status;
     pub fn vkjit_stats(out_: *mut vkjit_stats_t) -> vkjit_status;
     pub fn vkjit_stats_reset() -> vkjit_status;
     pub fn vkjit_cache_clear() -> vkjit_status;
@@ -130,4 +130,5 @@ extern "C" {
     pub fn vkjit_debug_eval_bookkeeping(ir: *mut vkjit_ir, ids: *const vkjit_var, n: usize) -> vkjit_status;
     pub fn vkjit_debug_codegen_reduce(ir: *mut vkjit_ir, id: vkjit_var, red: i32, compile: i32, buf: *mut c_char, cap: usize, out_len: *mut usize, out_cubin_bytes: *mut usize) -> vkjit_status;
     pub fn vkjit_debug_codegen_scan(ir: *mut vkjit_ir, ids: *const vkjit_var, n: usize, mode: i32, compile: i32, buf: *mut c_char, cap: usize, out_len: *mut usize, out_cubin_bytes: *mut usize) -> vkjit_status;
+    pub fn vkjit_debug_reduce_trace(out_: *mut u64, cap_words: usize, out_launches: *mut usize) -> vkjit_status;
 }

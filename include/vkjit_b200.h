@@ -324,6 +324,11 @@ vkjit_status vkjit_debug_codegen_reduce(vkjit_ir* ir, vkjit_var id, int32_t red,
  * 3 compress -> values (ids = {mask, values}). */
 vkjit_status vkjit_debug_codegen_scan(vkjit_ir* ir, const vkjit_var* ids, size_t n, int32_t mode, int32_t compile,
                                       char* buf, size_t cap, size_t* out_len, size_t* out_cubin_bytes);
+/* Debug ($VKJIT_REDUCE_TRACE=1 in the environment before the first reduction): per-launch %globaltimer stamps of the
+ * hand-written reduce kernel, 8 words per launch, oldest launch first: [0] CTA 0 enters; in the CTA that folds:
+ * [1] its streaming phase done, [2] previous kernel on the stream complete, [3] last ticket taken, [4] partials folded,
+ * [5] peer exchange done / result written; [6] launch number; [7] world size.  Synchronises; clears the ring. */
+vkjit_status vkjit_debug_reduce_trace(uint64_t* out, size_t cap_words, size_t* out_launches);
 
 #ifdef __cplusplus
 }

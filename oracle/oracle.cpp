@@ -49,6 +49,10 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#if defined(__linux__)
+#include <pthread.h>
+#include <sched.h>
+#endif
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -638,6 +642,28 @@ static void run_block(Plan& P, Lanes& L, size_t lo, size_t hi) {
   }
 }
 
+// Worker t runs on the t-th core this process is allowed to use (sched_getaffinity): with free-floating threads the
+// CPU baseline of bench.py moved by 1.5x between two runs on the same box.
+static void pin_worker(int t) {
+#if defined(__linux__)
+  static const std::vector<int> allowed = [] {
+    std::vector<int> a;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0)
+      for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &set)) a.push_back(c);
+    return a;
+  }();
+  if (allowed.empty()) return;
+  cpu_set_t one;
+  CPU_ZERO(&one);
+  CPU_SET(allowed[(size_t)t % allowed.size()], &one);
+  pthread_setaffinity_np(pthread_self(), sizeof one, &one);
+#else
+  (void)t;
+#endif
+}
+
 static void parallel_for(size_t n, size_t grain, const std::function<void(size_t, size_t, int)>& fn) {
   int T = std::max(1, g_threads);
   if (n < grain * 2) T = 1;
@@ -651,6 +677,7 @@ static void parallel_for(size_t n, size_t grain, const std::function<void(size_t
     size_t lo = std::min(n, (size_t)t * per), hi = std::min(n, lo + per);
     if (lo >= hi) break;
     th.emplace_back([&, lo, hi, t] {
+      pin_worker(t);
       try { fn(lo, hi, t); } catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
     });
   }

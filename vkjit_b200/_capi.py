@@ -134,6 +134,7 @@ _PRODUCT_SIGS = {
     "debug_codegen": [_p, _pu32, _sz, _i32, _p, _sz, _psz, _psz],
     "debug_walk_ns": [_p, _pu32, _sz, _u32, _pu64, _pu32],
     "debug_eval_bookkeeping": [_p, _pu32, _sz],
+    "debug_reduce_trace": [_pu64, _sz, _psz],
     "debug_codegen_reduce": [_p, _u32, _i32, _i32, _p, _sz, _psz, _psz],
     "debug_codegen_scan": [_p, _pu32, _sz, _i32, _i32, _p, _sz, _psz, _psz],
 }

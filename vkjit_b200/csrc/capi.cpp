@@ -697,6 +697,13 @@ vkjit_status vkjit_debug_walk_ns(vkjit_ir* h, const vkjit_var* ids, size_t n, ui
   });
 }
 
+vkjit_status vkjit_debug_reduce_trace(uint64_t* out, size_t cap_words, size_t* out_launches) {
+  return guard([&] {
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "64-bit stamps");
+    *out_launches = prims::reduce_trace_dump((unsigned long long*)out, cap_words, Backend::get().stream);
+  });
+}
+
 vkjit_status vkjit_debug_eval_bookkeeping(vkjit_ir* h, const vkjit_var* ids, size_t n) {
   return with_ir(h, [&](Ir& ir) {
     ir.do_schedule(ids, n);

@@ -49,6 +49,9 @@ uint64_t* g_mail_peer[prims::kMailRanks] = {};
 uint64_t** g_mail_table = nullptr;  // device copy of g_mail_peer
 bool g_p2p = false;
 uint32_t g_seq = 0;
+uint32_t* g_fault_host = nullptr;  // host-mapped word the exchange watchdog writes (prims.cu: mailbox_wait)
+uint32_t* g_fault_dev = nullptr;
+uint64_t g_timeout_ns = 0;
 
 void ckn(ncclResult_t r, const char* what) {
   if (r != ncclSuccess) fail(VKJIT_ERR_DIST, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error"));
@@ -117,6 +120,18 @@ void mailbox_open(const void* handles, int world) {
   }
   if (cudaMemcpy(g_mail_table, g_mail_peer, sizeof(g_mail_peer), cudaMemcpyHostToDevice) != cudaSuccess)
     fail(VKJIT_ERR_CUDA, "mailbox table upload failed");
+  if (!g_fault_host) {
+    void* hp = nullptr; void* dp = nullptr;
+    if (cudaHostAlloc(&hp, 64, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess)
+      fail(VKJIT_ERR_CUDA, "fault word allocation failed");
+    memset(hp, 0, 64);
+    g_fault_host = (uint32_t*)hp; g_fault_dev = (uint32_t*)dp;
+    set_fault_word(g_fault_host);
+  }
+  // NCCL has no deadline at all; the watchdog only exists so that a crashed peer cannot hang this GPU forever
+  const char* to = getenv("VKJIT_DIST_TIMEOUT_S");
+  const double secs = to ? atof(to) : 120.0;
+  g_timeout_ns = secs > 0 ? (uint64_t)(secs * 1e9) : 0;
   const char* force = getenv("VKJIT_DIST");
   g_p2p = !(force && std::string(force) == "nccl");
   g_seq = 0;
@@ -136,6 +151,7 @@ prims::Mailbox next_mailbox() {
   mb.rank = g_rank; mb.world = g_world;
   mb.seq = ++g_seq;
   if (g_seq == 0xFFFFFFFFu) g_seq = 0;
+  mb.fault = g_fault_dev; mb.timeout_ns = g_timeout_ns;
   Backend::counters().collectives += 1;  // no stream operation of its own: the exchange runs inside the reduce kernel
   return mb;
 }
@@ -149,6 +165,7 @@ void shutdown() {
     }
     if (g_mail_local) { cudaFree(g_mail_local); g_mail_local = nullptr; }
     if (g_mail_table) { cudaFree(g_mail_table); g_mail_table = nullptr; }
+    if (g_fault_host) { set_fault_word(nullptr); cudaFreeHost(g_fault_host); g_fault_host = g_fault_dev = nullptr; }
     g_p2p = false; g_seq = 0;
   }
   if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }

@@ -10,6 +10,9 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
+#include <string>
 
 #include "common.h"
 
@@ -103,6 +106,23 @@ __device__ __forceinline__ uint64_t sys_load(const uint64_t* p) {
   return v;
 }
 
+// Waits until rank r's word of exchange `seq` has arrived in this GPU's mailbox.  A peer that never arrives (crashed
+// process, rank stuck in host code for longer than the watchdog) does not hang the GPU: the exchange gives up, flags
+// the fault in host-mapped memory — the next synchronising call of the backend returns VKJIT_ERR_DIST — and the
+// kernel finishes with an unspecified value.
+__device__ __forceinline__ uint64_t mailbox_wait(const uint64_t* word, const Mailbox& mb, const unsigned long long t0) {
+  uint64_t w = sys_load(word);
+  uint32_t spins = 0;
+  while ((uint32_t)(w >> 32) != mb.seq) {
+    if ((++spins & 1023u) == 0 && mb.timeout_ns && global_ns() - t0 > mb.timeout_ns) {
+      if (mb.fault) { *(volatile uint32_t*)mb.fault = mb.seq; __threadfence_system(); }
+      break;
+    }
+    w = sys_load(word);
+  }
+  return w;
+}
+
 template <typename T, int RED>
 __device__ __forceinline__ T mailbox_allreduce(T mine, const Mailbox& mb) {
   const size_t slot = (size_t)(mb.seq % kMailSlots) * kMailRanks;
@@ -111,19 +131,17 @@ __device__ __forceinline__ T mailbox_allreduce(T mine, const Mailbox& mb) {
   const uint64_t* local = mb.local + slot;
   T acc = RedOp<T, RED>::identity();
   const unsigned long long t0 = global_ns();
-  for (int r = 0; r < mb.world; ++r) {  // fixed rank order: same bits on every GPU
-    uint64_t w = sys_load(local + r);
-    while ((uint32_t)(w >> 32) != mb.seq) {
-      if (global_ns() - t0 > 5000000000ull) __trap();  // a peer never arrived: fail loudly instead of hanging the GPU
-      w = sys_load(local + r);
-    }
-    acc = RedOp<T, RED>::apply(acc, from_bits<T>((uint32_t)w));
-  }
+  for (int r = 0; r < mb.world; ++r)  // fixed rank order: same bits on every GPU
+    acc = RedOp<T, RED>::apply(acc, from_bits<T>((uint32_t)mailbox_wait(local + r, mb, t0)));
   return acc;
 }
 
-// Exclusive scan over ranks of one u32 per GPU (mod 2^32): out[0] = sum of `mine` over all ranks below this one.
-// TOTAL: additionally out[1] = sum over all ranks (waits for every rank, not only the lower ones).
+// Exclusive scan over ranks of one u32 per GPU (mod 2^32): out[0] = sum of `mine` over all ranks below this one;
+// TOTAL: additionally out[1] = sum over all ranks.  EVERY exchange waits for every rank, also the plain exscan that
+// only needs the lower ranks' words: a rank that waited for nobody could run arbitrarily far ahead of the others and
+// rewrite ring slot seq % kMailSlots before a slower rank has read it.  With all ranks waiting for all, a rank can
+// publish exchange s + 1 only after every peer has published s, i.e. has finished reading s - 1: no rank is ever
+// more than one exchange ahead of another and the 64-slot ring cannot wrap.
 template <bool TOTAL>
 __global__ void p2p_exscan_kernel(const uint32_t* mine, uint32_t* out, Mailbox mb) {
   if (threadIdx.x != 0) return;
@@ -131,21 +149,15 @@ __global__ void p2p_exscan_kernel(const uint32_t* mine, uint32_t* out, Mailbox m
   const uint64_t word = ((uint64_t)mb.seq << 32) | mine[0];
   for (int p = 0; p < mb.world; ++p) sys_store(mb.peers[p] + slot + mb.rank, word);
   const uint64_t* local = mb.local + slot;
-  uint32_t acc = 0;
+  uint32_t acc = 0, below = 0;
   const unsigned long long t0 = global_ns();
-  uint32_t below = 0;
-  const int upto = TOTAL ? mb.world : mb.rank;
-  for (int r = 0; r < upto; ++r) {
-    uint64_t w = sys_load(local + r);
-    while ((uint32_t)(w >> 32) != mb.seq) {
-      if (global_ns() - t0 > 5000000000ull) __trap();
-      w = sys_load(local + r);
-    }
+  for (int r = 0; r < mb.world; ++r) {
+    const uint64_t w = mailbox_wait(local + r, mb, t0);
     if (r == mb.rank) below = acc;
     acc += (uint32_t)w;
   }
-  if (TOTAL) { out[0] = below; out[1] = acc; }
-  else out[0] = acc;
+  out[0] = below;
+  if (TOTAL) out[1] = acc;
 }
 
 // out[0] = sum of v[0..rank) — the NCCL path all-reduces a one-hot vector of the per-rank totals first
@@ -182,11 +194,12 @@ __global__ void p2p_allreduce_kernel(uint32_t* out, Mailbox mb) {
 template <typename T, int RED, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
 reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ partials, unsigned int* __restrict__ ticket,
-              uint32_t* __restrict__ out, const Mailbox mb, const uint32_t flags) {
+              uint32_t* __restrict__ out, const Mailbox mb, const uint32_t flags, unsigned long long* __restrict__ trace) {
   using O = RedOp<T, RED>;
   __shared__ T smem[THREADS / 32];
   __shared__ bool is_last;
   if (flags & kReduceWaitFirst) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[0] = global_ns();
 
   const size_t tid = (size_t)blockIdx.x * THREADS + threadIdx.x;
   const size_t nthreads = (size_t)gridDim.x * THREADS;
@@ -220,7 +233,10 @@ reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ 
   asm volatile("griddepcontrol.launch_dependents;");  // this CTA's input reads are done
   T acc = O::apply(O::apply(a0, a1), O::apply(a2, a3));
   acc = block_reduce<T, RED, THREADS>(acc, smem);
+  unsigned long long ts1 = 0, ts2 = 0;
+  if (trace && threadIdx.x == 0) ts1 = global_ns();
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous kernel on the stream has completed (no-op if it already had)
+  if (trace && threadIdx.x == 0) ts2 = global_ns();
 
   // publish the CTA partial; the last CTA to arrive folds all partials in a fixed order.  One acquire-release
   // atomic on the ticket orders the partial store before it and the partial loads of the last CTA after it
@@ -233,17 +249,56 @@ reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ 
   }
   __syncthreads();
   if (is_last) {
+    if (trace && threadIdx.x == 0) { trace[1] = ts1; trace[2] = ts2; trace[3] = global_ns(); }
     T f = O::identity();
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) f = O::apply(f, from_bits<T>(__ldcg(partials + i)));
     f = block_reduce<T, RED, THREADS>(f, smem);
     if (threadIdx.x == 0) {
       *ticket = 0u;  // self-reset for the next launch on this stream
+      if (trace) trace[4] = global_ns();
       // fused collective: the per-GPU partial goes straight to every peer's mailbox (no second
       // kernel, no NCCL launch); world == 1 compiles to the plain store
       if (mb.world > 1) f = mailbox_allreduce<T, RED>(f, mb);
       out[0] = to_bits(f);
+      if (trace) { trace[5] = global_ns(); trace[7] = (unsigned long long)mb.world; }
     }
   }
+}
+
+// $VKJIT_REDUCE_TRACE ring (see prims.h)
+static unsigned long long* g_reduce_trace = nullptr;
+static size_t g_reduce_trace_launches = 0;
+static unsigned long long* next_reduce_trace(cudaStream_t s) {
+  static const bool on = getenv("VKJIT_REDUCE_TRACE") != nullptr;
+  if (!on) return nullptr;
+  if (!g_reduce_trace) {
+    const size_t bytes = (size_t)kReduceTraceLaunches * kReduceTraceWords * 8;
+    if (cudaMalloc(&g_reduce_trace, bytes) != cudaSuccess || cudaMemset(g_reduce_trace, 0, bytes) != cudaSuccess)
+      fail(VKJIT_ERR_CUDA, "reduce trace allocation failed");
+  }
+  unsigned long long* slot = g_reduce_trace + (g_reduce_trace_launches % kReduceTraceLaunches) * kReduceTraceWords;
+  // no per-launch memset: it would sit between the kernels on the stream and break the programmatic overlap that is
+  // being measured; every launch overwrites all stamps of its slot
+  (void)s;
+  ++g_reduce_trace_launches;
+  return slot;
+}
+
+size_t reduce_trace_dump(unsigned long long* out, size_t cap_words, void* stream) {
+  if (!g_reduce_trace) return 0;
+  cudaStreamSynchronize((cudaStream_t)stream);
+  const size_t launches = std::min<size_t>(g_reduce_trace_launches, kReduceTraceLaunches);
+  const size_t words = std::min(cap_words, launches * kReduceTraceWords);
+  // oldest launch first
+  const size_t first = g_reduce_trace_launches > (size_t)kReduceTraceLaunches ? g_reduce_trace_launches % kReduceTraceLaunches : 0;
+  for (size_t i = 0; i * kReduceTraceWords < words; ++i) {
+    const size_t src = (first + i) % kReduceTraceLaunches;
+    cudaMemcpy(out + i * kReduceTraceWords, g_reduce_trace + src * kReduceTraceWords, kReduceTraceWords * 8, cudaMemcpyDeviceToHost);
+    out[i * kReduceTraceWords + 6] = g_reduce_trace_launches - launches + i;
+  }
+  const size_t n = words / kReduceTraceWords;
+  g_reduce_trace_launches = 0;
+  return n;
 }
 
 template <typename T, int RED>
@@ -263,8 +318,9 @@ static void launch_reduce(const void* in, size_t n, void* out, const Scratch& sc
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  unsigned long long* trace = next_reduce_trace(s);
   const cudaError_t e = cudaLaunchKernelEx(&cfg, reduce_kernel<T, RED, kReduceThreads>, (const uint32_t*)in, n, (uint32_t*)sc.partials,
-                                           sc.ticket, (uint32_t*)out, mb, flags);
+                                           sc.ticket, (uint32_t*)out, mb, flags, trace);
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(e));
 }
 

@@ -29,6 +29,8 @@ struct Mailbox {
   uint64_t* local = nullptr;         // this rank's mailbox
   int rank = 0, world = 1;
   uint32_t seq = 0;            // >= 1; identical on all ranks for the same collective
+  uint32_t* fault = nullptr;   // host-mapped word: receives `seq` when the watchdog below expires (checked at every sync)
+  uint64_t timeout_ns = 0;     // how long an exchange waits for a peer ($VKJIT_DIST_TIMEOUT_S, default 120 s); 0 = forever
 };
 
 constexpr int kReduceThreads = 512;
@@ -51,6 +53,12 @@ size_t scan_state_words(size_t n, size_t tile = kScanMinTile);
 constexpr uint32_t kReduceWaitFirst = 1u;
 void reduce(int red, uint32_t ty, const void* in, size_t n, void* out, const Scratch& sc, int sm_count, void* stream,
             const Mailbox* mailbox = nullptr, uint32_t flags = kReduceWaitFirst);
+// $VKJIT_REDUCE_TRACE=1: every reduce launch records eight %globaltimer stamps (kReduceTraceWords per launch, ring of
+// kReduceTraceLaunches launches): [0] CTA 0 enters, then in the LAST CTA (the one that folds): [1] its streaming phase
+// done, [2] previous kernel complete (griddepcontrol.wait returned), [3] ticket taken, [4] partials folded,
+// [5] peer exchange done, [6] launch number, [7] world.  Copies the ring to `out` (host); returns launches recorded.
+constexpr int kReduceTraceWords = 8, kReduceTraceLaunches = 4096;
+size_t reduce_trace_dump(unsigned long long* out, size_t cap_words, void* stream);
 // Stand-alone exchange: out[0] = combine over ranks of out[0] (used when a rank's shard is empty).
 void p2p_allreduce(int red, uint32_t ty, void* out, const Mailbox& mailbox, void* stream);
 

@@ -53,6 +53,18 @@ Driver g_drv;
 Backend* g_backend = nullptr;
 std::mutex g_init_mu;
 Counters g_counters;
+std::atomic<volatile uint32_t*> g_fault_word{nullptr};
+
+// after a stream synchronisation: did an exchange watchdog fire while the stream ran?
+void check_fault() {
+  volatile uint32_t* w = g_fault_word.load(std::memory_order_relaxed);
+  if (w && *w) {
+    const uint32_t seq = *w;
+    *w = 0;
+    fail(VKJIT_ERR_DIST, "multi-GPU exchange " + std::to_string(seq) + ": a peer did not arrive within the watchdog ($VKJIT_DIST_TIMEOUT_S); "
+                         "results produced since are unspecified");
+  }
+}
 
 void ck(cudaError_t e, const char* what) {
   if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -66,6 +78,8 @@ void cku(CUresult r, const char* what) {
 }
 
 }  // namespace
+
+void set_fault_word(volatile uint32_t* host_word) { g_fault_word.store(host_word); }
 
 Counters& Backend::counters() { return g_counters; }
 bool Backend::initialized() { return g_backend != nullptr; }
@@ -226,6 +240,7 @@ void Backend::h2d(void* dst, const void* src, size_t bytes) {
 void Backend::d2h(void* dst, const void* src, size_t bytes) {
   if (bytes) ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H copy");
   ck(cudaStreamSynchronize((cudaStream_t)stream), "D2H sync");
+  check_fault();
   g_counters.bytes_d2h += bytes;
   g_counters.stream_ops += 1;
 }
@@ -235,7 +250,10 @@ void Backend::d2d(void* dst, const void* src, size_t bytes) {
   g_counters.stream_ops += 1;
 }
 
-void Backend::sync() { ck(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
+void Backend::sync() {
+  ck(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+  check_fault();
+}
 
 void Backend::ensure_scan_scratch(size_t n, size_t tile) {
   const size_t need = prims::scan_state_words(n, tile);

@@ -98,6 +98,10 @@ class Backend {
   size_t recycle_bytes_ = 0;
 };
 
+// Host-mapped word a device-side watchdog writes when a peer exchange gave up (dist.cpp); every synchronising call of
+// the backend checks it and fails with VKJIT_ERR_DIST.  nullptr: nothing to check.
+void set_fault_word(volatile uint32_t* host_word);
+
 // Evaluate the Ir's schedule (+ ids): the body of Ir::eval (internal.rs:482-525).
 void eval(Ir& ir, const VarId* ids, size_t n);
 
