@@ -49,6 +49,8 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+
+#include "../vkjit_b200/csrc/vk_math.h"  // the ONE header shared with the product: f32 exp/log/sin/cos (see its head comment)
 #if defined(__linux__)
 #include <pthread.h>
 #include <sched.h>
@@ -563,10 +565,13 @@ static void run_block(Plan& P, Lanes& L, size_t lo, size_t hi) {
           case U_SQRT: LOOP1(as_w(sqrtf(FX))) break;  // IEEE correctly rounded
           // SPEC: transcendentals are the f64 libm value rounded to f32 (within 1 ulp of
           // the correctly rounded result); device results are compared with an ulp budget.
-          case U_EXP: LOOP1(as_w((float)std::exp((double)FX))) break;
-          case U_LOG: LOOP1(as_w((float)std::log((double)FX))) break;
-          case U_SIN: LOOP1(as_w((float)std::sin((double)FX))) break;
-          case U_COS: LOOP1(as_w((float)std::cos((double)FX))) break;
+          // SPEC (no reference op): the shared implementation of vkjit_b200/csrc/vk_math.h — plain IEEE binary32
+          // add/mul/fma + integer code, which the generated CUDA kernels compile too, so the device result must be
+          // these bits exactly; against the f64 libm value every function is within 1 ulp (profiles/r02_vk_math_ulp.md)
+          case U_EXP: LOOP1(as_w(vk_expf(FX))) break;
+          case U_LOG: LOOP1(as_w(vk_logf(FX))) break;
+          case U_SIN: LOOP1(as_w(vk_sinf(FX))) break;
+          case U_COS: LOOP1(as_w(vk_cosf(FX))) break;
           default: throw Error(E_INVALID, "unknown uop");
         }
         break;
@@ -800,8 +805,25 @@ void Ir::eval(const VarId* ids, size_t nids) {
 // ---- eager primitives (SPEC) ----------------------------------
 // SPEC: an unevaluated operand of an eager primitive is evaluated on the fly and is NOT turned into a buffer
 // (the device fuses the trace into the primitive's kernel instead of materialising the operand)
+// ...unless its trace has a side effect (a Scatter / ScatterAdd anywhere below it): evaluating it "on the side" would
+// run the scatter now and AGAIN at the var's own eval (dst [1 1 1 1] -> [2 2 2 2]).  Such an operand is evaluated
+// exactly like eval([id]) does — committed, the var becomes a buffer — so the side effect happens once.
+static bool trace_has_side_effect(Ir& ir, VarId root) {
+  std::vector<VarId> stack{root};
+  std::unordered_set<VarId> seen;
+  while (!stack.empty()) {
+    const VarId id = stack.back(); stack.pop_back();
+    if (!seen.insert(id).second) continue;
+    const Var& v = ir.var(id);
+    if (v.op == OP_SCATTER || v.op == OP_SCATTER_ADD) return true;
+    for (VarId d : v.deps) stack.push_back(d);
+  }
+  return false;
+}
 static std::shared_ptr<Words> operand_words(Ir& ir, VarId id) {
-  return ir.is_buffer(id) ? ir.arrays.at(id) : run_schedule(ir, std::vector<VarId>{id})[0];
+  if (ir.is_buffer(id)) return ir.arrays.at(id);
+  if (trace_has_side_effect(ir, id)) { ir.eval(&id, 1); return ir.arrays.at(id); }
+  return run_schedule(ir, std::vector<VarId>{id})[0];
 }
 
 static VarId reduce(Ir& ir, int red, VarId id) {

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=28)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline"))
     ap.add_argument("--no-align", action="store_true", help="skip the in-stream alignment before the chain (round-1 behaviour)")
+    ap.add_argument("--arrays", type=int, default=4, help="number of input arrays the chain rotates over")
     args = ap.parse_args()
     import torch
     import torch.distributed as td
@@ -50,7 +51,7 @@ def main():
     ir = Ir()
     n = 1 << args.log2n
     lanes = ir.arange_sharded(T.U32, n)
-    xs = [uniform_trace(ir, lanes, SEED_R28 + i) for i in range(4)]
+    xs = [uniform_trace(ir, lanes, SEED_R28 + i) for i in range(args.arrays)]
     for v in xs:
         ir.eval([v])
     tiny = ir.cast(ir.arange_sharded(T.U32, 4096 * world), T.F32) if world > 1 else None
@@ -66,8 +67,8 @@ def main():
     def chain(k):
         out = []
         for i in range(k):
-            out.append(ir.reduce(Red.Sum, xs[(2 * i) % 4]))
-            out.append(ir.reduce(Red.Max, xs[(2 * i + 1) % 4]))
+            out.append(ir.reduce(Red.Sum, xs[(2 * i) % len(xs)]))
+            out.append(ir.reduce(Red.Max, xs[(2 * i + 1) % len(xs)]))
         return out
 
     for v in chain(5):
@@ -110,6 +111,17 @@ def main():
         if vals:
             summary[key] = {"median": statistics.median(vals), "mean": sum(vals) / len(vals), "max": max(vals), "min": min(vals)}
     summary["first_launch"] = rec[0] if rec else None
+    # per input array: is the streaming time a property of where the array lives?
+    per = {}
+    for i, d in enumerate(rec):
+        per.setdefault(i % len(xs), []).append(d["stream_us"])
+    ptrs = []
+    for v in xs:
+        p = C.c_uint64()
+        api.call("var_device_ptr", ir._h, v, C.byref(p))
+        ptrs.append(p.value)
+    summary["per_array"] = [{"array": a, "ptr": hex(ptrs[a]), "ptr_mod_128MiB_MiB": (ptrs[a] % (128 << 20)) / (1 << 20),
+                             "stream_us_median": statistics.median(v[1:] or v), "stream_us_min": min(v)} for a, v in sorted(per.items())]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(f"{args.out}_rank{rank}.json", "w") as f:
         json.dump({"summary": summary, "launches": rec}, f)

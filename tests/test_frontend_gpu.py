@@ -139,6 +139,17 @@ def test_dlpack_round_trip_with_torch(vkjit, cuda_backend):
     assert np.array_equal(t.cpu().numpy().view(np.uint32), expect)
     del t; gc.collect()
     assert cuda_backend.stats()["pool_bytes_live"] < live             # deleter ran: the var and its array are gone
+    # re-evaluating an exported var replaces the var's array (eval of a Binding root copies, internal.rs:1192-1205);
+    # the exported tensor keeps the OLD array: nothing may recycle it while torch still reads it
+    y = vkjit.arange(vkjit.VarType.U32, 5000) * 3 + 1
+    t = torch.from_dlpack(y)
+    vkjit.eval([y])
+    junk = [vkjit.arange(vkjit.VarType.U32, 5000) + 77 for _ in range(6)]   # same-size blocks: would reuse a recycled one
+    vkjit.eval(junk)
+    cuda_backend.sync()
+    assert np.array_equal(t.cpu().numpy().view(np.uint32), expect)
+    assert np.array_equal(y.numpy(), expect)
+    del junk, y, t; gc.collect()
     # import: a Var over torch memory; the torch tensor object may die, the memory must not
     src = torch.arange(0, 4096, device="cuda", dtype=torch.float32)
     ptr = src.data_ptr()

@@ -78,6 +78,21 @@ void ensure_buffer(Ir& ir, VarId id) {
   if (!ir.is_buffer(id) || misaligned(ir, id)) eval(ir, &id, 1);
 }
 
+// Does the trace below `id` contain a Scatter / ScatterAdd?  The eager primitives evaluate an unevaluated operand
+// inside their own kernel (or into a temporary) WITHOUT committing it; a scatter in that trace would run there and
+// again at the var's own eval.  Such an operand is committed first — eval([id]), the side effect runs exactly once,
+// the var becomes a buffer — and the hand-written primitive reads the buffer (same rule in the oracle).
+bool commit_if_side_effects(Ir& ir, VarId id) {
+  if (ir.is_buffer(id)) return false;
+  static thread_local Program p;
+  std::vector<VarId> roots{id};
+  build_program(ir, roots, true, p);
+  bool se = false;
+  for (const Param& pr : p.params) se = se || (pr.use & USE_SCATTER);
+  if (se && p.n > 0) eval(ir, &id, 1);   // (an empty shard has nothing to run)
+  return se;
+}
+
 // Buffer::str (internal.rs:404-422) through a D2H copy
 std::string buffer_str(Ir& ir, VarId id) {
   const Var& v = ir.var(id);
@@ -195,10 +210,14 @@ struct DLTensor { void* data; DLDevice device; int32_t ndim; DLDataType dtype; i
 struct DLManagedTensor { DLTensor dl_tensor; void* manager_ctx; void (*deleter)(DLManagedTensor*); };
 enum { kDLCUDA = 2, kDLInt = 0, kDLUInt = 1, kDLFloat = 2 };
 
-struct ExportCtx { vkjit_ir* ir; vkjit_var id; int64_t shape; };
+// The exported tensor holds a reference on the ARRAY, not on the var or the Ir: re-evaluating the var (commit_roots
+// replaces a Binding root's array), dropping the var, or destroying the whole Ir only drops THEIR reference; the
+// memory stays valid until the consumer calls the deleter, which needs neither the Ir nor its lock.
+struct ExportCtx { Array* array; int64_t shape; };
 void export_deleter(DLManagedTensor* t) {
   ExportCtx* c = (ExportCtx*)t->manager_ctx;
-  vkjit_dec_ref(c->ir, c->id);  // the reference taken at export
+  release_array(c->array);  // the reference taken at export (exposed arrays are freed device-synchronously, runtime.cpp)
+  drain_foreign_releases();
   delete c;
   delete t;
 }
@@ -220,7 +239,7 @@ vkjit_status vkjit_var_to_dlpack(vkjit_ir* h, vkjit_var id, void** out) {
       default: fail(VKJIT_ERR_TYPE, "to_dlpack: scalar arrays only");
     }
     if (Backend::initialized()) Backend::get().sync();  // the consumer may use any stream
-    auto* c = new ExportCtx{h, id, (int64_t)(v.array->bytes / 4)};
+    auto* c = new ExportCtx{v.array, (int64_t)(v.array->bytes / 4)};
     auto* t = new DLManagedTensor();
     t->dl_tensor.data = v.array->ptr;
     v.array->exposed = true;  // the consumer may write it on its own streams from now on
@@ -232,7 +251,7 @@ vkjit_status vkjit_var_to_dlpack(vkjit_ir* h, vkjit_var id, void** out) {
     t->dl_tensor.byte_offset = 0;
     t->manager_ctx = c;
     t->deleter = export_deleter;
-    ir.inc_ref(id);  // the tensor keeps the array alive until the consumer calls the deleter
+    retain_array(v.array);  // the tensor keeps the array alive until the consumer calls the deleter
     *out = t;
   });
 }
@@ -350,6 +369,7 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
     if (!ty_is_num(ty)) fail(VKJIT_ERR_TYPE, "reduce needs U32/I32/F32");
     if (red < VKJIT_RED_SUM || red > VKJIT_RED_MAX) fail(VKJIT_ERR_INVALID, "unknown reduction");
     Backend& be = Backend::get();
+    commit_if_side_effects(ir, id);
     const bool sharded = ir.var(id).sharded;
     const bool combine = sharded && dist::active() && dist::world() > 1;
     // a rank whose shard of a tiny array is empty still has to take part in the collective
@@ -453,6 +473,7 @@ vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkji
     const TypeId ty = ir.var(id).ty;
     if (ty != VKJIT_TY_U32 && ty != VKJIT_TY_I32) fail(VKJIT_ERR_TYPE, "prefix_sum needs U32/I32");
     Backend& be = Backend::get();
+    commit_if_side_effects(ir, id);
     const bool sharded = ir.var(id).sharded && dist::active() && dist::world() > 1;
     // a rank whose shard is empty cannot evaluate it, but still has to take part in the exchange
     bool empty;
@@ -517,6 +538,8 @@ static void do_compress(Ir& ir, bool with_values, VarId values, VarId mask, vkji
     if (!ty_is_scalar(oty)) fail(VKJIT_ERR_TYPE, "compress values must be scalar");
   }
   Backend& be = Backend::get();
+  commit_if_side_effects(ir, mask);
+  if (with_values) commit_if_side_effects(ir, values);
   // Sharded compress: every rank compacts its own shard; the result is a ragged sharded array —
   // rank r holds the global elements [offset_r, offset_r + count_r), `count` is the GLOBAL number of selected lanes,
   // index results are global lane numbers.  Two small exchanges: exscan of the shard sizes (index base) and

@@ -7,6 +7,7 @@
 // var instead of in a side HashMap, and every var carries scratch fields so that the per-eval
 // trace walk needs no hashing or allocation (cached-launch budget: < 10 us).
 #pragma once
+#include <atomic>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -27,6 +28,7 @@ enum Op : uint8_t {
 
 // Device array owned by a Binding var — Backend::Array (backend/mod.rs:8-12).
 struct Array {
+  std::atomic<uint32_t> refs{1};  // the owning var holds one; every exported DLPack tensor holds one more
   void* ptr = nullptr;
   size_t bytes = 0;     // logical size (Array::size)
   size_t capacity = 0;  // allocation size (compress over-allocates)
@@ -139,7 +141,8 @@ std::string format_f32(float f);
 // Implemented by the runtime: returns the memory of a dying Binding to the pool.  Owner callbacks of foreign
 // views are queued per thread and run by drain_foreign_releases() once the caller holds no Ir lock (an owner
 // may be one of our own exported DLPack tensors, whose deleter takes that lock).
-void release_array(Array* a);
+void release_array(Array* a);   // drops one reference; the last one frees
+inline void retain_array(Array* a) { a->refs.fetch_add(1, std::memory_order_relaxed); }
 void drain_foreign_releases();
 
 }  // namespace vkjit

@@ -306,7 +306,16 @@ static void launch_reduce(const void* in, size_t n, void* out, const Scratch& sc
                           uint32_t flags) {
   const size_t n4 = n >> 2;
   size_t ctas = (std::max<size_t>(n4, 1) + kReduceThreads - 1) / kReduceThreads;
-  const size_t cap = (size_t)sm_count * (2048 / kReduceThreads);  // one full wave: 4 CTAs of 512 threads per SM
+  // One wave MINUS TWO CTAs (4 CTAs of 512 threads per SM).  Back-to-back reductions hand the SMs over through
+  // programmatic dependent launch: the CTAs of reduction k+1 take the slots the CTAs of k free when they exit.  All of
+  // them exit right after the ticket — except the one that folds (and, on several GPUs, sits in the peer exchange for
+  // ~10 us).  With a grid of exactly one wave, ONE CTA of k+1 finds no slot until that tail is over, starts 7 us (one
+  // GPU) to 17 us (eight GPUs) late and then streams its fixed 1/592 share almost alone: measured launch-to-launch
+  // period 22.0 / 24.5 us for a 128 MiB shard that streams in 19.5 (profiles/r02_n8_timeline.md).  Two spare slots
+  // (a second tail can still be alive when ranks are skewed) cost 0.34 % of the streaming parallelism.
+  const size_t wave = (size_t)sm_count * (2048 / kReduceThreads);
+  static const int spare = [] { const char* e = getenv("VKJIT_REDUCE_SPARE_CTAS"); return e ? atoi(e) : 2; }();
+  const size_t cap = wave > 8 + (size_t)spare ? wave - (size_t)spare : wave;
   if (ctas > cap) ctas = cap;
   if (ctas > (size_t)kReduceMaxCtas) ctas = kReduceMaxCtas;
   cudaLaunchConfig_t cfg = {};

@@ -349,6 +349,7 @@ struct Gen {
   std::vector<Val> vals;
 
   std::vector<int> trig_partner;  // sin(x)/cos(x) of the same x: local id of the sibling, else -1
+  bool uses_vk_math = false;      // the kernel text needs vk_math.h
 
   Gen(const Ir& i, const Program& pr) : ir(i), p(pr) {
     vals.resize(pr.order.size());
@@ -432,10 +433,11 @@ struct Gen {
         return t == VKJIT_TY_I32 ? "(" + a + " < 0) ? (i32)(0u - (u32)" + a + ") : " + a : a;
       case VKJIT_UOP_NOT: return t == VKJIT_TY_BOOL ? "!" + a : "~" + a;
       case VKJIT_UOP_SQRT: return "__fsqrt_rn(" + a + ")";
-      case VKJIT_UOP_EXP: return "expf(" + a + ")";
-      case VKJIT_UOP_LOG: return "logf(" + a + ")";
-      case VKJIT_UOP_SIN: return "sinf(" + a + ")";
-      case VKJIT_UOP_COS: return "cosf(" + a + ")";
+      // vk_math.h: the one implementation the oracle compiles too (GPU == oracle bit for bit; <= 1 ulp of the exact value)
+      case VKJIT_UOP_EXP: uses_vk_math = true; return "vk_expf(" + a + ")";
+      case VKJIT_UOP_LOG: uses_vk_math = true; return "vk_logf(" + a + ")";
+      case VKJIT_UOP_SIN: uses_vk_math = true; return "vk_sinf(" + a + ")";
+      case VKJIT_UOP_COS: uses_vk_math = true; return "vk_cosf(" + a + ")";
       default: fail(VKJIT_ERR_INVALID, "unknown uop");
     }
   }
@@ -492,7 +494,9 @@ struct Gen {
             const std::string other = "v" + std::to_string(partner);
             const bool i_am_sin = v.kind == VKJIT_UOP_SIN;
             line("f32 " + me + ", " + other + ";");
-            line("sincosf(" + dep(v, 0).name + ", &" + (i_am_sin ? me : other) + ", &" + (i_am_sin ? other : me) + ");");
+            // one range reduction for both; bit-identical to vk_sinf / vk_cosf called separately (checked over all 2^32 inputs)
+            line("vk_sincosf(" + dep(v, 0).name + ", &" + (i_am_sin ? me : other) + ", &" + (i_am_sin ? other : me) + ");");
+            uses_vk_math = true;
           }
           vals[li].name = me; vals[li].ty = v.ty;
           break;
@@ -680,6 +684,7 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   std::string s;
   s += "// vkjit-b200 fused trace kernel; key " + std::to_string(p.hash.lo) + ":" + std::to_string(p.hash.hi) + "\n";
   s += "typedef unsigned int u32;\ntypedef int i32;\ntypedef float f32;\n\n";
+  if (g.uses_vk_math) s += std::string(kVkMathSrc) + "\n";
   const bool scan = p.scan >= 0;
   if (scan) s += "typedef unsigned int uint32_t;\ntypedef unsigned long long uint64_t;\n\n";
   if (reduce) {

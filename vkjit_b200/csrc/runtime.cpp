@@ -212,7 +212,18 @@ thread_local std::vector<std::pair<void (*)(void*), void*>> g_pending_release;
 
 void release_array(Array* a) {
   if (!a) return;
-  if (g_backend && a->owned) g_backend->free_async(a->ptr, a->capacity);
+  if (a->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return;  // an exported tensor (or the var) still holds it
+  if (g_backend && a->owned) {
+    if (a->exposed) {
+      // Whoever received the pointer (torch, cupy, a raw device_ptr user) may have work on ITS streams that still
+      // touches the memory; the stream-ordered recycler / pool only order against the backend stream (and cudaFree of
+      // a stream-ordered allocation does not synchronise either).  Rare path (exports), correctness over speed.
+      cudaDeviceSynchronize();
+      g_backend->free_async(a->ptr, a->capacity);
+    } else {
+      g_backend->free_async(a->ptr, a->capacity);
+    }
+  }
   if (a->release) g_pending_release.emplace_back(a->release, a->release_ctx);
   delete a;
 }
@@ -302,6 +313,12 @@ bool nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string
   cubin.resize(cs);
   nvrtcGetCUBIN(prog, cubin.data());
   nvrtcDestroyProgram(&prog);
+  if (const char* dir = getenv("VKJIT_DUMP_CUBIN_DIR")) {  // for cuobjdump -sass (profiles/r02_sass.md); needs no device
+    static std::atomic<int> seq{0};
+    const std::string base = std::string(dir) + "/vkjit_" + std::to_string(seq++);
+    if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
+    if (FILE* f = fopen((base + ".cu").c_str(), "wb")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+  }
   return true;
 }
 
