@@ -28,7 +28,10 @@ def _timed(stream, flush_l2, sync, fn, reps=5, warm=2):
         sync()
         if i >= warm:
             ts.append(a.elapsed_time(b))
-    return sum(ts) / len(ts), min(ts), last
+    # median, not mean: one outlier among 3-5 repetitions (seen once in round 2: 0.93 ms reported for a 0.33 ms kernel)
+    # must not become the figure; the best time is reported next to it
+    ts.sort()
+    return ts[len(ts) // 2], ts[0], last
 
 
 def run(ir, vk, stream, flush_l2, peak):

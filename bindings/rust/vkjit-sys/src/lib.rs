@@ -94,6 +94,7 @@ extern "C" {
     pub fn vkjit_var_type(ir: *mut vkjit_ir, id: vkjit_var, out_ty: *mut vkjit_type) -> vkjit_status;
     pub fn vkjit_var_ref_count(ir: *mut vkjit_ir, id: vkjit_var, out_: *mut u32) -> vkjit_status;
     pub fn vkjit_var_count(ir: *mut vkjit_ir, out_: *mut usize) -> vkjit_status;
+    pub fn vkjit_var_deps(ir: *mut vkjit_ir, id: vkjit_var, deps: *mut vkjit_var, cap: usize, out_ndeps: *mut usize, out_has_side_effect: *mut i32, out_side_effect: *mut vkjit_var) -> vkjit_status;
     pub fn vkjit_array_count(ir: *mut vkjit_ir, out_: *mut usize) -> vkjit_status;
     pub fn vkjit_is_buffer(ir: *mut vkjit_ir, id: vkjit_var, out_: *mut i32) -> vkjit_status;
     pub fn vkjit_var_size(ir: *mut vkjit_ir, id: vkjit_var, out_elems: *mut usize) -> vkjit_status;

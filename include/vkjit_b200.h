@@ -193,6 +193,11 @@ vkjit_status vkjit_var_type(vkjit_ir* ir, vkjit_var id, vkjit_type* out_ty);
 vkjit_status vkjit_var_ref_count(vkjit_ir* ir, vkjit_var id, uint32_t* out);
 /* `ir.vars.len()` and `ir.arrays.len()` (test.rs:204, :206) */
 vkjit_status vkjit_var_count(vkjit_ir* ir, size_t* out);
+/* `ir.vars[id].deps` / `.side_effects` (internal.rs:108-109; what DepIterator / SeIterator walk, iterators.rs:6-61): up to
+ * `cap` dependency ids into deps[], the total count into *out_ndeps; *out_side_effect = the scatter target when
+ * *out_has_side_effect != 0 (a var has at most one, internal.rs:396). */
+vkjit_status vkjit_var_deps(vkjit_ir* ir, vkjit_var id, vkjit_var* deps, size_t cap, size_t* out_ndeps,
+                            int32_t* out_has_side_effect, vkjit_var* out_side_effect);
 vkjit_status vkjit_array_count(vkjit_ir* ir, size_t* out);
 /* Ir::is_buffer, internal.rs:401-403 */
 vkjit_status vkjit_is_buffer(vkjit_ir* ir, vkjit_var id, int32_t* out);

@@ -895,6 +895,12 @@ static VarId compress(Ir& ir, VarId mask, bool with_values, VarId values, size_t
     if (!vt.scalar()) throw Error(E_TYPE, "compress values must be scalar");
     vk = vt.k;
   }
+  {  // operands of ONE primitive call are committed by ONE eval: a scatter they share runs once
+    std::vector<VarId> commit;
+    if (!ir.is_buffer(mask) && trace_has_side_effect(ir, mask)) commit.push_back(mask);
+    if (with_values && !ir.is_buffer(values) && trace_has_side_effect(ir, values)) commit.push_back(values);
+    if (!commit.empty()) ir.eval(commit.data(), commit.size());
+  }
   auto m = operand_words(ir, mask);
   const size_t n = m->size();
   std::shared_ptr<Words> vals;

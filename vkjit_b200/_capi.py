@@ -86,6 +86,7 @@ _SIGS = {
     "var_type": [_p, _u32, _pu32],
     "var_ref_count": [_p, _u32, _pu32],
     "var_count": [_p, _psz],
+    "var_deps": [_p, _u32, _pu32, _sz, _psz, _pi32, _pu32],
     "array_count": [_p, _psz],
     "is_buffer": [_p, _u32, _pi32],
     "var_size": [_p, _u32, _psz],

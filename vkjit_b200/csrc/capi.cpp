@@ -82,15 +82,22 @@ void ensure_buffer(Ir& ir, VarId id) {
 // inside their own kernel (or into a temporary) WITHOUT committing it; a scatter in that trace would run there and
 // again at the var's own eval.  Such an operand is committed first — eval([id]), the side effect runs exactly once,
 // the var becomes a buffer — and the hand-written primitive reads the buffer (same rule in the oracle).
-bool commit_if_side_effects(Ir& ir, VarId id) {
+bool has_side_effects(Ir& ir, VarId id) {
   if (ir.is_buffer(id)) return false;
   static thread_local Program p;
   std::vector<VarId> roots{id};
   build_program(ir, roots, true, p);
-  bool se = false;
-  for (const Param& pr : p.params) se = se || (pr.use & USE_SCATTER);
-  if (se && p.n > 0) eval(ir, &id, 1);   // (an empty shard has nothing to run)
-  return se;
+  if (p.n == 0) return false;  // (an empty shard has nothing to run)
+  for (const Param& pr : p.params)
+    if (pr.use & USE_SCATTER) return true;
+  return false;
+}
+// Operands of ONE primitive call are committed by ONE eval: a scatter they share still runs once.
+void commit_if_side_effects(Ir& ir, const VarId* ids, size_t n) {
+  std::vector<VarId> roots;
+  for (size_t i = 0; i < n; ++i)
+    if (has_side_effects(ir, ids[i])) roots.push_back(ids[i]);
+  if (!roots.empty()) eval(ir, roots.data(), roots.size());
 }
 
 // Buffer::str (internal.rs:404-422) through a D2H copy
@@ -310,6 +317,18 @@ vkjit_status vkjit_var_ref_count(vkjit_ir* h, vkjit_var id, uint32_t* out) {
     *out = ir.vars[id].ref_count;  // readable for dead vars too (test.rs:205)
   });
 }
+vkjit_status vkjit_var_deps(vkjit_ir* h, vkjit_var id, vkjit_var* deps, size_t cap, size_t* out_ndeps, int32_t* out_has_se,
+                            vkjit_var* out_se) {
+  return with_ir(h, [&](Ir& ir) {
+    const Var& v = ir.var(id);
+    const bool leaf = v.op == OP_BINDING || v.op == OP_ARANGE;  // the inline dep slots hold num / base there
+    const size_t nd = leaf ? 0 : v.ndeps;
+    if (out_ndeps) *out_ndeps = nd;
+    for (size_t k = 0; k < nd && k < cap; ++k) deps[k] = v.deps()[k];
+    if (out_has_se) *out_has_se = (!leaf && v.has_se) ? 1 : 0;
+    if (out_se) *out_se = (!leaf && v.has_se) ? v.side_effect : 0;
+  });
+}
 vkjit_status vkjit_var_count(vkjit_ir* h, size_t* out) { return with_ir(h, [&](Ir& ir) { *out = ir.vars.size(); }); }
 vkjit_status vkjit_array_count(vkjit_ir* h, size_t* out) { return with_ir(h, [&](Ir& ir) { *out = ir.n_arrays; }); }
 vkjit_status vkjit_is_buffer(vkjit_ir* h, vkjit_var id, int32_t* out) { return with_ir(h, [&](Ir& ir) { ir.var(id); *out = ir.is_buffer(id); }); }
@@ -369,7 +388,7 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
     if (!ty_is_num(ty)) fail(VKJIT_ERR_TYPE, "reduce needs U32/I32/F32");
     if (red < VKJIT_RED_SUM || red > VKJIT_RED_MAX) fail(VKJIT_ERR_INVALID, "unknown reduction");
     Backend& be = Backend::get();
-    commit_if_side_effects(ir, id);
+    commit_if_side_effects(ir, &id, 1);
     const bool sharded = ir.var(id).sharded;
     const bool combine = sharded && dist::active() && dist::world() > 1;
     // a rank whose shard of a tiny array is empty still has to take part in the collective
@@ -473,7 +492,7 @@ vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkji
     const TypeId ty = ir.var(id).ty;
     if (ty != VKJIT_TY_U32 && ty != VKJIT_TY_I32) fail(VKJIT_ERR_TYPE, "prefix_sum needs U32/I32");
     Backend& be = Backend::get();
-    commit_if_side_effects(ir, id);
+    commit_if_side_effects(ir, &id, 1);
     const bool sharded = ir.var(id).sharded && dist::active() && dist::world() > 1;
     // a rank whose shard is empty cannot evaluate it, but still has to take part in the exchange
     bool empty;
@@ -538,8 +557,10 @@ static void do_compress(Ir& ir, bool with_values, VarId values, VarId mask, vkji
     if (!ty_is_scalar(oty)) fail(VKJIT_ERR_TYPE, "compress values must be scalar");
   }
   Backend& be = Backend::get();
-  commit_if_side_effects(ir, mask);
-  if (with_values) commit_if_side_effects(ir, values);
+  {
+    const VarId ops[2] = {mask, values};
+    commit_if_side_effects(ir, ops, with_values ? 2 : 1);
+  }
   // Sharded compress: every rank compacts its own shard; the result is a ragged sharded array —
   // rank r holds the global elements [offset_r, offset_r + count_r), `count` is the GLOBAL number of selected lanes,
   // index results are global lane numbers.  Two small exchanges: exscan of the shard sizes (index base) and

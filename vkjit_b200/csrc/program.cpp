@@ -60,6 +60,15 @@ void type_signature(const Ir& ir, TypeId t, std::vector<uint32_t>& key) {
 
 constexpr size_t kMaxVectorNodes = 96;
 
+// $VKJIT_FAST_MATH=1: exp/log/sin/cos lower to CUDA's expf/logf/sinf/cosf (MUFU-assisted, 1-2 ulp, NOT bit-identical to
+// the oracle) instead of vk_math.h.  A speed knob for users who do not need reproducible bits; never the default,
+// never what the parity tests run.  Part of the cache key.
+int g_fast_math = -1;
+bool fast_math() {
+  if (g_fast_math < 0) { const char* s = getenv("VKJIT_FAST_MATH"); g_fast_math = (s && s[0] == '1') ? 1 : 0; }
+  return g_fast_math == 1;
+}
+
 int g_unroll = -1;
 int unroll_factor() {
   if (g_unroll < 0) {
@@ -274,7 +283,7 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   if (kn + 12 + p.roots.size() > key.size()) { key.resize(kn + 64 + p.roots.size()); kw = key.data(); }
   if (p.sadd_param < 0 || reduce >= 0 || scan >= 0) p.privatize = false;
   kw[1] = (vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16) | (p.privatize ? 1u << 24 : 0u) |
-          ((uint32_t)(scan + 1) << 25);  // bit 28 (lagged fused scan) is patched once the streams are known
+          ((uint32_t)(scan + 1) << 25) | (fast_math() ? 1u << 29 : 0u);  // bit 28 (lagged fused scan) is patched once the streams are known
   for (size_t k = 0; k < p.params.size(); ++k) kw[binding_pos[k]] |= (uint32_t)p.params[k].use << 16;
   if (scan >= 0 && scan_fused_geom(stream_count(p), scan, p.order.size()).lag) kw[1] |= 1u << 28;
   kw[kn++] = 0xFFFFFFFFu;
@@ -434,10 +443,10 @@ struct Gen {
       case VKJIT_UOP_NOT: return t == VKJIT_TY_BOOL ? "!" + a : "~" + a;
       case VKJIT_UOP_SQRT: return "__fsqrt_rn(" + a + ")";
       // vk_math.h: the one implementation the oracle compiles too (GPU == oracle bit for bit; <= 1 ulp of the exact value)
-      case VKJIT_UOP_EXP: uses_vk_math = true; return "vk_expf(" + a + ")";
-      case VKJIT_UOP_LOG: uses_vk_math = true; return "vk_logf(" + a + ")";
-      case VKJIT_UOP_SIN: uses_vk_math = true; return "vk_sinf(" + a + ")";
-      case VKJIT_UOP_COS: uses_vk_math = true; return "vk_cosf(" + a + ")";
+      case VKJIT_UOP_EXP: if (fast_math()) return "expf(" + a + ")"; uses_vk_math = true; return "vk_expf(" + a + ")";
+      case VKJIT_UOP_LOG: if (fast_math()) return "logf(" + a + ")"; uses_vk_math = true; return "vk_logf(" + a + ")";
+      case VKJIT_UOP_SIN: if (fast_math()) return "sinf(" + a + ")"; uses_vk_math = true; return "vk_sinf(" + a + ")";
+      case VKJIT_UOP_COS: if (fast_math()) return "cosf(" + a + ")"; uses_vk_math = true; return "vk_cosf(" + a + ")";
       default: fail(VKJIT_ERR_INVALID, "unknown uop");
     }
   }
@@ -495,8 +504,8 @@ struct Gen {
             const bool i_am_sin = v.kind == VKJIT_UOP_SIN;
             line("f32 " + me + ", " + other + ";");
             // one range reduction for both; bit-identical to vk_sinf / vk_cosf called separately (checked over all 2^32 inputs)
-            line("vk_sincosf(" + dep(v, 0).name + ", &" + (i_am_sin ? me : other) + ", &" + (i_am_sin ? other : me) + ");");
-            uses_vk_math = true;
+            line(std::string(fast_math() ? "sincosf(" : "vk_sincosf(") + dep(v, 0).name + ", &" + (i_am_sin ? me : other) + ", &" + (i_am_sin ? other : me) + ");");
+            if (!fast_math()) uses_vk_math = true;
           }
           vals[li].name = me; vals[li].ty = v.ty;
           break;

@@ -68,10 +68,20 @@ VKM_FN float vkm_i2f(int v) { return (float)v; }
 #define VKM_MAGIC_BITS 0x4b400000u
 
 // ---------------------------------------------------------------------------------------------------------------
-// exp:  x = j ln2 + r, |r| <= ln2 / 2;  e^r = 1 + r + r^2 q(r) (degree-6 minimax, tools/fit_vk_math.py);  result =
-// (p * 2^(j/2)) * 2^(j - j/2): the second multiply is the only rounding in the subnormal range.
+// exp:  x = j ln2 + r, |r| <= ln2 / 2;  e^r by a degree-6 minimax polynomial in Horner form (tools/fit_vk_math.py).
+// |x| < 87: the result is a normal number and the scaling by 2^j is an integer add to the exponent field.  The rest
+// (NaN, overflow, results in the subnormal range) is one out-of-line copy per kernel.
 // ---------------------------------------------------------------------------------------------------------------
-VKM_FN float vk_expf(float x) {
+VKM_FN float vkm_exp_poly(float r) {
+  float q = 0.001382041140459478f;
+  q = vkm_fma(q, r, 0.008368677459657192f);
+  q = vkm_fma(q, r, 0.04166826978325844f);
+  q = vkm_fma(q, r, 0.1666652113199234f);
+  q = vkm_fma(q, r, 0.4999999403953552f);
+  q = vkm_fma(q, r, 1.0f);
+  return vkm_fma(q, r, 1.0f);
+}
+VKM_SLOW_FN float vkm_exp_slow(float x) {
   const unsigned int ax = vkm_bits(x) & 0x7fffffffu;
   if (ax > VKM_INF) return vkm_float(VKM_NAN);
   if (x > 88.72283935546875f) return vkm_float(VKM_INF);   // e^x >= 2^128 - 2^103 rounds to +inf
@@ -79,32 +89,29 @@ VKM_FN float vk_expf(float x) {
   const float t = vkm_fma(x, 1.44269502162933349609375f, VKM_MAGIC);
   const float j = vkm_sub(t, VKM_MAGIC);
   const int n = (int)(vkm_bits(t) - VKM_MAGIC_BITS);
+  float r = vkm_fma(j, -0.693145751953125f, x);
+  r = vkm_fma(j, -1.42860682030941723212e-6f, r);
+  const float p = vkm_exp_poly(r);
+  const int n1 = n >> 1, n2 = n - n1;                      // arithmetic shift (both compilers)
+  // (p 2^n1) 2^n2: the second multiply is the only rounding when the result is subnormal
+  return vkm_mul(vkm_mul(p, vkm_float((unsigned int)(n1 + 127) << 23)), vkm_float((unsigned int)(n2 + 127) << 23));
+}
+VKM_FN float vk_expf(float x) {
+  if ((vkm_bits(x) & 0x7fffffffu) >= 0x42ae0000u) return vkm_exp_slow(x);   // |x| >= 87, inf, NaN
+  const float t = vkm_fma(x, 1.44269502162933349609375f, VKM_MAGIC);
+  const float j = vkm_sub(t, VKM_MAGIC);
   float r = vkm_fma(j, -0.693145751953125f, x);            // ln2 high part: 16 bits, j * hi is exact
   r = vkm_fma(j, -1.42860682030941723212e-6f, r);
-  float q = 0.001382041140459478f;
-  q = vkm_fma(q, r, 0.008368677459657192f);
-  q = vkm_fma(q, r, 0.04166826978325844f);
-  q = vkm_fma(q, r, 0.1666652113199234f);
-  q = vkm_fma(q, r, 0.4999999403953552f);
-  // 1 + r + r^2 q with the rounding error of 1 + r carried into the small term (Fast2Sum: |1| >= |r|)
-  const float s = vkm_add(1.0f, r);
-  const float p = vkm_add(s, vkm_fma(vkm_mul(r, r), q, vkm_sub(r, vkm_sub(s, 1.0f))));
-  const int n1 = n >> 1, n2 = n - n1;                      // arithmetic shift (both compilers)
-  const float s1 = vkm_float((unsigned int)(n1 + 127) << 23), s2 = vkm_float((unsigned int)(n2 + 127) << 23);
-  return vkm_mul(vkm_mul(p, s1), s2);
+  // the low bits of t hold j (the bits of the magic constant vanish in the shift)
+  return vkm_float(vkm_bits(vkm_exp_poly(r)) + (vkm_bits(t) << 23));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // log:  x = m 2^e with m in [sqrt(1/2), sqrt(2)), f = m - 1 (exact);  log1p(f) = f - f^2/2 + f^3 P(f) (degree-10
-// minimax);  result = e ln2_hi + f (compensated) + (e ln2_lo + f^3 P - f^2/2).
+// minimax);  result = e ln2_hi + f (compensated) + (e ln2_lo + f^2 (f P - 1/2)).  Zero, subnormal, negative, inf and
+// NaN arguments take the out-of-line path.
 // ---------------------------------------------------------------------------------------------------------------
-VKM_FN float vk_logf(float x) {
-  unsigned int ix = vkm_bits(x);
-  if ((ix << 1) == 0u) return vkm_float(0xff800000u);      // log(+-0) = -inf
-  if (ix > VKM_INF) return vkm_float(VKM_NAN);             // negative, -inf or NaN
-  if (ix == VKM_INF) return x;
-  int e = 0;
-  if (ix < 0x00800000u) { ix = vkm_bits(vkm_mul(x, 8388608.0f)); e = -23; }   // subnormal: scale by 2^23 (exact)
+VKM_FN float vkm_log_core(unsigned int ix, int e) {
   const unsigned int d = ix - 0x3f3504f3u;                 // bits of sqrt(1/2)
   e += (int)d >> 23;                                       // arithmetic shift (both compilers)
   const float f = vkm_sub(vkm_float((d & 0x007fffffu) + 0x3f3504f3u), 1.0f);
@@ -116,17 +123,24 @@ VKM_FN float vk_logf(float x) {
   q = vkm_fma(q, f, VKM_LOG_C5);
   q = vkm_fma(q, f, VKM_LOG_C4);
   q = vkm_fma(q, f, VKM_LOG_C3);
-  const float f2 = vkm_mul(f, f);
-  const float f2e = vkm_fma(f, f, -f2);                    // f^2 = f2 + f2e exactly
-  // small = f^3 P(f) - f^2 / 2, with the rounding error of f^2 carried along
-  float small = vkm_fma(vkm_mul(f2, f), q, vkm_mul(-0.5f, f2e));
-  small = vkm_fma(-0.5f, f2, small);
-  if (e == 0) return vkm_add(f, small);
+  const float small = vkm_mul(vkm_mul(f, f), vkm_fma(f, q, -0.5f));
   const float fe = vkm_i2f(e);
   const float hi = vkm_mul(fe, 0.693145751953125f);        // exact: 16-bit constant times an 8-bit integer
-  const float s = vkm_add(hi, f);                          // |hi| >= 0.69 > |f|: Fast2Sum gives the exact error
-  const float serr = vkm_add(vkm_sub(hi, s), f);
+  const float s = vkm_add(hi, f);                          // e != 0: |hi| >= 0.69 > |f|, Fast2Sum gives the exact error;
+  const float serr = vkm_add(vkm_sub(hi, s), f);           // e == 0: s = f, serr = 0
   return vkm_add(s, vkm_add(serr, vkm_fma(fe, 1.42860682030941723212e-6f, small)));
+}
+VKM_SLOW_FN float vkm_log_slow(float x) {
+  const unsigned int ix = vkm_bits(x);
+  if ((ix << 1) == 0u) return vkm_float(0xff800000u);      // log(+-0) = -inf
+  if (ix > VKM_INF) return vkm_float(VKM_NAN);             // negative, -inf or NaN
+  if (ix == VKM_INF) return x;
+  return vkm_log_core(vkm_bits(vkm_mul(x, 8388608.0f)), -23);   // subnormal: scale by 2^23 (exact)
+}
+VKM_FN float vk_logf(float x) {
+  const unsigned int ix = vkm_bits(x);
+  if (ix - 0x00800000u >= 0x7f000000u) return vkm_log_slow(x);   // not a positive normal number
+  return vkm_log_core(ix, 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -137,48 +151,9 @@ VKM_FN float vk_logf(float x) {
 VKM_TABLE unsigned int vkm_two_over_pi[8] = {0x00000000u, 0xa2f9836eu, 0x4e441529u, 0xfc2757d1u,
                                               0xf534ddc0u, 0xdb629599u, 0x3c439041u, 0xfe5163abu};
 
-// |x| > 105615 (finite): Payne-Hanek.  |x| = M 2^E with M the 24-bit significand as an integer; x (2/pi) mod 4 only needs
-// the bits of 2/pi from position E - 1 on (higher ones contribute multiples of 4): take 96 of them, multiply by M mod
-// 2^96; bits 95..94 of the product are the quadrant, the rest the fraction of a quadrant.
-VKM_SLOW_FN int vkm_trig_reduce_large(float x, float* r_out, float* lo_out) {
-  const unsigned int ix = vkm_bits(x), ax = ix & 0x7fffffffu;
-  const int E = (int)(ax >> 23) - 150;                     // >= -7 here
-  const unsigned int M = (ax & 0x007fffffu) | 0x00800000u;
-  const int s = E - 2 + 32;                                // first needed bit, counted from the MSB of table word 0
-  const int wi = s >> 5, sh = s & 31;
-  const unsigned int t0 = vkm_two_over_pi[wi], t1 = vkm_two_over_pi[wi + 1], t2 = vkm_two_over_pi[wi + 2], t3 = vkm_two_over_pi[wi + 3];
-  const unsigned int w2 = sh ? (t0 << sh) | (t1 >> (32 - sh)) : t0;
-  const unsigned int w1 = sh ? (t1 << sh) | (t2 >> (32 - sh)) : t1;
-  const unsigned int w0 = sh ? (t2 << sh) | (t3 >> (32 - sh)) : t2;
-  const unsigned long long a0 = (unsigned long long)M * w0;
-  const unsigned long long a1 = (unsigned long long)M * w1 + (a0 >> 32);
-  const unsigned long long a2 = (unsigned long long)M * w2 + (a1 >> 32);
-  const unsigned int P0 = (unsigned int)a0, P1 = (unsigned int)a1, P2 = (unsigned int)a2;
-  int n = (int)(P2 >> 30);
-  unsigned long long frac = ((unsigned long long)P2 << 34) | ((unsigned long long)P1 << 2) | (unsigned long long)(P0 >> 30);
-  bool neg = false;
-  if (frac >> 63) { frac = 0ull - frac; n += 1; neg = true; }   // nearest quadrant: fraction in [-1/2, 1/2)
-  float r = 0.0f, lo = 0.0f;
-  if (frac != 0ull) {
-    const int lz = vkm_clz64(frac);
-    const unsigned long long mag = frac << lz;
-    const float fh = vkm_mul(vkm_i2f((int)(mag >> 40)), vkm_float((unsigned int)(127 - 24 - lz) << 23));              // top 24 bits
-    const float fl = vkm_mul(vkm_i2f((int)((mag >> 16) & 0xffffffu)), vkm_float((unsigned int)(127 - 48 - lz) << 23));  // next 24
-    // (fh + fl) * pi/2 with pi/2 = hi + lo
-    const float t = vkm_fma(fh, -4.371138828673793e-08f, vkm_mul(fl, 1.57079637050628662109375f));
-    r = vkm_fma(fh, 1.57079637050628662109375f, t);
-    lo = vkm_add(vkm_fma(fh, 1.57079637050628662109375f, -r), t);   // what the rounding of r dropped
-  }
-  if (neg != (bool)(ix >> 31)) { r = vkm_float(vkm_bits(r) ^ 0x80000000u); lo = vkm_float(vkm_bits(lo) ^ 0x80000000u); }
-  if (ix >> 31) n = -n;                                    // sin/cos of -x from those of x
-  *r_out = r;
-  *lo_out = lo;
-  return n;
-}
-
-// returns n (only n mod 4 matters); *r_out + *lo_out = reduced argument (|lo| <= ulp(r) / 2).  x must be finite.
-VKM_FN int vkm_trig_reduce(float x, float* r_out, float* lo_out) {
-  if ((vkm_bits(x) & 0x7fffffffu) > 0x47ce4780u) return vkm_trig_reduce_large(x, r_out, lo_out);   // |x| > 105615
+// Fast path, 0 < |x| <= 105615: three-constant Cody-Waite.  Returns n (only n mod 4 matters); *r_out + *lo_out = reduced
+// argument (|lo| <= ulp(r) / 2).
+VKM_FN unsigned int vkm_trig_reduce(float x, float* r_out, float* lo_out) {
   const float t = vkm_fma(x, 0.63661977236758138243f, VKM_MAGIC);
   const float j = vkm_sub(t, VKM_MAGIC);
   const float r1 = vkm_fma(j, -1.57079601287841796875f, x);   // pi/2, leading 21 bits: the product is exact, and so is r1
@@ -190,7 +165,7 @@ VKM_FN int vkm_trig_reduce(float x, float* r_out, float* lo_out) {
   const float se = vkm_sub(vkm_sub(r1, r), p);
   *r_out = r;
   *lo_out = vkm_fma(j, -5.390302953474238392694851e-15f, vkm_sub(se, pe));
-  return (int)(vkm_bits(t) - VKM_MAGIC_BITS);
+  return vkm_bits(t);                                      // the low bits of t hold n (the magic constant's are zero)
 }
 
 // sin(r + lo) = sin r + lo cos r = r + (r z S(z) + lo) up to lo z / 2
@@ -200,8 +175,7 @@ VKM_FN float vkm_sin_poly(float r, float lo) {
   s = vkm_fma(s, z, VKM_SIN_C7);
   s = vkm_fma(s, z, VKM_SIN_C5);
   s = vkm_fma(s, z, VKM_SIN_C3);
-  const float v = vkm_add(r, vkm_fma(r, vkm_mul(z, s), lo));
-  return v == 0.0f ? r : v;                                // sin(-0) = -0: (-0) + (+0) would be +0
+  return vkm_add(r, vkm_fma(r, vkm_mul(z, s), lo));
 }
 // cos(r + lo) = cos r - lo sin r = 1 + (z (z C(z) - 1/2) - lo r)
 VKM_FN float vkm_cos_poly(float r, float lo) {
@@ -214,30 +188,77 @@ VKM_FN float vkm_cos_poly(float r, float lo) {
   const float w = vkm_fma(r, lo, vkm_mul(0.5f, ze));
   return vkm_add(1.0f, vkm_fma(z, vkm_fma(z, c, -0.5f), -w));
 }
+// n mod 4 selects:  sin(x) = s, c, -s, -c   cos(x) = c, -s, -c, s
+VKM_FN float vkm_pick_sin(unsigned int n, float s, float c) {
+  return vkm_float(vkm_bits((n & 1u) ? c : s) ^ ((n << 30) & 0x80000000u));
+}
+VKM_FN float vkm_pick_cos(unsigned int n, float s, float c) {
+  return vkm_float(vkm_bits((n & 1u) ? s : c) ^ (((n + 1u) << 30) & 0x80000000u));
+}
+
+// Everything the fast path does not take: +-0 (sin(-0) = -0), inf and NaN (NaN), and |x| > 105615, reduced by
+// Payne-Hanek: |x| = M 2^E with M the 24-bit significand as an integer; x (2/pi) mod 4 only needs the bits of 2/pi
+// from position E - 1 on (higher ones contribute multiples of 4): take 96 of them, multiply by M mod 2^96; bits 95..94
+// of the product are the quadrant, the rest the fraction of a quadrant.  One out-of-line copy per kernel.
+VKM_SLOW_FN float vkm_sincos_slow(float x, int want_cos) {
+  const unsigned int ix = vkm_bits(x), ax = ix & 0x7fffffffu;
+  if (ax == 0u) return want_cos ? 1.0f : x;
+  if (ax >= VKM_INF) return vkm_float(VKM_NAN);
+  const int E = (int)(ax >> 23) - 150;                     // >= -7 here
+  const unsigned int M = (ax & 0x007fffffu) | 0x00800000u;
+  const int s = E - 2 + 32;                                // first needed bit, counted from the MSB of table word 0
+  const int wi = s >> 5, sh = s & 31;
+  const unsigned int t0 = vkm_two_over_pi[wi], t1 = vkm_two_over_pi[wi + 1], t2 = vkm_two_over_pi[wi + 2], t3 = vkm_two_over_pi[wi + 3];
+  const unsigned int w2 = sh ? (t0 << sh) | (t1 >> (32 - sh)) : t0;
+  const unsigned int w1 = sh ? (t1 << sh) | (t2 >> (32 - sh)) : t1;
+  const unsigned int w0 = sh ? (t2 << sh) | (t3 >> (32 - sh)) : t2;
+  const unsigned long long a0 = (unsigned long long)M * w0;
+  const unsigned long long a1 = (unsigned long long)M * w1 + (a0 >> 32);
+  const unsigned long long a2 = (unsigned long long)M * w2 + (a1 >> 32);
+  const unsigned int P0 = (unsigned int)a0, P1 = (unsigned int)a1, P2 = (unsigned int)a2;
+  unsigned int n = P2 >> 30;
+  unsigned long long frac = ((unsigned long long)P2 << 34) | ((unsigned long long)P1 << 2) | (unsigned long long)(P0 >> 30);
+  bool neg = false;
+  if (frac >> 63) { frac = 0ull - frac; n += 1u; neg = true; }   // nearest quadrant: fraction in [-1/2, 1/2)
+  float r = 0.0f, lo = 0.0f;
+  if (frac != 0ull) {
+    const int lz = vkm_clz64(frac);
+    const unsigned long long mag = frac << lz;
+    const float fh = vkm_mul(vkm_i2f((int)(mag >> 40)), vkm_float((unsigned int)(127 - 24 - lz) << 23));              // top 24 bits
+    const float fl = vkm_mul(vkm_i2f((int)((mag >> 16) & 0xffffffu)), vkm_float((unsigned int)(127 - 48 - lz) << 23));  // next 24
+    // (fh + fl) * pi/2 with pi/2 = hi + lo
+    const float t = vkm_fma(fh, -4.371138828673793e-08f, vkm_mul(fl, 1.57079637050628662109375f));
+    r = vkm_fma(fh, 1.57079637050628662109375f, t);
+    lo = vkm_add(vkm_fma(fh, 1.57079637050628662109375f, -r), t);   // what the rounding of r dropped
+  }
+  if (neg != (bool)(ix >> 31)) { r = vkm_float(vkm_bits(r) ^ 0x80000000u); lo = vkm_float(vkm_bits(lo) ^ 0x80000000u); }
+  if (ix >> 31) n = 0u - n;                                // sin/cos of -x from those of x
+  const float sv = vkm_sin_poly(r, lo), cv = vkm_cos_poly(r, lo);
+  return want_cos ? vkm_pick_cos(n, sv, cv) : vkm_pick_sin(n, sv, cv);
+}
+
+// fast-path test: 0 < |x| <= 105615  (one unsigned compare: |x| = 0 wraps around)
+VKM_FN bool vkm_trig_fast(float x) { return (vkm_bits(x) & 0x7fffffffu) - 1u < 0x47ce4780u; }
 
 VKM_FN void vk_sincosf(float x, float* sin_out, float* cos_out) {
-  if ((vkm_bits(x) & 0x7fffffffu) >= VKM_INF) { *sin_out = *cos_out = vkm_float(VKM_NAN); return; }
+  if (!vkm_trig_fast(x)) { *sin_out = vkm_sincos_slow(x, 0); *cos_out = vkm_sincos_slow(x, 1); return; }
   float r, lo;
-  const int n = vkm_trig_reduce(x, &r, &lo);
+  const unsigned int n = vkm_trig_reduce(x, &r, &lo);
   const float s = vkm_sin_poly(r, lo), c = vkm_cos_poly(r, lo);
-  const float a = (n & 1) ? c : s;                         // sin(x): s, c, -s, -c for n mod 4 = 0..3
-  const float b = (n & 1) ? s : c;                         // cos(x): c, -s, -c, s
-  *sin_out = (n & 2) ? vkm_float(vkm_bits(a) ^ 0x80000000u) : a;
-  *cos_out = ((n + 1) & 2) ? vkm_float(vkm_bits(b) ^ 0x80000000u) : b;
+  *sin_out = vkm_pick_sin(n, s, c);
+  *cos_out = vkm_pick_cos(n, s, c);
 }
 VKM_FN float vk_sinf(float x) {
-  if ((vkm_bits(x) & 0x7fffffffu) >= VKM_INF) return vkm_float(VKM_NAN);
+  if (!vkm_trig_fast(x)) return vkm_sincos_slow(x, 0);
   float r, lo;
-  const int n = vkm_trig_reduce(x, &r, &lo);
-  const float a = (n & 1) ? vkm_cos_poly(r, lo) : vkm_sin_poly(r, lo);
-  return (n & 2) ? vkm_float(vkm_bits(a) ^ 0x80000000u) : a;
+  const unsigned int n = vkm_trig_reduce(x, &r, &lo);
+  return vkm_pick_sin(n, vkm_sin_poly(r, lo), vkm_cos_poly(r, lo));
 }
 VKM_FN float vk_cosf(float x) {
-  if ((vkm_bits(x) & 0x7fffffffu) >= VKM_INF) return vkm_float(VKM_NAN);
+  if (!vkm_trig_fast(x)) return vkm_sincos_slow(x, 1);
   float r, lo;
-  const int n = vkm_trig_reduce(x, &r, &lo);
-  const float b = (n & 1) ? vkm_sin_poly(r, lo) : vkm_cos_poly(r, lo);
-  return ((n + 1) & 2) ? vkm_float(vkm_bits(b) ^ 0x80000000u) : b;
+  const unsigned int n = vkm_trig_reduce(x, &r, &lo);
+  return vkm_pick_cos(n, vkm_sin_poly(r, lo), vkm_cos_poly(r, lo));
 }
 
 #endif  // VK_MATH_H
