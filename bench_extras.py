@@ -196,7 +196,19 @@ def run(ir, vk, stream, flush_l2, peak):
         t.append(time.perf_counter() - t0)
         ir.dec_ref_count(z)
     out["E20_eval_plus_readback_us"] = {"median": 1e6 * sorted(t[2:])[len(t[2:]) // 2], "n": n20, "readback_bytes": 4 * n20,
-                                        "host_buffer": "pageable (numpy)"}
+                                        "host_buffer": "caller's pageable buffer (vkjit_read into a numpy array): through the pinned staging ring"}
+    t = []
+    for i in range(12):   # the DEFAULT front-end read: as_slice returns an array that lives in pinned memory (one DMA, no staging copy)
+        t0 = time.perf_counter()
+        z = ir.add(ir.mul(ir.arange(T.F32, n20), y20), half)
+        ir.eval([z])
+        res = ir.as_slice(z, T.F32)
+        t.append(time.perf_counter() - t0)
+        ir.dec_ref_count(z)
+    out["E20_eval_plus_readback_default_us"] = {"median": 1e6 * sorted(t[2:])[len(t[2:]) // 2], "n": n20, "readback_bytes": 4 * n20,
+                                                "host_buffer": "default: Ir.as_slice / Var.numpy() result array from the pinned pool",
+                                                "checksum": float(res[:16].sum())}
+    del res
     import ctypes as C
     hp = C.c_void_p()
     vk.product_api().call("host_alloc", 4 * n20, C.byref(hp))   # pinned staging (vkjit_host_alloc)

@@ -114,6 +114,8 @@ extern "C" {
     pub fn vkjit_dist_init(rank: i32, world: i32, id128: *const c_void) -> vkjit_status;
     pub fn vkjit_dist_mailbox_handle(out_handle64: *mut c_void) -> vkjit_status;
     pub fn vkjit_dist_mailbox_open(handles: *const c_void, world: i32) -> vkjit_status;
+    pub fn vkjit_dist_init_env() -> vkjit_status;
+    pub fn vkjit_debug_rendezvous(rank: i32, world: i32, addr: *const c_char, port: i32, blob64: *const c_void, root128: *mut c_void, out_all: *mut c_void, timeout_s: f64) -> vkjit_status;
     pub fn vkjit_dist_set_p2p(on: i32) -> vkjit_status;
     pub fn vkjit_dist_shutdown() -> vkjit_status;
     pub fn vkjit_dist_info(out_rank: *mut i32, out_world: *mut i32) -> vkjit_status;

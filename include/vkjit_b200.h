@@ -267,6 +267,16 @@ vkjit_status vkjit_dist_init(int32_t rank, int32_t world, const void* id128);
 vkjit_status vkjit_dist_mailbox_handle(void* out_handle64);
 vkjit_status vkjit_dist_mailbox_open(const void* handles, int32_t world);
 /* Switch between the fused mailbox path (1) and NCCL (0); every rank must make the same call. */
+/* Multi-GPU WITHOUT torch / MPI (one process per GPU, any launcher): reads RANK, WORLD_SIZE, LOCAL_RANK, MASTER_ADDR,
+ * MASTER_PORT from the environment, calls vkjit_init(LOCAL_RANK) if that has not happened, exchanges rank 0's NCCL id
+ * and every rank's mailbox handle over TCP (rank 0 listens on MASTER_ADDR : $VKJIT_RDZV_PORT, default MASTER_PORT + 1;
+ * $VKJIT_RDZV_TIMEOUT_S, default 120), then does what vkjit_dist_init + vkjit_dist_mailbox_open do.  A vkjit-rust or C
+ * caller shards with this one call; the front-end's single global `Ir` (vkjit-rust/src/lib.rs:9-11) stays as it is. */
+vkjit_status vkjit_dist_init_env(void);
+/* Debug / test: the rendezvous alone (no device, no NCCL): blob64 of every rank -> out_all (world x 64 bytes, rank
+ * order); root128 is rank 0's on entry and everyone's on return. */
+vkjit_status vkjit_debug_rendezvous(int32_t rank, int32_t world, const char* addr, int32_t port, const void* blob64,
+                                    void* root128, void* out_all, double timeout_s);
 vkjit_status vkjit_dist_set_p2p(int32_t on);
 vkjit_status vkjit_dist_shutdown(void);
 vkjit_status vkjit_dist_info(int32_t* out_rank, int32_t* out_world);

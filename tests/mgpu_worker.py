@@ -1,11 +1,20 @@
-"""One rank of the multi-GPU parity test (launched by torchrun, one process per GPU, NCCL)."""
+"""One rank of the multi-GPU parity test: one process per GPU.
+
+    torchrun ... tests/mgpu_worker.py             rendezvous through torch.distributed (NCCL process group)
+    RANK=r WORLD_SIZE=n LOCAL_RANK=r MASTER_ADDR=127.0.0.1 MASTER_PORT=p python tests/mgpu_worker.py --no-torch
+                                                  no torch at all: vkjit_dist_init_env (native TCP rendezvous), what a
+                                                  vkjit-rust or C caller uses
+"""
 import math
 import os
 import sys
 
 import numpy as np
-import torch
-import torch.distributed as td
+
+NO_TORCH = "--no-torch" in sys.argv
+if not NO_TORCH:
+    import torch
+    import torch.distributed as td
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -28,10 +37,14 @@ def trace_f32(ir, lanes):
 
 def main():
     local = int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    td.init_process_group("nccl", device_id=torch.device("cuda", local))
-    vk.init(local)
-    rank, world = dist.init_from_torch(torch.device("cuda", local))
+    if NO_TORCH:
+        assert "torch" not in sys.modules
+        rank, world = dist.init_from_env()      # binds the device, NCCL communicator, peer mailboxes
+    else:
+        torch.cuda.set_device(local)
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+        vk.init(local)
+        rank, world = dist.init_from_torch(torch.device("cuda", local))
     for p2p, n in [(m, k) for m in (True, False) for k in (5, 1000, (1 << 22) + 3)]:
         dist.set_p2p(p2p)  # fused reduce + all-reduce over NVLink peer memory, then the NCCL path
         ir = Ir()
@@ -91,19 +104,25 @@ def main():
             assert ir.is_sharded(gi) and ir.is_sharded(gv)
             off, k = ir.shard_base(gi), ir.size(gi)
             assert ir.shard_base(gv) == off and ir.size(gv) == k
-            counts = [None] * world
-            td.all_gather_object(counts, (off, k))
-            assert counts[0][0] == 0 and sum(c[1] for c in counts) == cg
-            assert all(a[0] + a[1] == b[0] for a, b in zip(counts, counts[1:]))
+            # this rank's ragged shard = the selected lanes of [lo, hi): its offset and size follow from the oracle's mask
+            mo = o.as_slice_eval(m_o, T.BOOL) != 0
+            assert off == int(mo[:lo].sum()) and k == int(mo[lo:hi].sum()), (n, p2p, fused, off, k)
             if k:
                 assert ir.as_slice(gi, T.U32).tobytes() == want_idx[off:off + k].tobytes(), (n, p2p, fused)   # GLOBAL lane numbers
                 assert ir.as_slice(gv, T.U32).tobytes() == want_val[off:off + k].tobytes(), (n, p2p, fused)
         ir.close(); o.close()
     st = vk.stats()
     assert st["collectives"] > 0 or world == 1
-    td.barrier()
-    dist.shutdown()
-    td.destroy_process_group()
+    if NO_TORCH:
+        assert "torch" not in sys.modules
+        ir = Ir()                                # a last sharded reduction doubles as the barrier before shutdown
+        ir.as_slice(ir.reduce(Red.Sum, ir.arange_sharded(T.U32, 64 * world)), T.U32)
+        ir.close()
+        dist.shutdown()
+    else:
+        td.barrier()
+        dist.shutdown()
+        td.destroy_process_group()
     print(f"rank {rank}/{world} ok collectives={st['collectives']}")
 
 

@@ -589,3 +589,23 @@ def test_side_effect_of_a_primitives_operand_runs_once(cir, oir):
             assert ir.is_buffer(s)                       # committed by the primitive
             ir.eval([s])                                 # a Binding root: copied, nothing re-executed
             assert np.array_equal(ir.as_slice(dst, U32), np.arange(1, n + 1, dtype=np.uint32)), prim
+
+
+@pytest.mark.parametrize("n", [1, 16383, 16384, (2 << 20) // 4 - 1, (2 << 20) // 4 + 1, 3 * (2 << 20) // 4 + 5, 9 * (1 << 20) + 3])
+def test_upload_and_readback_through_the_staging_ring(cir, n):
+    """Pageable host memory crosses PCIe through the pinned staging ring (csrc/staging.cpp: 2 MiB chunks, threaded
+    memcpy); sizes around the direct-copy threshold (64 KiB), one chunk, several chunks with a ragged tail.  The
+    upload returns once the caller's buffer is copied out, so overwriting it right away must not change the array."""
+    rng = np.random.default_rng(n)
+    src = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    keep = src.copy()
+    v = cir.array_u32(src)
+    src[:] = 0xDEADBEEF                                   # the reference's contract: the slice may be reused at once
+    y = cir.add(v, cir.const_u32(1))
+    got = cir.as_slice_eval(y, U32)                       # result array from the pinned pool (>= 64 KiB) or numpy
+    assert np.array_equal(got, keep + np.uint32(1))
+    host = np.empty(n, np.uint32)                         # the C ABI into the caller's pageable buffer
+    cir.read_into(v, U32, host.ctypes.data, host.nbytes)
+    assert np.array_equal(host, keep)
+    again = cir.as_slice(v, U32)                          # a second read: another block of the pool, same contents
+    assert np.array_equal(again, keep) and (n * 4 < (64 << 10) or again.ctypes.data != got.ctypes.data)

@@ -118,6 +118,8 @@ _PRODUCT_SIGS = {
     "dist_mailbox_handle": [_p],
     "dist_mailbox_open": [_p, _i32],
     "dist_set_p2p": [_i32],
+    "dist_init_env": [],
+    "debug_rendezvous": [_i32, _i32, C.c_char_p, _i32, _p, _p, _p, C.c_double],
     "dist_shutdown": [],
     "dist_info": [_pi32, _pi32],
     "arange_sharded": [_p, _u32, _sz, _pu32],

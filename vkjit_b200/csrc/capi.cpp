@@ -642,6 +642,11 @@ vkjit_status vkjit_dist_unique_id(void* out) { return guard([&] { dist::unique_i
 vkjit_status vkjit_dist_init(int32_t rank, int32_t world, const void* id) { return guard([&] { dist::init(rank, world, id); }); }
 vkjit_status vkjit_dist_mailbox_handle(void* out64) { return guard([&] { dist::mailbox_handle(out64); }); }
 vkjit_status vkjit_dist_mailbox_open(const void* handles, int32_t world) { return guard([&] { dist::mailbox_open(handles, world); }); }
+vkjit_status vkjit_dist_init_env(void) { return guard([&] { dist::init_env(); }); }
+vkjit_status vkjit_debug_rendezvous(int32_t rank, int32_t world, const char* addr, int32_t port, const void* blob64, void* root128,
+                                    void* out_all, double timeout_s) {
+  return guard([&] { dist::rendezvous(rank, world, addr, port, blob64, 64, root128, 128, out_all, timeout_s); });
+}
 vkjit_status vkjit_dist_set_p2p(int32_t on) { return guard([&] { dist::set_p2p(on != 0); }); }
 vkjit_status vkjit_dist_shutdown(void) { return guard([&] { dist::shutdown(); }); }
 vkjit_status vkjit_dist_info(int32_t* rank, int32_t* world) {

@@ -7,9 +7,11 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include <string>
+#include <vector>
 
 #include "runtime.h"
 
@@ -83,6 +85,25 @@ void init(int rank, int world, const void* id128) {
     ckn(g_nccl.CommInitRank(&g_comm, world, id, rank), "ncclCommInitRank");
   }
   g_active = true;
+}
+
+void init_env() {
+  if (g_active) fail(VKJIT_ERR_DIST, "vkjit_dist_init_env: already initialised");
+  auto env_int = [](const char* n, int d) { const char* v = getenv(n); return (v && *v) ? atoi(v) : d; };
+  const int world = env_int("WORLD_SIZE", 1), rank = env_int("RANK", 0);
+  if (!Backend::initialized()) Backend::init(env_int("LOCAL_RANK", rank));
+  unsigned char id[128] = {0}, mine[64] = {0};
+  std::vector<unsigned char> all((size_t)std::max(world, 1) * 64);
+  if (world > 1) {
+    if (rank == 0) unique_id(id);
+    mailbox_handle(mine);
+    std::string addr; int port = 0;
+    rendezvous_endpoint(addr, port);
+    const char* to = getenv("VKJIT_RDZV_TIMEOUT_S");
+    rendezvous(rank, world, addr.c_str(), port, mine, 64, id, 128, all.data(), to ? atof(to) : 120.0);
+  }
+  init(rank, world, id);
+  if (world > 1) mailbox_open(all.data(), world);
 }
 
 void mailbox_handle(void* out64) {

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <string>
 
 #include "prims.h"
 
@@ -26,6 +27,16 @@ void mailbox_open(const void* handles, int world);
 bool p2p_enabled();
 void set_p2p(bool on);  // switch between the fused mailbox path and NCCL (all ranks must agree)
 prims::Mailbox next_mailbox();  // bumps the collective sequence number
+
+// Torch-free bring-up (rendezvous.cpp): exchange over one TCP connection per rank to rank 0.  `mine` (blob_bytes) of
+// every rank lands in all_out (world x blob_bytes, rank order) on every rank; root_blob (root_bytes) is rank 0's on
+// entry and everyone's on return.  Returns only once all ranks have arrived.
+void rendezvous(int rank, int world, const char* addr, int port, const void* mine, size_t blob_bytes, void* root_blob,
+                size_t root_bytes, void* all_out, double timeout_s);
+// init_env(): RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT (VKJIT_RDZV_PORT) from the environment:
+// Backend::init(LOCAL_RANK) if needed, rendezvous, NCCL communicator, peer mailboxes.
+void init_env();
+void rendezvous_endpoint(std::string& addr, int& port);
 
 // contiguous shards in units of 4 lanes (16-byte aligned); the last rank takes the ragged tail
 void shard_range(size_t n, int rank, int world, size_t& lo, size_t& hi);

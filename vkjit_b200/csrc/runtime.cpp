@@ -138,6 +138,7 @@ void Backend::shutdown() {
   std::lock_guard<std::mutex> g(g_init_mu);
   if (!g_backend) return;
   Backend* b = g_backend;
+  staging_shutdown();
   b->trim();
   cudaStreamSynchronize((cudaStream_t)b->stream);
   b->clear_cache();
@@ -240,17 +241,16 @@ void drain_foreign_releases() {
 
 void Backend::h2d(void* dst, const void* src, size_t bytes) {
   if (!bytes) return;
-  ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), "H2D copy");
-  // the caller may reuse `src` as soon as we return (Backend::create_array_from_slice copies
-  // synchronously into mapped memory, vulkan/mod.rs:56-73)
-  ck(cudaStreamSynchronize((cudaStream_t)stream), "H2D sync");
+  // the caller may reuse `src` as soon as we return (Backend::create_array_from_slice copies synchronously into
+  // mapped memory, vulkan/mod.rs:56-73): pageable memory is copied out into the pinned ring (no device
+  // synchronisation), a direct DMA from pinned memory has to finish first
+  if (staged_h2d(dst, src, bytes, stream)) ck(cudaStreamSynchronize((cudaStream_t)stream), "H2D sync");
   g_counters.bytes_h2d += bytes;
   g_counters.stream_ops += 1;
 }
 
 void Backend::d2h(void* dst, const void* src, size_t bytes) {
-  if (bytes) ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H copy");
-  ck(cudaStreamSynchronize((cudaStream_t)stream), "D2H sync");
+  staged_d2h(dst, src, bytes, stream);
   check_fault();
   g_counters.bytes_d2h += bytes;
   g_counters.stream_ops += 1;

@@ -102,6 +102,11 @@ class Backend {
 // the backend checks it and fails with VKJIT_ERR_DIST.  nullptr: nothing to check.
 void set_fault_word(volatile uint32_t* host_word);
 
+// staging.cpp: copies between PAGEABLE host memory and the device through a pinned ring with a threaded host memcpy.
+bool staged_h2d(void* dst, const void* src, size_t bytes, void* stream);  // true: sync the stream before reusing src
+void staged_d2h(void* dst, const void* src, size_t bytes, void* stream);  // synchronous
+void staging_shutdown();
+
 // Evaluate the Ir's schedule (+ ids): the body of Ir::eval (internal.rs:482-525).
 void eval(Ir& ir, const VarId* ids, size_t n);
 

@@ -68,6 +68,26 @@ def open_mailboxes(rank: int, world: int, device=None):
     api.call("dist_mailbox_open", C.create_string_buffer(raw, 64 * world), world)
 
 
+def init_from_env():
+    """Multi-GPU bring-up WITHOUT torch (native TCP rendezvous, csrc/rendezvous.cpp): RANK / WORLD_SIZE / LOCAL_RANK /
+    MASTER_ADDR / MASTER_PORT from the environment, as any launcher sets them.  Binds the device (LOCAL_RANK), creates
+    the NCCL communicator and maps the peer mailboxes.  Returns (rank, world)."""
+    api = product_api()
+    api.call("dist_init_env")
+    r, w = C.c_int32(), C.c_int32()
+    api.call("dist_info", C.byref(r), C.byref(w))
+    return r.value, w.value
+
+
+def rendezvous(rank: int, world: int, blob64: bytes, root128: bytes, addr: str = "127.0.0.1", port: int = 29501, timeout_s: float = 60.0):
+    """The exchange alone (needs no device): every rank's 64-byte blob to everyone, rank 0's 128-byte blob to everyone."""
+    assert len(blob64) == 64 and len(root128) == 128
+    root = C.create_string_buffer(root128, 128)
+    out = C.create_string_buffer(64 * world)
+    product_api().call("debug_rendezvous", rank, world, addr.encode(), port, C.create_string_buffer(blob64, 64), root, out, timeout_s)
+    return bytes(root.raw), [bytes(out.raw[64 * r:64 * (r + 1)]) for r in range(world)]
+
+
 def shutdown():
     product_api().call("dist_shutdown")
 

@@ -48,6 +48,56 @@ def _u32arr(ids: Sequence[int]):
     return (C.c_uint32 * len(ids))(*[int(i) for i in ids])
 
 
+# ---- pinned result arrays ------------------------------------------------------------------------------------------
+_PINNED_MIN_BYTES = 64 << 10
+_PINNED_KEEP_BYTES = 1 << 30      # blocks kept for reuse, in total
+_pinned_free = {}                 # capacity -> [ptr]
+_pinned_kept = 0
+
+
+def _pinned_release(api, ptr, cap):
+    global _pinned_kept
+    if _pinned_kept + cap <= _PINNED_KEEP_BYTES and len(_pinned_free.setdefault(cap, [])) < 8:
+        _pinned_free[cap].append(ptr)
+        _pinned_kept += cap
+        return
+    try:
+        api._fn["host_free"](C.c_void_p(ptr))    # status ignored: at interpreter exit the context may be gone
+    except Exception:
+        pass
+
+
+def _pinned_empty(api, n, dtype):
+    """np.ndarray of n elements in pinned host memory (only with the product library and an initialised backend;
+    otherwise an ordinary array).  The block goes back to the pool when the last view of the array dies."""
+    global _pinned_kept
+    import weakref
+    nbytes = n * np.dtype(dtype).itemsize
+    if not api.has("host_alloc") or api.prefix != "vkjit_":
+        return np.empty(n, dtype=dtype)
+    cap = 1 << max(16, (nbytes - 1).bit_length())       # power-of-two size classes
+    lst = _pinned_free.get(cap)
+    if lst:
+        ptr = lst.pop()
+        _pinned_kept -= cap
+    else:
+        p = C.c_void_p()
+        try:
+            api.call("host_alloc", cap, C.byref(p))
+        except Exception:
+            return np.empty(n, dtype=dtype)
+        ptr = p.value
+    buf = (C.c_char * cap).from_address(ptr)
+    weakref.finalize(buf, _pinned_release, api, ptr, cap)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+def pinned_empty(n: int, dtype=np.float32) -> np.ndarray:
+    """An empty array in pinned host memory: build inputs here and `array_*` uploads them with one direct DMA."""
+    from ._capi import product_api
+    return _pinned_empty(product_api(), n, dtype)
+
+
 class Ir:
     def __init__(self, _api: Optional[CApi] = None):
         self.api = _api or product_api()
@@ -257,9 +307,13 @@ class Ir:
         self.api.call("eval", self._h, _u32arr(ids), len(ids))
 
     def as_slice(self, id: int, ty: int) -> np.ndarray:
-        """Ir::as_slice::<T> (internal.rs:443-449): `ty` plays the role of T."""
+        """Ir::as_slice::<T> (internal.rs:443-449): `ty` plays the role of T.  The reference returns a zero-copy view of
+        host-visible memory (vulkan/mod.rs:29-34); here the result array of a large read lives in PINNED host memory
+        (a pool of vkjit_host_alloc blocks, returned when the array is garbage collected), so the D2H copy is one DMA
+        at PCIe speed straight into the array the caller gets — no staging copy, no second pass over the data."""
         n = self.size(id)
-        out = np.empty(n, dtype=VarType.numpy(ty))
+        dt = VarType.numpy(ty)
+        out = _pinned_empty(self.api, n, dt) if n * 4 >= _PINNED_MIN_BYTES else np.empty(n, dtype=dt)
         self.api.call("read", self._h, id, ty, out.ctypes.data_as(C.c_void_p), out.nbytes)
         return out
 
