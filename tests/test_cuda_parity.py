@@ -591,10 +591,11 @@ def test_side_effect_of_a_primitives_operand_runs_once(cir, oir):
             assert np.array_equal(ir.as_slice(dst, U32), np.arange(1, n + 1, dtype=np.uint32)), prim
 
 
-@pytest.mark.parametrize("n", [1, 16383, 16384, (2 << 20) // 4 - 1, (2 << 20) // 4 + 1, 3 * (2 << 20) // 4 + 5, 9 * (1 << 20) + 3])
+@pytest.mark.parametrize("n", [1, 16383, 16384, (2 << 20) // 4 + 1, (16 << 20) // 4 - 1, (16 << 20) // 4, (18 << 20) // 4 + 5, 9 * (1 << 20) + 3])
 def test_upload_and_readback_through_the_staging_ring(cir, n):
     """Pageable host memory crosses PCIe through the pinned staging ring (csrc/staging.cpp: 2 MiB chunks, threaded
-    memcpy); sizes around the direct-copy threshold (64 KiB), one chunk, several chunks with a ragged tail.  The
+    memcpy) from 16 MiB on, the driver's pageable path below; sizes around the pinned-pool threshold of the front-end
+    (64 KiB), around the ring threshold, and several chunks with a ragged tail.  The
     upload returns once the caller's buffer is copied out, so overwriting it right away must not change the array."""
     rng = np.random.default_rng(n)
     src = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
@@ -609,3 +610,28 @@ def test_upload_and_readback_through_the_staging_ring(cir, n):
     assert np.array_equal(host, keep)
     again = cir.as_slice(v, U32)                          # a second read: another block of the pool, same contents
     assert np.array_equal(again, keep) and (n * 4 < (64 << 10) or again.ctypes.data != got.ctypes.data)
+
+
+@pytest.mark.parametrize("bins,n", [(1, 4099), (4, 100003), (16, (1 << 22) + 5), (1000, 50001), (70000, (1 << 22) + 7)])
+def test_scatter_add_hot_bins_warp_aggregated(cir, oir, bins, n):
+    """Integer scatter_add when the lanes of a warp collide (few distinct bins): every warp probes once, then adds one
+    atomic per distinct bin (match.any + redux.sync, program.cpp: kSaddHelper) — bit-exact against the oracle like the
+    plain path, with and without a mask, U32 and I32 (negative values), small launches and the shared-memory-privatised
+    variant of launches >= 2^22 lanes (bins above and below what fits in shared memory)."""
+    for ir in (cir, oir):
+        lanes = ir.arange(U32, n)
+        h = ir.mul(ir.bop(Bop.Xor, lanes, ir.const_u32(0x9E3779B9)), ir.const_u32(747796405))
+        idx = ir.bop(Bop.Shr, h, ir.const_u32(9))
+        idx = ir.sub(idx, ir.mul(ir.div(idx, ir.const_u32(bins)), ir.const_u32(bins)))        # idx mod bins
+        du = ir.array_u32(np.zeros(bins, np.uint32))
+        di = ir.array_i32(np.zeros(bins, np.int32))
+        wi = ir.sub(ir.cast(ir.bop(Bop.And, h, ir.const_u32(1023)), I32), ir.const_i32(700))  # in [-700, 323]
+        mask = ir.neq(ir.bop(Bop.And, h, ir.const_u32(4)), ir.const_u32(0))
+        s1 = ir.scatter_add(ir.bop(Bop.Shr, h, ir.const_u32(3)), du, idx)
+        s2 = ir.scatter_add(wi, di, idx, mask)
+        ir.eval([s1, s2])
+        if ir is cir:
+            got = (ir.as_slice(du, U32).copy(), ir.as_slice(di, I32).copy())
+        else:
+            want = (ir.as_slice(du, U32), ir.as_slice(di, I32))
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])

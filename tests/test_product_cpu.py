@@ -378,3 +378,23 @@ def test_shard_range_properties(oracle_api):
                         assert (hi.value - lo.value) % 4 == 0      # 16-byte aligned shards
                     prev = hi.value
                 assert prev == n
+
+
+def test_failed_composite_constructors_leak_nothing():
+    """linspace / zeros / ones build temporaries before a later step can fail (Bool `ty`, a Void struct member): every
+    temporary is released on the error path too (`len` stayed alive and pinned start/stop)."""
+    ir = Ir()
+    a, b = ir.const_f32(1.0), ir.const_f32(2.0)
+
+    def live():
+        return ir.repr().count("Var {") - ir.repr().count("op: Free")
+    before = live()
+    with pytest.raises(VkjitError):
+        ir.linspace(BOOL, a, b, 8)                         # arange(Bool) is unimplemented!() in the reference
+    with pytest.raises(VkjitError):
+        ir.linspace(F32, a, b, 1 << 33)                    # beyond the 32-bit lane index
+    with pytest.raises(VkjitError):
+        ir.zeros(ir.struct_type([F32, 1]))                 # a Void member (type code 1)
+    with pytest.raises(VkjitError):
+        ir.ones(ir.struct_type([U32, F32, 1]))
+    assert live() == before and ir.ref_count(a) == 1 and ir.ref_count(b) == 1

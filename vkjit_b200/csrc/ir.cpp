@@ -211,18 +211,28 @@ VarId Ir::select(VarId c, VarId l, VarId r) {
   return new_var(OP_SELECT, var(l).ty, d, 3);
 }
 
+// Temporaries of a composite constructor: owned by the expression that consumes them, released on EVERY exit — also
+// when a later step throws (a Bool / struct `ty`, n >= 2^32, a Void member): nothing stays pinned by a failed call.
+namespace {
+struct Temps {
+  Ir& ir;
+  std::vector<VarId> ids;
+  explicit Temps(Ir& i) : ir(i) {}
+  VarId keep(VarId id) { ids.push_back(id); return id; }
+  ~Temps() { for (size_t k = ids.size(); k-- > 0;) ir.dec_ref(ids[k]); }
+};
+}  // namespace
+
 // internal.rs:238-246: ((arange(ty, n) / u32(n)) * (stop - start)) + start
 VarId Ir::linspace(TypeId ty, VarId start, VarId stop, uint64_t n) {
   var(start); var(stop);
-  const VarId len = bop(VKJIT_BOP_SUB, stop, start);
-  const VarId idx = arange(ty, n, 0, false);
-  const VarId num = constant(VKJIT_TY_U32, (uint32_t)n);
-  const VarId a = bop(VKJIT_BOP_DIV, idx, num);
-  const VarId b = bop(VKJIT_BOP_MUL, a, len);
-  const VarId x = bop(VKJIT_BOP_ADD, b, start);
-  // deviation: temporaries are owned by the expression only
-  dec_ref(b); dec_ref(a); dec_ref(num); dec_ref(idx); dec_ref(len);
-  return x;
+  Temps t(*this);  // deviation: the reference leaks these five vars (internal.rs:238-246)
+  const VarId len = t.keep(bop(VKJIT_BOP_SUB, stop, start));
+  const VarId idx = t.keep(arange(ty, n, 0, false));
+  const VarId num = t.keep(constant(VKJIT_TY_U32, (uint32_t)n));
+  const VarId a = t.keep(bop(VKJIT_BOP_DIV, idx, num));
+  const VarId b = t.keep(bop(VKJIT_BOP_MUL, a, len));
+  return bop(VKJIT_BOP_ADD, b, start);
 }
 
 // internal.rs:291-300
@@ -240,11 +250,9 @@ VarId Ir::zeros(TypeId ty) {
   check_type(ty);
   if (ty_is_struct(ty)) {
     const std::vector<TypeId> elems = struct_elems(ty);
-    std::vector<VarId> es;
-    for (TypeId e : elems) es.push_back(zeros(e));
-    const VarId r = struct_init(es.data(), es.size());
-    for (VarId e : es) dec_ref(e);
-    return r;
+    Temps t(*this);
+    for (TypeId e : elems) t.keep(zeros(e));
+    return struct_init(t.ids.data(), t.ids.size());
   }
   if (!ty_is_scalar(ty)) fail(VKJIT_ERR_UNSUPPORTED, "zeros of Void");
   return constant(ty, 0u);
@@ -255,11 +263,9 @@ VarId Ir::ones(TypeId ty) {
   check_type(ty);
   if (ty_is_struct(ty)) {
     const std::vector<TypeId> elems = struct_elems(ty);
-    std::vector<VarId> es;
-    for (TypeId e : elems) es.push_back(ones(e));
-    const VarId r = struct_init(es.data(), es.size());
-    for (VarId e : es) dec_ref(e);  // deviation: see file header
-    return r;
+    Temps t(*this);  // deviation: see file header
+    for (TypeId e : elems) t.keep(ones(e));
+    return struct_init(t.ids.data(), t.ids.size());
   }
   if (!ty_is_scalar(ty)) fail(VKJIT_ERR_UNSUPPORTED, "ones of Void");
   return constant(ty, one_bits(ty));

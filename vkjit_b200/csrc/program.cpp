@@ -69,6 +69,13 @@ bool fast_math() {
   return g_fast_math == 1;
 }
 
+// $VKJIT_NO_AGG=1: integer scatter_add never aggregates within the warp (A/B measurements); part of the cache key
+int g_no_agg = -1;
+bool no_agg() {
+  if (g_no_agg < 0) { const char* s = getenv("VKJIT_NO_AGG"); g_no_agg = (s && s[0] == '1') ? 1 : 0; }
+  return g_no_agg == 1;
+}
+
 int g_unroll = -1;
 int unroll_factor() {
   if (g_unroll < 0) {
@@ -283,7 +290,7 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   if (kn + 12 + p.roots.size() > key.size()) { key.resize(kn + 64 + p.roots.size()); kw = key.data(); }
   if (p.sadd_param < 0 || reduce >= 0 || scan >= 0) p.privatize = false;
   kw[1] = (vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16) | (p.privatize ? 1u << 24 : 0u) |
-          ((uint32_t)(scan + 1) << 25) | (fast_math() ? 1u << 29 : 0u);  // bit 28 (lagged fused scan) is patched once the streams are known
+          ((uint32_t)(scan + 1) << 25) | (fast_math() ? 1u << 29 : 0u) | (no_agg() ? 1u << 30 : 0u);  // bit 28 (lagged fused scan) is patched once the streams are known
   for (size_t k = 0; k < p.params.size(); ++k) kw[binding_pos[k]] |= (uint32_t)p.params[k].use << 16;
   if (scan >= 0 && scan_fused_geom(stream_count(p), scan, p.order.size()).lag) kw[1] |= 1u << 28;
   kw[kn++] = 0xFFFFFFFFu;
@@ -359,6 +366,7 @@ struct Gen {
 
   std::vector<int> trig_partner;  // sin(x)/cos(x) of the same x: local id of the sibling, else -1
   bool uses_vk_math = false;      // the kernel text needs vk_math.h
+  bool uses_agg = false;          // integer scatter_add: vk_lane carries the warp-aggregation state
 
   Gen(const Ir& i, const Program& pr) : ir(i), p(pr) {
     vals.resize(pr.order.size());
@@ -546,19 +554,25 @@ struct Gen {
         const std::string at = "g" + std::to_string(pd) + " + (u32)" + dep(v, 1).name;
         std::string stmt;
         if (v.op == OP_SCATTER) stmt = "*(" + at + ") = " + to_word(v.ty, src.name) + ";";
+        else if (v.ty != VKJIT_TY_F32) {
+          // integer scatter_add (mod 2^32 for U32 and I32 alike): warp-aggregated when the warp's lanes collide
+          // (kSaddHelper), into the privatised shared-memory bins [0, kbins) where the variant keeps them
+          uses_agg = true;
+          const std::string act = v.ndeps >= 3 ? dep(v, 2).name : std::string("true");
+          const bool priv = p.privatize && (int)pd == p.sadd_param;
+          line("vk_sadd(g" + std::to_string(pd) + ", " + (priv ? "vk_sbins, kbins" : "(u32*)0, 0u") + ", (u32)" + dep(v, 1).name + ", " +
+               to_word(v.ty, src.name) + ", " + act + ", vk_agg);");
+          vals[li] = src;  // value of the scatter var = src (internal.rs:1076)
+          break;
+        }
         else if (p.privatize && (int)pd == p.sadd_param) {
           // bins [0, kbins) live in this CTA's shared memory (flushed once at the end of the kernel),
           // the rest go to L2 as before: shared-memory atomics and L2 REDs run side by side
           const std::string ix = "(u32)" + dep(v, 1).name;
-          if (v.ty == VKJIT_TY_F32)
-            stmt = "{ const u32 ix_ = " + ix + "; if (ix_ < kbins) atomicAdd(reinterpret_cast<f32*>(vk_sbins + ix_), " + src.name +
-                   "); else atomicAdd(reinterpret_cast<f32*>(g" + std::to_string(pd) + " + ix_), " + src.name + "); }";
-          else
-            stmt = "{ const u32 ix_ = " + ix + "; if (ix_ < kbins) atomicAdd(vk_sbins + ix_, " + to_word(v.ty, src.name) +
-                   "); else atomicAdd(g" + std::to_string(pd) + " + ix_, " + to_word(v.ty, src.name) + "); }";
+          stmt = "{ const u32 ix_ = " + ix + "; if (ix_ < kbins) atomicAdd(reinterpret_cast<f32*>(vk_sbins + ix_), " + src.name +
+                 "); else atomicAdd(reinterpret_cast<f32*>(g" + std::to_string(pd) + " + ix_), " + src.name + "); }";
         }
-        else if (v.ty == VKJIT_TY_F32) stmt = "atomicAdd(reinterpret_cast<f32*>(" + at + "), " + src.name + ");";
-        else stmt = "atomicAdd(" + at + ", " + to_word(v.ty, src.name) + ");";  // mod 2^32 for U32 and I32 alike
+        else stmt = "atomicAdd(reinterpret_cast<f32*>(" + at + "), " + src.name + ");";
         if (v.ndeps >= 3) stmt = "if (" + dep(v, 2).name + ") { " + stmt + " }";
         line(stmt);
         vals[li] = src;  // value of the scatter var = src (internal.rs:1076)
@@ -614,6 +628,37 @@ __device__ __forceinline__ void vk_finish(acc_t acc, u32* partials, unsigned int
     f = vk_block_reduce(f, smem);
     if (threadIdx.x == 0) { out[0] = VK_TO_WORD(f); *ticket = 0u; }
   }
+}
+)CUDA";
+
+// Integer scatter_add with WARP AGGREGATION (north_star: "scatter-add (warp-aggregated atomics)").  Lanes of a warp that
+// hit the same bin are found with match.any, their values summed with redux.sync, and the lowest lane of each group
+// issues ONE atomic.  That only pays when lanes collide: 2^26 uniform indices over 2^16 bins almost never do, and
+// MATCH + REDUX would be pure overhead on a kernel that is bound by LSU issue.  So every warp PROBES on its first
+// scatter_add (st = 2): more than a quarter of its active lanes sharing a bin with another lane -> aggregate from then
+// on (st = 1), else plain atomics (st = 0).  Hot-bin inputs (few distinct bins) go from one serialised L2 / shared-
+// memory atomic per lane to one per distinct bin per warp.  `sbins`: the privatised shared-memory bins [0, kbins) of
+// the variant that keeps part of the target per CTA, or null.
+const char* kSaddHelper = R"CUDA(
+__device__ __forceinline__ void vk_sadd_one(u32* __restrict__ g, u32* __restrict__ sbins, const u32 kbins, const u32 ix, const u32 val) {
+  if (ix < kbins) atomicAdd(sbins + ix, val);
+  else atomicAdd(g + ix, val);
+}
+__device__ __forceinline__ void vk_sadd(u32* __restrict__ g, u32* __restrict__ sbins, const u32 kbins, const u32 ix, const u32 val,
+                                        const bool active, u32& st) {
+  if (st == 0u) {
+    if (active) vk_sadd_one(g, sbins, kbins, ix, val);
+    return;
+  }
+  const unsigned vote = __ballot_sync(__activemask(), active);
+  if (!active) return;
+  const unsigned peers = __match_any_sync(vote, ix);   // the active lanes of this warp that target bin ix
+  if (st == 2u) {
+    const unsigned dup = __ballot_sync(vote, (peers & (peers - 1u)) != 0u);
+    st = (__popc(dup) * 4 > __popc(vote)) ? 1u : 0u;
+  }
+  const u32 total = __reduce_add_sync(peers, val);
+  if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) vk_sadd_one(g, sbins, kbins, ix, total);
 }
 )CUDA";
 
@@ -674,6 +719,21 @@ std::string reduce_defines(int red, TypeId ty) {
 
 }  // namespace
 
+// Fingerprint of everything that turns a canonical key into a cubin besides the key itself: the embedded device
+// sources (vk_math.h, scan_common.cuh, scan_fused.cuh, the reduction epilogue) and a generator revision that is bumped
+// whenever generate_cuda's output or a kernel's parameter layout changes.  The on-disk cubin cache stores it: a cubin
+// written by another build of the library is a miss, never a kernel with the wrong argument ABI.
+uint32_t generator_fingerprint() {
+  static const uint32_t fp = [] {
+    constexpr uint32_t kGeneratorRevision = 7;  // round 2: vk_math.h lowering, fast-math variant bit
+    uint32_t h = 2166136261u ^ kGeneratorRevision;
+    auto mix = [&](const char* t) { for (; *t; ++t) { h ^= (unsigned char)*t; h *= 16777619u; } };
+    mix(kVkMathSrc); mix(kScanCommonSrc); mix(kScanFusedSrc); mix(kReduceEpilogue); mix(kSaddHelper);
+    return h;
+  }();
+  return fp;
+}
+
 std::string generate_cuda(const Ir& ir, const Program& p) {
   const bool reduce = p.reduce >= 0;
   Gen g(ir, p);
@@ -708,9 +768,11 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
     s += "extern __shared__ u32 vk_sbins[];  // privatised scatter_add bins [0, kbins)\n\n";
   }
 
+  if (g.uses_agg) s += std::string(kSaddHelper) + "\n";
   // per-lane body
   s += "__device__ __forceinline__ void vk_lane(const u32 gi, const u32 li";
   if (priv) s += ", const u32 kbins";
+  if (g.uses_agg) s += ", u32& vk_agg";
   for (uint32_t k : streams) s += ", const u32 in" + std::to_string(k);
   for (size_t r = 0; r < nroots; ++r) s += ", u32& out" + std::to_string(r);
   for (uint32_t k : ptrs) {
@@ -723,6 +785,7 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   auto call = [&](const std::string& gi, const std::string& li, const char* comp, bool vec) {
     std::string c = "vk_lane(" + gi + ", " + li;
     if (priv) c += ", kbins";
+    if (g.uses_agg) c += ", vk_agg";
     for (uint32_t k : streams) c += ", a" + std::to_string(k) + (vec ? std::string(".") + comp : "");
     for (size_t r = 0; r < nroots; ++r) c += ", r" + std::to_string(r) + (vec ? std::string(".") + comp : "");
     for (uint32_t k : ptrs) c += ", p" + std::to_string(k);
@@ -740,6 +803,7 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   s += ") {\n";
   if (reduce) s += "  acc_t c0 = VK_IDENTITY, c1 = VK_IDENTITY, c2 = VK_IDENTITY, c3 = VK_IDENTITY;\n";
   if (priv) s += "  for (u32 i = threadIdx.x; i < kbins; i += blockDim.x) vk_sbins[i] = 0u;\n  __syncthreads();\n";
+  if (g.uses_agg) s += std::string("  u32 vk_agg = ") + (no_agg() ? "0u" : "2u") + ";  // warp aggregation of integer scatter_add: 2 probe, 1 aggregate, 0 plain atomics\n";
   s += "  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;\n";
   s += "  const u32 nthreads = gridDim.x * blockDim.x;\n";
   if (p.vectorized) {

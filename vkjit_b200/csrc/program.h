@@ -76,6 +76,9 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
 // number of params the kernel streams (one word per lane)
 size_t stream_count(const Program& p);
 
+// Fingerprint of the generator build (embedded device sources + generator revision); part of the disk cache header.
+uint32_t generator_fingerprint();
+
 // CUDA C source of the kernel for `p` (entry point "vkjit_trace").
 std::string generate_cuda(const Ir& ir, const Program& p);
 

@@ -281,6 +281,12 @@ void Backend::ensure_scan_scratch(size_t n, size_t tile) {
 }
 
 // ---- NVRTC -----------------------------------------------------------------------------
+namespace {
+// (also hashed into the disk cache header: a different option set is a different cubin)
+const char* const kNvrtcOptions[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
+                                     "-lineinfo",                  "--std=c++17",  "-default-device", "--minimal"};
+}  // namespace
+
 bool nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string& log) {
   nvrtcProgram prog;
   if (nvrtcCreateProgram(&prog, src.c_str(), "vkjit_trace.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
@@ -293,9 +299,7 @@ bool nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string
   // --minimal: leaves texture / surface / cudadevrt declarations out of the implicit header — 20 % less compile time
   // (3-op trace 84 -> 66 ms, 364-node trace 256 -> 200 ms on the build container's CPU) for byte-identical cubins
   // (checked for every kernel family the generator emits).
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
-                        "-lineinfo",                  "--std=c++17",  "-default-device", "--minimal"};
-  nvrtcResult r = nvrtcCompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+  nvrtcResult r = nvrtcCompileProgram(prog, (int)(sizeof(kNvrtcOptions) / sizeof(kNvrtcOptions[0])), kNvrtcOptions);
   size_t ls = 0;
   nvrtcGetProgramLogSize(prog, &ls);
   if (ls > 1) { log.resize(ls); nvrtcGetProgramLog(prog, &log[0]); }
@@ -323,10 +327,18 @@ bool nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string
 }
 
 // ---- on-disk cubin cache --------------------------------------------------
-// $VKJIT_CACHE_DIR/<hash>.cubin = {magic, nvrtc version, key_len, key words, cubin}.  The canonical key
-// is stored and compared, so a hash collision or a stale file can never load the wrong kernel.
+// $VKJIT_CACHE_DIR/<hash>.cubin = {magic, nvrtc version, generator fingerprint ^ options hash, key_len, key words,
+// cubin}.  The canonical key is stored and compared, so a hash collision can never load the wrong kernel, and the
+// fingerprint (program.cpp: embedded device sources + generator revision, plus the NVRTC option string) makes a
+// cubin written by a different build of this library a plain miss.
 namespace {
-constexpr uint32_t kDiskMagic = 0x564B4332u;  // "VKC2" (key format: node word carries ndeps)
+constexpr uint32_t kDiskMagic = 0x564B4333u;  // "VKC3" (header carries the generator fingerprint)
+uint32_t build_fingerprint() {
+  uint32_t h = generator_fingerprint();
+  for (const char* o : kNvrtcOptions)
+    for (const char* t = o; *t; ++t) { h ^= (unsigned char)*t; h *= 16777619u; }
+  return h;
+}
 
 std::string disk_path(const Hash128& h) {
   const char* dir = getenv("VKJIT_CACHE_DIR");
@@ -348,9 +360,10 @@ bool disk_load(const Program& p, std::vector<char>& cubin) {
   FILE* f = fopen(path.c_str(), "rb");
   if (!f) return false;
   bool ok = false;
-  uint32_t hdr[3];
-  if (fread(hdr, 4, 3, f) == 3 && hdr[0] == kDiskMagic && hdr[1] == nvrtc_version_word() && hdr[2] == p.key_len) {
-    std::vector<uint32_t> key(hdr[2]);
+  uint32_t hdr[4];
+  if (fread(hdr, 4, 4, f) == 4 && hdr[0] == kDiskMagic && hdr[1] == nvrtc_version_word() && hdr[2] == build_fingerprint() &&
+      hdr[3] == p.key_len) {
+    std::vector<uint32_t> key(hdr[3]);
     if (fread(key.data(), 4, key.size(), f) == key.size() && memcmp(key.data(), p.key.data(), key.size() * 4) == 0) {
       const long at = ftell(f);
       fseek(f, 0, SEEK_END);
@@ -372,8 +385,8 @@ void disk_store(const Program& p, const std::vector<char>& cubin) {
   const std::string tmp = path + ".tmp" + std::to_string((unsigned long long)now_ns());
   FILE* f = fopen(tmp.c_str(), "wb");
   if (!f) return;
-  const uint32_t hdr[3] = {kDiskMagic, nvrtc_version_word(), (uint32_t)p.key_len};
-  bool ok = fwrite(hdr, 4, 3, f) == 3 && fwrite(p.key.data(), 4, p.key_len, f) == p.key_len &&
+  const uint32_t hdr[4] = {kDiskMagic, nvrtc_version_word(), build_fingerprint(), (uint32_t)p.key_len};
+  bool ok = fwrite(hdr, 4, 4, f) == 4 && fwrite(p.key.data(), 4, p.key_len, f) == p.key_len &&
             fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
   fclose(f);
   if (ok) rename(tmp.c_str(), path.c_str());  // atomic publish

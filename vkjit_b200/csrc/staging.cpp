@@ -8,6 +8,11 @@
 // does the staging itself: kChunks pinned chunks, the DMA of chunk i overlapping the host memcpy of chunk i +- 1, and the
 // host memcpy split over a few worker threads (one core copies ~10 GB/s, PCIe 5 x16 moves ~55).
 //
+// Transfers below kRingMinBytes keep the driver's own pageable path: waking the copy threads costs ~0.1 ms, more than the
+// ring saves there (measured: 4 MiB readback 252 us through the driver, 720 us through the ring with cold workers;
+// 1 GiB upload 32 GB/s through the ring vs ~18 GB/s through the driver).  The front-ends avoid the question for reads:
+// their result arrays live in pinned memory (vkjit_b200/ir.py: as_slice), one DMA, 98-110 us for 4 MiB.
+//
 // H2D returns as soon as the caller's buffer has been copied OUT (the data waits in pinned chunks; a chunk is reused only
 // after the event behind its DMA) — the reference's contract "the slice may be reused when the call returns" without a
 // device synchronisation.  Pinned caller memory (vkjit_host_alloc, cudaHostRegister) skips the ring: one direct DMA.
@@ -38,7 +43,7 @@ class CopyPool {
     for (int i = 0; i < workers; ++i) threads_.emplace_back([this, i] { run(i); });
   }
   ~CopyPool() {
-    { std::lock_guard<std::mutex> g(mu_); stop_ = true; ++generation_; }
+    { std::lock_guard<std::mutex> g(mu_); stop_ = true; ++generation_; gen_atomic_.store(generation_, std::memory_order_release); }
     cv_.notify_all();
     for (auto& t : threads_) t.join();
   }
@@ -51,6 +56,7 @@ class CopyPool {
       dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; per_ = per;
       pending_.store((int)threads_.size(), std::memory_order_relaxed);
       ++generation_;
+      gen_atomic_.store(generation_, std::memory_order_release);
     }
     cv_.notify_all();
     part(0);
@@ -65,9 +71,16 @@ class CopyPool {
   void run(int i) {
     uint64_t seen = 0;
     for (;;) {
+      // spin briefly before sleeping: the chunks of one transfer follow each other within tens of microseconds, a
+      // condition-variable wake-up alone costs about as much as copying a chunk
+      bool got = false;
+      for (int spin = 0; spin < 20000 && !got; ++spin) {
+        if (gen_atomic_.load(std::memory_order_acquire) != seen) got = true;
+        else if ((spin & 63) == 63) std::this_thread::yield();
+      }
       {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return generation_ != seen; });
+        if (!got) cv_.wait(lk, [&] { return generation_ != seen; });
         seen = generation_;
         if (stop_) return;
       }
@@ -79,12 +92,14 @@ class CopyPool {
   std::mutex mu_;
   std::condition_variable cv_;
   uint64_t generation_ = 0;
+  std::atomic<uint64_t> gen_atomic_{0};
   bool stop_ = false;
   char* dst_ = nullptr; const char* src_ = nullptr; size_t bytes_ = 0, per_ = 0;
   std::atomic<int> pending_{0};
 };
 
 constexpr int kChunks = 4;
+constexpr size_t kRingMinBytes = 16u << 20;
 
 struct Ring {
   size_t chunk_bytes = 0;
@@ -136,7 +151,7 @@ void staging_shutdown() {
 bool staged_h2d(void* dst, const void* src, size_t bytes, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   static const bool off = getenv("VKJIT_NO_STAGING") != nullptr;
-  if (off || bytes < (64u << 10) || is_pinned(src)) {
+  if (off || bytes < kRingMinBytes || is_pinned(src)) {
     ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s), "H2D copy");
     return true;
   }
@@ -160,7 +175,7 @@ bool staged_h2d(void* dst, const void* src, size_t bytes, void* stream) {
 void staged_d2h(void* dst, const void* src, size_t bytes, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   static const bool off = getenv("VKJIT_NO_STAGING") != nullptr;
-  if (off || bytes < (64u << 10) || is_pinned(dst)) {
+  if (off || bytes < kRingMinBytes || is_pinned(dst)) {
     if (bytes) ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s), "D2H copy");
     ck(cudaStreamSynchronize(s), "D2H sync");
     return;
