@@ -190,6 +190,84 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_extras_arm():
+    """CPU legs of the secondary configs (BASELINE.json configs 0, 2-4 and the north_star's E28): the oracle port on all
+    host cores (pinned), each on a BOUNDED sample of the workload (the sample is stated; rates are per lane, so they
+    carry over).  Printed as one JSON line by `bench.py --impl reference --extras`; bench_extras attaches them as
+    `cpu_baseline` next to each GPU figure."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    from oracle_lib import OracleIr, oracle_api
+    from vkjit_b200.ir import Bop, Red, VarType as T
+    api = oracle_api()
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    api.call("set_threads", cores)
+    out = {}
+
+    def timed(fn, reps=2):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    def base(value, unit, sample):
+        return {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample}
+
+    ir = OracleIr()
+    c = ir.const_u32
+    half = ir.const_f32(0.5)
+    # E20 (configs[0]): arange * y + c over 2^20 f32 with readback — the full workload
+    n20 = 1 << 20
+    y20 = uniform_trace(ir, ir.arange(T.U32, n20), 7); ir.eval([y20])
+
+    def e20():
+        z = ir.add(ir.mul(ir.arange(T.F32, n20), y20), half); ir.eval([z]); ir.as_slice(z, T.F32); ir.dec_ref_count(z)
+    out["E20_eval_plus_readback_us"] = base(timed(e20, 5) * 1e6, "us", "full workload (2^20 lanes, eval + readback)")
+    # E28: z = x*y + c, sample 2^26 of 2^28 lanes
+    n = 1 << 26
+    lanes = ir.arange(T.U32, n)
+    x, y = uniform_trace(ir, lanes, 17), uniform_trace(ir, lanes, 18); ir.eval([x, y])
+
+    def e28():
+        z = ir.add(ir.mul(x, y), half); ir.eval([z]); ir.dec_ref_count(z)
+    out["E28_fused_elementwise"] = base(12 * n / timed(e28) / 1e9, "GB/s", "2^26 of 2^28 lanes (12 B/lane)")
+    ir.dec_ref_count(y)
+    # C28: prefix sum and compress, sample 2^26 of 2^28
+    vals = hash_trace(ir, lanes, 65); ir.eval([vals])
+    out["C28_prefix_sum"] = base(8 * n / timed(lambda: ir.dec_ref_count(ir.prefix_sum(vals, True))) / 1e9, "GB/s", "2^26 of 2^28 lanes (8 B/lane)")
+    mask = ir.neq(ir.bop(Bop.And, hash_trace(ir, lanes, 66), c(1)), c(0)); ir.eval([mask])
+
+    def comp():
+        r, _k = ir.compress_values(vals, mask); ir.dec_ref_count(r)
+    out["C28_compress"] = base(10 * n / timed(comp) / 1e9, "GB/s", "2^26 of 2^28 lanes (10 B/lane at p = 0.5)")
+    ir.dec_ref_count(mask); ir.dec_ref_count(vals); ir.dec_ref_count(x)
+    # H26: gather + scatter-add, sample 2^24 of 2^26 indices into 2^16 bins
+    m = 1 << 24
+    idx = ir.bop(Bop.And, hash_trace(ir, ir.arange(T.U32, m), 49), c(0xFFFF)); ir.eval([idx])
+    table = hash_trace(ir, ir.arange(T.U32, 1 << 16), 50); ir.eval([table])
+    bins = ir.array_u32(np.zeros(1 << 16, np.uint32))
+
+    def hist():
+        s = ir.scatter_add(ir.gather(table, idx), bins, idx); ir.eval([s]); ir.dec_ref_count(s)
+    out["H26_gather_scatter_add"] = base(m / timed(hist) / 1e9, "Gelem/s", "2^24 of 2^26 indices, 2^16 bins")
+    ir.close()
+    # M26: the Monte-Carlo mega-trace, sample 2^22 of 2^26 lanes
+    import monte_carlo
+    from ir_adapter import IrModule
+    ir = OracleIr()
+    nm = 1 << 22
+
+    def mc():
+        yv = monte_carlo.build(IrModule(ir), nm, 5); ir.eval([yv.id])
+    out["M26_monte_carlo"] = base(nm / timed(mc) / 1e9, "Glanes/s", "2^22 of 2^26 lanes (364-node trace, 5 rounds)")
+    ir.close()
+    print(json.dumps({"impl": "reference", "extras_cpu_baseline": out}), flush=True)
+
+
 def cpu_arm_subprocess(steps=5, warmup=2):
     """The CPU leg of OUR arm is the reference arm itself, run as a child process with the same code, thread count and
     pinning (`bench.py --impl reference`): the two figures cannot drift apart (round 1: 37.8 vs 57.3 GB/s on one box,
@@ -201,6 +279,33 @@ def cpu_arm_subprocess(steps=5, warmup=2):
     if r.returncode != 0 or not lines:
         raise RuntimeError("reference arm failed: " + r.stderr[-500:])
     return json.loads(lines[-1])
+
+
+def mgpu_parity(world):
+    """N>1: the sharded paths' parity test (tests/mgpu_worker.py: sharded elementwise, reduce sum/min/max, prefix sum,
+    compress -> indices / values, fused and hand-written, P2P mailbox and NCCL, every rank against the oracle) run as
+    `world` plain processes WITHOUT torch (vkjit_dist_init_env).  Rank 0 starts it after the timed legs are over and
+    the job's own communicator is shut down, so that the multi-GPU run the driver does also executes the parity check
+    (the driver's pytest box has one GPU).  The test lives in tests/; this only launches it and records the verdict."""
+    t0 = time.perf_counter()
+    port = int(os.environ.get("MASTER_PORT", "29500")) + 11
+    procs = []
+    for r in range(world):
+        env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC") and k not in ("GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE")}
+        env.update(RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VKJIT_RDZV_PORT=str(port + 1))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mgpu_worker.py"), "--no-torch"], env=env, cwd=ROOT,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    ok, tail = True, ""
+    for r, p in enumerate(procs):
+        try:
+            o, e = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            p.kill(); o, e = p.communicate()
+        if p.returncode != 0 or f"rank {r}/{world} ok" not in o:
+            ok, tail = False, (o[-300:] + e[-700:])
+    return {"ok": ok, "ranks": world, "seconds": time.perf_counter() - t0, "launcher": "plain processes, no torch (vkjit_dist_init_env)",
+            "test": "tests/mgpu_worker.py: sharded elementwise / reduce / prefix sum / compress, P2P and NCCL, bit-exact vs the oracle",
+            **({"error": tail} if not ok else {})}
 
 
 # ------------------------------------------------------------------------------------------
@@ -505,16 +610,33 @@ def ours(args):
             try:
                 import bench_extras
                 line["extras"] = bench_extras.run(ir, vk, stream, flush_l2, peak)
+                if not args.no_cpu_baseline:   # CPU legs of the same configs (child process, bounded samples)
+                    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE")}
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--extras"], capture_output=True,
+                                       text=True, timeout=900, env=env, cwd=ROOT)
+                    cpu = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+                    if r.returncode == 0 and cpu:
+                        for k, v in cpu[-1]["extras_cpu_baseline"].items():
+                            if k in line["extras"]:
+                                line["extras"][k]["cpu_baseline"] = v
+                    else:
+                        line["extras"]["cpu_baseline_error"] = r.stderr[-400:]
                 lc = line["extras"].get("LAUNCH_cached_trace", {})
                 line["cached_trace_launch_us"] = lc.get("vkjit_eval_us_median")   # second half of BASELINE.json's metric
             except Exception as ex:  # extras never take the headline down
                 line["extras"] = {"error": repr(ex)}
-        print(json.dumps(line), flush=True)
     barrier()
     ir.close()
     if world > 1:
         api.call("dist_shutdown")
         td.destroy_process_group()
+    if rank == 0:
+        if world > 1 and not args.no_extras:
+            try:
+                line["mgpu_parity"] = mgpu_parity(world)
+            except Exception as ex:  # never takes the headline down
+                line["mgpu_parity"] = {"ok": False, "error": repr(ex)}
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -525,9 +647,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory all-reduce (default) or NCCL")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="with --impl reference: the CPU legs of the secondary configs instead of the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "reference" and args.extras:
+        cpu_extras_arm()
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         ours(args)

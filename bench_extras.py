@@ -182,8 +182,8 @@ def run(ir, vk, stream, flush_l2, peak):
                                             "indices": "min(h & 0xFFFF, h >> 16)"}
     ir.dec_ref_count(idx_s); ir.dec_ref_count(hh)
 
-    # hot bins: 2^26 indices into 16 bins — every warp collides, so the warp-aggregated path is taken (one atomic per
-    # distinct bin and warp instead of one per lane); VKJIT_NO_AGG=1 measures the plain path (profiles/r02_h26_hot_bins.md)
+    # hot bins: 2^26 indices into 16 bins — every warp collides.  Shared-memory privatisation absorbs that; the
+    # warp-aggregated variant (match.any + redux.sync, VKJIT_AGG=1) measured 6.7x SLOWER here (profiles/r02_h26_hot_bins.md)
     idx_h = ir.bop(Bop.And, hash_trace(ir, lanes26, 0xB2000001 + 3 * 16 + 2), c(15))
     ir.eval([idx_h])
     bins16 = ir.array_u32(np.zeros(16, np.uint32))
@@ -196,7 +196,7 @@ def run(ir, vk, stream, flush_l2, peak):
     ms, best, _ = _timed(stream, flush_l2, sync, hist_hot)
     import os as _os
     out["H26_hot_bins_count"] = {"ms": ms, "best_ms": best, "Gelem_per_s": m / (ms * 1e-3) / 1e9, "bins": 16,
-                                 "warp_aggregation": "off (VKJIT_NO_AGG=1)" if _os.environ.get("VKJIT_NO_AGG") == "1" else "probed per warp",
+                                 "warp_aggregation": "probed per warp (VKJIT_AGG=1)" if _os.environ.get("VKJIT_AGG") == "1" else "off (default: plain atomics into privatised bins)",
                                  "sum_of_bins_ok": int(ir.as_slice(bins16, T.U32).astype(np.uint64).sum()) % m == 0}
     ir.dec_ref_count(idx_h); ir.dec_ref_count(bins16)
 

@@ -16,6 +16,7 @@ from trace_gen import BOOL, F32, I32, U32, TraceBuilder, same_bits, special_f32,
 from vkjit_b200.ir import Bop, Red, Uop
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def both(cir, oir):
@@ -612,26 +613,42 @@ def test_upload_and_readback_through_the_staging_ring(cir, n):
     assert np.array_equal(again, keep) and (n * 4 < (64 << 10) or again.ctypes.data != got.ctypes.data)
 
 
-@pytest.mark.parametrize("bins,n", [(1, 4099), (4, 100003), (16, (1 << 22) + 5), (1000, 50001), (70000, (1 << 22) + 7)])
-def test_scatter_add_hot_bins_warp_aggregated(cir, oir, bins, n):
-    """Integer scatter_add when the lanes of a warp collide (few distinct bins): every warp probes once, then adds one
-    atomic per distinct bin (match.any + redux.sync, program.cpp: kSaddHelper) — bit-exact against the oracle like the
-    plain path, with and without a mask, U32 and I32 (negative values), small launches and the shared-memory-privatised
-    variant of launches >= 2^22 lanes (bins above and below what fits in shared memory)."""
-    for ir in (cir, oir):
-        lanes = ir.arange(U32, n)
+@pytest.mark.parametrize("agg", ["0", "1"])
+def test_scatter_add_hot_bins(tmp_path, agg):
+    """Integer scatter_add when the lanes of a warp collide (few distinct bins), plain and with the opt-in warp-aggregated
+    path (VKJIT_AGG=1: every warp probes once, then one atomic per distinct bin through match.any + redux.sync,
+    program.cpp: kSaddHelper) — bit-exact against the oracle, with and without a mask (lanes that join a warp's
+    scatter_add later), U32 and I32 (negative values), small launches and the shared-memory-privatised variant of launches
+    >= 2^22 lanes.  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    script = tmp_path / "hot.py"
+    script.write_text('''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import vkjit_b200 as vk
+from oracle_lib import OracleIr
+from vkjit_b200.ir import Bop, Ir, VarType as T
+vk.init(0)
+for bins, n in [(1, 4099), (4, 100003), (16, (1 << 22) + 5), (1000, 50001), (70000, (1 << 22) + 7)]:
+    out = []
+    for ir in (Ir(), OracleIr()):
+        lanes = ir.arange(T.U32, n)
         h = ir.mul(ir.bop(Bop.Xor, lanes, ir.const_u32(0x9E3779B9)), ir.const_u32(747796405))
         idx = ir.bop(Bop.Shr, h, ir.const_u32(9))
         idx = ir.sub(idx, ir.mul(ir.div(idx, ir.const_u32(bins)), ir.const_u32(bins)))        # idx mod bins
         du = ir.array_u32(np.zeros(bins, np.uint32))
         di = ir.array_i32(np.zeros(bins, np.int32))
-        wi = ir.sub(ir.cast(ir.bop(Bop.And, h, ir.const_u32(1023)), I32), ir.const_i32(700))  # in [-700, 323]
+        wi = ir.sub(ir.cast(ir.bop(Bop.And, h, ir.const_u32(1023)), T.I32), ir.const_i32(700))  # in [-700, 323]
         mask = ir.neq(ir.bop(Bop.And, h, ir.const_u32(4)), ir.const_u32(0))
         s1 = ir.scatter_add(ir.bop(Bop.Shr, h, ir.const_u32(3)), du, idx)
         s2 = ir.scatter_add(wi, di, idx, mask)
         ir.eval([s1, s2])
-        if ir is cir:
-            got = (ir.as_slice(du, U32).copy(), ir.as_slice(di, I32).copy())
-        else:
-            want = (ir.as_slice(du, U32), ir.as_slice(di, I32))
-    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        out.append((ir.as_slice(du, T.U32).copy(), ir.as_slice(di, T.I32).copy()))
+        ir.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), (bins, n)
+print("hot bins ok")
+''' % (ROOT, os.path.join(ROOT, "tests")))
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, VKJIT_AGG=agg), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "hot bins ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]

@@ -69,10 +69,13 @@ bool fast_math() {
   return g_fast_math == 1;
 }
 
-// $VKJIT_NO_AGG=1: integer scatter_add never aggregates within the warp (A/B measurements); part of the cache key
+// Warp aggregation of integer scatter_add (kSaddHelper) is OFF unless $VKJIT_AGG=1: measured on B200
+// (profiles/r02_h26_hot_bins.md) it loses everywhere — shared-memory privatisation already absorbs hot bins (2^26 lanes
+// into 1..4096 bins: 0.096-0.100 ms with plain ATOMS, ptxas folds warp-uniform addresses into one REDUX + ATOMS itself),
+// while MATCH.ANY + REDUX per scatter_add cost 0.11 / 0.65 / 0.48 ms for 1 / 16 / 256 bins.  Part of the cache key.
 int g_no_agg = -1;
 bool no_agg() {
-  if (g_no_agg < 0) { const char* s = getenv("VKJIT_NO_AGG"); g_no_agg = (s && s[0] == '1') ? 1 : 0; }
+  if (g_no_agg < 0) { const char* s = getenv("VKJIT_AGG"); g_no_agg = (s && s[0] == '1') ? 0 : 1; }
   return g_no_agg == 1;
 }
 
@@ -93,11 +96,13 @@ ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes) {
   ScanFusedGeom g;
   // Lagging pays when the tile time is dominated by the look-back latency; ALU-heavy bodies (a hash per lane) are
   // issue bound and do better with the larger tiles of the immediate look-back (measured: profiles/r01_fused_scan.md).
-  if (streams <= 1 && nodes <= kScanFusedLagMaxNodes && !classic) {
+  static size_t lag_max_nodes = 0;
+  if (!lag_max_nodes) { const char* e = getenv("VKJIT_LAG_MAX_NODES"); lag_max_nodes = e ? (size_t)std::max(1, atoi(e)) : kScanFusedLagMaxNodes; }
+  if (streams <= 1 && nodes <= lag_max_nodes && !classic) {
     g.lag = true;
     if (mode == SCAN_COMPRESS_VALUE) { g.vpt = 3; g.slots = 4; }        // the tile's slot stays resident until its output
     else if (mode == SCAN_COMPRESS_INDEX) { g.vpt = 4; g.slots = 3; }
-    else { g.vpt = 4; g.slots = 2; g.staging = true; }
+    else { g.vpt = 4; g.slots = 2; g.staging = 1; }
   } else {
     g.vpt = streams <= 1 ? 6 : (int)(6 / streams);
   }
@@ -653,7 +658,10 @@ __device__ __forceinline__ void vk_sadd(u32* __restrict__ g, u32* __restrict__ s
   const unsigned vote = __ballot_sync(__activemask(), active);
   if (!active) return;
   const unsigned peers = __match_any_sync(vote, ix);   // the active lanes of this warp that target bin ix
-  if (st == 2u) {
+  // the decision is taken by ALL lanes of `vote` together whenever one of them still probes (lanes that were masked off
+  // at the warp's first scatter_add join later with st == 2): a ballot under `if (st == 2u)` alone would name lanes in
+  // its mask that never execute it
+  if (__ballot_sync(vote, st == 2u) != 0u) {
     const unsigned dup = __ballot_sync(vote, (peers & (peers - 1u)) != 0u);
     st = (__popc(dup) * 4 > __popc(vote)) ? 1u : 0u;
   }
@@ -725,7 +733,7 @@ std::string reduce_defines(int red, TypeId ty) {
 // written by another build of the library is a miss, never a kernel with the wrong argument ABI.
 uint32_t generator_fingerprint() {
   static const uint32_t fp = [] {
-    constexpr uint32_t kGeneratorRevision = 7;  // round 2: vk_math.h lowering, fast-math variant bit
+    constexpr uint32_t kGeneratorRevision = 9;  // round 2: vk_math.h lowering, fast-math variant bit
     uint32_t h = 2166136261u ^ kGeneratorRevision;
     auto mix = [&](const char* t) { for (; *t; ++t) { h ^= (unsigned char)*t; h *= 16777619u; } };
     mix(kVkMathSrc); mix(kScanCommonSrc); mix(kScanFusedSrc); mix(kReduceEpilogue); mix(kSaddHelper);

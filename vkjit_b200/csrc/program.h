@@ -32,9 +32,9 @@ struct ScanFusedGeom {
   bool lag = false;
   int vpt = 6;      // 128-bit vectors per thread and tile
   int slots = 2;    // ring slots per streamed array
-  bool staging = false;  // lagged prefix sums: one output staging tile for the TMA bulk store
+  int staging = 0;  // output staging tiles: lagged prefix sums 1 (TMA bulk store), lagged compress 2 (coalesced copy-out)
   size_t tile() const { return (size_t)1024 * 4 * vpt; }
-  size_t smem(size_t streams) const { return (streams * slots + (staging ? 1 : 0)) * tile() * 4; }
+  size_t smem(size_t streams) const { return (streams * slots + (size_t)staging) * tile() * 4; }
 };
 ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes);
 
