@@ -105,7 +105,7 @@ def main():
             off, k = ir.shard_base(gi), ir.size(gi)
             assert ir.shard_base(gv) == off and ir.size(gv) == k
             # this rank's ragged shard = the selected lanes of [lo, hi): its offset and size follow from the oracle's mask
-            mo = o.as_slice_eval(m_o, T.BOOL) != 0
+            mo = o.as_slice_eval(m_o, T.Bool) != 0
             assert off == int(mo[:lo].sum()) and k == int(mo[lo:hi].sum()), (n, p2p, fused, off, k)
             if k:
                 assert ir.as_slice(gi, T.U32).tobytes() == want_idx[off:off + k].tobytes(), (n, p2p, fused)   # GLOBAL lane numbers

@@ -613,13 +613,15 @@ def test_upload_and_readback_through_the_staging_ring(cir, n):
     assert np.array_equal(again, keep) and (n * 4 < (64 << 10) or again.ctypes.data != got.ctypes.data)
 
 
-@pytest.mark.parametrize("agg", ["0", "1"])
-def test_scatter_add_hot_bins(tmp_path, agg):
+@pytest.mark.parametrize("variant", ["plain", "agg", "cluster"])
+def test_scatter_add_hot_bins(tmp_path, variant):
     """Integer scatter_add when the lanes of a warp collide (few distinct bins), plain and with the opt-in warp-aggregated
     path (VKJIT_AGG=1: every warp probes once, then one atomic per distinct bin through match.any + redux.sync,
     program.cpp: kSaddHelper) — bit-exact against the oracle, with and without a mask (lanes that join a warp's
     scatter_add later), U32 and I32 (negative values), small launches and the shared-memory-privatised variant of launches
-    >= 2^22 lanes.  The switch is read once per process, hence the subprocess."""
+    >= 2^22 lanes — per CTA, and (VKJIT_SADD_CLUSTER=1) split over the two CTAs of a thread-block cluster through
+    distributed shared memory for targets that do not fit one CTA.  The switches are read once per process, hence the
+    subprocess."""
     import subprocess
     import sys
     script = tmp_path / "hot.py"
@@ -631,7 +633,7 @@ import vkjit_b200 as vk
 from oracle_lib import OracleIr
 from vkjit_b200.ir import Bop, Ir, VarType as T
 vk.init(0)
-for bins, n in [(1, 4099), (4, 100003), (16, (1 << 22) + 5), (1000, 50001), (70000, (1 << 22) + 7)]:
+for bins, n in [(1, 4099), (4, 100003), (16, (1 << 22) + 5), (1000, 50001), (65536, (1 << 22) + 1), (70000, (1 << 22) + 7), (120001, (1 << 22) + 64)]:
     out = []
     for ir in (Ir(), OracleIr()):
         lanes = ir.arange(T.U32, n)
@@ -650,5 +652,6 @@ for bins, n in [(1, 4099), (4, 100003), (16, (1 << 22) + 5), (1000, 50001), (700
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), (bins, n)
 print("hot bins ok")
 ''' % (ROOT, os.path.join(ROOT, "tests")))
-    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, VKJIT_AGG=agg), capture_output=True, text=True, timeout=300)
+    env = {"plain": {}, "agg": {"VKJIT_AGG": "1"}, "cluster": {"VKJIT_SADD_CLUSTER": "1"}}[variant]
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "hot bins ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]

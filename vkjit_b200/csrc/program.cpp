@@ -13,7 +13,7 @@ namespace vkjit {
 void Program::clear() {
   key_len = 0; order.clear(); params.clear(); roots.clear();
   n = 0; have_n = false; base = 0; have_base = false; sharded = false; vectorized = true; reduce = -1; scan = -1;
-  privatize = false; sadd_param = -1; has_gather = false;
+  privatize = 0; sadd_param = -1; has_gather = false;
   hash = Hash128();
 }
 
@@ -79,6 +79,17 @@ bool no_agg() {
   return g_no_agg == 1;
 }
 
+}  // namespace
+// Privatised scatter_add across a 2-CTA thread-block cluster: each CTA keeps HALF of the privatised bins in its own
+// shared memory and reaches the other half through distributed shared memory (mapa + red.shared::cluster), so a
+// 2^16-bin target (256 KiB) is privatised completely (no L2 RED at all) and each SM keeps ~100 KB of L1 for gathers.
+// $VKJIT_SADD_CLUSTER=0/1 overrides the default; part of the cache key.
+bool sadd_cluster() {
+  static const int on = [] { const char* s = getenv("VKJIT_SADD_CLUSTER"); return s ? (s[0] == '1' ? 1 : 0) : kSaddClusterDefault; }();
+  return on == 1;
+}
+namespace {
+
 int g_unroll = -1;
 int unroll_factor() {
   if (g_unroll < 0) {
@@ -94,15 +105,30 @@ ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes) {
   static int classic = -1;
   if (classic < 0) { const char* s = getenv("VKJIT_SCAN_IMPL"); classic = (s && std::string(s) == "classic") ? 1 : 0; }
   ScanFusedGeom g;
-  // Lagging pays when the tile time is dominated by the look-back latency; ALU-heavy bodies (a hash per lane) are
-  // issue bound and do better with the larger tiles of the immediate look-back (measured: profiles/r01_fused_scan.md).
+  // Lagging pays when the tile time is dominated by the look-back latency.  Prefix sums of ALU-heavy bodies (a hash
+  // per lane) are issue bound and do better with the larger tiles of the immediate look-back (profiles/r01_fused_scan.md);
+  // the compress modes take the lagged kernel up to 64 nodes since it runs as TWO 512-thread CTAs per SM
+  // (profiles/r02_fused_scan.md: the per-tile chain evaluate -> scan -> barrier -> resolve -> barrier -> stores of one
+  // CTA leaves the SM idle 57 % of the time; a second co-resident CTA fills it: compress_values(v, v > t) 0.436 -> 0.378 ms,
+  // compress_values(v, hash mask) 0.466 -> 0.415 ms).  Prefix sums got SLOWER that way (0.361 -> 0.507 ms: the staging
+  // tile + TMA bulk store want the big tile) and keep one 1024-thread CTA.
   static size_t lag_max_nodes = 0;
-  if (!lag_max_nodes) { const char* e = getenv("VKJIT_LAG_MAX_NODES"); lag_max_nodes = e ? (size_t)std::max(1, atoi(e)) : kScanFusedLagMaxNodes; }
-  if (streams <= 1 && nodes <= lag_max_nodes && !classic) {
+  if (!lag_max_nodes) { const char* e = getenv("VKJIT_LAG_MAX_NODES"); lag_max_nodes = e ? (size_t)std::max(1, atoi(e)) : 0; }
+  const size_t max_nodes = lag_max_nodes ? lag_max_nodes : (mode >= SCAN_COMPRESS_INDEX ? kScanFusedLagMaxNodesCompress : kScanFusedLagMaxNodes);
+  if (streams <= 1 && nodes <= max_nodes && !classic) {
     g.lag = true;
-    if (mode == SCAN_COMPRESS_VALUE) { g.vpt = 3; g.slots = 4; }        // the tile's slot stays resident until its output
-    else if (mode == SCAN_COMPRESS_INDEX) { g.vpt = 4; g.slots = 3; }
+    if (mode >= SCAN_COMPRESS_INDEX) { g.threads = 512; g.vpt = 4; g.slots = 3; }  // values: slot k-1 kept, k current, k+1 in flight
     else { g.vpt = 4; g.slots = 2; g.staging = 1; }
+    // experiments / tuning: $VKJIT_SCAN_T (512: two CTAs per SM), $VKJIT_SCAN_VPT, $VKJIT_SCAN_SLOTS
+    static int t_env = -1, vpt_env = -1, slots_env = -1;
+    if (t_env < 0) {
+      const char* e = getenv("VKJIT_SCAN_T"); t_env = e ? atoi(e) : 0;
+      e = getenv("VKJIT_SCAN_VPT"); vpt_env = e ? atoi(e) : 0;
+      e = getenv("VKJIT_SCAN_SLOTS"); slots_env = e ? atoi(e) : 0;
+    }
+    if (t_env == 512 || t_env == 1024) g.threads = t_env;
+    if (vpt_env > 0) g.vpt = vpt_env;
+    if (slots_env > 0) g.slots = slots_env;
   } else {
     g.vpt = streams <= 1 ? 6 : (int)(6 / streams);
   }
@@ -115,7 +141,7 @@ size_t stream_count(const Program& p) {
   return k;
 }
 
-void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce, bool privatize, int scan) {
+void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce, int privatize, int scan) {
   p.clear();
   p.vectorized = vectorized;
   p.reduce = reduce;
@@ -293,11 +319,16 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
   if (p.params.size() + p.roots.size() > 480) fail(VKJIT_ERR_UNSUPPORTED, "too many arrays in one kernel (4 KB parameter limit)");
 
   if (kn + 12 + p.roots.size() > key.size()) { key.resize(kn + 64 + p.roots.size()); kw = key.data(); }
-  if (p.sadd_param < 0 || reduce >= 0 || scan >= 0) p.privatize = false;
+  if (p.sadd_param < 0 || reduce >= 0 || scan >= 0) p.privatize = 0;
   kw[1] = (vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16) | (p.privatize ? 1u << 24 : 0u) |
-          ((uint32_t)(scan + 1) << 25) | (fast_math() ? 1u << 29 : 0u) | (no_agg() ? 1u << 30 : 0u);  // bit 28 (lagged fused scan) is patched once the streams are known
+          ((uint32_t)(scan + 1) << 25) | (fast_math() ? 1u << 29 : 0u) | (no_agg() ? 1u << 30 : 0u) | (p.privatize == 2 ? 1u << 31 : 0u);  // bit 28 (lagged fused scan) is patched once the streams are known
   for (size_t k = 0; k < p.params.size(); ++k) kw[binding_pos[k]] |= (uint32_t)p.params[k].use << 16;
-  if (scan >= 0 && scan_fused_geom(stream_count(p), scan, p.order.size()).lag) kw[1] |= 1u << 28;
+  if (scan >= 0) {
+    const ScanFusedGeom sg = scan_fused_geom(stream_count(p), scan, p.order.size());
+    if (sg.lag) kw[1] |= 1u << 28;
+    kw[kn++] = 0xFFFFFFFEu;  // geometry of the fused scan kernel (tunable through the environment)
+    kw[kn++] = (uint32_t)sg.threads | ((uint32_t)sg.vpt << 16) | ((uint32_t)sg.slots << 24);
+  }
   kw[kn++] = 0xFFFFFFFFu;
   for (uint32_t r : p.roots) kw[kn++] = r;
   while (kn & 7) kw[kn++] = 0u;
@@ -645,10 +676,28 @@ __device__ __forceinline__ void vk_finish(acc_t acc, u32* partials, unsigned int
 // memory atomic per lane to one per distinct bin per warp.  `sbins`: the privatised shared-memory bins [0, kbins) of
 // the variant that keeps part of the target per CTA, or null.
 const char* kSaddHelper = R"CUDA(
+#if VK_SADD_CLUSTER
+// bins [0, kbins) are split over the two CTAs of the cluster: CTA r holds [r * half, (r + 1) * half) in its shared memory
+__device__ __forceinline__ u32 vk_cluster_rank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void vk_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ u32 vk_half(const u32 kbins) { return (((kbins + 1u) >> 1) + 3u) & ~3u; }
+__device__ __forceinline__ void vk_sadd_one(u32* __restrict__ g, u32* __restrict__ sbins, const u32 kbins, const u32 ix, const u32 val) {
+  if (ix < kbins) {
+    const u32 half = vk_half(kbins), owner = ix >= half ? 1u : 0u;
+    const u32 local = (u32)__cvta_generic_to_shared(sbins + (ix - owner * half));
+    u32 remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(owner));
+    asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(remote), "r"(val) : "memory");
+  } else atomicAdd(g + ix, val);
+}
+#else
 __device__ __forceinline__ void vk_sadd_one(u32* __restrict__ g, u32* __restrict__ sbins, const u32 kbins, const u32 ix, const u32 val) {
   if (ix < kbins) atomicAdd(sbins + ix, val);
   else atomicAdd(g + ix, val);
 }
+#endif
 __device__ __forceinline__ void vk_sadd(u32* __restrict__ g, u32* __restrict__ sbins, const u32 kbins, const u32 ix, const u32 val,
                                         const bool active, u32& st) {
   if (st == 0u) {
@@ -683,7 +732,7 @@ std::string scan_shell(const Program& p, const std::vector<uint32_t>& streams, c
   const ScanFusedGeom geom = scan_fused_geom(ns, p.scan, p.order.size());
   s += "#define VK_SCAN_MODE " + std::to_string(p.scan) + "\n#define VK_NS " + std::to_string(ns) + "\n#define VK_VPT " +
        std::to_string(geom.vpt) + "\n#define VK_LAG " + std::to_string(geom.lag ? 1 : 0) + "\n#define VK_SLOTS " +
-       std::to_string(geom.slots) + "\n";
+       std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n";
   s += "struct VkPtrs {\n  const u32* s[" + std::to_string(std::max<size_t>(ns, 1)) + "];  // streamed arrays (staged by TMA)\n";
   for (uint32_t k : ptrs) {
     if (p.params[k].use & USE_SCATTER) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: the trace has side effects");
@@ -733,7 +782,7 @@ std::string reduce_defines(int red, TypeId ty) {
 // written by another build of the library is a miss, never a kernel with the wrong argument ABI.
 uint32_t generator_fingerprint() {
   static const uint32_t fp = [] {
-    constexpr uint32_t kGeneratorRevision = 9;  // round 2: vk_math.h lowering, fast-math variant bit
+    constexpr uint32_t kGeneratorRevision = 11;  // round 2: vk_math.h lowering, fast-math variant bit
     uint32_t h = 2166136261u ^ kGeneratorRevision;
     auto mix = [&](const char* t) { for (; *t; ++t) { h ^= (unsigned char)*t; h *= 16777619u; } };
     mix(kVkMathSrc); mix(kScanCommonSrc); mix(kScanFusedSrc); mix(kReduceEpilogue); mix(kSaddHelper);
@@ -769,14 +818,15 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
     s += reduce_defines(p.reduce, g.vals[p.roots[0]].ty) + kReduceEpilogue + "\n";
   }
 
-  const bool priv = p.privatize;
+  const bool priv = p.privatize != 0;
   bool priv_f32 = false;
   if (priv) {
     priv_f32 = ir.vars[p.params[p.sadd_param].var].ty == VKJIT_TY_F32;
     s += "extern __shared__ u32 vk_sbins[];  // privatised scatter_add bins [0, kbins)\n\n";
   }
 
-  if (g.uses_agg) s += std::string(kSaddHelper) + "\n";
+  const bool cluster = p.privatize == 2 && !priv_f32 && g.uses_agg;
+  if (g.uses_agg) s += std::string("#define VK_SADD_CLUSTER ") + (cluster ? "1" : "0") + "\n" + kSaddHelper + "\n";
   // per-lane body
   s += "__device__ __forceinline__ void vk_lane(const u32 gi, const u32 li";
   if (priv) s += ", const u32 kbins";
@@ -800,7 +850,8 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
     return c + ");";
   };
 
-  s += std::string("extern \"C\" __global__ void __launch_bounds__(") + (priv ? "1024" : "256") + ") vkjit_trace(const u32 n, const u32 base";
+  s += std::string("extern \"C\" __global__ void ") + (cluster ? "__cluster_dims__(2, 1, 1) " : "") + "__launch_bounds__(" + (priv ? "1024" : "256") +
+       ") vkjit_trace(const u32 n, const u32 base";
   if (priv) s += ", const u32 kbins";
   for (uint32_t k = 0; k < p.params.size(); ++k) {
     const bool w = p.params[k].use & USE_SCATTER;
@@ -810,7 +861,8 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   else for (size_t r = 0; r < nroots; ++r) s += ",\n    u32* __restrict__ o" + std::to_string(r);
   s += ") {\n";
   if (reduce) s += "  acc_t c0 = VK_IDENTITY, c1 = VK_IDENTITY, c2 = VK_IDENTITY, c3 = VK_IDENTITY;\n";
-  if (priv) s += "  for (u32 i = threadIdx.x; i < kbins; i += blockDim.x) vk_sbins[i] = 0u;\n  __syncthreads();\n";
+  if (cluster) s += "  for (u32 i = threadIdx.x; i < vk_half(kbins); i += blockDim.x) vk_sbins[i] = 0u;\n  vk_cluster_sync();  // both halves are zero before anyone adds\n";
+  else if (priv) s += "  for (u32 i = threadIdx.x; i < kbins; i += blockDim.x) vk_sbins[i] = 0u;\n  __syncthreads();\n";
   if (g.uses_agg) s += std::string("  u32 vk_agg = ") + (no_agg() ? "0u" : "2u") + ";  // warp aggregation of integer scatter_add: 2 probe, 1 aggregate, 0 plain atomics\n";
   s += "  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;\n";
   s += "  const u32 nthreads = gridDim.x * blockDim.x;\n";
@@ -846,10 +898,17 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   if (reduce) s += "  vk_finish(VK_APPLY(VK_APPLY(c0, c1), VK_APPLY(c2, c3)), partials, ticket, o0);\n";
   if (priv) {
     const std::string g = "p" + std::to_string(p.sadd_param);
-    s += "  __syncthreads();\n  for (u32 i = threadIdx.x; i < kbins; i += blockDim.x) {\n    const u32 w = vk_sbins[i];\n";
-    if (priv_f32) s += "    if (w != 0u) atomicAdd(reinterpret_cast<f32*>(" + g + " + i), __uint_as_float(w));\n";
-    else s += "    if (w != 0u) atomicAdd(" + g + " + i, w);\n";
-    s += "  }\n";
+    if (cluster) {
+      s += "  vk_cluster_sync();  // every add of both CTAs has landed\n";
+      s += "  { const u32 half = vk_half(kbins), lo = vk_cluster_rank() * half;\n";
+      s += "    for (u32 i = threadIdx.x; i < half && lo + i < kbins; i += blockDim.x) {\n      const u32 w = vk_sbins[i];\n";
+      s += "      if (w != 0u) atomicAdd(" + g + " + lo + i, w);\n    }\n  }\n";
+    } else {
+      s += "  __syncthreads();\n  for (u32 i = threadIdx.x; i < kbins; i += blockDim.x) {\n    const u32 w = vk_sbins[i];\n";
+      if (priv_f32) s += "    if (w != 0u) atomicAdd(reinterpret_cast<f32*>(" + g + " + i), __uint_as_float(w));\n";
+      else s += "    if (w != 0u) atomicAdd(" + g + " + i, w);\n";
+      s += "  }\n";
+    }
   }
   s += "}\n";
   return s;

@@ -24,7 +24,8 @@ enum ParamUse : uint8_t { USE_STREAM = 1, USE_GATHER = 2, USE_SCATTER = 4 };
 // fused trace -> scan kernels (scan_fused.cuh); numbering = scan.cu's ScanMode
 enum ScanKind : int { SCAN_EXCLUSIVE = 0, SCAN_INCLUSIVE = 1, SCAN_COMPRESS_INDEX = 2, SCAN_COMPRESS_VALUE = 3 };
 constexpr int kScanFusedMaxStreams = 6;
-constexpr size_t kScanFusedLagMaxNodes = 8;
+constexpr size_t kScanFusedLagMaxNodes = 8;           // prefix sums
+constexpr size_t kScanFusedLagMaxNodesCompress = 64;  // compress -> indices / values
 // Geometry of a fused scan kernel (scan_fused.cuh): 1024 threads x vpt 128-bit vectors per tile.  Traces that stream at
 // most one array get the lagged variant (look-back one tile behind, see scan.cu: scan_kernel_lag) unless
 // $VKJIT_SCAN_IMPL=classic; the others keep the immediate look-back with a 2-slot ring per streamed array.
@@ -33,7 +34,8 @@ struct ScanFusedGeom {
   int vpt = 6;      // 128-bit vectors per thread and tile
   int slots = 2;    // ring slots per streamed array
   int staging = 0;  // output staging tiles: lagged prefix sums 1 (TMA bulk store), lagged compress 2 (coalesced copy-out)
-  size_t tile() const { return (size_t)1024 * 4 * vpt; }
+  int threads = 1024;  // per CTA; 512: two co-resident CTAs per SM overlap each other's per-tile chains (lagged kernels)
+  size_t tile() const { return (size_t)threads * 4 * vpt; }
   size_t smem(size_t streams) const { return (streams * slots + (size_t)staging) * tile() * 4; }
 };
 ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes);
@@ -59,7 +61,7 @@ struct Program {
   bool vectorized = true;       // 128-bit ld/st variant
   int reduce = -1;              // >= 0: fused trace -> reduce kernel (VKJIT_RED_*), the single root is not stored
   int scan = -1;                // >= 0: fused trace -> scan kernel (SCAN_*): root 0 is scanned / is the compress mask
-  bool privatize = false;       // variant: the first scatter_add target is partly privatised in shared memory
+  int privatize = 0;            // variant: the first scatter_add target is (partly) privatised in shared memory: 1 per CTA, 2 split over a 2-CTA cluster
   int sadd_param = -1;          // param index of the first scatter_add target (-1: none)
   bool has_gather = false;      // the trace gathers (wants L1 for its table)
   Hash128 hash;
@@ -71,10 +73,14 @@ struct Program {
 // reference's panics: size mismatch (internal.rs:699-702), size-less schedule (:1202),
 // gather from a non-buffer (:1054), scatter into a non-buffer (:1059-1062), struct roots.
 void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, Program& p, int reduce = -1,
-                   bool privatize = false, int scan = -1);
+                   int privatize = 0, int scan = -1);
 
 // number of params the kernel streams (one word per lane)
 size_t stream_count(const Program& p);
+
+// privatised scatter_add split over a 2-CTA cluster (see program.cpp); default decided by measurement
+constexpr int kSaddClusterDefault = 0;
+bool sadd_cluster();
 
 // Fingerprint of the generator build (embedded device sources + generator revision); part of the disk cache header.
 uint32_t generator_fingerprint();

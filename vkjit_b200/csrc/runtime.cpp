@@ -425,12 +425,13 @@ CachedKernel* Backend::compile(const Ir& ir, const Program& p) {
     cku(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kPrivatizeMaxBytesNoGather), "cuFuncSetAttribute");
   int ctas_per_sm = 0;
   if (p.scan >= 0) {
-    const size_t smem = scan_fused_geom(stream_count(p), p.scan, p.order.size()).smem(stream_count(p));
+    const ScanFusedGeom sg = scan_fused_geom(stream_count(p), p.scan, p.order.size());
+    const size_t smem = sg.smem(stream_count(p));
     if (smem) cku(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem), "cuFuncSetAttribute");
-    // the look-back needs every CTA of the grid co-resident: check the real occupancy (one 1024-thread CTA per SM)
-    cku(g_drv.OccupancyMaxActiveBlocks(&ctas_per_sm, fn, 1024, smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    // the look-back needs every CTA of the grid co-resident: check the real occupancy
+    cku(g_drv.OccupancyMaxActiveBlocks(&ctas_per_sm, fn, sg.threads, smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
     if (ctas_per_sm < 1) fail(VKJIT_ERR_CUDA, "fused scan kernel does not fit on an SM");
-    ctas_per_sm = 1;
+    ctas_per_sm = std::min(ctas_per_sm, 1024 / sg.threads);  // one 1024-thread CTA or two 512-thread CTAs per SM (64 registers per thread)
   }
   auto* k = new CachedKernel();
   k->ctas_per_sm = (uint32_t)ctas_per_sm;
@@ -496,6 +497,7 @@ void run_group(Ir& ir, Backend& be, const std::vector<VarId>& roots, bool commit
     // scatter_add with many lanes: keep as many bins of the target as fit in shared memory (zeroing and
     // flushing them costs ~2 x kbins atomics per CTA, so small launches keep the plain L2 path)
     uint32_t kbins = 0;
+    bool cluster_bins = false;
     if (prog.sadd_param >= 0 && prog.n >= kPrivatizeMinLanes && !getenv("VKJIT_NO_PRIVATIZE")) {
       const size_t bins = ir.vars[prog.params[prog.sadd_param].var].array->bytes / 4;
       // measured on H26 (profiles/hist_ab.py): with a gather in the trace 192 KB of bins is the optimum (more
@@ -503,9 +505,17 @@ void run_group(Ir& ir, Backend& be, const std::vector<VarId>& roots, bool commit
       // one, more is better (counting histogram: 0.25 ms at 192 KB, 0.19 ms at 224 KB)
       size_t max_bytes = prog.has_gather ? kPrivatizeMaxBytes : kPrivatizeMaxBytesNoGather;
       if (const char* e = getenv("VKJIT_PRIV_KB")) max_bytes = std::min<size_t>((size_t)atoi(e) * 1024, kPrivatizeMaxBytesNoGather);
-      kbins = (uint32_t)std::min<size_t>(bins, max_bytes / 4);
+      const bool f32_target = ir.vars[prog.params[prog.sadd_param].var].ty == VKJIT_TY_F32;
+      if (sadd_cluster() && !f32_target && bins * 4 > max_bytes) {
+        // two CTAs of a cluster hold half of the privatised bins each (distributed shared memory): twice the reach,
+        // half the shared memory per SM (the rest stays L1 for the trace's gathers)
+        cluster_bins = true;
+        kbins = (uint32_t)std::min<size_t>(bins, 2 * (kPrivatizeMaxBytesNoGather / 4));
+      } else {
+        kbins = (uint32_t)std::min<size_t>(bins, max_bytes / 4);
+      }
     }
-    if (!aligned || kbins) build_program(ir, roots, aligned, prog, -1, kbins != 0);  // variant rebuild
+    if (!aligned || kbins) build_program(ir, roots, aligned, prog, -1, kbins ? (cluster_bins ? 2 : 1) : 0);  // variant rebuild
 
     if (trace) ts[1] = now_ns();
     CachedKernel* k = be.lookup(prog);
@@ -526,10 +536,16 @@ void run_group(Ir& ir, Backend& be, const std::vector<VarId>& roots, bool commit
 
     const uint64_t items = prog.vectorized ? std::max<uint64_t>(prog.n >> 2, 1) : prog.n;
     if (prog.privatize) {
-      // persistent CTAs of 1024 threads, each with its own copy of the privatised bins
-      const uint32_t smem = kbins * 4;
-      const uint32_t per_sm = smem <= 100 * 1024 ? 2 : 1;
-      be.launch(k, (uint32_t)be.sm_count * per_sm, 1024, argv.data(), smem);
+      // persistent CTAs of 1024 threads, each with its own copy of the privatised bins (cluster variant: each CTA
+      // of a pair holds half of them; the grid is a multiple of 2)
+      if (cluster_bins) {
+        const uint32_t half = ((((kbins + 1u) >> 1) + 3u) & ~3u);
+        be.launch(k, (uint32_t)be.sm_count & ~1u, 1024, argv.data(), half * 4);
+      } else {
+        const uint32_t smem = kbins * 4;
+        const uint32_t per_sm = smem <= 100 * 1024 ? 2 : 1;
+        be.launch(k, (uint32_t)be.sm_count * per_sm, 1024, argv.data(), smem);
+      }
     } else {
       // grid-stride launch: enough CTAs of 256 threads to fill every SM (8 x 256 = 2048 threads/SM)
       uint64_t grid = (items + 255) / 256;
@@ -689,7 +705,7 @@ bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t
            initp = (uint64_t)(uintptr_t)initial, ibasep = (uint64_t)(uintptr_t)index_base;
   void* argv[] = {&n32, &base32, block.data(), &outp, &cntp, &tiles32, &statep, &initp, &ibasep};
   try {
-    be.launch(k, (uint32_t)std::min<size_t>(tiles, (size_t)be.sm_count * k->ctas_per_sm), 1024, argv, (uint32_t)geom.smem(ns));
+    be.launch(k, (uint32_t)std::min<size_t>(tiles, (size_t)be.sm_count * k->ctas_per_sm), (uint32_t)geom.threads, argv, (uint32_t)geom.smem(ns));
   } catch (...) { release_array(o); throw; }
   *out = o;
   return true;

@@ -240,11 +240,11 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
 // VK_NS <= 1.  Modes 0/1: row-relative results wait in registers and leave through a staging tile + one TMA bulk store.
 // Mode 2: 4 selection bits + an 8-bit row offset per vector wait in two registers.  Mode 3: additionally the tile's ring slot
 // stays resident one more iteration (VK_SLOTS = 4) and the selected lanes' values are re-evaluated from it.
-extern "C" __global__ void __launch_bounds__(1024, 1)
+extern "C" __global__ void __launch_bounds__(VK_T, 1024 / VK_T)
 vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, u32* __restrict__ count_out,
             const u32 num_tiles, uint64_t* __restrict__ state, const u32* __restrict__ initial_ptr,
             const u32* __restrict__ index_base_ptr) {
-  constexpr int T = 1024, VPT = VK_VPT, TILE = T * 4 * VPT, NS = VK_NS, NSA = 1, S = VK_SLOTS;
+  constexpr int T = VK_T, VPT = VK_VPT, TILE = T * 4 * VPT, NS = VK_NS, NSA = 1, S = VK_SLOTS;
   constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = NTOT / 32;
   constexpr u32 TILE_BYTES = TILE * 4;
   constexpr bool COMPRESS = VK_SCAN_MODE >= 2, VALUES = VK_SCAN_MODE == 3;
