@@ -111,6 +111,34 @@ def main():
                 assert ir.as_slice(gi, T.U32).tobytes() == want_idx[off:off + k].tobytes(), (n, p2p, fused)   # GLOBAL lane numbers
                 assert ir.as_slice(gv, T.U32).tobytes() == want_val[off:off + k].tobytes(), (n, p2p, fused)
         ir.close(); o.close()
+    # Mailbox flow control: far more than kMailSlots = 64 exchanges back to back with no host sync, one
+    # rank lagging on the host — all-reduces (fused into the reduce kernel and stand-alone) and exclusive scans over
+    # ranks mixed.  Every exchange waits for all ranks, so a fast rank can never lap the 64-slot ring.
+    import time
+    dist.set_p2p(True)
+    ir = Ir()
+    n = 40000 * world + 12
+    lo, hi = dist.shard_range(n, rank, world)
+    lanes = ir.arange_sharded(T.U32, n)
+    xb = ir.add(lanes, ir.const_u32(0)); ir.eval([xb])                      # a bound sharded array: hand-written reduce
+    sums, scans = [], []
+    for i in range(300):
+        if rank == world - 1 and i % 75 == 10:
+            time.sleep(0.05)                                                # this rank falls 50 ms behind
+        if i % 3 == 0:
+            sums.append((i, ir.reduce(Red.Sum, ir.add(lanes, ir.const_u32(i)))))   # fused trace -> reduce + stand-alone exchange
+        elif i % 3 == 1:
+            sums.append((0, ir.reduce(Red.Sum, xb)))                        # exchange inside the reduce kernel's last CTA
+        else:
+            scans.append(ir.prefix_sum(xb, True))                           # exclusive scan over ranks of the shard totals
+    M = 1 << 32
+    for i, v in sums:
+        assert int(ir.as_slice(v, T.U32)[0]) == (n * (n - 1) // 2 + n * i) % M, i
+    for v in scans:
+        got = ir.as_slice(v, T.U32)
+        if hi > lo:
+            assert int(got[0]) == (lo * (lo - 1) // 2) % M and int(got[-1]) == ((hi - 1) * (hi - 2) // 2) % M
+    ir.close()
     st = vk.stats()
     assert st["collectives"] > 0 or world == 1
     if NO_TORCH:

@@ -131,6 +131,9 @@ ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes) {
     if (slots_env > 0) g.slots = slots_env;
   } else {
     g.vpt = streams <= 1 ? 6 : (int)(6 / streams);
+    static int t_nolag = -1;
+    if (t_nolag < 0) { const char* e = getenv("VKJIT_SCAN_T_NOLAG"); t_nolag = e ? atoi(e) : 0; }
+    if (t_nolag == 512 || t_nolag == 1024) g.threads = t_nolag;
   }
   return g;
 }

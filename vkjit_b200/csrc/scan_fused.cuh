@@ -17,11 +17,11 @@ template <bool B> struct VkBool { static constexpr bool value = B; };
 
 #if !VK_LAG
 
-extern "C" __global__ void __launch_bounds__(1024, 1)
+extern "C" __global__ void __launch_bounds__(VK_T, 1024 / VK_T)
 vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, u32* __restrict__ count_out,
             const u32 num_tiles, uint64_t* __restrict__ state, const u32* __restrict__ initial_ptr,
             const u32* __restrict__ index_base_ptr) {  // mode 2: global index of lane 0 (sharded masks)
-  constexpr int T = 1024, VPT = VK_VPT, TILE = T * 4 * VPT, NS = VK_NS, NSA = NS > 0 ? NS : 1, S = 2;
+  constexpr int T = VK_T, VPT = VK_VPT, TILE = T * 4 * VPT, NS = VK_NS, NSA = NS > 0 ? NS : 1, S = 2;
   constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = (NTOT + 31) / 32;
   constexpr u32 TILE_BYTES = TILE * 4;
   constexpr bool COMPRESS = VK_SCAN_MODE >= 2, VALUES = VK_SCAN_MODE == 3;
