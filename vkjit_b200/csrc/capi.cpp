@@ -133,7 +133,7 @@ vkjit_status vkjit_shutdown(void) { return guard([&] { dist::shutdown(); Backend
 int32_t vkjit_is_initialized(void) { return Backend::initialized() ? 1 : 0; }
 const char* vkjit_last_error(void) { return g_last_error.c_str(); }
 uint32_t vkjit_abi_version(void) { return VKJIT_B200_ABI_VERSION; }
-vkjit_status vkjit_stream(void** out) { return guard([&] { *out = Backend::get().stream; }); }
+vkjit_status vkjit_stream(void** out) { return guard([&] { *out = Backend::get().wait_stream(); }); }
 vkjit_status vkjit_device(int32_t* out) { return guard([&] { *out = Backend::get().device; }); }
 vkjit_status vkjit_sync(void) { return guard([&] { Backend::get().sync(); }); }
 vkjit_status vkjit_host_alloc(size_t bytes, void** out) {
@@ -409,13 +409,13 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
     try {
       if (empty) {
         o = be.new_array(4);
-        prims::fill_u32((uint32_t*)o->ptr, reduce_identity(red, ty), 1, be.stream);
-        if (p2p) prims::p2p_allreduce(red, ty, o->ptr, mb, be.stream);
+        prims::fill_u32((uint32_t*)o->ptr, reduce_identity(red, ty), 1, be.enqueue_stream());
+        if (p2p) prims::p2p_allreduce(red, ty, o->ptr, mb, be.enqueue_stream());
       } else if (!ir.is_buffer(id) || misaligned(ir, id)) {
         // unevaluated operand (or a misaligned foreign view): ONE generated kernel evaluates the trace and reduces
         // it; the operand is not materialised and stays as it is
         o = eval_reduce(ir, id, red);
-        if (p2p) prims::p2p_allreduce(red, ty, o->ptr, mb, be.stream);
+        if (p2p) prims::p2p_allreduce(red, ty, o->ptr, mb, be.enqueue_stream());
       } else {
         o = be.new_array(4);
         const Var& v = ir.var(id);
@@ -434,7 +434,7 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
         for (size_t i = 0; overlap && i < ch.outs.size(); ++i) overlap = ch.outs[i] != in;
         if (!overlap) ch.outs.clear();
         // p2p: the last CTA of the reduction exchanges the per-GPU partial over NVLink peer memory
-        prims::reduce(red, ty, in, v.array->bytes / 4, o->ptr, be.scratch, be.sm_count, be.stream, p2p ? &mb : nullptr,
+        prims::reduce(red, ty, in, v.array->bytes / 4, o->ptr, be.scratch, be.sm_count, be.enqueue_stream(), p2p ? &mb : nullptr,
                       overlap ? 0u : prims::kReduceWaitFirst);
         Backend::counters().note_prim();
         ch.outs.push_back(o->ptr);
@@ -454,13 +454,13 @@ vkjit_status vkjit_reduce(vkjit_ir* h, int32_t red, vkjit_var id, vkjit_var* out
 void rank_exscan(Backend& be, const uint32_t* mine, uint32_t* out, bool total, uint32_t* vec) {
   const int world = dist::world(), rank = dist::rank();
   if (dist::p2p_enabled()) {
-    if (total) prims::p2p_exscan_total_u32(mine, out, dist::next_mailbox(), be.stream);
-    else prims::p2p_exscan_u32(mine, out, dist::next_mailbox(), be.stream);
+    if (total) prims::p2p_exscan_total_u32(mine, out, dist::next_mailbox(), be.enqueue_stream());
+    else prims::p2p_exscan_u32(mine, out, dist::next_mailbox(), be.enqueue_stream());
   } else {
-    prims::one_hot_u32(mine, rank, world, vec, be.stream);
+    prims::one_hot_u32(mine, rank, world, vec, be.enqueue_stream());
     dist::allreduce(vec, VKJIT_TY_U32, VKJIT_RED_SUM, (size_t)world);
-    prims::prefix_of_rank_u32(vec, rank, out, be.stream);
-    if (total) prims::prefix_of_rank_u32(vec, world, out + 1, be.stream);
+    prims::prefix_of_rank_u32(vec, rank, out, be.enqueue_stream());
+    if (total) prims::prefix_of_rank_u32(vec, world, out + 1, be.enqueue_stream());
   }
   Backend::counters().note_prim();
 }
@@ -518,8 +518,8 @@ vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkji
         tmp = be.alloc(tmp_bytes);
         uint32_t* w = (uint32_t*)tmp;
         const uint32_t* tot = w;
-        if (empty) prims::fill_u32(w, 0u, 1, be.stream);
-        else if (direct) prims::reduce(VKJIT_RED_SUM, VKJIT_TY_U32, in.ptr, in.n, w, be.scratch, be.sm_count, be.stream);
+        if (empty) prims::fill_u32(w, 0u, 1, be.enqueue_stream());
+        else if (direct) prims::reduce(VKJIT_RED_SUM, VKJIT_TY_U32, in.ptr, in.n, w, be.scratch, be.sm_count, be.enqueue_stream());
         else { total = eval_reduce(ir, id, VKJIT_RED_SUM); tot = (const uint32_t*)total->ptr; }
         rank_exscan(be, tot, w + 1, false, w + 2);
         initial = w + 1;
@@ -535,7 +535,7 @@ vkjit_status vkjit_prefix_sum(vkjit_ir* h, vkjit_var id, int32_t exclusive, vkji
       if (!done) {
         be.ensure_scan_scratch(in.n);
         o = be.new_array(in.n * 4);
-        prims::prefix_sum(in.ptr, (uint32_t*)o->ptr, in.n, exclusive != 0, be.scratch, be.sm_count, be.stream, initial);
+        prims::prefix_sum(in.ptr, (uint32_t*)o->ptr, in.n, exclusive != 0, be.scratch, be.sm_count, be.enqueue_stream(), initial);
       }
       Backend::counters().note_prim();
     } catch (...) {
@@ -586,7 +586,7 @@ static void do_compress(Ir& ir, bool with_values, VarId values, VarId mask, vkji
   try {
     const uint32_t* index_base = nullptr;
     if (sharded && !with_values) {
-      prims::fill_u32(w + 3, (uint32_t)n_local, 1, be.stream);
+      prims::fill_u32(w + 3, (uint32_t)n_local, 1, be.enqueue_stream());
       rank_exscan(be, w + 3, w + 3, false, w + 4);
       index_base = w + 3;
     }
@@ -615,10 +615,10 @@ static void do_compress(Ir& ir, bool with_values, VarId values, VarId mask, vkji
       n = m.n;
       be.ensure_scan_scratch(n);
       o = be.new_array(n * 4);  // worst case; logical size is trimmed to the count below
-      if (n) prims::compress(m.ptr, with_values ? v.ptr : nullptr, (uint32_t*)o->ptr, w, n, be.scratch, be.sm_count, be.stream, index_base);
+      if (n) prims::compress(m.ptr, with_values ? v.ptr : nullptr, (uint32_t*)o->ptr, w, n, be.scratch, be.sm_count, be.enqueue_stream(), index_base);
     }
     if (n) Backend::counters().note_prim();
-    else if (sharded) prims::fill_u32(w, 0u, 1, be.stream);
+    else if (sharded) prims::fill_u32(w, 0u, 1, be.enqueue_stream());
     if (sharded) rank_exscan(be, w, w + 1, true, w + 4);
     // the size of the result is data dependent: one small readback
     if (n || sharded) be.d2h(host, w, sharded ? 12 : 4);
@@ -749,7 +749,7 @@ vkjit_status vkjit_debug_walk_ns(vkjit_ir* h, const vkjit_var* ids, size_t n, ui
 vkjit_status vkjit_debug_reduce_trace(uint64_t* out, size_t cap_words, size_t* out_launches) {
   return guard([&] {
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "64-bit stamps");
-    *out_launches = prims::reduce_trace_dump((unsigned long long*)out, cap_words, Backend::get().stream);
+    *out_launches = prims::reduce_trace_dump((unsigned long long*)out, cap_words, Backend::get().wait_stream());
   });
 }
 

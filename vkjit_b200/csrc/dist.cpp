@@ -197,7 +197,7 @@ void allreduce(void* buf, uint32_t ty, int red, size_t count) {
   if (!g_active || g_world == 1) return;
   ncclDataType_t dt = ty == VKJIT_TY_F32 ? ncclFloat32 : ty == VKJIT_TY_I32 ? ncclInt32 : ncclUint32;
   ncclRedOp_t op = red == VKJIT_RED_SUM ? ncclSum : red == VKJIT_RED_MIN ? ncclMin : ncclMax;
-  ckn(g_nccl.AllReduce(buf, buf, count, dt, op, g_comm, (cudaStream_t)Backend::get().stream), "ncclAllReduce");
+  ckn(g_nccl.AllReduce(buf, buf, count, dt, op, g_comm, (cudaStream_t)Backend::get().enqueue_stream()), "ncclAllReduce");
   Backend::counters().collectives += 1;
   Backend::counters().stream_ops += 1;
 }

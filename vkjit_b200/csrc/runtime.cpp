@@ -119,7 +119,7 @@ void Backend::init(int device) {
   b->sm_count = sms;
   cudaStream_t s;
   ck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
-  b->stream = s;
+  b->stream_ = s;
   cudaMemPool_t pool;
   ck(cudaDeviceGetDefaultMemPool(&pool, device), "cudaDeviceGetDefaultMemPool");
   uint64_t keep = ~0ull;  // never trim: freed blocks stay in the pool for the next eval
@@ -140,12 +140,12 @@ void Backend::shutdown() {
   Backend* b = g_backend;
   staging_shutdown();
   b->trim();
-  cudaStreamSynchronize((cudaStream_t)b->stream);
+  cudaStreamSynchronize((cudaStream_t)b->stream_);
   b->clear_cache();
   cudaFree(b->scratch.partials);
   cudaFree(b->scratch.ticket);
   if (b->scratch.tile_state) cudaFree(b->scratch.tile_state);
-  cudaStreamDestroy((cudaStream_t)b->stream);
+  cudaStreamDestroy((cudaStream_t)b->stream_);
   g_backend = nullptr;
   delete b;
 }
@@ -170,7 +170,7 @@ void* Backend::alloc(size_t bytes) {
       recycle_bytes_ -= sz;
     }
   }
-  if (!p) ck(cudaMallocAsync(&p, sz, (cudaStream_t)stream), "cudaMallocAsync");
+  if (!p) ck(cudaMallocAsync(&p, sz, (cudaStream_t)stream_), "cudaMallocAsync");
   g_counters.pool_bytes_live += sz;
   return p;
 }
@@ -188,13 +188,13 @@ void Backend::free_async(void* p, size_t bytes) {
       return;
     }
   }
-  cudaFreeAsync(p, (cudaStream_t)stream);
+  cudaFreeAsync(p, (cudaStream_t)stream_);
 }
 
 void Backend::trim() {
   std::lock_guard<std::mutex> g(recycle_mu_);
   for (auto& kv : recycle_)
-    for (void* p : kv.second) cudaFreeAsync(p, (cudaStream_t)stream);
+    for (void* p : kv.second) cudaFreeAsync(p, (cudaStream_t)stream_);
   recycle_.clear();
   recycle_bytes_ = 0;
 }
@@ -234,7 +234,7 @@ void drain_foreign_releases() {
     auto pr = g_pending_release.back();
     g_pending_release.pop_back();
     // the consumer may still have work queued on our stream that reads the memory
-    if (g_backend) cudaStreamSynchronize((cudaStream_t)g_backend->stream);
+    if (g_backend) cudaStreamSynchronize((cudaStream_t)g_backend->stream_);
     pr.first(pr.second);
   }
 }
@@ -244,25 +244,25 @@ void Backend::h2d(void* dst, const void* src, size_t bytes) {
   // the caller may reuse `src` as soon as we return (Backend::create_array_from_slice copies synchronously into
   // mapped memory, vulkan/mod.rs:56-73): pageable memory is copied out into the pinned ring (no device
   // synchronisation), a direct DMA from pinned memory has to finish first
-  if (staged_h2d(dst, src, bytes, stream)) ck(cudaStreamSynchronize((cudaStream_t)stream), "H2D sync");
+  if (staged_h2d(dst, src, bytes, stream_)) ck(cudaStreamSynchronize((cudaStream_t)stream_), "H2D sync");
   g_counters.bytes_h2d += bytes;
   g_counters.stream_ops += 1;
 }
 
 void Backend::d2h(void* dst, const void* src, size_t bytes) {
-  staged_d2h(dst, src, bytes, stream);
+  staged_d2h(dst, src, bytes, stream_);
   check_fault();
   g_counters.bytes_d2h += bytes;
   g_counters.stream_ops += 1;
 }
 
 void Backend::d2d(void* dst, const void* src, size_t bytes) {
-  if (bytes) ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "D2D copy");
+  if (bytes) ck(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_), "D2D copy");
   g_counters.stream_ops += 1;
 }
 
 void Backend::sync() {
-  ck(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+  ck(cudaStreamSynchronize((cudaStream_t)stream_), "cudaStreamSynchronize");
   check_fault();
 }
 
@@ -270,7 +270,7 @@ void Backend::ensure_scan_scratch(size_t n, size_t tile) {
   const size_t need = prims::scan_state_words(n, tile);
   if (need <= scratch.tile_state_words) return;
   if (scratch.tile_state) {
-    ck(cudaStreamSynchronize((cudaStream_t)stream), "sync");
+    ck(cudaStreamSynchronize((cudaStream_t)stream_), "sync");
     cudaFree(scratch.tile_state);
   }
   size_t words = std::max<size_t>(need, 1 << 19);
@@ -454,7 +454,7 @@ CachedKernel* Backend::compile(const Ir& ir, const Program& p) {
 
 void Backend::clear_cache() {
   std::lock_guard<std::mutex> g(cache_mu_);
-  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream_);
   for (auto& kv : cache_) {
     if (g_drv.ModuleUnload) g_drv.ModuleUnload((CUmodule)kv.second->module);
     delete kv.second;
@@ -463,7 +463,7 @@ void Backend::clear_cache() {
 }
 
 void Backend::launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args, uint32_t smem_bytes) {
-  cku(g_drv.LaunchKernel((CUfunction)k->function, grid, 1, 1, block, 1, 1, smem_bytes, (CUstream)stream, args, nullptr), "cuLaunchKernel");
+  cku(g_drv.LaunchKernel((CUfunction)k->function, grid, 1, 1, block, 1, 1, smem_bytes, (CUstream)stream_, args, nullptr), "cuLaunchKernel");
   g_counters.trace_launches += 1;
   g_counters.stream_ops += 1;
 }
@@ -693,7 +693,7 @@ bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t
   const size_t tile = geom.tile();
   const size_t tiles = (prog.n + tile - 1) / tile;
   be.ensure_scan_scratch(prog.n, tile);
-  ck(cudaMemsetAsync(be.scratch.tile_state, 0, (size_t)prims::kStatusWordsPerTile * (1 + tiles) * 8, (cudaStream_t)be.stream), "scan status memset");
+  ck(cudaMemsetAsync(be.scratch.tile_state, 0, (size_t)prims::kStatusWordsPerTile * (1 + tiles) * 8, (cudaStream_t)be.enqueue_stream()), "scan status memset");
   Array* o = be.new_array((size_t)prog.n * 4);  // compress: worst case, trimmed by the caller
   // VkPtrs: streamed arrays (at least one slot), then the gather pointers in parameter order
   std::vector<uint64_t> block;

@@ -59,7 +59,13 @@ class Backend {
 
   int device = 0;
   int sm_count = 148;
-  void* stream = nullptr;           // cudaStream_t
+  // The ONE stream of this backend.  Whoever wants to ENQUEUE work on it goes through enqueue_stream(), which bumps
+  // Counters::stream_ops: the overlap proof of back-to-back reductions (capi.cpp: vkjit_reduce — "nothing else was put
+  // on the stream since the previous reduction of the chain") then holds by construction; a new stream operation
+  // cannot forget the bump (the proof used to rest on every call site remembering it).  Over-counting
+  // only costs an overlap, never correctness.  wait_stream() is for synchronising / querying only.
+  void* enqueue_stream() { counters().stream_ops += 1; return stream_; }
+  void* wait_stream() const { return stream_; }
   prims::Scratch scratch;
 
   // Backend::create_array (backend/mod.rs:22): stream-ordered allocation from the pool
@@ -88,6 +94,8 @@ class Backend {
     uint64_t sig = ~0ull;
     std::vector<const void*> outs;
   } reduce_chain;
+
+  void* stream_ = nullptr;          // cudaStream_t (use the accessors above)
 
  private:
   std::mutex cache_mu_;
