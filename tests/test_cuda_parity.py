@@ -87,6 +87,33 @@ def test_transcendentals_bit_exact(cir, oir, seed):
     assert np.array_equal(outs[0][3].view(np.uint32), outs[0][6].view(np.uint32))
 
 
+def test_range_proven_fast_paths_bit_exact(cir, oir):
+    """Traces whose transcendental arguments have PROVABLE ranges take the unchecked vk_math.h fast paths in the generated
+    kernel (program.cpp: FRange; which calls are proven is checked on the CPU tier) — the oracle always runs the checked
+    functions.  Bit-exact over 2^20 pseudo-random arguments plus both endpoints of every range."""
+    n = 1 << 20
+    outs = []
+    for ir in (cir, oir):
+        lane = ir.arange(U32, n)
+        u24 = ir.bop(Bop.Shr, ir.mul(lane, ir.const_u32(2654435761)), ir.const_u32(8))
+        u24 = ir.select(ir.lt(lane, ir.const_u32(1)), ir.const_u32(0),
+                        ir.select(ir.lt(lane, ir.const_u32(2)), ir.const_u32(0xFFFFFF), u24))   # lanes 0 / 1: the endpoints
+        unit = ir.mul(ir.cast(u24, F32), ir.const_f32(2.0 ** -24))                               # [0, 1 - 2^-24]
+        unit1 = ir.mul(ir.cast(ir.add(u24, ir.const_u32(1)), F32), ir.const_f32(2.0 ** -24))     # [2^-24, 1]
+        th = ir.mul(unit, ir.const_f32(105615.0))
+        rad = ir.sqrt(ir.mul(ir.log(unit1), ir.const_f32(-2.0)))
+        r = [ir.log(unit1), ir.log(ir.mul(unit1, ir.const_f32(1e30))), ir.log(ir.mul(unit1, ir.const_f32(2.0 ** -102))),
+             ir.exp(ir.sub(ir.mul(unit, ir.const_f32(173.8)), ir.const_f32(86.9))),
+             ir.sin(th), ir.cos(th), ir.sin(ir.mul(unit, ir.const_f32(6.2831854820251465))),
+             ir.exp(ir.add(ir.mul(ir.mul(rad, ir.cos(th)), ir.const_f32(0.2)), ir.const_f32(0.01))),
+             ir.exp(ir.exp(ir.mul(unit, ir.const_f32(4.4))))]
+        ir.eval(r)
+        outs.append([read(ir, v) for v in r])
+    for k, (a, b) in enumerate(zip(*outs)):
+        bad = np.nonzero(a.view(np.uint32) != b.view(np.uint32))[0]
+        assert bad.size == 0, (k, bad[:4], a[bad[:4]], b[bad[:4]])
+
+
 def test_large_elementwise_and_cache_hit(cuda_backend, cir, oir):
     """x*y+c at 2^20 (config-1 shape); second eval of the same structure must be a cache hit."""
     n = 1 << 20

@@ -139,6 +139,58 @@ def test_generated_cuda_compiles_for_sm100a(seed):
     assert "fma" not in body.lower()                       # never contract mul+add (OpFMul/OpFAdd are separate)
 
 
+def _calls(src):
+    """vk_math.h calls in the per-lane body of a generated kernel: {name: count}"""
+    import re
+    body = src.split("#endif  // VK_MATH_H")[-1]
+    out = {}
+    for m in re.finditer(r"\b(vk_(?:expf|logf|sinf|cosf|sincosf)(?:_fast)?)\(", body):
+        out[m.group(1)] = out.get(m.group(1), 0) + 1
+    return out
+
+
+def test_range_proven_fast_paths():
+    """The generator calls the UNCHECKED fast path of a vk_math.h function only when the trace itself proves that the
+    argument never takes the out-of-line path (program.cpp: FRange); one step outside the proof and the checked entry
+    point is used.  Same bits either way (GPU tier: test_range_proven_fast_paths_bit_exact)."""
+    from vkjit_b200.ir import Bop
+    ir = Ir()
+    n = 4096
+    lane = ir.arange(U32, n)
+    u24 = ir.bop(Bop.Shr, ir.mul(lane, ir.const_u32(2654435761)), ir.const_u32(8))       # [0, 2^24)
+    unit = ir.mul(ir.cast(u24, F32), ir.const_f32(2.0 ** -24))                             # [0, 1)
+    unit1 = ir.mul(ir.cast(ir.add(u24, ir.const_u32(1)), F32), ir.const_f32(2.0 ** -24))   # (0, 1]
+
+    def calls(*roots):
+        return _calls(ir.debug_codegen(list(roots), compile=True)[0])
+
+    # provable: log of (0, 1], exp of |x| <= 86.9, sin/cos of [+0, 105615]
+    assert calls(ir.log(unit1)) == {"vk_logf_fast": 1}
+    assert calls(ir.exp(ir.sub(ir.mul(unit, ir.const_f32(173.8)), ir.const_f32(86.9)))) == {"vk_expf_fast": 1}
+    th = ir.mul(unit, ir.const_f32(105615.0))
+    assert calls(ir.sin(th), ir.cos(th)) == {"vk_sincosf_fast": 1}
+    assert calls(ir.sin(th)) == {"vk_sinf_fast": 1}
+    # a chain: sqrt(-2 log u) * cos(..) scaled into exp's range, as in Box-Muller
+    rad = ir.sqrt(ir.mul(ir.log(unit1), ir.const_f32(-2.0)))
+    assert calls(ir.exp(ir.mul(ir.mul(rad, ir.cos(th)), ir.const_f32(0.2)))) == {"vk_logf_fast": 1, "vk_cosf_fast": 1, "vk_expf_fast": 1}
+    # NOT provable -> the checked functions
+    assert calls(ir.log(unit)) == {"vk_logf": 1}                                            # 0 is possible
+    assert calls(ir.exp(ir.mul(unit, ir.const_f32(87.5)))) == {"vk_expf": 1}               # may reach 87
+    assert calls(ir.sin(ir.neg(th))) == {"vk_sinf": 1}                                      # -0 is possible
+    assert calls(ir.cos(ir.mul(unit, ir.const_f32(105616.0)))) == {"vk_cosf": 1}           # beyond Cody-Waite
+    assert calls(ir.exp(ir.cast(lane, F32))) == {"vk_expf": 1}                              # lane index: up to 2^32
+    assert calls(ir.exp(ir.bitcast(lane, F32))) == {"vk_expf": 1}                           # any bit pattern
+    assert calls(ir.log(ir.div(unit1, unit1))) == {"vk_logf": 1}                            # division: not modelled
+    assert calls(ir.exp(ir.log(ir.mul(unit1, ir.const_f32(1e30))))) == {"vk_logf_fast": 1, "vk_expf_fast": 1}   # log < 70
+    assert calls(ir.exp(ir.exp(ir.mul(unit, ir.const_f32(4.4))))) == {"vk_expf_fast": 2}   # e^4.4 = 81.5 < 87
+    assert calls(ir.exp(ir.exp(ir.mul(unit, ir.const_f32(4.47))))) == {"vk_expf_fast": 1, "vk_expf": 1}   # e^4.47 = 87.4
+    # the Monte-Carlo mega-trace (BASELINE configs[4]): all 15 calls proven
+    import monte_carlo
+    from ir_adapter import IrModule
+    y = monte_carlo.build(IrModule(ir), 1 << 20, 5)
+    assert calls(y.id) == {"vk_logf_fast": 5, "vk_sincosf_fast": 5, "vk_expf_fast": 5}
+
+
 def test_struct_select_gather_scatter_codegen():
     ir = Ir()
     i = ir.arange(U32, 64)

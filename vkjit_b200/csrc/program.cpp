@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <cmath>
 
 namespace vkjit {
 
@@ -67,6 +68,13 @@ int g_fast_math = -1;
 bool fast_math() {
   if (g_fast_math < 0) { const char* s = getenv("VKJIT_FAST_MATH"); g_fast_math = (s && s[0] == '1') ? 1 : 0; }
   return g_fast_math == 1;
+}
+
+// $VKJIT_NO_RANGES=1: never use the range-proven unchecked vk_math.h fast paths (A/B knob).  Part of the cache key.
+int g_no_ranges = -1;
+bool no_ranges() {
+  if (g_no_ranges < 0) { const char* s = getenv("VKJIT_NO_RANGES"); g_no_ranges = (s && s[0] == '1') ? 1 : 0; }
+  return g_no_ranges == 1;
 }
 
 // Warp aggregation of integer scatter_add (kSaddHelper) is OFF unless $VKJIT_AGG=1: measured on B200
@@ -323,7 +331,7 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
 
   if (kn + 12 + p.roots.size() > key.size()) { key.resize(kn + 64 + p.roots.size()); kw = key.data(); }
   if (p.sadd_param < 0 || reduce >= 0 || scan >= 0) p.privatize = 0;
-  kw[1] = (vectorized ? 1u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16) | (p.privatize ? 1u << 24 : 0u) |
+  kw[1] = (vectorized ? 1u : 0u) | (no_ranges() ? 2u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16) | (p.privatize ? 1u << 24 : 0u) |
           ((uint32_t)(scan + 1) << 25) | (fast_math() ? 1u << 29 : 0u) | (no_agg() ? 1u << 30 : 0u) | (p.privatize == 2 ? 1u << 31 : 0u);  // bit 28 (lagged fused scan) is patched once the streams are known
   for (size_t k = 0; k < p.params.size(); ++k) kw[binding_pos[k]] |= (uint32_t)p.params[k].use << 16;
   if (scan >= 0) {
@@ -361,11 +369,35 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
 // ---------------------------------------------------------------------------------------
 namespace {
 
+// Value ranges the generator can PROVE from the trace alone (constants, lane indices, shifts, casts, f32 arithmetic
+// through monotone rounding, the documented <= 1 ulp bounds of vk_math.h).  Used for one thing: calling the unchecked
+// fast path of a vk_math.h function when its argument provably never takes the out-of-line path (NaN / inf / huge /
+// subnormal / -0 handling) — same bits, no test, no branch, and the compiler can schedule across the call.  Nothing here
+// depends on n, addresses or data, so a cached kernel stays valid for every launch of its canonical key.
+struct FRange {            // f32: every value is finite, not NaN and inside [lo, hi]
+  bool ok = false;
+  float lo = 0.0f, hi = 0.0f;
+  bool negzero = true;     // the value may be -0.0 (sin(-0) = -0 is the one thing the trig fast path gets wrong)
+};
+struct URange { uint32_t lo = 0u, hi = 0xFFFFFFFFu; };   // u32: always valid
+
 struct Val {
   std::string name;        // scalar expression name
   TypeId ty = VKJIT_TY_VOID;
   std::vector<Val> elems;  // struct members (scalar replacement: structs never reach memory)
+  FRange fr;
+  URange ur;
 };
+
+inline float f_down(float x, int steps) { for (int i = 0; i < steps; ++i) x = std::nextafterf(x, -INFINITY); return x; }
+inline float f_up(float x, int steps) { for (int i = 0; i < steps; ++i) x = std::nextafterf(x, INFINITY); return x; }
+inline bool f_finite(float x) { return std::isfinite(x); }
+inline FRange fr_make(float lo, float hi, bool negzero) {
+  FRange r;
+  r.ok = f_finite(lo) && f_finite(hi) && lo <= hi;
+  r.lo = lo; r.hi = hi; r.negzero = negzero;
+  return r;
+}
 
 const char* ctype(TypeId t) {
   switch (t) {
@@ -478,7 +510,14 @@ struct Gen {
     }
   }
 
-  std::string uop_expr(const Var& v, const std::string& a) {
+  // which vk_math.h entry point: the checked one, or the unchecked fast path when the argument's range proves that the
+  // check can never fire
+  bool exp_fast(const FRange& a) const { return !no_ranges() && a.ok && a.lo > -87.0f && a.hi < 87.0f; }
+  bool log_fast(const FRange& a) const { return !no_ranges() && a.ok && a.lo >= 1.17549435e-38f; }   // positive normal
+  bool trig_fast(const FRange& a) const { return !no_ranges() && a.ok && !a.negzero && a.lo >= -105615.0f && a.hi <= 105615.0f; }
+
+  std::string uop_expr(const Var& v, const Val& av) {
+    const std::string& a = av.name;
     const TypeId t = v.ty;
     switch (v.kind) {
       case VKJIT_UOP_NEG:
@@ -490,10 +529,10 @@ struct Gen {
       case VKJIT_UOP_NOT: return t == VKJIT_TY_BOOL ? "!" + a : "~" + a;
       case VKJIT_UOP_SQRT: return "__fsqrt_rn(" + a + ")";
       // vk_math.h: the one implementation the oracle compiles too (GPU == oracle bit for bit; <= 1 ulp of the exact value)
-      case VKJIT_UOP_EXP: if (fast_math()) return "expf(" + a + ")"; uses_vk_math = true; return "vk_expf(" + a + ")";
-      case VKJIT_UOP_LOG: if (fast_math()) return "logf(" + a + ")"; uses_vk_math = true; return "vk_logf(" + a + ")";
-      case VKJIT_UOP_SIN: if (fast_math()) return "sinf(" + a + ")"; uses_vk_math = true; return "vk_sinf(" + a + ")";
-      case VKJIT_UOP_COS: if (fast_math()) return "cosf(" + a + ")"; uses_vk_math = true; return "vk_cosf(" + a + ")";
+      case VKJIT_UOP_EXP: if (fast_math()) return "expf(" + a + ")"; uses_vk_math = true; return (exp_fast(av.fr) ? "vk_expf_fast(" : "vk_expf(") + a + ")";
+      case VKJIT_UOP_LOG: if (fast_math()) return "logf(" + a + ")"; uses_vk_math = true; return (log_fast(av.fr) ? "vk_logf_fast(" : "vk_logf(") + a + ")";
+      case VKJIT_UOP_SIN: if (fast_math()) return "sinf(" + a + ")"; uses_vk_math = true; return (trig_fast(av.fr) ? "vk_sinf_fast(" : "vk_sinf(") + a + ")";
+      case VKJIT_UOP_COS: if (fast_math()) return "cosf(" + a + ")"; uses_vk_math = true; return (trig_fast(av.fr) ? "vk_cosf_fast(" : "vk_cosf(") + a + ")";
       default: fail(VKJIT_ERR_INVALID, "unknown uop");
     }
   }
@@ -514,7 +553,124 @@ struct Gen {
     fail(VKJIT_ERR_UNSUPPORTED, "cast");
   }
 
+  // ---- value ranges (see FRange) --------------------------------------------------------------------------------
+  static float bits_f(uint32_t w) { float x; memcpy(&x, &w, 4); return x; }
+  void node_ranges(uint32_t li) {
+    Val& out = vals[li];
+    if (!out.elems.empty() || !ty_is_scalar(out.ty)) return;   // struct values carry the ranges of their members
+    const Var& v = ir.vars[p.order[li]];
+    FRange f; URange u;
+    auto D = [&](uint32_t k) -> const Val& { return dep(v, k); };
+    switch (v.op) {
+      case OP_CONST:
+        if (v.ty == VKJIT_TY_F32) f = fr_make(bits_f(v.aux), bits_f(v.aux), v.aux == 0x80000000u);
+        else if (v.ty == VKJIT_TY_U32) u.lo = u.hi = v.aux;
+        else if (v.ty == VKJIT_TY_BOOL) u.lo = u.hi = v.aux ? 1u : 0u;
+        break;
+      case OP_ARANGE:   // the lane index: anything below 2^32 (n is a kernel parameter, not part of the key)
+        if (v.ty == VKJIT_TY_F32) f = fr_make(0.0f, 4294967296.0f, false);
+        break;
+      case OP_CAST: {
+        const Val& a = D(0);
+        if (v.ty == VKJIT_TY_F32 && (a.ty == VKJIT_TY_U32 || a.ty == VKJIT_TY_BOOL))
+          f = fr_make((float)a.ur.lo, (float)a.ur.hi, false);       // round-to-nearest is monotone; 0 converts to +0
+        else if (v.ty == VKJIT_TY_U32 && a.ty == VKJIT_TY_BOOL) { u.lo = 0u; u.hi = 1u; }
+        else if (v.ty == VKJIT_TY_BOOL) { u.lo = 0u; u.hi = 1u; }
+        break;
+      }
+      case OP_BOP: {
+        const Val &a = D(0), &b = D(1);
+        if (a.ty == VKJIT_TY_F32 && v.ty == VKJIT_TY_F32 && a.fr.ok && b.fr.ok) {
+          const FRange &x = a.fr, &y = b.fr;
+          switch (v.kind) {
+            case VKJIT_BOP_ADD: f = fr_make(x.lo + y.lo, x.hi + y.hi, x.negzero && y.negzero); break;   // x + y = -0 only for (-0) + (-0)
+            case VKJIT_BOP_SUB: f = fr_make(x.lo - y.hi, x.hi - y.lo, x.negzero); break;                // only (-0) - (+0)
+            case VKJIT_BOP_MUL: {
+              const float c[4] = {x.lo * y.lo, x.lo * y.hi, x.hi * y.lo, x.hi * y.hi};
+              float lo = c[0], hi = c[0];
+              bool fin = true;
+              for (float t : c) { fin = fin && f_finite(t); lo = t < lo ? t : lo; hi = t > hi ? t : hi; }
+              // a product is +0 or positive when both factors are (and neither is -0); anything else may give -0
+              const bool nonneg = x.lo >= 0.0f && !x.negzero && y.lo >= 0.0f && !y.negzero;
+              if (fin) f = fr_make(lo, hi, !nonneg);
+              break;
+            }
+            case VKJIT_BOP_MIN: f = fr_make(x.lo < y.lo ? x.lo : y.lo, x.hi < y.hi ? x.hi : y.hi, true); break;
+            case VKJIT_BOP_MAX: f = fr_make(x.lo > y.lo ? x.lo : y.lo, x.hi > y.hi ? x.hi : y.hi, true); break;
+            default: break;
+          }
+        } else if (v.ty == VKJIT_TY_U32 && a.ty == VKJIT_TY_U32) {
+          const URange &x = a.ur, &y = b.ur;
+          auto below_pow2 = [](uint32_t m) { uint32_t r = m; r |= r >> 1; r |= r >> 2; r |= r >> 4; r |= r >> 8; r |= r >> 16; return r; };
+          switch (v.kind) {
+            case VKJIT_BOP_ADD: if ((uint64_t)x.hi + y.hi <= 0xFFFFFFFFull) { u.lo = x.lo + y.lo; u.hi = x.hi + y.hi; } break;
+            case VKJIT_BOP_MUL: if ((uint64_t)x.hi * y.hi <= 0xFFFFFFFFull) { u.lo = x.lo * y.lo; u.hi = x.hi * y.hi; } break;
+            case VKJIT_BOP_SHR:   // the generated code shifts by (b & 31)
+              if (y.lo == y.hi) { u.lo = x.lo >> (y.lo & 31u); u.hi = x.hi >> (y.lo & 31u); }
+              else { u.lo = 0u; u.hi = x.hi; }
+              break;
+            case VKJIT_BOP_AND: u.lo = 0u; u.hi = x.hi < y.hi ? x.hi : y.hi; break;
+            case VKJIT_BOP_OR: case VKJIT_BOP_XOR: u.lo = 0u; u.hi = below_pow2(x.hi | y.hi); break;
+            case VKJIT_BOP_MIN: u.lo = x.lo < y.lo ? x.lo : y.lo; u.hi = x.hi < y.hi ? x.hi : y.hi; break;
+            case VKJIT_BOP_MAX: u.lo = x.lo > y.lo ? x.lo : y.lo; u.hi = x.hi > y.hi ? x.hi : y.hi; break;
+            default: break;
+          }
+        } else if (v.ty == VKJIT_TY_BOOL) { u.lo = 0u; u.hi = 1u; }
+        break;
+      }
+      case OP_UOP: {
+        const Val& a = D(0);
+        if (v.ty != VKJIT_TY_F32 || !a.fr.ok || fast_math()) break;
+        const FRange& x = a.fr;
+        switch (v.kind) {
+          case VKJIT_UOP_NEG: f = fr_make(-x.hi, -x.lo, x.lo <= 0.0f && x.hi >= 0.0f); break;
+          case VKJIT_UOP_ABS: {
+            const float m = std::fabs(x.lo) > std::fabs(x.hi) ? std::fabs(x.lo) : std::fabs(x.hi);
+            f = fr_make((x.lo <= 0.0f && x.hi >= 0.0f) ? 0.0f : (std::fabs(x.lo) < std::fabs(x.hi) ? std::fabs(x.lo) : std::fabs(x.hi)), m, false);
+            break;
+          }
+          case VKJIT_UOP_SQRT:   // correctly rounded, monotone; sqrt(-0) = -0
+            if (x.lo >= 0.0f) f = fr_make(std::sqrt(x.lo > 0.0f ? x.lo : 0.0f), std::sqrt(x.hi), x.negzero);
+            break;
+          // vk_math.h results are within 1 ulp of the exact value (exhaustively checked, profiles/r02_vk_math_ulp.md);
+          // the bounds below leave 4 ulp plus the rounding of the host's double-precision evaluation
+          case VKJIT_UOP_LOG:
+            if (x.lo >= 1.17549435e-38f) {
+              float lo = f_down((float)std::log((double)x.lo), 4), hi = f_up((float)std::log((double)x.hi), 4);
+              if (x.hi <= 1.0f) hi = 0.0f;   // log(x <= 1) is +0 (x = 1) or negative: an error of 1 ulp cannot cross zero
+              if (x.lo >= 1.0f) lo = 0.0f;
+              f = fr_make(lo, hi, false);    // vk_logf(1) = +0
+            }
+            break;
+          case VKJIT_UOP_EXP:
+            if (x.hi < 88.0f) f = fr_make(0.0f, f_up((float)std::exp((double)x.hi), 4), false);
+            break;
+          case VKJIT_UOP_SIN: case VKJIT_UOP_COS: f = fr_make(-1.00000048f, 1.00000048f, true); break;
+          default: break;
+        }
+        break;
+      }
+      case OP_SELECT: {
+        const Val &a = D(1), &b = D(2);
+        if (v.ty == VKJIT_TY_F32 && a.fr.ok && b.fr.ok)
+          f = fr_make(a.fr.lo < b.fr.lo ? a.fr.lo : b.fr.lo, a.fr.hi > b.fr.hi ? a.fr.hi : b.fr.hi, a.fr.negzero || b.fr.negzero);
+        else if (v.ty == VKJIT_TY_U32 || v.ty == VKJIT_TY_BOOL) {
+          u.lo = a.ur.lo < b.ur.lo ? a.ur.lo : b.ur.lo; u.hi = a.ur.hi > b.ur.hi ? a.ur.hi : b.ur.hi;
+        }
+        break;
+      }
+      default: break;   // loads, gathers, bit casts, I32 arithmetic: nothing is known
+    }
+    if (v.op == OP_GETATTR || v.op == OP_SETATTR || v.op == OP_STRUCTINIT || v.op == OP_SCATTER || v.op == OP_SCATTER_ADD) return;  // copies of other values: keep theirs
+    out.fr = f; out.ur = u;
+  }
+
   void emit_node(uint32_t li) {
+    emit_node_text(li);
+    node_ranges(li);
+  }
+
+  void emit_node_text(uint32_t li) {
     const Var& v = ir.vars[p.order[li]];
     const std::string me = "v" + std::to_string(li);
     switch (v.op) {
@@ -551,13 +707,13 @@ struct Gen {
             const bool i_am_sin = v.kind == VKJIT_UOP_SIN;
             line("f32 " + me + ", " + other + ";");
             // one range reduction for both; bit-identical to vk_sinf / vk_cosf called separately (checked over all 2^32 inputs)
-            line(std::string(fast_math() ? "sincosf(" : "vk_sincosf(") + dep(v, 0).name + ", &" + (i_am_sin ? me : other) + ", &" + (i_am_sin ? other : me) + ");");
+            line(std::string(fast_math() ? "sincosf(" : trig_fast(dep(v, 0).fr) ? "vk_sincosf_fast(" : "vk_sincosf(") + dep(v, 0).name + ", &" + (i_am_sin ? me : other) + ", &" + (i_am_sin ? other : me) + ");");
             if (!fast_math()) uses_vk_math = true;
           }
           vals[li].name = me; vals[li].ty = v.ty;
           break;
         }
-        def(li, v.ty, uop_expr(v, dep(v, 0).name));
+        def(li, v.ty, uop_expr(v, dep(v, 0)));
         break;
       }
       case OP_CAST: def(li, v.ty, cast_expr(dep(v, 0).ty, v.ty, dep(v, 0).name)); break;
@@ -785,7 +941,7 @@ std::string reduce_defines(int red, TypeId ty) {
 // written by another build of the library is a miss, never a kernel with the wrong argument ABI.
 uint32_t generator_fingerprint() {
   static const uint32_t fp = [] {
-    constexpr uint32_t kGeneratorRevision = 11;  // round 2: vk_math.h lowering, fast-math variant bit
+    constexpr uint32_t kGeneratorRevision = 12;  // round 2: vk_math.h lowering, fast-math variant bit, range-proven fast paths
     uint32_t h = 2166136261u ^ kGeneratorRevision;
     auto mix = [&](const char* t) { for (; *t; ++t) { h ^= (unsigned char)*t; h *= 16777619u; } };
     mix(kVkMathSrc); mix(kScanCommonSrc); mix(kScanFusedSrc); mix(kReduceEpilogue); mix(kSaddHelper);

@@ -96,14 +96,18 @@ VKM_SLOW_FN float vkm_exp_slow(float x) {
   // (p 2^n1) 2^n2: the second multiply is the only rounding when the result is subnormal
   return vkm_mul(vkm_mul(p, vkm_float((unsigned int)(n1 + 127) << 23)), vkm_float((unsigned int)(n2 + 127) << 23));
 }
-VKM_FN float vk_expf(float x) {
-  if ((vkm_bits(x) & 0x7fffffffu) >= 0x42ae0000u) return vkm_exp_slow(x);   // |x| >= 87, inf, NaN
+// |x| < 87 (the caller has checked, or the code generator has PROVED it from the ranges of the trace: program.cpp)
+VKM_FN float vk_expf_fast(float x) {
   const float t = vkm_fma(x, 1.44269502162933349609375f, VKM_MAGIC);
   const float j = vkm_sub(t, VKM_MAGIC);
   float r = vkm_fma(j, -0.693145751953125f, x);            // ln2 high part: 16 bits, j * hi is exact
   r = vkm_fma(j, -1.42860682030941723212e-6f, r);
   // the low bits of t hold j (the bits of the magic constant vanish in the shift)
   return vkm_float(vkm_bits(vkm_exp_poly(r)) + (vkm_bits(t) << 23));
+}
+VKM_FN float vk_expf(float x) {
+  if ((vkm_bits(x) & 0x7fffffffu) >= 0x42ae0000u) return vkm_exp_slow(x);   // |x| >= 87, inf, NaN
+  return vk_expf_fast(x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -137,6 +141,7 @@ VKM_SLOW_FN float vkm_log_slow(float x) {
   if (ix == VKM_INF) return x;
   return vkm_log_core(vkm_bits(vkm_mul(x, 8388608.0f)), -23);   // subnormal: scale by 2^23 (exact)
 }
+VKM_FN float vk_logf_fast(float x) { return vkm_log_core(vkm_bits(x), 0); }   // x is a positive normal number
 VKM_FN float vk_logf(float x) {
   const unsigned int ix = vkm_bits(x);
   if (ix - 0x00800000u >= 0x7f000000u) return vkm_log_slow(x);   // not a positive normal number
@@ -240,6 +245,25 @@ VKM_SLOW_FN float vkm_sincos_slow(float x, int want_cos) {
 // fast-path test: 0 < |x| <= 105615  (one unsigned compare: |x| = 0 wraps around)
 VKM_FN bool vkm_trig_fast(float x) { return (vkm_bits(x) & 0x7fffffffu) - 1u < 0x47ce4780u; }
 
+// The unchecked forms: +0 <= x <= 105615 (x = +0 comes out right — r = lo = +0, sin = +0, cos = 1 — only -0 needs the
+// slow path's sign rule, and a negative x is fine too; the generator only proves the non-negative case).
+VKM_FN void vk_sincosf_fast(float x, float* sin_out, float* cos_out) {
+  float r, lo;
+  const unsigned int n = vkm_trig_reduce(x, &r, &lo);
+  const float s = vkm_sin_poly(r, lo), c = vkm_cos_poly(r, lo);
+  *sin_out = vkm_pick_sin(n, s, c);
+  *cos_out = vkm_pick_cos(n, s, c);
+}
+VKM_FN float vk_sinf_fast(float x) {
+  float r, lo;
+  const unsigned int n = vkm_trig_reduce(x, &r, &lo);
+  return vkm_pick_sin(n, vkm_sin_poly(r, lo), vkm_cos_poly(r, lo));
+}
+VKM_FN float vk_cosf_fast(float x) {
+  float r, lo;
+  const unsigned int n = vkm_trig_reduce(x, &r, &lo);
+  return vkm_pick_cos(n, vkm_sin_poly(r, lo), vkm_cos_poly(r, lo));
+}
 VKM_FN void vk_sincosf(float x, float* sin_out, float* cos_out) {
   if (!vkm_trig_fast(x)) { *sin_out = vkm_sincos_slow(x, 0); *cos_out = vkm_sincos_slow(x, 1); return; }
   float r, lo;
