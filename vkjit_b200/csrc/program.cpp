@@ -143,6 +143,12 @@ ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes) {
     if (t_nolag < 0) { const char* e = getenv("VKJIT_SCAN_T_NOLAG"); t_nolag = e ? atoi(e) : 0; }
     if (t_nolag == 512 || t_nolag == 1024) g.threads = t_nolag;
   }
+  // two 512-thread CTAs per SM = 296 tiles per generation: a 160-wide window would leave the upper half of every
+  // generation with a second look-back round
+  g.look_wide = g.threads == 512 ? 10 : 5;
+  static int lw_env = -1;
+  if (lw_env < 0) { const char* e = getenv("VKJIT_LOOK_WIDE"); lw_env = e ? atoi(e) : 0; }
+  if (lw_env >= 1 && lw_env <= 16) g.look_wide = lw_env;
   return g;
 }
 
@@ -338,7 +344,7 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
     const ScanFusedGeom sg = scan_fused_geom(stream_count(p), scan, p.order.size());
     if (sg.lag) kw[1] |= 1u << 28;
     kw[kn++] = 0xFFFFFFFEu;  // geometry of the fused scan kernel (tunable through the environment)
-    kw[kn++] = (uint32_t)sg.threads | ((uint32_t)sg.vpt << 16) | ((uint32_t)sg.slots << 24);
+    kw[kn++] = (uint32_t)sg.threads | ((uint32_t)sg.look_wide << 11) | ((uint32_t)sg.vpt << 16) | ((uint32_t)sg.slots << 24);
   }
   kw[kn++] = 0xFFFFFFFFu;
   for (uint32_t r : p.roots) kw[kn++] = r;
@@ -891,7 +897,7 @@ std::string scan_shell(const Program& p, const std::vector<uint32_t>& streams, c
   const ScanFusedGeom geom = scan_fused_geom(ns, p.scan, p.order.size());
   s += "#define VK_SCAN_MODE " + std::to_string(p.scan) + "\n#define VK_NS " + std::to_string(ns) + "\n#define VK_VPT " +
        std::to_string(geom.vpt) + "\n#define VK_LAG " + std::to_string(geom.lag ? 1 : 0) + "\n#define VK_SLOTS " +
-       std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n";
+       std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n#define VK_LOOK_WIDE " + std::to_string(geom.look_wide) + "\n";
   s += "struct VkPtrs {\n  const u32* s[" + std::to_string(std::max<size_t>(ns, 1)) + "];  // streamed arrays (staged by TMA)\n";
   for (uint32_t k : ptrs) {
     if (p.params[k].use & USE_SCATTER) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: the trace has side effects");
