@@ -143,9 +143,10 @@ ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes) {
     if (t_nolag < 0) { const char* e = getenv("VKJIT_SCAN_T_NOLAG"); t_nolag = e ? atoi(e) : 0; }
     if (t_nolag == 512 || t_nolag == 1024) g.threads = t_nolag;
   }
-  // two 512-thread CTAs per SM = 296 tiles per generation: a 160-wide window would leave the upper half of every
-  // generation with a second look-back round
-  g.look_wide = g.threads == 512 ? 10 : 5;
+  // 160 predecessors per look-back round.  Two 512-thread CTAs per SM make 296 tiles per generation, so the upper half of
+  // a generation needs a second round — yet a 320-wide window measured SLOWER (profiles/r02_fused_scan.md, experiment 3:
+  // compress_values(v, v > t) 0.376 -> 0.410 ms, 384-wide 0.469 ms): the status traffic costs more than the second round.
+  g.look_wide = 5;
   static int lw_env = -1;
   if (lw_env < 0) { const char* e = getenv("VKJIT_LOOK_WIDE"); lw_env = e ? atoi(e) : 0; }
   if (lw_env >= 1 && lw_env <= 16) g.look_wide = lw_env;

@@ -35,8 +35,7 @@ struct ScanFusedGeom {
   int slots = 2;    // ring slots per streamed array
   int staging = 0;  // output staging tiles: lagged prefix sums 1 (TMA bulk store), lagged compress 2 (coalesced copy-out)
   int threads = 1024;  // per CTA; 512: two co-resident CTAs per SM overlap each other's per-tile chains (lagged kernels)
-  int look_wide = 5;   // status words per lane and look-back round: one round (32 x look_wide predecessors) must span the
-                       // whole co-resident grid, or every tile past the window pays a second, un-prefetched L2 round trip
+  int look_wide = 5;   // status words per lane and look-back round (32 x look_wide predecessors); $VKJIT_LOOK_WIDE
   size_t tile() const { return (size_t)threads * 4 * vpt; }
   size_t smem(size_t streams) const { return (streams * slots + (size_t)staging) * tile() * 4; }
 };
