@@ -153,6 +153,20 @@ ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes) {
   return g;
 }
 
+// $VKJIT_FSCAN_TRACE=<file>: the lagged fused scan kernels stamp %globaltimer per tile and phase (scan_fused.cuh: VK_STAMP);
+// runtime.cpp: eval_scan writes the stamps to the file after every launch.  Part of the cache key.
+const char* fscan_trace_file() {
+  static const char* f = getenv("VKJIT_FSCAN_TRACE");
+  return (f && f[0]) ? f : nullptr;
+}
+
+// $VKJIT_SCAN_EARLY=0: the lagged fused scan kernels request a tile's status window at the start of the iteration that
+// resolves it (round 1/2 schedule) instead of one phase earlier.  A/B knob, part of the cache key.
+bool scan_early() {
+  static const int on = [] { const char* e = getenv("VKJIT_SCAN_EARLY"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on == 1;
+}
+
 size_t stream_count(const Program& p) {
   size_t k = 0;
   for (const Param& pr : p.params) k += (pr.use & USE_STREAM) ? 1 : 0;
@@ -345,7 +359,8 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
     const ScanFusedGeom sg = scan_fused_geom(stream_count(p), scan, p.order.size());
     if (sg.lag) kw[1] |= 1u << 28;
     kw[kn++] = 0xFFFFFFFEu;  // geometry of the fused scan kernel (tunable through the environment)
-    kw[kn++] = (uint32_t)sg.threads | ((uint32_t)sg.look_wide << 11) | ((uint32_t)sg.vpt << 16) | ((uint32_t)sg.slots << 24);
+    kw[kn++] = (uint32_t)sg.threads | ((uint32_t)sg.look_wide << 11) | ((uint32_t)sg.vpt << 16) | ((uint32_t)sg.slots << 24) |
+               (fscan_trace_file() ? 1u << 30 : 0u) | (scan_early() ? 1u << 29 : 0u);
   }
   kw[kn++] = 0xFFFFFFFFu;
   for (uint32_t r : p.roots) kw[kn++] = r;
@@ -898,7 +913,7 @@ std::string scan_shell(const Program& p, const std::vector<uint32_t>& streams, c
   const ScanFusedGeom geom = scan_fused_geom(ns, p.scan, p.order.size());
   s += "#define VK_SCAN_MODE " + std::to_string(p.scan) + "\n#define VK_NS " + std::to_string(ns) + "\n#define VK_VPT " +
        std::to_string(geom.vpt) + "\n#define VK_LAG " + std::to_string(geom.lag ? 1 : 0) + "\n#define VK_SLOTS " +
-       std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n#define VK_LOOK_WIDE " + std::to_string(geom.look_wide) + "\n";
+       std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n#define VK_LOOK_WIDE " + std::to_string(geom.look_wide) + "\n#define VK_TRACE " + (fscan_trace_file() ? "1" : "0") + "\n#define VK_EARLY " + (scan_early() ? "1" : "0") + "\n";
   s += "struct VkPtrs {\n  const u32* s[" + std::to_string(std::max<size_t>(ns, 1)) + "];  // streamed arrays (staged by TMA)\n";
   for (uint32_t k : ptrs) {
     if (p.params[k].use & USE_SCATTER) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: the trace has side effects");

@@ -40,6 +40,7 @@ struct ScanFusedGeom {
   size_t smem(size_t streams) const { return (streams * slots + (size_t)staging) * tile() * 4; }
 };
 ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes);
+const char* fscan_trace_file();  // $VKJIT_FSCAN_TRACE (per-tile phase stamps of the lagged fused scan kernels)
 
 struct Param {
   VarId var;     // the Binding var whose array is passed

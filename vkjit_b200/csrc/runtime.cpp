@@ -707,6 +707,12 @@ bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t
   try {
     be.launch(k, (uint32_t)std::min<size_t>(tiles, (size_t)be.sm_count * k->ctas_per_sm), (uint32_t)geom.threads, argv, (uint32_t)geom.smem(ns));
   } catch (...) { release_array(o); throw; }
+  if (const char* tf = fscan_trace_file()) {  // per-tile phase stamps live in the spare words of the status lines
+    ck(cudaStreamSynchronize((cudaStream_t)be.enqueue_stream()), "sync");
+    std::vector<uint64_t> h((size_t)prims::kStatusWordsPerTile * (1 + tiles));
+    ck(cudaMemcpy(h.data(), be.scratch.tile_state, h.size() * 8, cudaMemcpyDeviceToHost), "trace readback");
+    if (FILE* fp = fopen(tf, "wb")) { fwrite(h.data(), 8, h.size(), fp); fclose(fp); }
+  }
   *out = o;
   return true;
 }

@@ -289,7 +289,8 @@ scan_kernel(const uint32_t* __restrict__ in,      // scan: addends; compress: ma
 template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel_lag(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t num_tiles,
-                uint64_t* __restrict__ state, const uint32_t* __restrict__ initial_ptr, unsigned long long* __restrict__ trace) {
+                uint64_t* __restrict__ state, const uint32_t* __restrict__ initial_ptr, unsigned long long* __restrict__ trace,
+                const bool early) {  // early: request a tile's status window right after the previous resolve ($VKJIT_SCAN_EARLY_PRIM)
   constexpr int T = kScanThreads, VPT = kScanLagVpt, TILE = T * 4 * VPT, S = 2;
   constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = NTOT / 32;
   constexpr uint32_t TILE_BYTES = TILE * 4;
@@ -337,7 +338,7 @@ scan_kernel_lag(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, siz
     for (int j = 0; j < VPT; ++j) xc[j] = make_uint4(0u, 0u, 0u, 0u);
     // warp 0: the previous tile's predecessors published a whole iteration ago — fetch their status words now,
     // use them after this tile's local scan
-    if (warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
+    if (!early && warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
     if (have_cur) {  // ---- local scan of tile k
       const size_t tile_base = (size_t)tile * TILE;
       if (trace && threadIdx.x == 0) trace[(size_t)tile * 8 + 0] = global_ns();
@@ -416,6 +417,7 @@ scan_kernel_lag(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, siz
     }
     if (threadIdx.x == 0) tma_store_wait_read();  // the previous bulk store has read the staging tile
     __syncthreads();
+    if (early && warp == 0 && have_cur) prefetch_window(status, tile, s_window);  // resolved in the next iteration
     if (have_prev) {  // ---- results of tile k-1, from registers, through shared memory and ONE bulk store
       const uint32_t tprev = tile - stride;
       const size_t tile_base = (size_t)tprev * TILE;
@@ -460,7 +462,7 @@ template <bool VALUES>
 __global__ void __launch_bounds__(kScanThreads, 1)
 compress_kernel_lag(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ values, uint32_t* __restrict__ out,
                     uint32_t* __restrict__ count_out, size_t n, uint32_t num_tiles, uint64_t* __restrict__ state,
-                    const uint32_t* __restrict__ index_base_ptr) {
+                    const uint32_t* __restrict__ index_base_ptr, const bool early) {
   constexpr int T = kScanThreads, VPT = VALUES ? kCompressLagVptValues : kCompressLagVptIndex, TILE = T * 4 * VPT;
   constexpr int S = VALUES ? 2 : 3;  // mask slots
   constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = NTOT / 32;
@@ -509,7 +511,7 @@ compress_kernel_lag(const uint32_t* __restrict__ mask, const uint32_t* __restric
     const uint32_t tile = first + k * stride;
     const bool staged = have_cur && !(ragged && tile == num_tiles - 1);
     uint32_t flags_c = 0u, pre_c = 0u;
-    if (warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
+    if (!early && warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
     if (have_cur) {  // ---- selection bits and packed local scan of tile k
       const size_t tile_base = (size_t)tile * TILE;
       uint32_t pk = 0u, own = 0u;
@@ -591,6 +593,7 @@ compress_kernel_lag(const uint32_t* __restrict__ mask, const uint32_t* __restric
       agg_prev = agg_cur;
     }
     __syncthreads();
+    if (early && warp == 0 && have_cur) prefetch_window(status, tile, s_window);  // resolved in the next iteration
     if (have_prev) {  // ---- selected lanes of tile k-1, written at their rank
       const uint32_t kp = k - 1, tprev = tile - stride;
       const size_t tile_base = (size_t)tprev * TILE;
@@ -643,6 +646,7 @@ static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* ou
   using G = ScanGeom<MODE>;
   static int impl = -1;
   if (impl < 0) { const char* d = getenv("VKJIT_SCAN_IMPL"); impl = (d && std::string(d) == "classic") ? 0 : 1; }  // prefix sums: lagged kernel unless "classic"
+  static const bool early = [] { const char* e = getenv("VKJIT_SCAN_EARLY_PRIM"); return e && e[0] == '1'; }();  // A/B knob (default: off)
   if constexpr (MODE < MODE_COMPRESS_INDEX) {
     if (impl == 1) {
       constexpr size_t TILE = (size_t)kScanThreads * 4 * kScanLagVpt, SMEM = 3 * TILE * 4;  // 2 input slots + 1 output staging tile
@@ -662,7 +666,7 @@ static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* ou
       if (tf && !d_trace) cudaMalloc(&d_trace, tiles * 64);
       if (tf) cudaMemsetAsync(d_trace, 0, tiles * 64, s);
       const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);
-      scan_kernel_lag<MODE><<<grid, kScanThreads, SMEM, s>>>(in, out, n, (uint32_t)tiles, sc.tile_state, initial, tf ? d_trace : nullptr);
+      scan_kernel_lag<MODE><<<grid, kScanThreads, SMEM, s>>>(in, out, n, (uint32_t)tiles, sc.tile_state, initial, tf ? d_trace : nullptr, early);
       e = cudaGetLastError();
       if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e));
       if (tf) {
@@ -692,7 +696,7 @@ static void launch_scan(const uint32_t* in, const uint32_t* values, uint32_t* ou
         configured_lag = true;
       }
       const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count);
-      compress_kernel_lag<VALUES><<<grid, kScanThreads, SMEM, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state, index_base);
+      compress_kernel_lag<VALUES><<<grid, kScanThreads, SMEM, s>>>(in, values, out, count_out, n, (uint32_t)tiles, sc.tile_state, index_base, early);
       e = cudaGetLastError();
       if (e != cudaSuccess) fail(VKJIT_ERR_CUDA, std::string("compress launch: ") + cudaGetErrorString(e));
       return;

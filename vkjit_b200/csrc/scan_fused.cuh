@@ -240,11 +240,33 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
 // VK_NS <= 1.  Modes 0/1: row-relative results wait in registers and leave through a staging tile + one TMA bulk store.
 // Mode 2: 4 selection bits + an 8-bit row offset per vector wait in two registers.  Mode 3: additionally the tile's ring slot
 // stays resident one more iteration (VK_SLOTS = 4) and the selected lanes' values are re-evaluated from it.
+// $VKJIT_FSCAN_TRACE=<file> (VK_TRACE): %globaltimer stamps per tile in the spare words 1..11 of the tile's 128-byte
+// status line (word 0 is the status): [1] iteration start, [2] tile data landed, [3] evaluated + scanned locally,
+// [4] past barrier 1, [5] aggregate published, [6] prefix resolved, [7] a worker warp past barrier 2, [8] its output
+// written, [9] past the slot-release barrier, [10] blockIdx, [11] that worker warp reaches barrier 1.
+#ifndef VK_TRACE
+#define VK_TRACE 0
+#endif
+#ifndef VK_EARLY
+#define VK_EARLY 1
+#endif
+#if VK_TRACE
+// "memory": the timer read must not move across a barrier or the code it brackets
+__device__ __forceinline__ unsigned long long vk_stamp_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+  return t;
+}
+#define VK_STAMP(cond, tile_, w) do { if (cond) status[(size_t)(tile_) * kStatusStride + (w)] = vk_stamp_ns(); } while (0)
+#else
+#define VK_STAMP(cond, tile_, w) do { } while (0)
+#endif
 extern "C" __global__ void __launch_bounds__(VK_T, 1024 / VK_T)
 vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, u32* __restrict__ count_out,
             const u32 num_tiles, uint64_t* __restrict__ state, const u32* __restrict__ initial_ptr,
             const u32* __restrict__ index_base_ptr) {
   constexpr int T = VK_T, VPT = VK_VPT, TILE = T * 4 * VPT, NS = VK_NS, NSA = 1, S = VK_SLOTS;
+  constexpr int TW = 64;  // the traced worker thread (warp 2)
   constexpr int WARPS = T / 32, NTOT = VPT * WARPS, PER_LANE = NTOT / 32;
   constexpr u32 TILE_BYTES = TILE * 4;
   constexpr bool COMPRESS = VK_SCAN_MODE >= 2, VALUES = VK_SCAN_MODE == 3;
@@ -307,11 +329,17 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
     u32 flags_c = 0u, pre_c = 0u;
 #pragma unroll
     for (int j = 0; j < VPT; ++j) xc[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
+    // status window of the tile that is resolved in THIS iteration (tile k-1).  VK_EARLY: it was requested one phase
+    // earlier, right after the previous iteration's resolve (below) — with two 512-thread CTAs per SM the evaluation of an
+    // 8192-lane tile takes 0.35-0.45 us, less than the L2 round trip, and warp 0 sat in cp.async.wait_group for the rest
+    // (per-phase trace, profiles/r02_fused_scan.md: resolve 1.4 us of a 3.5 us tile period).
+    if (!VK_EARLY && warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
     if (have_cur) {  // ---- evaluate tile k and scan it locally
       const size_t tile_base = (size_t)tile * TILE;
       const bool whole = !(ragged && tile == num_tiles - 1);
+      VK_STAMP(threadIdx.x == 0, tile, 1);
       if (whole && NS > 0) mbar_wait(&full[k % S], (k / S) & 1);
+      VK_STAMP(threadIdx.x == 0, tile, 2);
       u32 own = 0u;
       auto evaluate = [&](auto whole_c) {
         constexpr bool W = decltype(whole_c)::value;
@@ -372,7 +400,13 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
         }
       }
     }
+    VK_STAMP(have_cur && threadIdx.x == 0, tile, 3);
+    VK_STAMP(have_cur && threadIdx.x == TW, tile, 11);
     __syncthreads();  // s_tot[k % 3] complete; (modes 0-2) every thread has consumed ring slot k % S
+    VK_STAMP(have_cur && threadIdx.x == 0, tile, 4);
+#if VK_TRACE
+    if (have_cur && threadIdx.x == 0) status[(size_t)tile * kStatusStride + 10] = blockIdx.x;
+#endif
     if (!VALUES && have_cur && threadIdx.x == 32) fill(k + S);
     if (warp == 0) {
       u32 agg_cur = 0u;
@@ -396,6 +430,7 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
           if (tile == 0) status_store(status, ((uint64_t)ST_INCLUSIVE << 32) | (initial + agg_cur));
           else status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_AGGREGATE << 32) | agg_cur);
         }
+        VK_STAMP(lane == 0, tile, 5);
       }
       if (have_prev) {
         const u32 tprev = tile - stride;
@@ -406,11 +441,16 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
           s_tile_excl = excl;
           if (COMPRESS && tprev == num_tiles - 1) *count_out = excl + agg_prev;
         }
+        VK_STAMP(lane == 0, tprev, 6);
       }
       agg_prev = agg_cur;
     }
     if (!COMPRESS && threadIdx.x == 0) tma_store_wait_read();  // the previous bulk store has read the staging tile
     __syncthreads();
+    // tile k's aggregate was published a moment ago; its window is read now, ~1 us before it is needed, while the
+    // predecessors' aggregates of the same generation (published at about the same time as ours) become visible
+    if (VK_EARLY && warp == 0 && have_cur) prefetch_window(status, tile, s_window);
+    VK_STAMP(have_prev && threadIdx.x == TW, tile - stride, 7);
     if (have_prev) {  // ---- output of tile k-1
       const u32 kp = k - 1, tprev = tile - stride;
       const size_t tile_base = (size_t)tprev * TILE;
@@ -473,10 +513,12 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
           }
         };
         if (whole) emit(VkBool<true>{}); else emit(VkBool<false>{});
+        VK_STAMP(threadIdx.x == TW, tprev, 8);
         if (VALUES && NS > 0) {  // the slot of tile k-1 was kept for the re-evaluation: free now
           __syncthreads();
           if (threadIdx.x == 32) fill(kp + S);
         }
+        VK_STAMP(threadIdx.x == TW, tprev, 9);
       }
     }
 #pragma unroll
