@@ -53,6 +53,8 @@ rows = [
     ("worker warp waits at barrier 1", cur[:, 4] - cur[:, 11]),
     ("warp 0: scan of the totals + publish", cur[:, 5] - cur[:, 4]),
     ("warp 0: resolve the previous tile's prefix (tile k-1 of this CTA, same iteration)", nx[:, 5] * 0 + (cur[:, 6] - nx[:, 5])),
+    ("   of which: until the prefetched status window has landed (cp.async.wait_group)", cur[:, 12] - nx[:, 5]),
+    ("   of which: the look-back walk itself", cur[:, 6] - cur[:, 12]),
     ("worker warp: barrier 1 passed -> barrier 2 passed (serial section seen by a worker)", cur[:, 7] - nx[:, 4]),
     ("worker warp: output of the tile", cur[:, 8] - cur[:, 7]),
     ("worker warp: slot-release barrier", cur[:, 9] - cur[:, 8]),
@@ -60,3 +62,42 @@ rows = [
 print(f"case {which}: {tiles} tiles, grid {grid}, {per} tiles per CTA, kernel span {(st[:, 1:10][st[:, 1:10] > 0].max() - st[:, 1][st[:, 1] > 0].min()) / 1e3:.1f} us")
 for name, x in rows:
     print(f"  {med(x):7.2f} us  {name}")
+rounds, polls = cur[:, 14], cur[:, 13]
+print(f"  look-back rounds per tile: mean {rounds.mean():.2f} (1: {np.mean(rounds == 1):.2f}, 2: {np.mean(rounds == 2):.2f}, >2: {np.mean(rounds > 2):.2f});"
+      f" tiles that polled an INVALID status word: {np.mean(polls > 0):.3f}, polls per tile (mean over lanes and tiles) {polls.mean():.2f}")
+by = {}
+for lo, hi in ((0, 80), (80, 160), (160, 230), (230, 296)):
+    m = (cur[:, 10] >= lo) & (cur[:, 10] < hi)
+    if m.any():
+        print(f"    CTAs {lo:3d}-{hi - 1:3d}: resolve {med((cur[:, 6] - nx[:, 5])[m]):5.2f} us, window wait {med((cur[:, 12] - nx[:, 5])[m]):5.2f}, walk {med((cur[:, 6] - cur[:, 12])[m]):5.2f},"
+              f" rounds {rounds[m].mean():.2f}, polled {np.mean(polls[m] > 0):.3f}")
+
+# ---- skew between CTAs: when does a tile publish its aggregate relative to the others of its generation, and how long
+# before (negative: AFTER) the start of its successor's resolve was each of the 160 predecessors' aggregate published?
+pub = st[:, 5]
+g0 = 50
+gen = pub[g0 * grid:(g0 + 1) * grid] - pub[g0 * grid:(g0 + 1) * grid].min()
+q = np.percentile(gen, [0, 10, 50, 90, 100]) / 1e3
+print(f"  generation {g0}: publish time of the {grid} tiles relative to the first: p0 {q[0]:.2f} p10 {q[1]:.2f} p50 {q[2]:.2f} p90 {q[3]:.2f} p100 {q[4]:.2f} us;"
+      f" median first half (CTAs 0-147) {np.median(gen[:148]) / 1e3:.2f}, second half {np.median(gen[148:]) / 1e3:.2f}")
+ts = t[ok]
+res_start = nx[:, 5]           # resolve of tile t starts right after its successor's publish (same warp, same iteration)
+for d in (1, 2, 4, 8, 16, 32, 64, 128, 160):
+    slack = (res_start - pub[ts - d]) / 1e3
+    print(f"    predecessor t-{d:3d}: published {np.median(slack):6.2f} us before the resolve starts (p10 {np.percentile(slack, 10):6.2f}, p1 {np.percentile(slack, 1):6.2f}); not yet: {np.mean(slack < 0):.3f}")
+
+# ---- who paces the kernel?  Per CTA: share of tiles that had to poll, and the phases of the CTAs that (almost) never wait
+cta_ok = cur[:, 10]
+frac = np.array([np.mean(polls[cta_ok == b] > 0) if np.any(cta_ok == b) else np.nan for b in range(grid)])
+order = np.argsort(frac)
+print(f"  per-CTA share of tiles that polled: min {np.nanmin(frac):.2f} p10 {np.nanpercentile(frac, 10):.2f} p50 {np.nanpercentile(frac, 50):.2f} p90 {np.nanpercentile(frac, 90):.2f} max {np.nanmax(frac):.2f}")
+def phases(mask, label):
+    print(f"    {label}: period {med((nx[:, 1] - cur[:, 1])[mask]):.2f}  data wait {med((cur[:, 2] - cur[:, 1])[mask]):.2f}  evaluate (worker) {med((cur[:, 11] - cur[:, 1])[mask]):.2f}"
+          f"  totals+publish {med((cur[:, 5] - cur[:, 4])[mask]):.2f}  resolve {med((cur[:, 6] - nx[:, 5])[mask]):.2f}  output {med((cur[:, 8] - cur[:, 7])[mask]):.2f}"
+          f"  start->b1 exit (thread 0) {med((cur[:, 4] - cur[:, 1])[mask]):.2f}  b1 exit -> next start {med((nx[:, 1] - cur[:, 4])[mask]):.2f}")
+pacers = order[:15]
+waiters = order[-15:]
+phases(np.isin(cta_ok, pacers), f"15 CTAs that poll least {sorted(pacers.tolist())}")
+phases(np.isin(cta_ok, waiters), f"15 CTAs that poll most  {sorted(waiters.tolist())}")
+phases(polls == 0, "tiles without a poll")
+phases(polls > 0, "tiles with a poll   ")

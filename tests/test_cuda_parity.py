@@ -640,6 +640,58 @@ def test_upload_and_readback_through_the_staging_ring(cir, n):
     assert np.array_equal(again, keep) and (n * 4 < (64 << 10) or again.ctypes.data != got.ctypes.data)
 
 
+@pytest.mark.parametrize("variant", ["default", "ctrl", "ctrl_deep", "ctrl_small_tiles", "wreg", "early"])
+def test_fused_compress_kernel_variants(tmp_path, variant):
+    """The fused trace -> compress kernels in every schedule the library can generate (scan_fused.cuh): the shipped lagged
+    kernel, the opt-in control-warp pipeline (VKJIT_SCAN_CTRL=1: a dedicated warp owns the totals scan / publish / anchored
+    look-back, the workers write tile k - D; coalesced warp-row output) at several lags and tile sizes, the status window
+    through strong loads (VKJIT_SCAN_WREG=1) and requested early (VKJIT_SCAN_EARLY=1) — all bit-exact against the oracle:
+    indices and values, a mask computed from the streamed array and one computed from the lane index, sizes from one
+    lane over ragged tiles to several generations of the persistent grid.  The switches are read once per process."""
+    import subprocess
+    import sys
+    script = tmp_path / "fc.py"
+    script.write_text('''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import vkjit_b200 as vk
+from oracle_lib import OracleIr
+from vkjit_b200.ir import Bop, Ir, VarType as T
+vk.init(0)
+def h(ir, x, seed):
+    s = ir.add(ir.mul(ir.bop(Bop.Xor, x, ir.const_u32(seed)), ir.const_u32(747796405)), ir.const_u32(2891336453))
+    return ir.bop(Bop.Xor, ir.bop(Bop.Shr, s, ir.const_u32(15)), s)
+for n in (1, 5, 4095, 8191, 8192, 8193, 100003, 296 * 8192 + 17, 3 * 296 * 8192 + 4099, 9 * 296 * 4096 + 1):
+    res = []
+    for ir in (Ir(), OracleIr()):
+        lanes = ir.arange(T.U32, n)
+        vals = h(ir, lanes, 3)
+        ir.eval([vals])
+        got = []
+        for thr in (0x80000000, 0xF0000000, 0x00000010):            # p = 1/2, 1/16, ~1
+            m = ir.gt(vals, ir.const_u32(thr))
+            r, k = ir.compress_values(vals, m); got.append((k, ir.as_slice(r, T.U32).copy()))
+            m = ir.gt(vals, ir.const_u32(thr))
+            r, k = ir.compress(m); got.append((k, ir.as_slice(r, T.U32).copy()))
+        m = ir.neq(ir.bop(Bop.And, h(ir, lanes, 4), ir.const_u32(1)), ir.const_u32(0))   # mask from the lane index
+        r, k = ir.compress_values(vals, m); got.append((k, ir.as_slice(r, T.U32).copy()))
+        m = ir.lt(lanes, ir.const_u32(0))                             # nothing selected
+        r, k = ir.compress(m); got.append((k, ir.as_slice(r, T.U32).copy()))
+        res.append(got)
+        ir.close()
+    for (ka, a), (kb, b) in zip(*res):
+        assert ka == kb and np.array_equal(a, b), (n, ka, kb)
+print("fused compress ok")
+''' % (ROOT, os.path.join(ROOT, "tests")))
+    env = {"default": {}, "ctrl": {"VKJIT_SCAN_CTRL": "1"},
+           "ctrl_deep": {"VKJIT_SCAN_CTRL": "1", "VKJIT_CTRL_LAG": "4", "VKJIT_CTRL_DEPTH": "6", "VKJIT_FSCAN_DIAG": "2"},
+           "ctrl_small_tiles": {"VKJIT_SCAN_CTRL": "1", "VKJIT_CTRL_VPT": "2", "VKJIT_CTRL_LAG": "1", "VKJIT_CTRL_DEPTH": "1"},
+           "wreg": {"VKJIT_SCAN_WREG": "1"}, "early": {"VKJIT_SCAN_EARLY": "1"}}[variant]
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "fused compress ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
 @pytest.mark.parametrize("variant", ["plain", "agg", "cluster"])
 def test_scatter_add_hot_bins(tmp_path, variant):
     """Integer scatter_add when the lanes of a warp collide (few distinct bins), plain and with the opt-in warp-aggregated

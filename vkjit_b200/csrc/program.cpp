@@ -143,10 +143,49 @@ ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes) {
     if (t_nolag < 0) { const char* e = getenv("VKJIT_SCAN_T_NOLAG"); t_nolag = e ? atoi(e) : 0; }
     if (t_nolag == 512 || t_nolag == 1024) g.threads = t_nolag;
   }
+  // $VKJIT_SCAN_CTRL=1 (experiment): compress modes over at most one streamed array take the control-warp kernel.
+  // Geometry through $VKJIT_CTRL_T (workers), $VKJIT_CTRL_VPT, $VKJIT_CTRL_SLOTS, $VKJIT_CTRL_DEPTH, $VKJIT_CTRL_CTAS.
+  {
+    static int ctrl_env = -1, ct = 0, cv = 0, cs = 0, cd = 0, cc = 0, cl = 0;
+    if (ctrl_env < 0) {
+      const char* e = getenv("VKJIT_SCAN_CTRL"); ctrl_env = e ? (e[0] == '1' ? 1 : 0) : kScanCtrlDefault;
+      e = getenv("VKJIT_CTRL_T"); ct = e ? atoi(e) : 0;
+      e = getenv("VKJIT_CTRL_VPT"); cv = e ? atoi(e) : 0;
+      e = getenv("VKJIT_CTRL_SLOTS"); cs = e ? atoi(e) : 0;
+      e = getenv("VKJIT_CTRL_DEPTH"); cd = e ? atoi(e) : 0;
+      e = getenv("VKJIT_CTRL_CTAS"); cc = e ? atoi(e) : 0;
+      e = getenv("VKJIT_CTRL_LAG"); cl = e ? atoi(e) : 0;
+    }
+    if (ctrl_env == 1 && mode >= SCAN_COMPRESS_INDEX && streams <= 1 && nodes <= max_nodes && !classic) {
+      const bool values = mode == SCAN_COMPRESS_VALUE;
+      g.ctrl = true; g.lag = true; g.staging = 0;
+      g.threads = (ct == 256 || ct == 512 || ct == 1024) ? ct : 512;
+      g.vpt = (cv >= 1 && cv <= 4) ? cv : 4;
+      g.clag = (cl >= 1 && cl <= 12) ? cl : 2;
+      g.depth = (cd >= 1 && cd <= 13) ? cd : g.clag + 1;
+      if (g.depth < g.clag) g.depth = g.clag;
+      g.slots = cs > 0 ? cs : (values ? g.depth + 2 : 3);
+      if (values && g.slots < g.depth + 2) g.slots = g.depth + 2;
+      if (g.slots < 2) g.slots = 2;
+      // the ring must fit next to ~14 KB of static shared memory: smaller tiles first, then less depth
+      while (streams && (size_t)g.slots * g.tile() * 4 > 208 * 1024) {
+        if (g.vpt > 2 && g.threads * (g.vpt / 2) % 1024 == 0) g.vpt /= 2;
+        else if (values && g.depth > g.clag) { g.depth -= 1; g.slots = g.depth + 2; }
+        else if (values && g.clag > 1) { g.clag -= 1; g.depth = g.clag; g.slots = g.depth + 2; }
+        else if (g.slots > 2) g.slots -= 1;
+        else break;
+      }
+      // co-resident CTAs: what 227 KB of shared memory and 2048 threads allow, at most 2
+      const size_t smem = std::max<size_t>(streams, 0) * g.slots * g.tile() * 4 + 8192;
+      int fit = (int)std::min<size_t>(2, std::min<size_t>((227 * 1024) / std::max<size_t>(smem, 1), 2048 / (size_t)(g.threads + 64)));
+      if (fit < 1) fit = 1;
+      g.ctas = (cc == 1 || cc == 2) ? std::min(cc, fit) : fit;
+    }
+  }
   // 160 predecessors per look-back round.  Two 512-thread CTAs per SM make 296 tiles per generation, so the upper half of
   // a generation needs a second round — yet a 320-wide window measured SLOWER (profiles/r02_fused_scan.md, experiment 3:
   // compress_values(v, v > t) 0.376 -> 0.410 ms, 384-wide 0.469 ms): the status traffic costs more than the second round.
-  g.look_wide = 5;
+  g.look_wide = (g.ctrl && g.ctas == 2) ? 10 : 5;  // control-warp kernels request the window a whole iteration early: width is free
   static int lw_env = -1;
   if (lw_env < 0) { const char* e = getenv("VKJIT_LOOK_WIDE"); lw_env = e ? atoi(e) : 0; }
   if (lw_env >= 1 && lw_env <= 16) g.look_wide = lw_env;
@@ -160,11 +199,27 @@ const char* fscan_trace_file() {
   return (f && f[0]) ? f : nullptr;
 }
 
-// $VKJIT_SCAN_EARLY=0: the lagged fused scan kernels request a tile's status window at the start of the iteration that
-// resolves it (round 1/2 schedule) instead of one phase earlier.  A/B knob, part of the cache key.
+// $VKJIT_SCAN_EARLY=1: the lagged fused scan kernels request a tile's status window one phase EARLIER than at the start
+// of the iteration that resolves it.  Measured slower (profiles/r02_fused_scan.md, experiment 4: the predecessors of the
+// same generation have not published yet, the early window is full of INVALID words that must be polled again).
+// A/B knob, default off, part of the cache key.
 bool scan_early() {
-  static const int on = [] { const char* e = getenv("VKJIT_SCAN_EARLY"); return (e && e[0] == '0') ? 0 : 1; }();
+  static const int on = [] { const char* e = getenv("VKJIT_SCAN_EARLY"); return (e && e[0] == '1') ? 1 : 0; }();
   return on == 1;
+}
+
+// $VKJIT_SCAN_WREG=0/1: the lagged fused scan kernels read a tile's status window with strong loads into registers
+// (scan_fused.cuh: VK_WREG) instead of cp.async.cg into shared memory.  Part of the cache key.
+bool scan_wreg() {
+  static const int on = [] { const char* e = getenv("VKJIT_SCAN_WREG"); return e ? (e[0] == '1' ? 1 : 0) : kScanWregDefault; }();
+  return on == 1;
+}
+
+// $VKJIT_FSCAN_DIAG bit 0: timing-only diagnostic of the control-warp compress kernels (no output stores; WRONG results);
+// bit 1: lane-by-lane output instead of the staged, coalesced warp rows (A/B).  Part of the key.
+int scan_diag() {
+  static const int d = [] { const char* e = getenv("VKJIT_FSCAN_DIAG"); return e ? atoi(e) : 0; }();
+  return d;
 }
 
 size_t stream_count(const Program& p) {
@@ -359,8 +414,9 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
     const ScanFusedGeom sg = scan_fused_geom(stream_count(p), scan, p.order.size());
     if (sg.lag) kw[1] |= 1u << 28;
     kw[kn++] = 0xFFFFFFFEu;  // geometry of the fused scan kernel (tunable through the environment)
-    kw[kn++] = (uint32_t)sg.threads | ((uint32_t)sg.look_wide << 11) | ((uint32_t)sg.vpt << 16) | ((uint32_t)sg.slots << 24) |
-               (fscan_trace_file() ? 1u << 30 : 0u) | (scan_early() ? 1u << 29 : 0u);
+    kw[kn++] = (uint32_t)sg.threads | ((uint32_t)sg.look_wide << 11) | ((uint32_t)sg.vpt << 16) | ((uint32_t)sg.slots << 24);
+    kw[kn++] = (sg.ctrl ? 1u : 0u) | ((uint32_t)sg.depth << 4) | ((uint32_t)sg.ctas << 8) | ((uint32_t)sg.clag << 12) |
+               (fscan_trace_file() ? 1u << 30 : 0u) | (scan_early() ? 1u << 29 : 0u) | (scan_wreg() ? 1u << 28 : 0u) | ((uint32_t)(scan_diag() & 3) << 26);
   }
   kw[kn++] = 0xFFFFFFFFu;
   for (uint32_t r : p.roots) kw[kn++] = r;
@@ -913,7 +969,8 @@ std::string scan_shell(const Program& p, const std::vector<uint32_t>& streams, c
   const ScanFusedGeom geom = scan_fused_geom(ns, p.scan, p.order.size());
   s += "#define VK_SCAN_MODE " + std::to_string(p.scan) + "\n#define VK_NS " + std::to_string(ns) + "\n#define VK_VPT " +
        std::to_string(geom.vpt) + "\n#define VK_LAG " + std::to_string(geom.lag ? 1 : 0) + "\n#define VK_SLOTS " +
-       std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n#define VK_LOOK_WIDE " + std::to_string(geom.look_wide) + "\n#define VK_TRACE " + (fscan_trace_file() ? "1" : "0") + "\n#define VK_EARLY " + (scan_early() ? "1" : "0") + "\n";
+       std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n#define VK_LOOK_WIDE " + std::to_string(geom.look_wide) + "\n#define VK_TRACE " + (fscan_trace_file() ? "1" : "0") + "\n#define VK_EARLY " + (scan_early() ? "1" : "0") + "\n#define VK_WREG " + (scan_wreg() ? "1" : "0") + "\n#define VK_CTRL " + (geom.ctrl ? "1" : "0") +
+       "\n#define VK_DEPTH " + std::to_string(geom.depth) + "\n#define VK_CTAS " + std::to_string(geom.ctas) + "\n#define VK_CLAG " + std::to_string(geom.clag) + "\n#define VK_DIAG " + std::to_string(scan_diag() & 1) + "\n#define VK_COALESCE " + ((scan_diag() & 2) ? "0" : "1") + "\n";
   s += "struct VkPtrs {\n  const u32* s[" + std::to_string(std::max<size_t>(ns, 1)) + "];  // streamed arrays (staged by TMA)\n";
   for (uint32_t k : ptrs) {
     if (p.params[k].use & USE_SCATTER) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: the trace has side effects");

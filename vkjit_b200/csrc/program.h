@@ -36,10 +36,19 @@ struct ScanFusedGeom {
   int staging = 0;  // output staging tiles: lagged prefix sums 1 (TMA bulk store), lagged compress 2 (coalesced copy-out)
   int threads = 1024;  // per CTA; 512: two co-resident CTAs per SM overlap each other's per-tile chains (lagged kernels)
   int look_wide = 5;   // status words per lane and look-back round (32 x look_wide predecessors); $VKJIT_LOOK_WIDE
+  // control-warp variant (compress modes, scan_fused.cuh: VK_CTRL): `threads` workers + one control warp that owns the
+  // totals scan / publish / look-back chain; the workers write tile k - depth while the chain of tile k runs
+  bool ctrl = false;
+  int depth = 3;       // tiles between evaluation and output (workers)
+  int clag = 2;        // tiles between a tile's publish and its resolve (control warp); depth >= clag
+  int ctas = 1;        // co-resident CTAs per SM the kernel is compiled for
+  int launch_threads() const { return ctrl ? threads + 64 : threads; }  // + control warp + TMA producer warp
   size_t tile() const { return (size_t)threads * 4 * vpt; }
   size_t smem(size_t streams) const { return (streams * slots + (size_t)staging) * tile() * 4; }
 };
 ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes);
+constexpr int kScanWregDefault = 0;
+constexpr int kScanCtrlDefault = 0;  // control-warp fused compress kernel ($VKJIT_SCAN_CTRL)
 const char* fscan_trace_file();  // $VKJIT_FSCAN_TRACE (per-tile phase stamps of the lagged fused scan kernels)
 
 struct Param {

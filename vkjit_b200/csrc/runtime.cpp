@@ -429,9 +429,10 @@ CachedKernel* Backend::compile(const Ir& ir, const Program& p) {
     const size_t smem = sg.smem(stream_count(p));
     if (smem) cku(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem), "cuFuncSetAttribute");
     // the look-back needs every CTA of the grid co-resident: check the real occupancy
-    cku(g_drv.OccupancyMaxActiveBlocks(&ctas_per_sm, fn, sg.threads, smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    cku(g_drv.OccupancyMaxActiveBlocks(&ctas_per_sm, fn, sg.launch_threads(), smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
     if (ctas_per_sm < 1) fail(VKJIT_ERR_CUDA, "fused scan kernel does not fit on an SM");
-    ctas_per_sm = std::min(ctas_per_sm, 1024 / sg.threads);  // one 1024-thread CTA or two 512-thread CTAs per SM (64 registers per thread)
+    if (sg.ctrl) ctas_per_sm = std::min(ctas_per_sm, sg.ctas);
+    else ctas_per_sm = std::min(ctas_per_sm, 1024 / sg.threads);  // one 1024-thread CTA or two 512-thread CTAs per SM (64 registers per thread)
   }
   auto* k = new CachedKernel();
   k->ctas_per_sm = (uint32_t)ctas_per_sm;
@@ -705,7 +706,7 @@ bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t
            initp = (uint64_t)(uintptr_t)initial, ibasep = (uint64_t)(uintptr_t)index_base;
   void* argv[] = {&n32, &base32, block.data(), &outp, &cntp, &tiles32, &statep, &initp, &ibasep};
   try {
-    be.launch(k, (uint32_t)std::min<size_t>(tiles, (size_t)be.sm_count * k->ctas_per_sm), (uint32_t)geom.threads, argv, (uint32_t)geom.smem(ns));
+    be.launch(k, (uint32_t)std::min<size_t>(tiles, (size_t)be.sm_count * k->ctas_per_sm), (uint32_t)geom.launch_threads(), argv, (uint32_t)geom.smem(ns));
   } catch (...) { release_array(o); throw; }
   if (const char* tf = fscan_trace_file()) {  // per-tile phase stamps live in the spare words of the status lines
     ck(cudaStreamSynchronize((cudaStream_t)be.enqueue_stream()), "sync");

@@ -116,14 +116,16 @@ __device__ __forceinline__ void load_window(const uint64_t* window, uint64_t (&s
   for (int i = 0; i < kLookWide; ++i) s[i] = window[(size_t)(i * 32 + lane) * 2];
 }
 // The look-back walk for a tile whose aggregate was published earlier; `first_round` = the prefetched window.
+// dbg (tracing builds only): [0] += polls of a status word that was still INVALID, [1] += look-back rounds
 __device__ __forceinline__ uint32_t resolve_prefix(uint64_t* status, uint32_t tile, uint32_t aggregate, uint32_t initial,
-                                                   uint64_t (&first_round)[kLookWide]) {
+                                                   uint64_t (&first_round)[kLookWide], uint32_t* dbg = nullptr) {
   const int lane = threadIdx.x & 31;
   if (tile == 0) return initial;  // tile 0 published its inclusive prefix at once
   uint32_t exclusive = 0;
   int top = (int)tile - 1;
   bool preloaded = true;
   for (;;) {
+    if (dbg) dbg[1] += 1u;
     uint64_t s[kLookWide];
 #pragma unroll
     for (int i = 0; i < kLookWide; ++i) {
@@ -141,6 +143,7 @@ __device__ __forceinline__ uint32_t resolve_prefix(uint64_t* status, uint32_t ti
       while ((uint32_t)(s[i] >> 32) == ST_INVALID) {
         __nanosleep(40);
         s[i] = status_load(status + (size_t)idx * kStatusStride);
+        if (dbg) dbg[0] += 1u;
         if (++spins > (1u << 25)) __trap();
       }
       const unsigned incl = __ballot_sync(0xFFFFFFFFu, (uint32_t)(s[i] >> 32) == ST_INCLUSIVE);
@@ -154,6 +157,54 @@ __device__ __forceinline__ uint32_t resolve_prefix(uint64_t* status, uint32_t ti
     }
     if (done) break;
     top -= 32 * kLookWide;
+  }
+  if (lane == 0) status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_INCLUSIVE << 32) | (exclusive + aggregate));
+  return exclusive;
+}
+
+// Look-back with an ANCHOR: in a persistent grid of `stride` CTAs the tile `stride` places back is the caller's own
+// previous tile, whose inclusive prefix (`own_incl`) it has in a register.  So the walk never needs to FIND an inclusive
+// status: it sums the aggregates of the stride - 1 tiles in between (stopping early at an inclusive one if it meets one)
+// and adds the anchor.  With 32 * kLookWide >= stride - 1 one window always suffices — no second round, whatever the
+// other CTAs have resolved so far.  `first_round`: the prefetched window (distance 32 i + lane + 1 in word i).
+__device__ __forceinline__ uint32_t resolve_anchored(uint64_t* status, uint32_t tile, uint32_t aggregate, uint32_t initial,
+                                                     uint64_t (&first_round)[kLookWide], uint32_t stride, uint32_t own_incl,
+                                                     bool have_own) {
+  const int lane = threadIdx.x & 31;
+  if (tile == 0) return initial;  // tile 0 published its inclusive prefix at once
+  // pass 1: make sure every word that counts is there (not expected to spin: the window is requested iterations after
+  // the publish), and find the NEAREST inclusive status, if any.  The ballots are independent of each other.
+  uint32_t val[kLookWide];
+  uint32_t near_dist = 0xFFFFFFFFu;  // distance of the nearest inclusive predecessor
+#pragma unroll
+  for (int i = 0; i < kLookWide; ++i) {
+    const uint32_t dist = 32u * i + (uint32_t)lane + 1u;
+    const bool counts = !have_own || dist < stride;   // tiles at distance >= stride are covered by the anchor
+    uint64_t s = first_round[i];
+    if (counts && (uint32_t)(s >> 32) == ST_INVALID) {
+      const int idx = (int)tile - (int)dist;
+      uint32_t spins = 0;
+      do {
+        __nanosleep(40);
+        s = status_load(status + (size_t)idx * kStatusStride);
+        if (++spins > (1u << 25)) __trap();
+      } while ((uint32_t)(s >> 32) == ST_INVALID);
+    }
+    val[i] = counts ? (uint32_t)s : 0u;
+    const unsigned incl = __ballot_sync(0xFFFFFFFFu, counts && (uint32_t)(s >> 32) == ST_INCLUSIVE);
+    if (incl && near_dist == 0xFFFFFFFFu) near_dist = 32u * i + (uint32_t)__ffs(incl);
+  }
+  // pass 2: every lane adds up its own words up to that distance, ONE warp reduction
+  uint32_t mine = 0u;
+#pragma unroll
+  for (int i = 0; i < kLookWide; ++i) {
+    const uint32_t dist = 32u * i + (uint32_t)lane + 1u;
+    mine += dist <= near_dist ? val[i] : 0u;
+  }
+  uint32_t exclusive = warp_sum(mine);
+  if (near_dist == 0xFFFFFFFFu) {
+    if (!have_own || 32u * (uint32_t)kLookWide + 1u < stride) __trap();  // caller's contract: the window reaches the anchor
+    exclusive += own_incl;
   }
   if (lane == 0) status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_INCLUSIVE << 32) | (exclusive + aggregate));
   return exclusive;
@@ -184,6 +235,11 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// plain arrival (release.cta): what the arriving thread wrote to shared memory before is visible to whoever the
+// completed phase wakes up
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done, spins = 0;
   do {
