@@ -191,6 +191,75 @@ def test_range_proven_fast_paths():
     assert calls(y.id) == {"vk_logf_fast": 5, "vk_sincosf_fast": 5, "vk_expf_fast": 5}
 
 
+def _ranged_trace(ir, seed, n):
+    """A random trace over the ops the generator's range analysis models (program.cpp: node_ranges), lane-index leaves
+    only — the same DAG on any Ir."""
+    from vkjit_b200.ir import Bop
+    rng = np.random.default_rng(seed)
+    lane = ir.arange(U32, n)
+    us = [lane, ir.bop(Bop.Shr, ir.mul(lane, ir.const_u32(2654435761)), ir.const_u32(int(rng.integers(4, 28))))]
+    fs = []
+    cu = lambda: ir.const_u32(int(rng.choice([0, 1, 3, 7, 255, 4096, 65535, 1 << 20, (1 << 24) - 1, 0x7FFFFFFF, 0xFFFFFFFF])))
+    cf = lambda: ir.const_f32(float(np.float32(rng.choice([0.0, -0.0, 1.0, -1.0, 0.5, -2.0, 2.0 ** -24, 6.2831855, 1e-3, -1e-3, 87.0, -90.0,
+                                                               3e4, 1e30, 1e-30, 1e-38, 1e-42, 3.4e38, float(rng.standard_normal() * 10)]))))
+    for _ in range(int(rng.integers(10, 28))):
+        k = int(rng.integers(0, 20))
+        pu = lambda: us[int(rng.integers(0, len(us)))]
+        pf = lambda: fs[int(rng.integers(0, len(fs)))] if fs and rng.random() < 0.8 else cf()
+        if k == 0: us.append(ir.bop(Bop.Shr, pu(), ir.const_u32(int(rng.integers(0, 40)))))
+        elif k == 1: us.append(ir.bop(Bop.And, pu(), cu()))
+        elif k == 2: us.append(ir.add(pu(), cu()))
+        elif k == 3: us.append(ir.mul(pu(), cu()))
+        elif k == 4: us.append(ir.bop(int(rng.choice([Bop.Xor, Bop.Or, Bop.Min, Bop.Max])), pu(), pu()))
+        elif k in (5, 6, 7): fs.append(ir.cast(pu(), F32))
+        elif k in (8, 9): fs.append(ir.mul(pf(), pf()))
+        elif k == 10: fs.append(ir.add(pf(), pf()))
+        elif k == 11: fs.append(ir.sub(pf(), pf()))
+        elif k == 12: fs.append(ir.bop(int(rng.choice([Bop.Min, Bop.Max])), pf(), pf()))
+        elif k == 13: fs.append(ir.select(ir.lt(pf(), pf()), pf(), pf()))
+        elif k == 14: fs.append(ir.neg(pf()) if rng.random() < 0.5 else ir.abs(pf()))
+        elif k == 15: fs.append(ir.sqrt(pf()))
+        elif k == 16: fs.append(ir.log(pf()))
+        elif k == 17: fs.append(ir.exp(pf()))
+        elif k == 18: fs.append(ir.sin(pf()))
+        else: fs.append(ir.cos(pf()))
+    return fs[-20:] + us[-3:]   # every f32 value is a root: the claim checked is the one the fast-path decisions used
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_proven_ranges_are_sound(oir, block):
+    """Soundness of the range analysis behind the unchecked vk_math.h fast paths: for random traces, every range the
+    generator claims for a root (written next to the root's store in the generated source) must contain EVERY value the
+    oracle computes for it — finite, inside [lo, hi], and not -0.0 where the generator says so — over 4096 lanes.  An
+    unsound range would silently break bit-exactness (a fast path taken outside its domain)."""
+    import re
+    n = 4096
+    checked = 0
+    for seed in range(block * 40, block * 40 + 40):
+        ir = Ir()
+        roots = _ranged_trace(ir, seed, n)
+        src, _ = ir.debug_codegen(roots)
+        claims = {}
+        for m in re.finditer(r"out(\d+) = [^;]*;  // range (f32|u32) (\S+) (\S+)( negzero| no-negzero)?", src):
+            claims[int(m.group(1))] = (m.group(2), m.group(3), m.group(4), m.group(5))
+        oroots = _ranged_trace(oir, seed, n)
+        oir.eval(oroots)
+        for r, (kind, lo, hi, nz) in claims.items():
+            if kind == "f32":
+                v = oir.as_slice(oroots[r], F32)
+                lo_f, hi_f = np.array([int(lo[:-1], 16), int(hi[:-1], 16)], np.uint32).view(np.float32)
+                assert np.isfinite(v).all(), (seed, r, "a proven range excludes NaN / inf", v[~np.isfinite(v)][:4])
+                assert (v >= lo_f).all() and (v <= hi_f).all(), (seed, r, lo_f, hi_f, v.min(), v.max())
+                if nz.strip() == "no-negzero":
+                    assert not (v.view(np.uint32) == 0x80000000).any(), (seed, r, "-0.0 where the generator excludes it")
+            else:
+                v = oir.as_slice(oroots[r], U32)
+                assert (v >= int(lo)).all() and (v <= int(hi)).all(), (seed, r, lo, hi, v.min(), v.max())
+            checked += 1
+        ir.close()
+    assert checked > 150, checked   # the generator does prove something for most values
+
+
 def test_struct_select_gather_scatter_codegen():
     ir = Ir()
     i = ir.arange(U32, 64)

@@ -1035,7 +1035,15 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   for (uint32_t li = 0; li < p.order.size(); ++li) g.emit_node(li);
   for (size_t r = 0; r < p.roots.size(); ++r) {
     const Val& v = g.vals[p.roots[r]];
-    g.line("out" + std::to_string(r) + " = " + to_word(v.ty, v.name) + ";");
+    // (the proven range travels as a comment: tests/test_product_cpu.py checks it against the oracle's values)
+    std::string note;
+    if (v.elems.empty() && v.ty == VKJIT_TY_F32 && v.fr.ok) {
+      uint32_t lo, hi; memcpy(&lo, &v.fr.lo, 4); memcpy(&hi, &v.fr.hi, 4);
+      note = "  // range f32 " + hex32(lo) + " " + hex32(hi) + (v.fr.negzero ? " negzero" : " no-negzero");
+    } else if (v.elems.empty() && v.ty == VKJIT_TY_U32 && !(v.ur.lo == 0u && v.ur.hi == 0xFFFFFFFFu)) {
+      note = "  // range u32 " + std::to_string(v.ur.lo) + " " + std::to_string(v.ur.hi);
+    }
+    g.line("out" + std::to_string(r) + " = " + to_word(v.ty, v.name) + ";" + note);
   }
 
   std::vector<uint32_t> streams, ptrs;
