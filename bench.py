@@ -478,10 +478,10 @@ def ours(args):
     achieved = n_local * 4 / (kern_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:  # DRAM traffic of this kernel at this size from the committed ncu capture (never measured under the bench)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         ent = tr.get(f"reduce_kernel<float, SUM, 512> @ 2^{int(math.log2(n_local))} lanes") if n_local & (n_local - 1) == 0 else None
         if ent:
-            traffic, traffic_src = ent["dram_read_bytes"] + ent["dram_write_bytes"], "profiles/r01_traffic.json (ncu --set full, round 1)"
+            traffic, traffic_src = ent["dram_read_bytes"] + ent["dram_write_bytes"], "profiles/r02_traffic.json (ncu --set full)"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "reduce_kernel<float, SUM, 512>" + (" / <float, MAX, 512> (mean over the timed region's launches)" if world == 1 else " (kernel only, isolated)"), "achieved": achieved, "peak": peak, "unit": "GB/s",
