@@ -319,7 +319,7 @@ vkjit_status vkjit_cache_clear(void);
 /* Debug: generated CUDA C for the given roots without launching (needs no
  * device).  compile bit 0: additionally run NVRTC for sm_100a and report its verdict (out_cubin_bytes
  * receives the cubin size, 0 if not compiled); compile bit 1: generate the shared-memory-privatised
- * scatter_add variant that large launches use. */
+ * scatter_add variant that large launches use (bit 2: the 2-CTA cluster variant, bit 3: the bin-range pass variant). */
 vkjit_status vkjit_debug_codegen(vkjit_ir* ir, const vkjit_var* ids, size_t n, int32_t compile,
                                  char* buf, size_t cap, size_t* out_len, size_t* out_cubin_bytes);
 /* Debug: average host time of the per-eval trace walk + hash (the cache-hit critical path) and the

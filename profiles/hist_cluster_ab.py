@@ -33,7 +33,7 @@ def gs(ix):
     s = ir.scatter_add(ir.gather(table, ix), bins, ix); ir.eval([s]); ir.dec_ref_count(s)
 def cnt(ix):
     s = ir.scatter_add(one, bins, ix); ir.eval([s]); ir.dec_ref_count(s)
-out = {"VKJIT_SADD_CLUSTER": os.environ.get("VKJIT_SADD_CLUSTER", "default"),
+out = {"VKJIT_SADD_CLUSTER": os.environ.get("VKJIT_SADD_CLUSTER", "default"), "VKJIT_SADD_PASSES": os.environ.get("VKJIT_SADD_PASSES", "default"), "VKJIT_PASS_KB": os.environ.get("VKJIT_PASS_KB", "default"),
        "gather_scatter_add_ms": timed(lambda: gs(idx)), "count_ms": timed(lambda: cnt(idx)),
        "skewed_gather_scatter_add_ms": timed(lambda: gs(idx_s))}
 total = int(ir.as_slice(bins, T.U32).astype(np.uint64).sum() % (1 << 32))

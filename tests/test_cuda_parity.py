@@ -714,7 +714,7 @@ print("fused compress ok")
     assert r.returncode == 0 and "fused compress ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("variant", ["plain", "agg", "cluster"])
+@pytest.mark.parametrize("variant", ["plain", "agg", "cluster", "passes"])
 def test_scatter_add_hot_bins(tmp_path, variant):
     """Integer scatter_add when the lanes of a warp collide (few distinct bins), plain and with the opt-in warp-aggregated
     path (VKJIT_AGG=1: every warp probes once, then one atomic per distinct bin through match.any + redux.sync,
@@ -753,6 +753,7 @@ for bins, n in [(1, 4099), (4, 100003), (16, (1 << 22) + 5), (1000, 50001), (655
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), (bins, n)
 print("hot bins ok")
 ''' % (ROOT, os.path.join(ROOT, "tests")))
-    env = {"plain": {}, "agg": {"VKJIT_AGG": "1"}, "cluster": {"VKJIT_SADD_CLUSTER": "1"}}[variant]
+    env = {"plain": {}, "agg": {"VKJIT_AGG": "1"}, "cluster": {"VKJIT_SADD_CLUSTER": "1"},
+           "passes": {"VKJIT_SADD_PASSES": "1", "VKJIT_PASS_KB": "96"}}[variant]   # bin-range passes (opt-in, measured slower: profiles/r02_h26.md)
     r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "hot bins ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]

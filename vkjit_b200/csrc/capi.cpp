@@ -714,7 +714,7 @@ vkjit_status vkjit_debug_codegen(vkjit_ir* h, const vkjit_var* ids, size_t n, in
       if (std::find(sched.begin(), sched.end(), ids[i]) == sched.end()) sched.push_back(ids[i]);
     }
     Program p;
-    build_program(ir, sched, true, p, -1, (compile & 4) ? 2 : (compile & 2) ? 1 : 0);  // compile bit 1: privatised scatter_add variant; bit 2: 2-CTA cluster variant
+    build_program(ir, sched, true, p, -1, (compile & 8) ? 3 : (compile & 4) ? 2 : (compile & 2) ? 1 : 0);  // compile bit 1: privatised scatter_add variant; bit 2: 2-CTA cluster variant; bit 3: bin-range passes
     const std::string src = generate_cuda(ir, p);
     if (out_cubin) *out_cubin = 0;
     if (compile & 1) {

@@ -14,7 +14,7 @@ namespace vkjit {
 void Program::clear() {
   key_len = 0; order.clear(); params.clear(); roots.clear();
   n = 0; have_n = false; base = 0; have_base = false; sharded = false; vectorized = true; reduce = -1; scan = -1;
-  privatize = 0; sadd_param = -1; has_gather = false;
+  privatize = 0; sadd_param = -1; has_gather = false; sadd_idx_node = -1; n_sadd = 0; n_scatter = 0; sadd_target_use = 0;
   hash = Hash128();
 }
 
@@ -380,7 +380,9 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
           if (!ty_is_scalar(v.ty)) fail(VKJIT_ERR_UNSUPPORTED, "gather/scatter of a struct");
           if (v.op != OP_GATHER && vars[v.side_effect].ty != v.ty) fail(VKJIT_ERR_TYPE, "scatter: source and target types differ");
           if (v.op == OP_SCATTER_ADD && v.ty == VKJIT_TY_BOOL) fail(VKJIT_ERR_TYPE, "scatter_add on Bool");
-          if (v.op == OP_SCATTER_ADD && p.sadd_param < 0) p.sadd_param = (int)vars[v.side_effect].aux;
+          if (v.op == OP_SCATTER_ADD && p.sadd_param < 0) { p.sadd_param = (int)vars[v.side_effect].aux; p.sadd_idx_node = (int)vars[v.deps()[1]].local; }
+          if (v.op == OP_SCATTER_ADD) p.n_sadd += 1;
+          if (v.op == OP_SCATTER) p.n_scatter += 1;
           if (v.op == OP_GATHER) p.has_gather = true;
           number_node(id, v);
           break;
@@ -407,8 +409,14 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
 
   if (kn + 12 + p.roots.size() > key.size()) { key.resize(kn + 64 + p.roots.size()); kw = key.data(); }
   if (p.sadd_param < 0 || reduce >= 0 || scan >= 0) p.privatize = 0;
+  if (p.sadd_param >= 0) p.sadd_target_use = p.params[p.sadd_param].use;
+  if (p.privatize == 3) {
+    // bin-range passes predicate the WHOLE lane body on the bin: only sound when that scatter_add is the trace's one
+    // side effect and its target is not read in the same trace
+    if (p.n_sadd != 1 || p.n_scatter != 0 || (p.sadd_target_use & (USE_STREAM | USE_GATHER))) p.privatize = 1;
+  }
   kw[1] = (vectorized ? 1u : 0u) | (no_ranges() ? 2u : 0u) | ((uint32_t)unroll_factor() << 8) | ((uint32_t)(reduce + 1) << 16) | (p.privatize ? 1u << 24 : 0u) |
-          ((uint32_t)(scan + 1) << 25) | (fast_math() ? 1u << 29 : 0u) | (no_agg() ? 1u << 30 : 0u) | (p.privatize == 2 ? 1u << 31 : 0u);  // bit 28 (lagged fused scan) is patched once the streams are known
+          ((uint32_t)(scan + 1) << 25) | (fast_math() ? 1u << 29 : 0u) | (no_agg() ? 1u << 30 : 0u) | (p.privatize == 2 ? 1u << 31 : 0u) | (p.privatize == 3 ? 4u : 0u);  // bit 28 (lagged fused scan) is patched once the streams are known
   for (size_t k = 0; k < p.params.size(); ++k) kw[binding_pos[k]] |= (uint32_t)p.params[k].use << 16;
   if (scan >= 0) {
     const ScanFusedGeom sg = scan_fused_geom(stream_count(p), scan, p.order.size());
@@ -746,6 +754,9 @@ struct Gen {
   void emit_node(uint32_t li) {
     emit_node_text(li);
     node_ranges(li);
+    // bin-range passes: everything after the index of the scatter_add only runs for the lanes of this pass
+    if (p.privatize == 3 && (int)li == p.sadd_idx_node)
+      line("if ((u32)" + vals[li].name + " - bin_lo >= kbins) return false;");
   }
 
   void emit_node_text(uint32_t li) {
@@ -833,6 +844,9 @@ struct Gen {
           uses_agg = true;
           const std::string act = v.ndeps >= 3 ? dep(v, 2).name : std::string("true");
           const bool priv = p.privatize && (int)pd == p.sadd_param;
+          if (priv && p.privatize == 3)   // every lane that gets here has its bin inside this pass's shared-memory range
+            line("vk_sadd(g" + std::to_string(pd) + " + bin_lo, vk_sbins, kbins, (u32)" + dep(v, 1).name + " - bin_lo, " + to_word(v.ty, src.name) + ", " + act + ", vk_agg);");
+          else
           line("vk_sadd(g" + std::to_string(pd) + ", " + (priv ? "vk_sbins, kbins" : "(u32*)0, 0u") + ", (u32)" + dep(v, 1).name + ", " +
                to_word(v.ty, src.name) + ", " + act + ", vk_agg);");
           vals[li] = src;  // value of the scatter var = src (internal.rs:1076)
@@ -841,7 +855,10 @@ struct Gen {
         else if (p.privatize && (int)pd == p.sadd_param) {
           // bins [0, kbins) live in this CTA's shared memory (flushed once at the end of the kernel),
           // the rest go to L2 as before: shared-memory atomics and L2 REDs run side by side
-          const std::string ix = "(u32)" + dep(v, 1).name;
+          const std::string ix = "(u32)" + dep(v, 1).name + (p.privatize == 3 ? " - bin_lo" : "");
+          if (p.privatize == 3)
+            stmt = "atomicAdd(reinterpret_cast<f32*>(vk_sbins + (" + ix + ")), " + src.name + ");";
+          else
           stmt = "{ const u32 ix_ = " + ix + "; if (ix_ < kbins) atomicAdd(reinterpret_cast<f32*>(vk_sbins + ix_), " + src.name +
                  "); else atomicAdd(reinterpret_cast<f32*>(g" + std::to_string(pd) + " + ix_), " + src.name + "); }";
         }
@@ -1020,7 +1037,7 @@ std::string reduce_defines(int red, TypeId ty) {
 // written by another build of the library is a miss, never a kernel with the wrong argument ABI.
 uint32_t generator_fingerprint() {
   static const uint32_t fp = [] {
-    constexpr uint32_t kGeneratorRevision = 12;  // round 2: vk_math.h lowering, fast-math variant bit, range-proven fast paths
+    constexpr uint32_t kGeneratorRevision = 13;  // round 2: vk_math.h lowering, fast-math variant bit, range-proven fast paths
     uint32_t h = 2166136261u ^ kGeneratorRevision;
     auto mix = [&](const char* t) { for (; *t; ++t) { h ^= (unsigned char)*t; h *= 16777619u; } };
     mix(kVkMathSrc); mix(kScanCommonSrc); mix(kScanFusedSrc); mix(kReduceEpilogue); mix(kSaddHelper);
@@ -1074,8 +1091,10 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   const bool cluster = p.privatize == 2 && !priv_f32 && g.uses_agg;
   if (g.uses_agg) s += std::string("#define VK_SADD_CLUSTER ") + (cluster ? "1" : "0") + "\n" + kSaddHelper + "\n";
   // per-lane body
-  s += "__device__ __forceinline__ void vk_lane(const u32 gi, const u32 li";
+  const bool passes = p.privatize == 3;   // vk_lane returns whether the lane belongs to this bin-range pass
+  s += std::string("__device__ __forceinline__ ") + (passes ? "bool" : "void") + " vk_lane(const u32 gi, const u32 li";
   if (priv) s += ", const u32 kbins";
+  if (passes) s += ", const u32 bin_lo";
   if (g.uses_agg) s += ", u32& vk_agg";
   for (uint32_t k : streams) s += ", const u32 in" + std::to_string(k);
   for (size_t r = 0; r < nroots; ++r) s += ", u32& out" + std::to_string(r);
@@ -1083,22 +1102,24 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
     const bool w = p.params[k].use & USE_SCATTER;
     s += std::string(", ") + (w ? "u32* " : "const u32* __restrict__ ") + "g" + std::to_string(k);
   }
-  s += ") {\n" + g.body + "}\n\n";
+  s += ") {\n" + g.body + (passes ? "  return true;\n" : "") + "}\n\n";
   if (scan) return s + scan_shell(p, streams, ptrs, nroots);
 
   auto call = [&](const std::string& gi, const std::string& li, const char* comp, bool vec) {
     std::string c = "vk_lane(" + gi + ", " + li;
     if (priv) c += ", kbins";
+    if (passes) c += ", bin_lo";
     if (g.uses_agg) c += ", vk_agg";
     for (uint32_t k : streams) c += ", a" + std::to_string(k) + (vec ? std::string(".") + comp : "");
     for (size_t r = 0; r < nroots; ++r) c += ", r" + std::to_string(r) + (vec ? std::string(".") + comp : "");
     for (uint32_t k : ptrs) c += ", p" + std::to_string(k);
-    return c + ");";
+    return c + ")" + (passes ? "" : ";");
   };
 
   s += std::string("extern \"C\" __global__ void ") + (cluster ? "__cluster_dims__(2, 1, 1) " : "") + "__launch_bounds__(" + (priv ? "1024" : "256") +
        ") vkjit_trace(const u32 n, const u32 base";
   if (priv) s += ", const u32 kbins";
+  if (passes) s += ", const u32 bin_lo";
   for (uint32_t k = 0; k < p.params.size(); ++k) {
     const bool w = p.params[k].use & USE_SCATTER;
     s += std::string(",\n    ") + (w ? "u32* " : "const u32* __restrict__ ") + "p" + std::to_string(k);
@@ -1122,9 +1143,16 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
     for (size_t r = 0; r < nroots; ++r) s += "    uint4 r" + std::to_string(r) + ";\n";
     s += "    const u32 l0 = v << 2;\n";
     const char* comps[4] = {"x", "y", "z", "w"};
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
+      if (passes) {  // 128-bit loads, but a lane's roots are written (4 bytes) in the pass that owns its bin
+        s += "    if (" + call("base + l0 + " + std::to_string(j) + "u", "l0 + " + std::to_string(j) + "u", comps[j], true) + ") {";
+        for (size_t r = 0; r < nroots; ++r) s += " o" + std::to_string(r) + "[l0 + " + std::to_string(j) + "u] = r" + std::to_string(r) + "." + comps[j] + ";";
+        s += " }\n";
+      } else
       s += "    " + call("base + l0 + " + std::to_string(j) + "u", "l0 + " + std::to_string(j) + "u", comps[j], true) + "\n";
-    if (reduce)
+    }
+    if (passes) {}
+    else if (reduce)
       s += "    c0 = VK_APPLY(c0, VK_FROM_WORD(r0.x)); c1 = VK_APPLY(c1, VK_FROM_WORD(r0.y));\n"
            "    c2 = VK_APPLY(c2, VK_FROM_WORD(r0.z)); c3 = VK_APPLY(c3, VK_FROM_WORD(r0.w));\n";
     else
@@ -1137,9 +1165,15 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
   }
   for (uint32_t k : streams) s += "    const u32 a" + std::to_string(k) + " = p" + std::to_string(k) + "[i];\n";
   for (size_t r = 0; r < nroots; ++r) s += "    u32 r" + std::to_string(r) + ";\n";
+  if (passes) {  // the lane's roots are written in the pass that owns its bin
+    s += "    if (" + call("base + (u32)i", "(u32)i", "", false) + ") {\n";
+    for (size_t r = 0; r < nroots; ++r) s += "      o" + std::to_string(r) + "[i] = r" + std::to_string(r) + ";\n";
+    s += "    }\n";
+  } else {
   s += "    " + call("base + (u32)i", "(u32)i", "", false) + "\n";
   if (reduce) s += "    c0 = VK_APPLY(c0, VK_FROM_WORD(r0));\n";
   else for (size_t r = 0; r < nroots; ++r) s += "    o" + std::to_string(r) + "[i] = r" + std::to_string(r) + ";\n";
+  }
   s += "  }\n";
   if (reduce) s += "  vk_finish(VK_APPLY(VK_APPLY(c0, c1), VK_APPLY(c2, c3)), partials, ticket, o0);\n";
   if (priv) {
@@ -1151,8 +1185,9 @@ std::string generate_cuda(const Ir& ir, const Program& p) {
       s += "      if (w != 0u) atomicAdd(" + g + " + lo + i, w);\n    }\n  }\n";
     } else {
       s += "  __syncthreads();\n  for (u32 i = threadIdx.x; i < kbins; i += blockDim.x) {\n    const u32 w = vk_sbins[i];\n";
-      if (priv_f32) s += "    if (w != 0u) atomicAdd(reinterpret_cast<f32*>(" + g + " + i), __uint_as_float(w));\n";
-      else s += "    if (w != 0u) atomicAdd(" + g + " + i, w);\n";
+      const std::string at = passes ? g + " + bin_lo + i" : g + " + i";
+      if (priv_f32) s += "    if (w != 0u) atomicAdd(reinterpret_cast<f32*>(" + at + "), __uint_as_float(w));\n";
+      else s += "    if (w != 0u) atomicAdd(" + at + ", w);\n";
       s += "  }\n";
     }
   }

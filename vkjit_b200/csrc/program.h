@@ -72,8 +72,12 @@ struct Program {
   bool vectorized = true;       // 128-bit ld/st variant
   int reduce = -1;              // >= 0: fused trace -> reduce kernel (VKJIT_RED_*), the single root is not stored
   int scan = -1;                // >= 0: fused trace -> scan kernel (SCAN_*): root 0 is scanned / is the compress mask
-  int privatize = 0;            // variant: the first scatter_add target is (partly) privatised in shared memory: 1 per CTA, 2 split over a 2-CTA cluster
+  int privatize = 0;            // variant: the first scatter_add target is (partly) privatised in shared memory: 1 per CTA, 2 split over a 2-CTA
+                                // cluster, 3 bin-range passes (each launch handles the lanes whose bin lies in [bin_lo, bin_lo + kbins), all of them in shared memory)
   int sadd_param = -1;          // param index of the first scatter_add target (-1: none)
+  int sadd_idx_node = -1;       // local node id of that scatter_add's index
+  uint32_t n_sadd = 0, n_scatter = 0;  // side-effect nodes in the trace
+  uint8_t sadd_target_use = 0;  // how else the target array is used in the trace (USE_* bits)
   bool has_gather = false;      // the trace gathers (wants L1 for its table)
   Hash128 hash;
 

@@ -470,6 +470,10 @@ void Backend::launch(CachedKernel* k, uint32_t grid, uint32_t block, void** args
 }
 
 // ---- Ir::eval (internal.rs:482-525) ---------------------------------------------------------
+bool scatter_passes() {
+  static const int on = [] { const char* s = getenv("VKJIT_SADD_PASSES"); return s ? (s[0] == '1' ? 1 : 0) : kSaddPassesDefault; }();
+  return on == 1;
+}
 namespace {
 
 // Compile-or-lookup + launch of one group of roots that share a kernel size.  commit: the roots become
@@ -516,7 +520,23 @@ void run_group(Ir& ir, Backend& be, const std::vector<VarId>& roots, bool commit
         kbins = (uint32_t)std::min<size_t>(bins, max_bytes / 4);
       }
     }
-    if (!aligned || kbins) build_program(ir, roots, aligned, prog, -1, kbins ? (cluster_bins ? 2 : 1) : 0);  // variant rebuild
+    // Bin-range passes (profiles/r02_h26.md, experiment 4): a target that does not fit one CTA's shared memory is
+    // processed in P launches, pass p handling only the lanes whose bin lies in its range — ALL atomics of a pass go to
+    // shared memory (no L2 RED at all) and, when the trace gathers with the same index, each pass only touches its slice
+    // of the gather table, which then fits the L1 that is left.  Costs P reads of the index stream.  Only for traces
+    // whose one side effect is that scatter_add (build_program falls back to variant 1 otherwise).
+    uint32_t pass_bins = 0;
+    if (kbins && !cluster_bins && scatter_passes()) {
+      const size_t bins = ir.vars[prog.params[prog.sadd_param].var].array->bytes / 4;
+      if (bins > kbins) {
+        size_t chunk_bytes = prog.has_gather ? kPassBytesGather : kPassBytesNoGather;
+        if (const char* e = getenv("VKJIT_PASS_KB")) chunk_bytes = std::min<size_t>((size_t)std::max(1, atoi(e)) * 1024, kPrivatizeMaxBytesNoGather);
+        const size_t npass = (bins * 4 + chunk_bytes - 1) / chunk_bytes;
+        if (npass <= kMaxPasses) pass_bins = (uint32_t)((((bins + npass - 1) / npass) + 3) & ~(size_t)3);
+      }
+    }
+    if (!aligned || kbins) build_program(ir, roots, aligned, prog, -1, kbins ? (pass_bins ? 3 : cluster_bins ? 2 : 1) : 0);  // variant rebuild
+    if (prog.privatize != 3) pass_bins = 0;
 
     if (trace) ts[1] = now_ns();
     CachedKernel* k = be.lookup(prog);
@@ -531,15 +551,24 @@ void run_group(Ir& ir, Backend& be, const std::vector<VarId>& roots, bool commit
     ptrs.clear(); argv.clear();
     for (const Param& pr : prog.params) ptrs.push_back((uint64_t)(uintptr_t)ir.vars[pr.var].array->ptr);
     for (Array* a : outs) ptrs.push_back((uint64_t)(uintptr_t)a->ptr);
+    uint32_t bin_lo = 0;
     argv.push_back(&n32); argv.push_back(&base32);
     if (prog.privatize) argv.push_back(&kbins);
+    if (prog.privatize == 3) argv.push_back(&bin_lo);
     for (uint64_t& p : ptrs) argv.push_back(&p);
 
     const uint64_t items = prog.vectorized ? std::max<uint64_t>(prog.n >> 2, 1) : prog.n;
     if (prog.privatize) {
       // persistent CTAs of 1024 threads, each with its own copy of the privatised bins (cluster variant: each CTA
       // of a pair holds half of them; the grid is a multiple of 2)
-      if (cluster_bins) {
+      if (pass_bins) {
+        const uint32_t bins = (uint32_t)(ir.vars[prog.params[prog.sadd_param].var].array->bytes / 4);
+        for (bin_lo = 0; bin_lo < bins; bin_lo += pass_bins) {   // argv points at bin_lo / kbins
+          kbins = std::min(pass_bins, bins - bin_lo);
+          const uint32_t smem = kbins * 4;
+          be.launch(k, (uint32_t)be.sm_count * (smem <= 100 * 1024 ? 2 : 1), 1024, argv.data(), smem);
+        }
+      } else if (cluster_bins) {
         const uint32_t half = ((((kbins + 1u) >> 1) + 3u) & ~3u);
         be.launch(k, (uint32_t)be.sm_count & ~1u, 1024, argv.data(), half * 4);
       } else {

@@ -23,6 +23,12 @@ namespace vkjit {
 constexpr size_t kPrivatizeMaxBytes = 192 * 1024;
 constexpr size_t kPrivatizeMaxBytesNoGather = 224 * 1024;
 constexpr uint64_t kPrivatizeMinLanes = 1ull << 22;
+// bin-range passes: bins per pass (bytes of shared memory) with / without a gather in the trace, most passes
+constexpr size_t kPassBytesGather = 128 * 1024;
+constexpr size_t kPassBytesNoGather = 128 * 1024;
+constexpr size_t kMaxPasses = 4;
+bool scatter_passes();  // $VKJIT_SADD_PASSES (default kSaddPassesDefault)
+constexpr int kSaddPassesDefault = 0;
 
 struct HashOf {
   size_t operator()(const Hash128& h) const { return (size_t)(h.lo ^ (h.hi * 0x9E3779B97F4A7C15ull)); }
