@@ -643,7 +643,7 @@ def test_side_effect_of_a_primitives_operand_runs_once(cir, oir):
 
 @pytest.mark.parametrize("n", [1, 16383, 16384, (2 << 20) // 4 + 1, (16 << 20) // 4 - 1, (16 << 20) // 4, (18 << 20) // 4 + 5, 9 * (1 << 20) + 3])
 def test_upload_and_readback_through_the_staging_ring(cir, n):
-    """Pageable host memory crosses PCIe through the pinned staging ring (csrc/staging.cpp: 2 MiB chunks, threaded
+    """Pageable host memory crosses PCIe through the pinned staging ring (csrc/staging.cpp: 4 x 8 MiB chunks, threaded
     memcpy) from 16 MiB on, the driver's pageable path below; sizes around the pinned-pool threshold of the front-end
     (64 KiB), around the ring threshold, and several chunks with a ragged tail.  The
     upload returns once the caller's buffer is copied out, so overwriting it right away must not change the array."""

@@ -5,7 +5,7 @@
 // vulkan/mod.rs:29-34).  HBM is not host-visible, so every upload / readback crosses PCIe.  A cudaMemcpy straight
 // from / to pageable memory makes the driver stage through its own small pinned buffers with ONE thread
 // (measured round 1: 4 MiB readback 252 us pageable vs 98 us pinned; 1 GiB upload ~3x slower than pinned).  This ring
-// does the staging itself: kChunks pinned chunks, the DMA of chunk i overlapping the host memcpy of chunk i +- 1, and the
+// does the staging itself: kChunks pinned chunks (8 MiB each), the DMA of chunk i overlapping the host memcpy of chunk i +- 1, and the
 // host memcpy split over a few worker threads (one core copies ~10 GB/s, PCIe 5 x16 moves ~55).
 //
 // Transfers below kRingMinBytes keep the driver's own pageable path: waking the copy threads costs ~0.1 ms, more than the
@@ -117,7 +117,7 @@ Ring& ring() {
   if (!g_ring) {
     auto* r = new Ring();
     const char* cb = getenv("VKJIT_STAGING_CHUNK_KB");
-    r->chunk_bytes = (size_t)(cb ? std::max(64, atoi(cb)) : 2048) << 10;
+    r->chunk_bytes = (size_t)(cb ? std::max(64, atoi(cb)) : 8192) << 10;  // 8 MiB: measured optimum (profiles/r02_staging.md: 2 MiB 33.5, 8 MiB 50.7, 16 MiB 36.6 GB/s H2D from pageable memory)
     for (int i = 0; i < kChunks; ++i) {
       ck(cudaHostAlloc(&r->chunk[i], r->chunk_bytes, cudaHostAllocDefault), "staging chunk allocation");
       ck(cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming), "staging event");
