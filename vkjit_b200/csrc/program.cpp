@@ -143,6 +143,20 @@ ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes) {
     if (t_nolag < 0) { const char* e = getenv("VKJIT_SCAN_T_NOLAG"); t_nolag = e ? atoi(e) : 0; }
     if (t_nolag == 512 || t_nolag == 1024) g.threads = t_nolag;
   }
+  // Prefix sums of traces that stream NOTHING (e.g. prefix_sum(hash(lane))): no input ring, so two tile-sized buffers
+  // of shared memory park the row-relative results while the look-back lags one tile behind — large tiles (VPT 6, as the
+  // immediate-look-back kernel) AND a lagged look-back.  $VKJIT_SCAN_PARK=0/1.
+  {
+    static const int park_env = [] { const char* e = getenv("VKJIT_SCAN_PARK"); return e ? (e[0] == '1' ? 1 : 0) : kScanParkDefault; }();
+    if (park_env == 1 && mode < SCAN_COMPRESS_INDEX && streams == 0 && nodes <= kScanFusedLagMaxNodesCompress && !classic) {
+      g = ScanFusedGeom();
+      g.lag = true; g.park = true; g.threads = 1024; g.vpt = 6; g.slots = 2; g.staging = 2;  // (slots only sizes arrays: no streams)
+      static const int pt = [] { const char* e = getenv("VKJIT_PARK_T"); return e ? atoi(e) : 0; }();
+      static const int pv = [] { const char* e = getenv("VKJIT_PARK_VPT"); return e ? atoi(e) : 0; }();
+      if (pt == 512 || pt == 1024) g.threads = pt;
+      if (pv >= 1 && pv <= 8 && (g.threads / 32 * pv) % 32 == 0) g.vpt = pv;
+    }
+  }
   // $VKJIT_SCAN_CTRL=1 (experiment): compress modes over at most one streamed array take the control-warp kernel.
   // Geometry through $VKJIT_CTRL_T (workers), $VKJIT_CTRL_VPT, $VKJIT_CTRL_SLOTS, $VKJIT_CTRL_DEPTH, $VKJIT_CTRL_CTAS.
   {
@@ -423,7 +437,7 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
     if (sg.lag) kw[1] |= 1u << 28;
     kw[kn++] = 0xFFFFFFFEu;  // geometry of the fused scan kernel (tunable through the environment)
     kw[kn++] = (uint32_t)sg.threads | ((uint32_t)sg.look_wide << 11) | ((uint32_t)sg.vpt << 16) | ((uint32_t)sg.slots << 24);
-    kw[kn++] = (sg.ctrl ? 1u : 0u) | ((uint32_t)sg.depth << 4) | ((uint32_t)sg.ctas << 8) | ((uint32_t)sg.clag << 12) |
+    kw[kn++] = (sg.ctrl ? 1u : 0u) | (sg.park ? 2u : 0u) | ((uint32_t)sg.depth << 4) | ((uint32_t)sg.ctas << 8) | ((uint32_t)sg.clag << 12) |
                (fscan_trace_file() ? 1u << 30 : 0u) | (scan_early() ? 1u << 29 : 0u) | (scan_wreg() ? 1u << 28 : 0u) | ((uint32_t)(scan_diag() & 3) << 26);
   }
   kw[kn++] = 0xFFFFFFFFu;
@@ -986,7 +1000,7 @@ std::string scan_shell(const Program& p, const std::vector<uint32_t>& streams, c
   const ScanFusedGeom geom = scan_fused_geom(ns, p.scan, p.order.size());
   s += "#define VK_SCAN_MODE " + std::to_string(p.scan) + "\n#define VK_NS " + std::to_string(ns) + "\n#define VK_VPT " +
        std::to_string(geom.vpt) + "\n#define VK_LAG " + std::to_string(geom.lag ? 1 : 0) + "\n#define VK_SLOTS " +
-       std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n#define VK_LOOK_WIDE " + std::to_string(geom.look_wide) + "\n#define VK_TRACE " + (fscan_trace_file() ? "1" : "0") + "\n#define VK_EARLY " + (scan_early() ? "1" : "0") + "\n#define VK_WREG " + (scan_wreg() ? "1" : "0") + "\n#define VK_CTRL " + (geom.ctrl ? "1" : "0") +
+       std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n#define VK_LOOK_WIDE " + std::to_string(geom.look_wide) + "\n#define VK_TRACE " + (fscan_trace_file() ? "1" : "0") + "\n#define VK_EARLY " + (scan_early() ? "1" : "0") + "\n#define VK_WREG " + (scan_wreg() ? "1" : "0") + "\n#define VK_PARK " + (geom.park ? "1" : "0") + "\n#define VK_CTRL " + (geom.ctrl ? "1" : "0") +
        "\n#define VK_DEPTH " + std::to_string(geom.depth) + "\n#define VK_CTAS " + std::to_string(geom.ctas) + "\n#define VK_CLAG " + std::to_string(geom.clag) + "\n#define VK_DIAG " + std::to_string(scan_diag() & 1) + "\n#define VK_COALESCE " + ((scan_diag() & 2) ? "0" : "1") + "\n";
   s += "struct VkPtrs {\n  const u32* s[" + std::to_string(std::max<size_t>(ns, 1)) + "];  // streamed arrays (staged by TMA)\n";
   for (uint32_t k : ptrs) {

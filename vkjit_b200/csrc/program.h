@@ -38,6 +38,7 @@ struct ScanFusedGeom {
   int look_wide = 5;   // status words per lane and look-back round (32 x look_wide predecessors); $VKJIT_LOOK_WIDE
   // control-warp variant (compress modes, scan_fused.cuh: VK_CTRL): `threads` workers + one control warp that owns the
   // totals scan / publish / look-back chain; the workers write tile k - depth while the chain of tile k runs
+  bool park = false;   // lagged prefix sums of traces that stream nothing: results wait in shared memory (VK_PARK), VPT 6
   bool ctrl = false;
   int depth = 3;       // tiles between evaluation and output (workers)
   int clag = 2;        // tiles between a tile's publish and its resolve (control warp); depth >= clag
@@ -48,6 +49,7 @@ struct ScanFusedGeom {
 };
 ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes);
 constexpr int kScanWregDefault = 0;
+constexpr int kScanParkDefault = 0;  // parked-result lagged prefix sums for traces without streamed inputs ($VKJIT_SCAN_PARK)
 constexpr int kScanCtrlDefault = 0;  // control-warp fused compress kernel ($VKJIT_SCAN_CTRL)
 const char* fscan_trace_file();  // $VKJIT_FSCAN_TRACE (per-tile phase stamps of the lagged fused scan kernels)
 

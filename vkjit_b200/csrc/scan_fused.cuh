@@ -28,6 +28,9 @@ template <bool B> struct VkBool { static constexpr bool value = B; };
 #ifndef VK_WREG
 #define VK_WREG 0
 #endif
+#ifndef VK_PARK
+#define VK_PARK 0
+#endif
 #if VK_TRACE
 // "memory": the timer read must not move across a barrier or the code it brackets
 __device__ __forceinline__ unsigned long long vk_stamp_ns() {
@@ -594,6 +597,13 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
   extern __shared__ __align__(128) unsigned char ring_raw[];
   u32* ring = reinterpret_cast<u32*>(ring_raw);          // NS * S input slots
   u32* stage_out = ring + (size_t)NS * S * TILE;         // modes 0/1: output staging tile
+  // VK_PARK (prefix sums of traces that stream nothing): there is no input ring, so the whole shared memory can hold
+  // results instead — every thread PARKS its row-relative results of tile k in one of two tile-sized buffers and adds the
+  // tile's prefix to them one iteration later, straight into 128-bit stores.  No registers are held across the
+  // look-back, so the tile can be as large as the immediate-look-back kernel's (VPT 6) while the look-back still lags.
+  constexpr bool PARK = VK_PARK != 0;
+  static_assert(!PARK || (NS == 0 && !COMPRESS), "parked results: prefix sums without streamed inputs");
+  uint4* park = reinterpret_cast<uint4*>(ring_raw);      // [2][TILE / 4]
   __shared__ __align__(8) uint64_t full[S];
   __shared__ u32 s_tot[3][NTOT];
   __shared__ u32 s_tile_excl;
@@ -636,11 +646,11 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
       for (u32 k = 0; k < (u32)S; ++k) fill(k);
   }
 
-  uint4 xp[VPT];                // modes 0/1, previous tile: results relative to the start of the vector's warp row
+  uint4 xp[PARK ? 1 : VPT];     // modes 0/1, previous tile: results relative to the start of the vector's warp row
   u32 flags_p = 0u, pre_p = 0u; // modes 2/3, previous tile: selection bits / 8-bit exclusive row offsets
   u32 agg_prev = 0u;            // warp 0: aggregate of the previous tile
 #pragma unroll
-  for (int j = 0; j < VPT; ++j) xp[j] = make_uint4(0u, 0u, 0u, 0u);
+  for (int j = 0; j < (PARK ? 1 : VPT); ++j) xp[j] = make_uint4(0u, 0u, 0u, 0u);
 
   for (u32 k = 0; k <= my_tiles; ++k) {
     const bool have_cur = k < my_tiles, have_prev = k > 0;
@@ -726,6 +736,7 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
           const u32 p = s - vs;
           if (VK_SCAN_MODE == 0) { xc[j].x = p; xc[j].y = p + a.x; xc[j].z = xc[j].y + a.y; xc[j].w = xc[j].z + a.z; }
           else { xc[j].x = p + a.x; xc[j].y = xc[j].x + a.y; xc[j].z = xc[j].y + a.z; xc[j].w = xc[j].z + a.w; }
+          if (PARK) park[(size_t)(k & 1) * (TILE / 4) + j * T + threadIdx.x] = xc[j];  // read back by this same thread
         }
       }
     }
@@ -788,7 +799,7 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
       }
       agg_prev = agg_cur;
     }
-    if (!COMPRESS && threadIdx.x == 0) tma_store_wait_read();  // the previous bulk store has read the staging tile
+    if (!COMPRESS && !PARK && threadIdx.x == 0) tma_store_wait_read();  // the previous bulk store has read the staging tile
     __syncthreads();
     // tile k's aggregate was published a moment ago; its window is read now, ~1 us before it is needed, while the
     // predecessors' aggregates of the same generation (published at about the same time as ours) become visible
@@ -806,8 +817,9 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
           const size_t e = tile_base + ((size_t)j * T + threadIdx.x) * 4;
           const u32 p = tile_excl + tot[j * WARPS + warp];
           uint4 r;
-          r.x = xp[j].x + p; r.y = xp[j].y + p; r.z = xp[j].z + p; r.w = xp[j].w + p;
-          if (whole) reinterpret_cast<uint4*>(stage_out)[j * T + threadIdx.x] = r;
+          const uint4 x = PARK ? park[(size_t)(kp & 1) * (TILE / 4) + j * T + threadIdx.x] : xp[PARK ? 0 : j];
+          r.x = x.x + p; r.y = x.y + p; r.z = x.z + p; r.w = x.w + p;
+          if (whole && !PARK) reinterpret_cast<uint4*>(stage_out)[j * T + threadIdx.x] = r;
           else if (e + 3 < n) st_stream(reinterpret_cast<uint4*>(out + e), r);
           else {
             if (e + 0 < n) out[e + 0] = r.x;
@@ -815,7 +827,7 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
             if (e + 2 < n) out[e + 2] = r.z;
           }
         }
-        if (whole) {
+        if (whole && !PARK) {
           fence_proxy_async();
           __syncthreads();
           if (threadIdx.x == 0) tma_store_1d(out + tile_base, stage_out, TILE_BYTES);
@@ -864,10 +876,12 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
         VK_STAMP(threadIdx.x == TW, tprev, 9);
       }
     }
+    if (!PARK) {
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) xp[j] = xc[j];
+      for (int j = 0; j < VPT; ++j) xp[PARK ? 0 : j] = xc[j];
+    }
     flags_p = flags_c; pre_p = pre_c;
   }
-  if (!COMPRESS && threadIdx.x == 0) tma_store_wait_all();  // shared memory must outlive the last bulk store
+  if (!COMPRESS && !PARK && threadIdx.x == 0) tma_store_wait_all();  // shared memory must outlive the last bulk store
 }
 #endif
