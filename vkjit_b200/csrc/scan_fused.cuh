@@ -320,10 +320,10 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
           if ((v[0] ^ v[1] ^ v[2] ^ v[3]) == 0x9E3779B9u && f == 0x1Fu) out[start + off + s1 + s2 + s3] = v[0];
 #elif VK_COALESCE
           // The selected lanes of a warp row (128 consecutive lanes) form ONE contiguous run of the output.  Written lane by
-          // lane, every 32-byte sector of it is hit by four different predicated store instructions — 4 x the L2 write
-          // requests for the same bytes, and the L2 request rate is what bounded these kernels (profiles/r02_fused_scan.md,
-          // experiment 6: 0.37 ms with the stores, 0.25 ms without).  So the run is packed in a 512-byte per-warp staging
-          // row first and leaves as 128-byte-aligned, fully coalesced stores.
+          // lane, every 32-byte sector of it is hit by several predicated store instructions; here the run is packed in a
+          // 512-byte per-warp staging row first and leaves as 128-byte-aligned, fully coalesced stores.  Measured SLOWER
+          // (profiles/r02_fused_scan.md, experiment 8; ncu: the L2 runs at 29 % with the lane-by-lane stores, it was never
+          // the limit) — $VKJIT_FSCAN_DIAG=2 selects the lane-by-lane form.
           u32* stg = s_stage[warp];
           if (f & 1u) stg[off] = v[0];
           if (f & 2u) stg[off + s1] = v[1];
