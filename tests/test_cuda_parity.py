@@ -666,7 +666,7 @@ def test_upload_and_readback_through_the_staging_ring(cir, n):
 def test_fused_compress_kernel_variants(tmp_path, variant):
     """The fused trace -> compress kernels in every schedule the library can generate (scan_fused.cuh): the shipped lagged
     kernel, the opt-in control-warp pipeline (VKJIT_SCAN_CTRL=1: a dedicated warp owns the totals scan / publish / anchored
-    look-back, the workers write tile k - D; coalesced warp-row output) at several lags and tile sizes, the status window
+    look-back, the workers write tile k - D; lane-by-lane and coalesced warp-row output) at several lags and tile sizes, the status window
     through strong loads (VKJIT_SCAN_WREG=1) and requested early (VKJIT_SCAN_EARLY=1) — all bit-exact against the oracle:
     indices and values, a mask computed from the streamed array and one computed from the lane index, sizes from one
     lane over ragged tiles to several generations of the persistent grid.  The switches are read once per process."""

@@ -230,7 +230,7 @@ bool scan_wreg() {
 }
 
 // $VKJIT_FSCAN_DIAG bit 0: timing-only diagnostic of the control-warp compress kernels (no output stores; WRONG results);
-// bit 1: lane-by-lane output instead of the staged, coalesced warp rows (A/B).  Part of the key.
+// bit 1: staged, coalesced warp-row output instead of lane-by-lane stores (A/B; measured slower).  Part of the key.
 int scan_diag() {
   static const int d = [] { const char* e = getenv("VKJIT_FSCAN_DIAG"); return e ? atoi(e) : 0; }();
   return d;
@@ -1001,7 +1001,7 @@ std::string scan_shell(const Program& p, const std::vector<uint32_t>& streams, c
   s += "#define VK_SCAN_MODE " + std::to_string(p.scan) + "\n#define VK_NS " + std::to_string(ns) + "\n#define VK_VPT " +
        std::to_string(geom.vpt) + "\n#define VK_LAG " + std::to_string(geom.lag ? 1 : 0) + "\n#define VK_SLOTS " +
        std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n#define VK_LOOK_WIDE " + std::to_string(geom.look_wide) + "\n#define VK_TRACE " + (fscan_trace_file() ? "1" : "0") + "\n#define VK_EARLY " + (scan_early() ? "1" : "0") + "\n#define VK_WREG " + (scan_wreg() ? "1" : "0") + "\n#define VK_PARK " + (geom.park ? "1" : "0") + "\n#define VK_CTRL " + (geom.ctrl ? "1" : "0") +
-       "\n#define VK_DEPTH " + std::to_string(geom.depth) + "\n#define VK_CTAS " + std::to_string(geom.ctas) + "\n#define VK_CLAG " + std::to_string(geom.clag) + "\n#define VK_DIAG " + std::to_string(scan_diag() & 1) + "\n#define VK_COALESCE " + ((scan_diag() & 2) ? "0" : "1") + "\n";
+       "\n#define VK_DEPTH " + std::to_string(geom.depth) + "\n#define VK_CTAS " + std::to_string(geom.ctas) + "\n#define VK_CLAG " + std::to_string(geom.clag) + "\n#define VK_DIAG " + std::to_string(scan_diag() & 1) + "\n#define VK_COALESCE " + ((scan_diag() & 2) ? "1" : "0") + "\n";
   s += "struct VkPtrs {\n  const u32* s[" + std::to_string(std::max<size_t>(ns, 1)) + "];  // streamed arrays (staged by TMA)\n";
   for (uint32_t k : ptrs) {
     if (p.params[k].use & USE_SCATTER) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: the trace has side effects");

@@ -49,7 +49,7 @@ __device__ __forceinline__ unsigned long long vk_stamp_ns() {
 #define VK_DIAG 0
 #endif
 #ifndef VK_COALESCE
-#define VK_COALESCE 1
+#define VK_COALESCE 0
 #endif
 
 #if VK_CTRL
@@ -68,8 +68,8 @@ __device__ __forceinline__ unsigned long long vk_stamp_ns() {
 //                         requested one iteration ago -> s_excl, arrive resolved
 // The look-back is ANCHORED (scan_common.cuh: resolve_anchored): the tile `stride` places back is this CTA's own previous
 // tile, whose inclusive prefix the control warp has in a register, so one window of stride - 1 aggregates always
-// suffices — no search for an inclusive status, no second round.  A warp row's selected words leave through a 512-byte
-// staging row as 128-byte-aligned coalesced stores (VK_COALESCE).
+// suffices — no search for an inclusive status, no second round.  (VK_COALESCE: a warp row's selected words can leave
+// through a 512-byte staging row as 128-byte-aligned coalesced stores; measured slower, off by default.)
 // No __syncthreads in the loop: all hand-overs are mbarriers (phase parity = use count of the buffer).  R = 2 D + 1
 // buffers: the slowest worker warp can still be writing tile k - 2 D + 1 while the fastest evaluates tile k + 1.
 extern "C" __global__ void __launch_bounds__(VK_T + 64, VK_CTAS)
@@ -323,7 +323,7 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
           // lane, every 32-byte sector of it is hit by several predicated store instructions; here the run is packed in a
           // 512-byte per-warp staging row first and leaves as 128-byte-aligned, fully coalesced stores.  Measured SLOWER
           // (profiles/r02_fused_scan.md, experiment 8; ncu: the L2 runs at 29 % with the lane-by-lane stores, it was never
-          // the limit) — $VKJIT_FSCAN_DIAG=2 selects the lane-by-lane form.
+          // the limit) — so it is only compiled in under $VKJIT_FSCAN_DIAG=2; the default writes lane by lane.
           u32* stg = s_stage[warp];
           if (f & 1u) stg[off] = v[0];
           if (f & 2u) stg[off + s1] = v[1];
