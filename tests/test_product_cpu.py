@@ -260,6 +260,42 @@ def test_proven_ranges_are_sound(oir, block):
     assert checked > 150, checked   # the generator does prove something for most values
 
 
+@pytest.mark.parametrize("env", [
+    {"VKJIT_SCAN_CTRL": "1"},
+    {"VKJIT_SCAN_CTRL": "1", "VKJIT_CTRL_LAG": "4", "VKJIT_CTRL_DEPTH": "6", "VKJIT_FSCAN_DIAG": "2"},
+    {"VKJIT_SCAN_CTRL": "1", "VKJIT_CTRL_VPT": "2", "VKJIT_FSCAN_TRACE": "/dev/null"},
+    {"VKJIT_SCAN_WREG": "1", "VKJIT_SCAN_EARLY": "1", "VKJIT_FSCAN_TRACE": "/dev/null"},
+    {"VKJIT_SCAN_PARK": "1"},
+    {"VKJIT_LOOK_WIDE": "10", "VKJIT_SCAN_T": "1024"},
+], ids=["ctrl", "ctrl_deep_coalesced", "ctrl_small_traced", "wreg_early_traced", "park", "wide_1024"])
+def test_opt_in_scan_kernel_variants_compile_for_sm100a(env, tmp_path):
+    """Every opt-in schedule of the fused scan / compress kernels still generates CUDA C that NVRTC accepts
+    for sm_100a, without register spills beyond a few words — offline, no device.  (Their results are checked on the GPU
+    tier: test_fused_compress_kernel_variants.)  The switches are read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    script = tmp_path / "v.py"
+    script.write_text('''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from vkjit_b200 import Ir, VarType as T
+from vkjit_b200.ir import Bop
+ir = Ir()
+n = 1 << 24
+v = ir.array_wrap_device(T.U32, 0x7F0000000000, n)
+lane = ir.arange(T.U32, n)
+h = ir.bop(Bop.Xor, ir.bop(Bop.Shr, ir.mul(lane, ir.const_u32(747796405)), ir.const_u32(15)), lane)
+m = ir.gt(v, ir.const_u32(1 << 31))
+hm = ir.neq(ir.bop(Bop.And, h, ir.const_u32(1)), ir.const_u32(0))
+for ids, mode in (([m, v], 3), ([hm, v], 3), ([m], 2), ([hm], 2), ([h], 0), ([h], 1), ([ir.bop(Bop.Shr, v, ir.const_u32(3))], 0)):
+    src, cubin = ir.debug_codegen_scan(ids, mode, compile=True)
+    assert cubin > 1000, (mode, cubin)
+print("variants ok")
+''' % (ROOT, os.path.join(ROOT, "tests")))
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "variants ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
 def test_struct_select_gather_scatter_codegen():
     ir = Ir()
     i = ir.arange(U32, 64)
