@@ -714,7 +714,59 @@ print("fused compress ok")
     assert r.returncode == 0 and "fused compress ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("variant", ["plain", "agg", "cluster", "passes"])
+@pytest.mark.parametrize("pass_kb", ["128", "96", "40"])
+def test_scatter_add_bin_range_passes(tmp_path, pass_kb):
+    """Opt-in bin-range passes (VKJIT_SADD_PASSES=1, program.cpp variant 3): a trace whose ONE side effect is a scatter_add
+    into a target too large for one CTA's shared memory runs in P launches, pass p executing only the lanes whose bin lies
+    in its range — every lane's roots are written exactly once, every atomic lands in shared memory.  Bit-exact against
+    the oracle: gather + scatter_add with the same index (H26's shape), a masked I32 scatter_add with a root that is NOT
+    the scatter var, an f32 target (exactly representable sums), bins that do not divide into the passes, and a target so
+    large that the pass variant is refused (> 4 passes: the per-CTA variant runs instead)."""
+    import subprocess
+    import sys
+    script = tmp_path / "passes.py"
+    script.write_text('''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import vkjit_b200 as vk
+from oracle_lib import OracleIr
+from vkjit_b200.ir import Bop, Ir, VarType as T
+vk.init(0)
+for bins, n in [(65536, (1 << 22) + 5), (70001, (1 << 22) + 64), (40000, (1 << 22) + 1), (300007, (1 << 22) + 3)]:
+    out = []
+    for ir in (Ir(), OracleIr()):
+        lanes = ir.arange(T.U32, n)
+        h = ir.mul(ir.bop(Bop.Xor, lanes, ir.const_u32(0x9E3779B9)), ir.const_u32(747796405))
+        idx = ir.bop(Bop.Shr, h, ir.const_u32(9))
+        idx = ir.sub(idx, ir.mul(ir.div(idx, ir.const_u32(bins)), ir.const_u32(bins)))        # idx mod bins
+        ir.eval([idx])
+        table = ir.array_u32((np.arange(bins, dtype=np.uint64) * 2654435761 %% (1 << 32)).astype(np.uint32))
+        du = ir.array_u32(np.zeros(bins, np.uint32))
+        s1 = ir.scatter_add(ir.gather(table, idx), du, idx)                  # H26: gather and scatter with the same index
+        ir.eval([s1])
+        di = ir.array_i32(np.zeros(bins, np.int32))
+        wi = ir.sub(ir.cast(ir.bop(Bop.And, h, ir.const_u32(1023)), T.I32), ir.const_i32(700))
+        mask = ir.neq(ir.bop(Bop.And, h, ir.const_u32(4)), ir.const_u32(0))
+        s2 = ir.scatter_add(wi, di, idx, mask)
+        other = ir.add(ir.bop(Bop.Shr, h, ir.const_u32(7)), idx)            # a second root next to the scatter var
+        ir.eval([s2, other])
+        df = ir.array_f32(np.zeros(bins, np.float32))
+        s3 = ir.scatter_add(ir.cast(ir.bop(Bop.And, h, ir.const_u32(3)), T.F32), df, idx)
+        ir.eval([s3])
+        out.append([ir.as_slice(du, T.U32).copy(), ir.as_slice(s1, T.U32).copy(), ir.as_slice(di, T.I32).copy(), ir.as_slice(s2, T.I32).copy(),
+                    ir.as_slice(other, T.U32).copy(), ir.as_slice(df, T.F32).copy(), ir.as_slice(s3, T.F32).copy()])
+        ir.close()
+    for k, (a, b) in enumerate(zip(*out)):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (bins, n, k)
+print("passes ok")
+''' % (ROOT, os.path.join(ROOT, "tests")))
+    env = {"VKJIT_SADD_PASSES": "1", "VKJIT_PASS_KB": pass_kb}
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "passes ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("variant", ["plain", "agg", "cluster"])
 def test_scatter_add_hot_bins(tmp_path, variant):
     """Integer scatter_add when the lanes of a warp collide (few distinct bins), plain and with the opt-in warp-aggregated
     path (VKJIT_AGG=1: every warp probes once, then one atomic per distinct bin through match.any + redux.sync,
@@ -753,7 +805,6 @@ for bins, n in [(1, 4099), (4, 100003), (16, (1 << 22) + 5), (1000, 50001), (655
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), (bins, n)
 print("hot bins ok")
 ''' % (ROOT, os.path.join(ROOT, "tests")))
-    env = {"plain": {}, "agg": {"VKJIT_AGG": "1"}, "cluster": {"VKJIT_SADD_CLUSTER": "1"},
-           "passes": {"VKJIT_SADD_PASSES": "1", "VKJIT_PASS_KB": "96"}}[variant]   # bin-range passes (opt-in, measured slower: profiles/r02_h26.md)
+    env = {"plain": {}, "agg": {"VKJIT_AGG": "1"}, "cluster": {"VKJIT_SADD_CLUSTER": "1"}}[variant]
     r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "hot bins ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
