@@ -101,3 +101,18 @@ phases(np.isin(cta_ok, pacers), f"15 CTAs that poll least {sorted(pacers.tolist(
 phases(np.isin(cta_ok, waiters), f"15 CTAs that poll most  {sorted(waiters.tolist())}")
 phases(polls == 0, "tiles without a poll")
 phases(polls > 0, "tiles with a poll   ")
+
+# ---- per CTA: its own work per tile (no waiting for others) vs the time it spends waiting in the resolve
+own = (cur[:, 2] - cur[:, 1]) + (cur[:, 11] - cur[:, 1]) + (cur[:, 5] - cur[:, 4]) + (cur[:, 8] - cur[:, 7])   # data wait + evaluate + totals/publish + output
+walkt = cur[:, 6] - cur[:, 12]
+percta = []
+for b in range(grid):
+    m = cta_ok == b
+    if m.any(): percta.append((b, float(np.mean(own[m])) / 1e3, float(np.mean(walkt[m])) / 1e3, float(np.mean(polls[m] > 0)), float(np.mean((cur[:, 2] - cur[:, 1])[m])) / 1e3, float(np.mean((cur[:, 8] - cur[:, 7])[m])) / 1e3))
+percta.sort(key=lambda r: -r[1])
+print("  CTAs with the most OWN work per tile (data wait + evaluate + totals + output, us) / walk / polled share / data wait / output:")
+for r in percta[:12]: print(f"    CTA {r[0]:3d}: own {r[1]:.2f}  walk {r[2]:.2f}  polled {r[3]:.2f}  data {r[4]:.2f}  output {r[5]:.2f}")
+print("  ... and the least:")
+for r in percta[-6:]: print(f"    CTA {r[0]:3d}: own {r[1]:.2f}  walk {r[2]:.2f}  polled {r[3]:.2f}  data {r[4]:.2f}  output {r[5]:.2f}")
+o = np.array([r[1] for r in percta]); w = np.array([r[2] for r in percta])
+print(f"  own work per tile over the CTAs: min {o.min():.2f} p50 {np.median(o):.2f} max {o.max():.2f} us; correlation(own work, walk time) = {np.corrcoef(o, w)[0, 1]:.2f}")

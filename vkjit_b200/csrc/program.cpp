@@ -199,7 +199,7 @@ ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes) {
   // 160 predecessors per look-back round.  Two 512-thread CTAs per SM make 296 tiles per generation, so the upper half of
   // a generation needs a second round — yet a 320-wide window measured SLOWER (profiles/r02_fused_scan.md, experiment 3:
   // compress_values(v, v > t) 0.376 -> 0.410 ms, 384-wide 0.469 ms): the status traffic costs more than the second round.
-  g.look_wide = (g.ctrl && g.ctas == 2) ? 10 : 5;  // control-warp kernels request the window a whole iteration early: width is free
+  g.look_wide = 5;  // (control-warp kernels read a packed window of up to 318 aggregates through the same 5 x 32 x 16 bytes)
   static int lw_env = -1;
   if (lw_env < 0) { const char* e = getenv("VKJIT_LOOK_WIDE"); lw_env = e ? atoi(e) : 0; }
   if (lw_env >= 1 && lw_env <= 16) g.look_wide = lw_env;
@@ -438,7 +438,7 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
     kw[kn++] = 0xFFFFFFFEu;  // geometry of the fused scan kernel (tunable through the environment)
     kw[kn++] = (uint32_t)sg.threads | ((uint32_t)sg.look_wide << 11) | ((uint32_t)sg.vpt << 16) | ((uint32_t)sg.slots << 24);
     kw[kn++] = (sg.ctrl ? 1u : 0u) | (sg.park ? 2u : 0u) | ((uint32_t)sg.depth << 4) | ((uint32_t)sg.ctas << 8) | ((uint32_t)sg.clag << 12) |
-               (fscan_trace_file() ? 1u << 30 : 0u) | (scan_early() ? 1u << 29 : 0u) | (scan_wreg() ? 1u << 28 : 0u) | ((uint32_t)(scan_diag() & 3) << 26);
+               (fscan_trace_file() ? 1u << 30 : 0u) | (scan_early() ? 1u << 29 : 0u) | (scan_wreg() ? 1u << 28 : 0u) | ((uint32_t)(scan_diag() & 3) << 26) | ((uint32_t)((scan_diag() >> 2) & 1) << 25);
   }
   kw[kn++] = 0xFFFFFFFFu;
   for (uint32_t r : p.roots) kw[kn++] = r;
@@ -1001,7 +1001,7 @@ std::string scan_shell(const Program& p, const std::vector<uint32_t>& streams, c
   s += "#define VK_SCAN_MODE " + std::to_string(p.scan) + "\n#define VK_NS " + std::to_string(ns) + "\n#define VK_VPT " +
        std::to_string(geom.vpt) + "\n#define VK_LAG " + std::to_string(geom.lag ? 1 : 0) + "\n#define VK_SLOTS " +
        std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n#define VK_LOOK_WIDE " + std::to_string(geom.look_wide) + "\n#define VK_TRACE " + (fscan_trace_file() ? "1" : "0") + "\n#define VK_EARLY " + (scan_early() ? "1" : "0") + "\n#define VK_WREG " + (scan_wreg() ? "1" : "0") + "\n#define VK_PARK " + (geom.park ? "1" : "0") + "\n#define VK_CTRL " + (geom.ctrl ? "1" : "0") +
-       "\n#define VK_DEPTH " + std::to_string(geom.depth) + "\n#define VK_CTAS " + std::to_string(geom.ctas) + "\n#define VK_CLAG " + std::to_string(geom.clag) + "\n#define VK_DIAG " + std::to_string(scan_diag() & 1) + "\n#define VK_COALESCE " + ((scan_diag() & 2) ? "1" : "0") + "\n";
+       "\n#define VK_DEPTH " + std::to_string(geom.depth) + "\n#define VK_CTAS " + std::to_string(geom.ctas) + "\n#define VK_CLAG " + std::to_string(geom.clag) + "\n#define VK_DIAG " + std::to_string(scan_diag() & 1) + "\n#define VK_COALESCE " + ((scan_diag() & 2) ? "1" : "0") + "\n#define VK_PACKED " + ((scan_diag() & 4) ? "0" : "1") + "\n";
   s += "struct VkPtrs {\n  const u32* s[" + std::to_string(std::max<size_t>(ns, 1)) + "];  // streamed arrays (staged by TMA)\n";
   for (uint32_t k : ptrs) {
     if (p.params[k].use & USE_SCATTER) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: the trace has side effects");

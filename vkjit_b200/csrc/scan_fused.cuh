@@ -51,6 +51,9 @@ __device__ __forceinline__ unsigned long long vk_stamp_ns() {
 #ifndef VK_COALESCE
 #define VK_COALESCE 0
 #endif
+#ifndef VK_PACKED
+#define VK_PACKED 1
+#endif
 
 #if VK_CTRL
 
@@ -131,6 +134,13 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
     // ======================================================================================== control warp
     u32 own_incl = 0u;                                            // inclusive prefix of the tile resolved last
     const bool anchored = 32u * (u32)kLookWide + 1u >= stride;    // one window spans the stride - 1 tiles back to it
+    // VK_PACKED: besides its padded status line every tile publishes {AGGREGATE | value} into a PACKED array (8 bytes per
+    // tile, behind the status lines).  With the anchor, a tile's prefix is own_incl + the stride - 1 aggregates between the
+    // CTA's previous tile and this one — CONTIGUOUS in the packed array: 5 coalesced 16-byte cp.async per lane (20 L2
+    // lines) instead of 320 scattered status lines, no search for an inclusive status, one warp reduction.  (Padded lines
+    // were introduced against L2-slice hammering by POLLING warps; this window is read once, iterations after the publish.)
+    uint64_t* packed = status + (size_t)(num_tiles + 1) * kStatusStride;
+    const bool use_packed = VK_PACKED && stride - 1u <= 32u * 2u * (u32)kLookWide - 2u;
     u32 agg_q[L];  // aggregates of tiles j-1 .. j-L
 #pragma unroll
     for (int l = 0; l < L; ++l) agg_q[l] = 0u;
@@ -142,7 +152,18 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
       // L - 1 iterations ago, and the round trip (0.3-1.5 us under load) overlaps this iteration's wait for the workers
       {
         const int pj = (int)j - (L - 1);
-        if (pj >= 0 && (u32)pj < my_tiles) prefetch_window(status, first + (u32)pj * stride, s_window[pj & 1]);
+        if (pj > 0 && (u32)pj < my_tiles && use_packed) {
+          // entries [t - stride + 1, t - 1] of the packed array, from an even (16-byte aligned) start
+          const u32 t = first + (u32)pj * stride, a0 = (t - stride + 1u) & ~1u;
+          uint64_t* dst = s_window[pj & 1];
+#pragma unroll
+          for (int i = 0; i < kLookWide; ++i) {
+            const u32 c = 32u * i + (u32)lane;  // 16-byte chunk: entries a0 + 2c, a0 + 2c + 1
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + 2 * c)), "l"(packed + a0 + 2 * c) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        else if (pj >= 0 && (u32)pj < my_tiles) prefetch_window(status, first + (u32)pj * stride, s_window[pj & 1]);
         else asm volatile("cp.async.commit_group;" ::: "memory");  // keep one group per iteration
       }
       // (2) totals of tile j -> row offsets, aggregate published
@@ -169,6 +190,7 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
         if (lane == 0) {
           if (tile == 0) status_store(status, ((uint64_t)ST_INCLUSIVE << 32) | (initial + agg_cur));
           else status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_AGGREGATE << 32) | agg_cur);
+          if (use_packed) status_store(packed + tile, ((uint64_t)ST_AGGREGATE << 32) | agg_cur);
         }
         VK_STAMP(lane == 0, tj, 3);
       }
@@ -177,16 +199,40 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
         const u32 rj = j - L, tres = first + rj * stride;
         asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but this iteration's request has landed
         VK_STAMP(have_cur && lane == 0, tj, 4);
-        uint64_t window[kLookWide];
-        {
+        const u32 init0 = (tres == 0 && initial_ptr) ? __ldcg(initial_ptr) : 0u;
+        u32 excl;
+        if (use_packed && rj > 0) {
+          const u32 lo = tres - stride + 1u, a0 = lo & ~1u;   // entries [lo, tres - 1] count
+          const uint64_t* wsrc = s_window[rj & 1];
+          u32 mine = 0u;
+#pragma unroll
+          for (int i = 0; i < kLookWide; ++i) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const u32 e = a0 + 2u * (32u * i + (u32)lane) + (u32)h;
+              if (e >= lo && e < tres) {
+                uint64_t w = wsrc[2 * (32 * i + lane) + h];
+                u32 spins = 0;
+                while ((u32)(w >> 32) == ST_INVALID) {  // (not expected: requested iterations after the publish)
+                  __nanosleep(40);
+                  w = status_load(packed + e);
+                  if (++spins > (1u << 25)) __trap();
+                }
+                mine += (u32)w;
+              }
+            }
+          }
+          excl = own_incl + warp_sum(mine);
+          if (lane == 0) status_store(status + (size_t)tres * kStatusStride, ((uint64_t)ST_INCLUSIVE << 32) | (excl + agg_q[L - 1]));
+        } else {
+          uint64_t window[kLookWide];
           const uint64_t* wsrc = s_window[rj & 1];
 #pragma unroll
           for (int i = 0; i < kLookWide; ++i) window[i] = wsrc[(size_t)(i * 32 + lane) * 2];
+          // the anchor: this CTA's previous tile (tres - stride), whose inclusive prefix is in own_incl
+          excl = anchored ? resolve_anchored(status, tres, agg_q[L - 1], init0, window, stride, own_incl, rj > 0)
+                          : resolve_prefix(status, tres, agg_q[L - 1], init0, window);
         }
-        // the anchor: this CTA's previous tile (tres - stride), whose inclusive prefix is in own_incl
-        const u32 init0 = (tres == 0 && initial_ptr) ? __ldcg(initial_ptr) : 0u;
-        const u32 excl = anchored ? resolve_anchored(status, tres, agg_q[L - 1], init0, window, stride, own_incl, rj > 0)
-                                  : resolve_prefix(status, tres, agg_q[L - 1], init0, window);
         own_incl = excl + agg_q[L - 1];
         if (lane == 0) {
           s_excl[rj % R] = excl;
