@@ -296,6 +296,34 @@ print("variants ok")
     assert r.returncode == 0 and "variants ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
 
 
+def test_scatter_add_pass_variant_codegen():
+    """The opt-in bin-range pass variant of a privatised scatter_add (program.cpp, variant 3; debug_codegen compile bit 3)
+    compiles for sm_100a for integer and f32 targets, predicates the lane body on the bin range, and is refused — the
+    per-CTA variant is generated instead — when the trace has a second side effect or reads the target."""
+    ir = Ir()
+    def wrap(ty, n, k): return ir.array_wrap_device(ty, 0x7F0000000000 + k * (1 << 33), n)
+    idx, table, bins = wrap(U32, 1 << 26, 2), wrap(U32, 1 << 16, 3), wrap(U32, 1 << 16, 4)
+    fbins, ftab = wrap(F32, 1 << 16, 5), wrap(F32, 1 << 16, 6)
+
+    def gen(roots):
+        ids = (ctypes.c_uint32 * len(roots))(*roots)
+        n_, cub = ctypes.c_size_t(), ctypes.c_size_t()
+        ir.api.call("debug_codegen", ir._h, ids, len(roots), 9, None, 0, ctypes.byref(n_), ctypes.byref(cub))
+        buf = ctypes.create_string_buffer(n_.value + 1)
+        ir.api.call("debug_codegen", ir._h, ids, len(roots), 9, buf, n_.value + 1, ctypes.byref(n_), ctypes.byref(cub))
+        return buf.value.decode(), cub.value
+
+    src, cubin = gen([ir.scatter_add(ir.gather(table, idx), bins, idx)])
+    assert cubin > 1000 and "const u32 bin_lo" in src and "- bin_lo >= kbins) return false;" in src
+    src, cubin = gen([ir.scatter_add(ir.gather(ftab, idx), fbins, idx)])
+    assert cubin > 1000 and "bin_lo" in src
+    bins2 = wrap(U32, 1 << 16, 7)
+    src, cubin = gen([ir.scatter_add(ir.const_u32(1), bins, idx), ir.scatter_add(ir.const_u32(2), bins2, idx)])
+    assert cubin > 1000 and "bin_lo" not in src and "vk_sbins" in src            # two side effects: per-CTA variant
+    src, cubin = gen([ir.scatter_add(ir.gather(bins, idx), bins, idx)])
+    assert cubin > 1000 and "bin_lo" not in src                                   # the target is read in the same trace
+
+
 def test_struct_select_gather_scatter_codegen():
     ir = Ir()
     i = ir.arange(U32, 64)
