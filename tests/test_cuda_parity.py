@@ -662,12 +662,13 @@ def test_upload_and_readback_through_the_staging_ring(cir, n):
     assert np.array_equal(again, keep) and (n * 4 < (64 << 10) or again.ctypes.data != got.ctypes.data)
 
 
-@pytest.mark.parametrize("variant", ["default", "ctrl", "ctrl_deep", "ctrl_small_tiles", "wreg", "early"])
+@pytest.mark.parametrize("variant", ["default", "ctrl", "ctrl_deep", "ctrl_small_tiles", "wreg", "early", "lag_packed"])
 def test_fused_compress_kernel_variants(tmp_path, variant):
     """The fused trace -> compress kernels in every schedule the library can generate (scan_fused.cuh): the shipped lagged
     kernel, the opt-in control-warp pipeline (VKJIT_SCAN_CTRL=1: a dedicated warp owns the totals scan / publish / anchored
     look-back, the workers write tile k - D; lane-by-lane and coalesced warp-row output) at several lags and tile sizes, the status window
-    through strong loads (VKJIT_SCAN_WREG=1) and requested early (VKJIT_SCAN_EARLY=1) — all bit-exact against the oracle:
+    through strong loads (VKJIT_SCAN_WREG=1), requested early (VKJIT_SCAN_EARLY=1), and the packed anchored look-back in the
+    lagged kernel (VKJIT_LAG_PACKED=1) — all bit-exact against the oracle:
     indices and values, a mask computed from the streamed array and one computed from the lane index, sizes from one
     lane over ragged tiles to several generations of the persistent grid.  The switches are read once per process."""
     import subprocess
@@ -709,7 +710,7 @@ print("fused compress ok")
     env = {"default": {}, "ctrl": {"VKJIT_SCAN_CTRL": "1"},
            "ctrl_deep": {"VKJIT_SCAN_CTRL": "1", "VKJIT_CTRL_LAG": "4", "VKJIT_CTRL_DEPTH": "6", "VKJIT_FSCAN_DIAG": "2"},
            "ctrl_small_tiles": {"VKJIT_SCAN_CTRL": "1", "VKJIT_CTRL_VPT": "2", "VKJIT_CTRL_LAG": "1", "VKJIT_CTRL_DEPTH": "1"},
-           "wreg": {"VKJIT_SCAN_WREG": "1"}, "early": {"VKJIT_SCAN_EARLY": "1"}}[variant]
+           "wreg": {"VKJIT_SCAN_WREG": "1"}, "early": {"VKJIT_SCAN_EARLY": "1"}, "lag_packed": {"VKJIT_LAG_PACKED": "1"}}[variant]
     r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "fused compress ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
 

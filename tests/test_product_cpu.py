@@ -267,7 +267,8 @@ def test_proven_ranges_are_sound(oir, block):
     {"VKJIT_SCAN_WREG": "1", "VKJIT_SCAN_EARLY": "1", "VKJIT_FSCAN_TRACE": "/dev/null"},
     {"VKJIT_SCAN_PARK": "1"},
     {"VKJIT_LOOK_WIDE": "10", "VKJIT_SCAN_T": "1024"},
-], ids=["ctrl", "ctrl_deep_coalesced", "ctrl_small_traced", "wreg_early_traced", "park", "wide_1024"])
+    {"VKJIT_LAG_PACKED": "1", "VKJIT_FSCAN_TRACE": "/dev/null"},
+], ids=["ctrl", "ctrl_deep_coalesced", "ctrl_small_traced", "wreg_early_traced", "park", "wide_1024", "lag_packed_traced"])
 def test_opt_in_scan_kernel_variants_compile_for_sm100a(env, tmp_path):
     """Every opt-in schedule of the fused scan / compress kernels still generates CUDA C that NVRTC accepts
     for sm_100a, without register spills beyond a few words — offline, no device.  (Their results are checked on the GPU

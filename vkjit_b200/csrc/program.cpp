@@ -236,6 +236,13 @@ int scan_diag() {
   return d;
 }
 
+// $VKJIT_LAG_PACKED=0/1: the lagged fused scan kernels resolve a tile's prefix from a packed copy of the tile aggregates,
+// anchored at the CTA's own previous tile (scan_fused.cuh: VK_LAGPACK).  Part of the cache key.
+bool scan_lag_packed() {
+  static const int on = [] { const char* e = getenv("VKJIT_LAG_PACKED"); return e ? (e[0] == '1' ? 1 : 0) : kScanLagPackedDefault; }();
+  return on == 1;
+}
+
 size_t stream_count(const Program& p) {
   size_t k = 0;
   for (const Param& pr : p.params) k += (pr.use & USE_STREAM) ? 1 : 0;
@@ -437,7 +444,7 @@ void build_program(Ir& ir, const std::vector<VarId>& schedule, bool vectorized, 
     if (sg.lag) kw[1] |= 1u << 28;
     kw[kn++] = 0xFFFFFFFEu;  // geometry of the fused scan kernel (tunable through the environment)
     kw[kn++] = (uint32_t)sg.threads | ((uint32_t)sg.look_wide << 11) | ((uint32_t)sg.vpt << 16) | ((uint32_t)sg.slots << 24);
-    kw[kn++] = (sg.ctrl ? 1u : 0u) | (sg.park ? 2u : 0u) | ((uint32_t)sg.depth << 4) | ((uint32_t)sg.ctas << 8) | ((uint32_t)sg.clag << 12) |
+    kw[kn++] = (sg.ctrl ? 1u : 0u) | (sg.park ? 2u : 0u) | ((sg.lag && !sg.ctrl && scan_lag_packed()) ? 4u : 0u) | ((uint32_t)sg.depth << 4) | ((uint32_t)sg.ctas << 8) | ((uint32_t)sg.clag << 12) |
                (fscan_trace_file() ? 1u << 30 : 0u) | (scan_early() ? 1u << 29 : 0u) | (scan_wreg() ? 1u << 28 : 0u) | ((uint32_t)(scan_diag() & 3) << 26) | ((uint32_t)((scan_diag() >> 2) & 1) << 25);
   }
   kw[kn++] = 0xFFFFFFFFu;
@@ -1001,7 +1008,7 @@ std::string scan_shell(const Program& p, const std::vector<uint32_t>& streams, c
   s += "#define VK_SCAN_MODE " + std::to_string(p.scan) + "\n#define VK_NS " + std::to_string(ns) + "\n#define VK_VPT " +
        std::to_string(geom.vpt) + "\n#define VK_LAG " + std::to_string(geom.lag ? 1 : 0) + "\n#define VK_SLOTS " +
        std::to_string(geom.slots) + "\n#define VK_T " + std::to_string(geom.threads) + "\n#define VK_LOOK_WIDE " + std::to_string(geom.look_wide) + "\n#define VK_TRACE " + (fscan_trace_file() ? "1" : "0") + "\n#define VK_EARLY " + (scan_early() ? "1" : "0") + "\n#define VK_WREG " + (scan_wreg() ? "1" : "0") + "\n#define VK_PARK " + (geom.park ? "1" : "0") + "\n#define VK_CTRL " + (geom.ctrl ? "1" : "0") +
-       "\n#define VK_DEPTH " + std::to_string(geom.depth) + "\n#define VK_CTAS " + std::to_string(geom.ctas) + "\n#define VK_CLAG " + std::to_string(geom.clag) + "\n#define VK_DIAG " + std::to_string(scan_diag() & 1) + "\n#define VK_COALESCE " + ((scan_diag() & 2) ? "1" : "0") + "\n#define VK_PACKED " + ((scan_diag() & 4) ? "0" : "1") + "\n";
+       "\n#define VK_DEPTH " + std::to_string(geom.depth) + "\n#define VK_CTAS " + std::to_string(geom.ctas) + "\n#define VK_CLAG " + std::to_string(geom.clag) + "\n#define VK_DIAG " + std::to_string(scan_diag() & 1) + "\n#define VK_COALESCE " + ((scan_diag() & 2) ? "1" : "0") + "\n#define VK_PACKED " + ((scan_diag() & 4) ? "0" : "1") + "\n#define VK_LAGPACK " + ((geom.lag && !geom.ctrl && scan_lag_packed()) ? "1" : "0") + "\n";
   s += "struct VkPtrs {\n  const u32* s[" + std::to_string(std::max<size_t>(ns, 1)) + "];  // streamed arrays (staged by TMA)\n";
   for (uint32_t k : ptrs) {
     if (p.params[k].use & USE_SCATTER) fail(VKJIT_ERR_UNSUPPORTED, "fused scan: the trace has side effects");

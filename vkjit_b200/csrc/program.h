@@ -49,6 +49,8 @@ struct ScanFusedGeom {
 };
 ScanFusedGeom scan_fused_geom(size_t streams, int mode, size_t nodes);
 constexpr int kScanWregDefault = 0;
+constexpr int kScanLagPackedDefault = 0;  // packed, anchored look-back in the lagged fused scan kernels ($VKJIT_LAG_PACKED)
+bool scan_lag_packed();
 constexpr int kScanParkDefault = 0;  // parked-result lagged prefix sums for traces without streamed inputs ($VKJIT_SCAN_PARK)
 constexpr int kScanCtrlDefault = 0;  // control-warp fused compress kernel ($VKJIT_SCAN_CTRL)
 const char* fscan_trace_file();  // $VKJIT_FSCAN_TRACE (per-tile phase stamps of the lagged fused scan kernels)

@@ -723,10 +723,11 @@ bool eval_scan(Ir& ir, int mode, const std::vector<VarId>& roots, const uint32_t
   const size_t tile = geom.tile();
   const size_t tiles = (prog.n + tile - 1) / tile;
   // control-warp kernels keep a packed copy of the tile aggregates (8 bytes per tile) behind the status lines
-  const size_t packed_words = geom.ctrl ? tiles + 1024 : 0;
-  be.ensure_scan_scratch(prog.n + (geom.ctrl ? prog.n / 8 + 128 * tile : 0), tile);
+  const bool has_packed = geom.ctrl || (geom.lag && scan_lag_packed());
+  const size_t packed_words = has_packed ? tiles + 1024 : 0;
+  be.ensure_scan_scratch(prog.n + (has_packed ? prog.n / 8 + 128 * tile : 0), tile);
   // status lines: a header line + one per tile (what ensure_scan_scratch sizes); control-warp kernels: one more line, then the packed array
-  const size_t clear_words = geom.ctrl ? (size_t)prims::kStatusWordsPerTile * (2 + tiles) + packed_words : (size_t)prims::kStatusWordsPerTile * (1 + tiles);
+  const size_t clear_words = has_packed ? (size_t)prims::kStatusWordsPerTile * (2 + tiles) + packed_words : (size_t)prims::kStatusWordsPerTile * (1 + tiles);
   if (clear_words > be.scratch.tile_state_words) fail(VKJIT_ERR_INVALID, "scan scratch too small");
   ck(cudaMemsetAsync(be.scratch.tile_state, 0, clear_words * 8, (cudaStream_t)be.enqueue_stream()), "scan status memset");
   Array* o = be.new_array((size_t)prog.n * 4);  // compress: worst case, trimmed by the caller

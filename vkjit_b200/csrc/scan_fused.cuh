@@ -31,6 +31,9 @@ template <bool B> struct VkBool { static constexpr bool value = B; };
 #ifndef VK_PARK
 #define VK_PARK 0
 #endif
+#ifndef VK_LAGPACK
+#define VK_LAGPACK 0
+#endif
 #if VK_TRACE
 // "memory": the timer read must not move across a barrier or the code it brackets
 __device__ __forceinline__ unsigned long long vk_stamp_ns() {
@@ -695,6 +698,15 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
   uint4 xp[PARK ? 1 : VPT];     // modes 0/1, previous tile: results relative to the start of the vector's warp row
   u32 flags_p = 0u, pre_p = 0u; // modes 2/3, previous tile: selection bits / 8-bit exclusive row offsets
   u32 agg_prev = 0u;            // warp 0: aggregate of the previous tile
+  // VK_LAGPACK: anchored look-back over a PACKED copy of the tile aggregates (8 bytes per tile behind the status lines).
+  // The tile `stride` places back is this CTA's own previous tile, whose inclusive prefix warp 0 keeps in own_incl; the
+  // stride - 1 aggregates in between are contiguous in the packed array: the same 5 cp.async per lane as for the padded
+  // status window, but 20 L2 lines instead of 160, a window that always reaches the anchor (296 tiles per generation
+  // with two CTAs per SM) — so never a second round and no search for an inclusive status.  The first tile of a CTA
+  // takes the generic walk over the padded status lines.
+  u32 own_incl = 0u;
+  uint64_t* packed = status + (size_t)(num_tiles + 1) * kStatusStride;
+  const bool use_packed = VK_LAGPACK && !VK_WREG && !VK_EARLY && stride - 1u <= 32u * 2u * (u32)kLookWide - 2u;
 #pragma unroll
   for (int j = 0; j < (PARK ? 1 : VPT); ++j) xp[j] = make_uint4(0u, 0u, 0u, 0u);
 
@@ -718,6 +730,15 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
         wreg[i] = idx >= 0 ? status_load(status + (size_t)idx * kStatusStride) : ((uint64_t)ST_INCLUSIVE << 32);
       }
     }
+    if (use_packed && warp == 0 && k > 1) {   // tile k-1 has a predecessor in this CTA: the packed, anchored window
+      const u32 t = tile - stride, a0 = (t - stride + 1u) & ~1u;   // entries [t - stride + 1, t - 1], from an even start
+#pragma unroll
+      for (int i = 0; i < kLookWide; ++i) {
+        const u32 c = 32u * i + (u32)lane;  // 16-byte chunk: entries a0 + 2c, a0 + 2c + 1
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(s_window + 2 * c)), "l"(packed + a0 + 2 * c) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    } else
     if (!VK_WREG && !VK_EARLY && warp == 0 && have_prev) prefetch_window(status, tile - stride, s_window);
     if (have_cur) {  // ---- evaluate tile k and scan it locally
       const size_t tile_base = (size_t)tile * TILE;
@@ -815,9 +836,46 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
         if (lane == 0) {
           if (tile == 0) status_store(status, ((uint64_t)ST_INCLUSIVE << 32) | (initial + agg_cur));
           else status_store(status + (size_t)tile * kStatusStride, ((uint64_t)ST_AGGREGATE << 32) | agg_cur);
+          if (use_packed) status_store(packed + tile, ((uint64_t)ST_AGGREGATE << 32) | agg_cur);
         }
         VK_STAMP(lane == 0, tile, 5);
       }
+      if (have_prev && use_packed && k > 1) {
+        const u32 tprev = tile - stride, lo = tprev - stride + 1u, a0 = lo & ~1u;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        VK_STAMP(lane == 0, tprev, 12);
+        u32 mine = 0u, polled = 0u;
+#pragma unroll
+        for (int i = 0; i < kLookWide; ++i) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const u32 e = a0 + 2u * (32u * i + (u32)lane) + (u32)h;
+            if (e >= lo && e < tprev) {
+              uint64_t w = s_window[2 * (32 * i + lane) + h];
+              u32 spins = 0;
+              while ((u32)(w >> 32) == ST_INVALID) {  // a predecessor that runs more than a tile period behind
+                __nanosleep(40);
+                w = status_load(packed + e);
+                polled += 1u;
+                if (++spins > (1u << 25)) __trap();
+              }
+              mine += (u32)w;
+            }
+          }
+        }
+        const u32 excl = own_incl + warp_sum(mine);
+        own_incl = excl + agg_prev;
+        if (lane == 0) {
+          status_store(status + (size_t)tprev * kStatusStride, ((uint64_t)ST_INCLUSIVE << 32) | own_incl);
+          s_tile_excl = excl;
+          if (COMPRESS && tprev == num_tiles - 1) *count_out = excl + agg_prev;
+        }
+#if VK_TRACE
+        { const u32 polls = __reduce_add_sync(0xFFFFFFFFu, polled);
+          if (lane == 0) { status[(size_t)tprev * kStatusStride + 13] = polls; status[(size_t)tprev * kStatusStride + 14] = 1u; } }
+#endif
+        VK_STAMP(lane == 0, tprev, 6);
+      } else
       if (have_prev) {
         const u32 tprev = tile - stride;
         uint64_t window[kLookWide];
@@ -837,6 +895,7 @@ vkjit_trace(const u32 n, const u32 base, const VkPtrs P, u32* __restrict__ out, 
 #else
         const u32 excl = resolve_prefix(status, tprev, agg_prev, (tprev == 0 && initial_ptr) ? __ldcg(initial_ptr) : 0u, window);
 #endif
+        own_incl = excl + agg_prev;
         if (lane == 0) {
           s_tile_excl = excl;
           if (COMPRESS && tprev == num_tiles - 1) *count_out = excl + agg_prev;
